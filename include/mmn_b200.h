@@ -1,0 +1,126 @@
+/* mmn_b200.h -- C ABI of libmmn_b200.so: the B200 (sm_100a) attention hot path of
+ * Transconnectome/multimodal_neuroimage.
+ *
+ * The reference has no FFI/plugin interface for this path (it is pure PyTorch); the
+ * boundary it exposes is the nn.Module API of modules/*.py.  The entry points below are
+ * what a binding for that path binds, one per reference call site:
+ *
+ *   mmn_winattn_fwd / _bwd   replace, between `qkv = F.linear(x, ...)` and `self.proj(x)`:
+ *       modules/swin_v2_module.py:149-175      (WindowAttention.forward, cosine + CPB bias)
+ *       modules/swinfusion_module.py:121-142   (WindowAttention_fusion.forward)
+ *       modules/swinfusion_module.py:221-243   (Cross_WindowAttention.forward)
+ *     and, fused into the same kernel, the data movement of the enclosing blocks:
+ *       torch.roll / window_partition / window_reverse / roll back
+ *       modules/swin_v2_module.py:277-297, modules/swinfusion_module.py:350-373,497-530
+ *       and the shift mask of swin_v2_module.py:244-266 (generated in-kernel).
+ *   mmn_mha_fwd / _bwd       replace modules/multihead_attention.py:85-127
+ *       (q*scaling, bmm, +attn_mask, softmax, dropout, bmm) incl. the future mask of
+ *       modules/crossmodal_transformer.py:179-186 (generated in-kernel).
+ *   mmn_mha_avg_weights      replaces modules/multihead_attention.py:131-133.
+ *
+ * Conventions: plain C structs, device pointers owned by the caller, the callee never
+ * allocates or frees device memory, launches on the given stream of the given device and
+ * never synchronises.  Return 0 on success, a negative MMN_ERR_* otherwise;
+ * mmn_last_error() gives the thread-local message.  There is NO CPU path: every entry
+ * point fails with MMN_ERR_CUDA when no CUDA device is usable.
+ *
+ * Token addressing.  A "token row" is num_heads*head_dim contiguous elements; row r of
+ * head h of tensor X lives at  X + row_offset(r) + h*head_dim  (element units).
+ *   window attention: tokens are indexed in the UN-windowed, UN-shifted (batch, grid...)
+ *     order, row_offset = token * X_row_stride.  Packed qkv of shape (..., 3C) is passed
+ *     as q = base, k = base + C, v = base + 2C with row stride 3C.
+ *   multi-head attention: row (t, b) has row_offset = t*X_stride_t + b*X_stride_b.
+ */
+#ifndef MMN_B200_H_
+#define MMN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMN_ABI_VERSION 1
+
+enum { MMN_OK = 0, MMN_ERR_INVALID = -1, MMN_ERR_UNSUPPORTED = -2, MMN_ERR_CUDA = -3 };
+enum { MMN_DT_F32 = 0, MMN_DT_BF16 = 1 };
+enum { MMN_SCORE_SCALED = 0,   /* s = (q*scale) . k            swinfusion_module.py:124-125 */
+       MMN_SCORE_COSINE = 1 }; /* s = g_h * q^ . k^            swin_v2_module.py:153-156    */
+enum { MMN_MASK_NONE = 0,
+       MMN_MASK_SHIFT = 1,     /* {0,-100} region mask of the shifted frame, made in-kernel  */
+       MMN_MASK_TENSOR = 2,    /* additive fp32 tensor: (mask_windows,N,N) or (T,S)          */
+       MMN_MASK_FUTURE = 3 };  /* -inf where j - i >= mask_diagonal, made in-kernel          */
+enum { MMN_PATH_AUTO = 0, MMN_PATH_GENERIC = 1, MMN_PATH_TCGEN05 = 2 };
+
+typedef struct mmn_winattn_desc {
+  int32_t ndim;            /* 1..3 spatial dims; unused trailing entries below are ignored   */
+  int32_t batch;
+  int32_t grid[3];         /* tokens per axis                                                 */
+  int32_t window[3];       /* window extent per axis, divides grid                            */
+  int32_t shift[3];        /* cyclic shift per axis, 0 <= shift < window                      */
+  int32_t num_heads, head_dim;
+  int32_t score_kind;      /* MMN_SCORE_*                                                     */
+  int32_t mask_kind;       /* NONE | SHIFT | TENSOR                                           */
+  int32_t mask_windows;    /* TENSOR: leading extent nW of the mask, window w uses w % nW     */
+  int32_t io_dtype;        /* MMN_DT_*: dtype of q,k,v,out,dout,dq,dk,dv                      */
+  int32_t path;            /* MMN_PATH_*; AUTO picks tcgen05 when the shape qualifies         */
+  float scale;             /* SCALED: multiplier on q                                         */
+  float dropout_p;         /* attention-probability dropout; 0 disables                       */
+  uint64_t seed, offset;   /* Philox stream for dropout (same values in fwd and bwd)          */
+  int64_t q_row_stride, k_row_stride, v_row_stride, o_row_stride;
+  int64_t do_row_stride, dq_row_stride, dk_row_stride, dv_row_stride;   /* bwd only          */
+} mmn_winattn_desc;
+
+typedef struct mmn_mha_desc {
+  int32_t tgt_len, src_len, batch, num_heads, head_dim;
+  int32_t mask_kind;       /* NONE | FUTURE | TENSOR                                          */
+  int32_t mask_diagonal;   /* FUTURE: 1 + |S - T|   (crossmodal_transformer.py:183)           */
+  int32_t io_dtype, path;
+  float scale;             /* multiplier on q (head_dim^-0.5, multihead_attention.py:85)      */
+  float dropout_p;
+  uint64_t seed, offset;
+  int64_t q_stride_t, q_stride_b, k_stride_t, k_stride_b, v_stride_t, v_stride_b;
+  int64_t o_stride_t, o_stride_b;
+  int64_t do_stride_t, do_stride_b, dq_stride_t, dq_stride_b, dk_stride_t, dk_stride_b;
+  int64_t dv_stride_t, dv_stride_b;
+} mmn_mha_desc;
+
+int mmn_abi_version(void);
+const char* mmn_last_error(void);
+/* Name of the code path AUTO would take for this descriptor: "tcgen05" or "generic". */
+const char* mmn_winattn_path(const mmn_winattn_desc* desc);
+const char* mmn_mha_path(const mmn_mha_desc* desc);
+/* Number of kernels this library has launched in the calling process (monotonic). */
+uint64_t mmn_launch_count(void);
+
+/* bias (num_heads,N,N) fp32 or NULL; head_scale (num_heads) fp32, COSINE only;
+ * mask (mask_windows,N,N) fp32, TENSOR only; out: token rows; lse (batch*nW*num_heads*N) fp32. */
+int mmn_winattn_fwd(const mmn_winattn_desc* desc, const void* q, const void* k, const void* v,
+                    const float* bias, const float* head_scale, const float* mask,
+                    void* out, float* lse, int device, void* stream);
+
+/* dbias (num_heads,N,N) fp32 and dhead_scale (num_heads) fp32 are ACCUMULATED into (the
+ * caller zeroes them); either may be NULL to skip. */
+int mmn_winattn_bwd(const mmn_winattn_desc* desc, const void* q, const void* k, const void* v,
+                    const float* bias, const float* head_scale, const float* mask,
+                    const void* out, const float* lse, const void* dout,
+                    void* dq, void* dk, void* dv, float* dbias, float* dhead_scale,
+                    int device, void* stream);
+
+/* mask (T,S) fp32, TENSOR only; out (T,B,E)-addressed rows; lse (batch*num_heads*T) fp32. */
+int mmn_mha_fwd(const mmn_mha_desc* desc, const void* q, const void* k, const void* v,
+                const float* mask, void* out, float* lse, int device, void* stream);
+
+int mmn_mha_bwd(const mmn_mha_desc* desc, const void* q, const void* k, const void* v,
+                const float* mask, const void* out, const float* lse, const void* dout,
+                void* dq, void* dk, void* dv, int device, void* stream);
+
+/* avg (batch,T,S) fp32 = mean over heads of the (dropped-out) attention probabilities. */
+int mmn_mha_avg_weights(const mmn_mha_desc* desc, const void* q, const void* k, const float* mask,
+                        const float* lse, float* avg, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMN_B200_H_ */

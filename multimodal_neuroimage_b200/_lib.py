@@ -1,0 +1,125 @@
+"""ctypes binding of libmmn_b200.so (C ABI: include/mmn_b200.h) and its in-tree build.
+
+The library is the product; there is no Python/CPU fallback.  `load()` raises if the
+shared object is missing and every op raises if the C call returns an error.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+import threading
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG_DIR)
+CSRC = os.path.join(PKG_DIR, "csrc")
+LIB_PATH = os.path.join(PKG_DIR, "libmmn_b200.so")
+SOURCES = ["mmn_abi.cu"]
+HEADERS = ["attn_generic.cuh", "winattn_tc.cuh", "tc_common.cuh"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+# enums of include/mmn_b200.h
+DT_F32, DT_BF16 = 0, 1
+SCORE_SCALED, SCORE_COSINE = 0, 1
+MASK_NONE, MASK_SHIFT, MASK_TENSOR, MASK_FUTURE = 0, 1, 2, 3
+PATH_AUTO, PATH_GENERIC, PATH_TCGEN05 = 0, 1, 2
+
+EXPORTS = ["mmn_abi_version", "mmn_last_error", "mmn_winattn_path", "mmn_mha_path", "mmn_launch_count",
+           "mmn_winattn_fwd", "mmn_winattn_bwd", "mmn_mha_fwd", "mmn_mha_bwd", "mmn_mha_avg_weights"]
+
+
+class WinAttnDesc(C.Structure):
+    _fields_ = [("ndim", C.c_int32), ("batch", C.c_int32),
+                ("grid", C.c_int32 * 3), ("window", C.c_int32 * 3), ("shift", C.c_int32 * 3),
+                ("num_heads", C.c_int32), ("head_dim", C.c_int32),
+                ("score_kind", C.c_int32), ("mask_kind", C.c_int32), ("mask_windows", C.c_int32),
+                ("io_dtype", C.c_int32), ("path", C.c_int32),
+                ("scale", C.c_float), ("dropout_p", C.c_float),
+                ("seed", C.c_uint64), ("offset", C.c_uint64),
+                ("q_row_stride", C.c_int64), ("k_row_stride", C.c_int64), ("v_row_stride", C.c_int64),
+                ("o_row_stride", C.c_int64), ("do_row_stride", C.c_int64), ("dq_row_stride", C.c_int64),
+                ("dk_row_stride", C.c_int64), ("dv_row_stride", C.c_int64)]
+
+
+class MhaDesc(C.Structure):
+    _fields_ = [("tgt_len", C.c_int32), ("src_len", C.c_int32), ("batch", C.c_int32),
+                ("num_heads", C.c_int32), ("head_dim", C.c_int32),
+                ("mask_kind", C.c_int32), ("mask_diagonal", C.c_int32),
+                ("io_dtype", C.c_int32), ("path", C.c_int32),
+                ("scale", C.c_float), ("dropout_p", C.c_float),
+                ("seed", C.c_uint64), ("offset", C.c_uint64)] + \
+               [(f"{t}_stride_{a}", C.c_int64) for t in ("q", "k", "v", "o", "do", "dq", "dk", "dv") for a in ("t", "b")]
+
+
+def source_stamp() -> float:
+    files = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(ROOT, "include", "mmn_b200.h")]
+    return max(os.path.getmtime(f) for f in files if os.path.exists(f))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into PKG_DIR/libmmn_b200.so (nvcc cross-compiles
+    without a GPU).  Skips when the library is newer than every source."""
+    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= source_stamp():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build libmmn_b200.so")
+    cmd = [nvcc] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH + ".tmp"]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    return LIB_PATH
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the library and type its entry points.  Raises loudly when it is absent."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(multimodal_neuroimage_b200 has no CPU or PyTorch fallback)")
+        lib = C.CDLL(LIB_PATH)
+        vp, fp = C.c_void_p, C.c_void_p
+        lib.mmn_abi_version.restype = C.c_int
+        lib.mmn_last_error.restype = C.c_char_p
+        lib.mmn_launch_count.restype = C.c_uint64
+        lib.mmn_winattn_path.restype = C.c_char_p
+        lib.mmn_winattn_path.argtypes = [C.POINTER(WinAttnDesc)]
+        lib.mmn_mha_path.restype = C.c_char_p
+        lib.mmn_mha_path.argtypes = [C.POINTER(MhaDesc)]
+        lib.mmn_winattn_fwd.restype = C.c_int
+        lib.mmn_winattn_fwd.argtypes = [C.POINTER(WinAttnDesc), vp, vp, vp, fp, fp, fp, vp, fp, C.c_int, vp]
+        lib.mmn_winattn_bwd.restype = C.c_int
+        lib.mmn_winattn_bwd.argtypes = [C.POINTER(WinAttnDesc), vp, vp, vp, fp, fp, fp, vp, fp, vp, vp, vp, vp, fp, fp,
+                                        C.c_int, vp]
+        lib.mmn_mha_fwd.restype = C.c_int
+        lib.mmn_mha_fwd.argtypes = [C.POINTER(MhaDesc), vp, vp, vp, fp, vp, fp, C.c_int, vp]
+        lib.mmn_mha_bwd.restype = C.c_int
+        lib.mmn_mha_bwd.argtypes = [C.POINTER(MhaDesc), vp, vp, vp, fp, vp, fp, vp, vp, vp, vp, C.c_int, vp]
+        lib.mmn_mha_avg_weights.restype = C.c_int
+        lib.mmn_mha_avg_weights.argtypes = [C.POINTER(MhaDesc), vp, vp, fp, fp, fp, C.c_int, vp]
+        if lib.mmn_abi_version() != 1:
+            raise RuntimeError("libmmn_b200.so ABI version mismatch")
+        _lib = lib
+        return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().mmn_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().mmn_launch_count())

@@ -1,0 +1,305 @@
+// mmn_abi.cu -- the extern "C" surface declared in include/mmn_b200.h.
+// Validates descriptors, picks a code path (tcgen05 tensor-core kernels for the tuned
+// bf16 shapes, the generic fp32-arithmetic kernels for everything else) and launches on
+// the caller's stream.  No ATen / pybind here: plain pointers and sizes only.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/mmn_b200.h"
+#include "attn_generic.cuh"
+#include "winattn_tc.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); return; }
+    if (dev != prev && cudaSetDevice(dev) != cudaSuccess) { cudaGetLastError(); return; }
+    ok = true;
+  }
+  ~DeviceGuard() { if (ok && prev >= 0) cudaSetDevice(prev); }
+};
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MMN_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return MMN_OK;
+}
+
+int prod3(const int32_t* a, int n) { int p = 1; for (int i = 0; i < n; ++i) p *= a[i]; return p; }
+
+int validate_win(const mmn_winattn_desc* d) {
+  if (!d) return fail(MMN_ERR_INVALID, "null descriptor");
+  if (d->ndim < 1 || d->ndim > 3) return fail(MMN_ERR_INVALID, "ndim %d not in 1..3", d->ndim);
+  if (d->batch < 1 || d->num_heads < 1 || d->head_dim < 1) return fail(MMN_ERR_INVALID, "batch/heads/head_dim must be positive");
+  for (int a = 0; a < d->ndim; ++a) {
+    if (d->window[a] < 1 || d->grid[a] < 1 || d->grid[a] % d->window[a] != 0)
+      return fail(MMN_ERR_INVALID, "axis %d: window %d does not divide grid %d", a, d->window[a], d->grid[a]);
+    if (d->shift[a] < 0 || d->shift[a] >= d->window[a])
+      return fail(MMN_ERR_INVALID, "axis %d: shift %d not in [0, window %d)", a, d->shift[a], d->window[a]);
+  }
+  if (d->score_kind != MMN_SCORE_SCALED && d->score_kind != MMN_SCORE_COSINE) return fail(MMN_ERR_INVALID, "bad score_kind");
+  if (d->mask_kind != MMN_MASK_NONE && d->mask_kind != MMN_MASK_SHIFT && d->mask_kind != MMN_MASK_TENSOR)
+    return fail(MMN_ERR_INVALID, "bad mask_kind %d for window attention", d->mask_kind);
+  if (d->mask_kind == MMN_MASK_TENSOR && d->mask_windows < 1) return fail(MMN_ERR_INVALID, "mask_windows must be >= 1");
+  if (d->io_dtype != MMN_DT_F32 && d->io_dtype != MMN_DT_BF16) return fail(MMN_ERR_INVALID, "bad io_dtype");
+  if (d->dropout_p < 0.f || d->dropout_p >= 1.f) return fail(MMN_ERR_INVALID, "dropout_p must be in [0,1)");
+  if (d->head_dim > 128) return fail(MMN_ERR_UNSUPPORTED, "head_dim %d > 128", d->head_dim);
+  return MMN_OK;
+}
+
+int validate_mha(const mmn_mha_desc* d) {
+  if (!d) return fail(MMN_ERR_INVALID, "null descriptor");
+  if (d->tgt_len < 1 || d->src_len < 1 || d->batch < 1 || d->num_heads < 1 || d->head_dim < 1)
+    return fail(MMN_ERR_INVALID, "sizes must be positive");
+  if (d->mask_kind != MMN_MASK_NONE && d->mask_kind != MMN_MASK_FUTURE && d->mask_kind != MMN_MASK_TENSOR)
+    return fail(MMN_ERR_INVALID, "bad mask_kind %d for multi-head attention", d->mask_kind);
+  if (d->io_dtype != MMN_DT_F32 && d->io_dtype != MMN_DT_BF16) return fail(MMN_ERR_INVALID, "bad io_dtype");
+  if (d->dropout_p < 0.f || d->dropout_p >= 1.f) return fail(MMN_ERR_INVALID, "dropout_p must be in [0,1)");
+  if (d->head_dim > 128) return fail(MMN_ERR_UNSUPPORTED, "head_dim %d > 128", d->head_dim);
+  return MMN_OK;
+}
+
+mmn::GenericProblem problem_from(const mmn_winattn_desc* d, const float* bias, const float* head_scale, const float* mask) {
+  mmn::GenericProblem P{};
+  P.kind = 0;
+  for (int a = 0; a < 3; ++a) { P.grid[a] = 1; P.win[a] = 1; P.shift[a] = 0; P.nwin[a] = 1; }
+  for (int a = 0; a < d->ndim; ++a) {          // right-align the used axes
+    int t = 3 - d->ndim + a;
+    P.grid[t] = d->grid[a]; P.win[t] = d->window[a]; P.shift[t] = d->shift[a]; P.nwin[t] = d->grid[a] / d->window[a];
+  }
+  P.nW = P.nwin[0] * P.nwin[1] * P.nwin[2];
+  P.nq = P.nk = P.win[0] * P.win[1] * P.win[2];
+  P.d = d->head_dim; P.nH = d->num_heads;
+  P.n_items = d->batch * P.nW * P.nH;
+  P.q_s0 = d->q_row_stride; P.k_s0 = d->k_row_stride; P.v_s0 = d->v_row_stride; P.o_s0 = d->o_row_stride;
+  P.do_s0 = d->do_row_stride; P.dq_s0 = d->dq_row_stride; P.dk_s0 = d->dk_row_stride; P.dv_s0 = d->dv_row_stride;
+  P.cosine = d->score_kind == MMN_SCORE_COSINE;
+  P.mask_kind = d->mask_kind; P.mask_windows = d->mask_windows > 0 ? d->mask_windows : 1;
+  P.scale = d->scale; P.dropout_p = d->dropout_p; P.seed = d->seed; P.offset = d->offset;
+  P.bias = bias; P.head_scale = head_scale; P.mask = mask;
+  return P;
+}
+
+mmn::GenericProblem problem_from(const mmn_mha_desc* d, const float* mask) {
+  mmn::GenericProblem P{};
+  P.kind = 1;
+  for (int a = 0; a < 3; ++a) { P.grid[a] = 1; P.win[a] = 1; P.shift[a] = 0; P.nwin[a] = 1; }
+  P.nW = 1;
+  P.nq = d->tgt_len; P.nk = d->src_len; P.d = d->head_dim; P.nH = d->num_heads;
+  P.n_items = d->batch * d->num_heads;
+  P.q_s0 = d->q_stride_t; P.q_s1 = d->q_stride_b; P.k_s0 = d->k_stride_t; P.k_s1 = d->k_stride_b;
+  P.v_s0 = d->v_stride_t; P.v_s1 = d->v_stride_b; P.o_s0 = d->o_stride_t; P.o_s1 = d->o_stride_b;
+  P.do_s0 = d->do_stride_t; P.do_s1 = d->do_stride_b; P.dq_s0 = d->dq_stride_t; P.dq_s1 = d->dq_stride_b;
+  P.dk_s0 = d->dk_stride_t; P.dk_s1 = d->dk_stride_b; P.dv_s0 = d->dv_stride_t; P.dv_s1 = d->dv_stride_b;
+  P.cosine = 0;
+  P.mask_kind = d->mask_kind; P.mask_diag = d->mask_diagonal; P.mask_windows = 1;
+  P.scale = d->scale; P.dropout_p = d->dropout_p; P.seed = d->seed; P.offset = d->offset;
+  P.mask = mask;
+  return P;
+}
+
+// rows: extent of the thread-per-row side; other: extent of the staged side;
+// floats_per_staged_row: shared floats per staged row excluding the 12-byte offset/rid.
+mmn::GenericLaunch plan(int rows, int other, int bytes_per_staged_row) {
+  mmn::GenericLaunch L{};
+  L.rows_per_slot = rows < mmn::kGenericThreads ? rows : mmn::kGenericThreads;
+  L.slots = mmn::kGenericThreads / L.rows_per_slot;
+  const size_t budget = 96 * 1024;
+  int cap = (int)(budget / ((size_t)L.slots * bytes_per_staged_row));
+  if (cap > other) cap = other;
+  if (cap > 256) cap = 256;
+  if (cap < 1) cap = 1;
+  L.chunk = cap;
+  L.smem_bytes = (size_t)L.slots * cap * bytes_per_staged_row;
+  return L;
+}
+
+constexpr int kMaxSmem = 100 * 1024;
+
+template <typename T, int DMAX>
+int launch_fwd(const mmn::GenericProblem& P, const void* q, const void* k, const void* v, void* out, float* lse, cudaStream_t st) {
+  mmn::GenericLaunch L = plan(P.nq, P.nk, 2 * P.d * 4 + 12);
+  auto kern = mmn::attn_fwd_generic<T, DMAX>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  dim3 grid((P.n_items + L.slots - 1) / L.slots, (P.nq + L.rows_per_slot - 1) / L.rows_per_slot);
+  kern<<<grid, mmn::kGenericThreads, L.smem_bytes, st>>>(P, L, (const T*)q, (const T*)k, (const T*)v, (T*)out, lse);
+  return check_launch("attn_fwd_generic");
+}
+
+template <typename T, int DMAX>
+int launch_bwd(const mmn::GenericProblem& P, const void* q, const void* k, const void* v, const void* out, const float* lse,
+               const void* dout, void* dq, void* dk, void* dv, float* dbias, float* dhs, cudaStream_t st) {
+  {
+    mmn::GenericLaunch L = plan(P.nq, P.nk, 2 * P.d * 4 + 12);
+    auto kern = mmn::attn_bwd_dq_generic<T, DMAX>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    dim3 grid((P.n_items + L.slots - 1) / L.slots, (P.nq + L.rows_per_slot - 1) / L.rows_per_slot);
+    kern<<<grid, mmn::kGenericThreads, L.smem_bytes, st>>>(P, L, (const T*)q, (const T*)k, (const T*)v, (const T*)out, lse,
+                                                          (const T*)dout, (T*)dq, dbias, dhs);
+    int rc = check_launch("attn_bwd_dq_generic");
+    if (rc) return rc;
+  }
+  {
+    mmn::GenericLaunch L = plan(P.nk, P.nq, 3 * P.d * 4 + 20);
+    auto kern = mmn::attn_bwd_dkv_generic<T, DMAX>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    dim3 grid((P.n_items + L.slots - 1) / L.slots, (P.nk + L.rows_per_slot - 1) / L.rows_per_slot);
+    kern<<<grid, mmn::kGenericThreads, L.smem_bytes, st>>>(P, L, (const T*)q, (const T*)k, (const T*)v, (const T*)out, lse,
+                                                          (const T*)dout, (T*)dk, (T*)dv);
+    return check_launch("attn_bwd_dkv_generic");
+  }
+}
+
+#define MMN_DISPATCH_D(T, FN, ...)                                            \
+  do {                                                                         \
+    if (P.d <= 4) return FN<T, 4>(__VA_ARGS__);                                \
+    if (P.d <= 8) return FN<T, 8>(__VA_ARGS__);                                \
+    if (P.d <= 16) return FN<T, 16>(__VA_ARGS__);                              \
+    if (P.d <= 32) return FN<T, 32>(__VA_ARGS__);                              \
+    if (P.d <= 64) return FN<T, 64>(__VA_ARGS__);                              \
+    return FN<T, 128>(__VA_ARGS__);                                            \
+  } while (0)
+
+int generic_fwd(const mmn::GenericProblem& P, int dt, const void* q, const void* k, const void* v, void* out, float* lse, cudaStream_t st) {
+  if (dt == MMN_DT_F32) MMN_DISPATCH_D(float, launch_fwd, P, q, k, v, out, lse, st);
+  MMN_DISPATCH_D(__nv_bfloat16, launch_fwd, P, q, k, v, out, lse, st);
+}
+
+int generic_bwd(const mmn::GenericProblem& P, int dt, const void* q, const void* k, const void* v, const void* out, const float* lse,
+                const void* dout, void* dq, void* dk, void* dv, float* dbias, float* dhs, cudaStream_t st) {
+  if (dt == MMN_DT_F32) MMN_DISPATCH_D(float, launch_bwd, P, q, k, v, out, lse, dout, dq, dk, dv, dbias, dhs, st);
+  MMN_DISPATCH_D(__nv_bfloat16, launch_bwd, P, q, k, v, out, lse, dout, dq, dk, dv, dbias, dhs, st);
+}
+
+bool have_device() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return false; }
+  return n > 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mmn_abi_version(void) { return MMN_ABI_VERSION; }
+const char* mmn_last_error(void) { return g_err; }
+uint64_t mmn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+const char* mmn_winattn_path(const mmn_winattn_desc* d) {
+  if (validate_win(d) != MMN_OK) return "invalid";
+  if (d->path == MMN_PATH_GENERIC) return "generic";
+  return mmn::tc::winattn_supported(d) ? "tcgen05" : "generic";
+}
+
+const char* mmn_mha_path(const mmn_mha_desc* d) {
+  if (validate_mha(d) != MMN_OK) return "invalid";
+  return "generic";
+}
+
+int mmn_winattn_fwd(const mmn_winattn_desc* d, const void* q, const void* k, const void* v, const float* bias,
+                    const float* head_scale, const float* mask, void* out, float* lse, int device, void* stream) {
+  int rc = validate_win(d);
+  if (rc) return rc;
+  if (!q || !k || !v || !out || !lse) return fail(MMN_ERR_INVALID, "null tensor pointer");
+  if (d->score_kind == MMN_SCORE_COSINE && !head_scale) return fail(MMN_ERR_INVALID, "cosine attention needs head_scale");
+  if (d->mask_kind == MMN_MASK_TENSOR && !mask) return fail(MMN_ERR_INVALID, "MMN_MASK_TENSOR needs a mask");
+  if (!have_device()) return fail(MMN_ERR_CUDA, "no CUDA device: libmmn_b200 has no CPU path");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(MMN_ERR_CUDA, "cannot select device %d", device);
+  cudaStream_t st = (cudaStream_t)stream;
+  bool tc_ok = mmn::tc::winattn_supported(d);
+  if (d->path == MMN_PATH_TCGEN05 && !tc_ok) return fail(MMN_ERR_UNSUPPORTED, "shape not supported by the tcgen05 path: %s", mmn::tc::why_not(d));
+  if (d->path != MMN_PATH_GENERIC && tc_ok) {
+    rc = mmn::tc::winattn_fwd(d, q, k, v, bias, head_scale, mask, out, lse, st, g_err, sizeof(g_err));
+    if (rc == MMN_OK) g_launches.fetch_add(1, std::memory_order_relaxed);
+    return rc;
+  }
+  return generic_fwd(problem_from(d, bias, head_scale, mask), d->io_dtype, q, k, v, out, lse, st);
+}
+
+int mmn_winattn_bwd(const mmn_winattn_desc* d, const void* q, const void* k, const void* v, const float* bias,
+                    const float* head_scale, const float* mask, const void* out, const float* lse, const void* dout,
+                    void* dq, void* dk, void* dv, float* dbias, float* dhead_scale, int device, void* stream) {
+  int rc = validate_win(d);
+  if (rc) return rc;
+  if (!q || !k || !v || !out || !lse || !dout || !dq || !dk || !dv) return fail(MMN_ERR_INVALID, "null tensor pointer");
+  if (d->score_kind == MMN_SCORE_COSINE && !head_scale) return fail(MMN_ERR_INVALID, "cosine attention needs head_scale");
+  if (d->mask_kind == MMN_MASK_TENSOR && !mask) return fail(MMN_ERR_INVALID, "MMN_MASK_TENSOR needs a mask");
+  if (!have_device()) return fail(MMN_ERR_CUDA, "no CUDA device: libmmn_b200 has no CPU path");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(MMN_ERR_CUDA, "cannot select device %d", device);
+  cudaStream_t st = (cudaStream_t)stream;
+  bool tc_ok = mmn::tc::winattn_bwd_supported(d);
+  if (d->path == MMN_PATH_TCGEN05 && !tc_ok) return fail(MMN_ERR_UNSUPPORTED, "shape not supported by the tcgen05 backward path");
+  if (d->path != MMN_PATH_GENERIC && tc_ok) {
+    rc = mmn::tc::winattn_bwd(d, q, k, v, bias, head_scale, mask, out, lse, dout, dq, dk, dv, dbias, dhead_scale, st, g_err, sizeof(g_err));
+    if (rc == MMN_OK) g_launches.fetch_add(1, std::memory_order_relaxed);
+    return rc;
+  }
+  mmn::GenericProblem P = problem_from(d, bias, head_scale, mask);
+  return generic_bwd(P, d->io_dtype, q, k, v, out, lse, dout, dq, dk, dv, bias ? dbias : nullptr,
+                     P.cosine ? dhead_scale : nullptr, st);
+}
+
+int mmn_mha_fwd(const mmn_mha_desc* d, const void* q, const void* k, const void* v, const float* mask, void* out,
+                float* lse, int device, void* stream) {
+  int rc = validate_mha(d);
+  if (rc) return rc;
+  if (!q || !k || !v || !out || !lse) return fail(MMN_ERR_INVALID, "null tensor pointer");
+  if (d->mask_kind == MMN_MASK_TENSOR && !mask) return fail(MMN_ERR_INVALID, "MMN_MASK_TENSOR needs a mask");
+  if (!have_device()) return fail(MMN_ERR_CUDA, "no CUDA device: libmmn_b200 has no CPU path");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(MMN_ERR_CUDA, "cannot select device %d", device);
+  return generic_fwd(problem_from(d, mask), d->io_dtype, q, k, v, out, lse, (cudaStream_t)stream);
+}
+
+int mmn_mha_bwd(const mmn_mha_desc* d, const void* q, const void* k, const void* v, const float* mask, const void* out,
+                const float* lse, const void* dout, void* dq, void* dk, void* dv, int device, void* stream) {
+  int rc = validate_mha(d);
+  if (rc) return rc;
+  if (!q || !k || !v || !out || !lse || !dout || !dq || !dk || !dv) return fail(MMN_ERR_INVALID, "null tensor pointer");
+  if (d->mask_kind == MMN_MASK_TENSOR && !mask) return fail(MMN_ERR_INVALID, "MMN_MASK_TENSOR needs a mask");
+  if (!have_device()) return fail(MMN_ERR_CUDA, "no CUDA device: libmmn_b200 has no CPU path");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(MMN_ERR_CUDA, "cannot select device %d", device);
+  return generic_bwd(problem_from(d, mask), d->io_dtype, q, k, v, out, lse, dout, dq, dk, dv, nullptr, nullptr,
+                     (cudaStream_t)stream);
+}
+
+int mmn_mha_avg_weights(const mmn_mha_desc* d, const void* q, const void* k, const float* mask, const float* lse,
+                        float* avg, int device, void* stream) {
+  int rc = validate_mha(d);
+  if (rc) return rc;
+  if (!q || !k || !lse || !avg) return fail(MMN_ERR_INVALID, "null tensor pointer");
+  if (!have_device()) return fail(MMN_ERR_CUDA, "no CUDA device: libmmn_b200 has no CPU path");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(MMN_ERR_CUDA, "cannot select device %d", device);
+  mmn::GenericProblem P = problem_from(d, mask);
+  long long total = (long long)d->batch * d->tgt_len * d->src_len;
+  int blocks = (int)((total + 255) / 256);
+  if (d->io_dtype == MMN_DT_F32)
+    mmn::mha_avg_weights_generic<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(P, d->batch, (const float*)q, (const float*)k, lse, avg);
+  else
+    mmn::mha_avg_weights_generic<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(P, d->batch, (const __nv_bfloat16*)q,
+                                                                                         (const __nv_bfloat16*)k, lse, avg);
+  return check_launch("mha_avg_weights_generic");
+}
+
+}  // extern "C"

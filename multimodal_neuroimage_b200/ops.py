@@ -1,0 +1,313 @@
+"""torch.library custom ops over the C ABI (include/mmn_b200.h).
+
+PyTorch is plumbing here: it owns device memory and streams and records the autograd
+graph; the arithmetic happens in libmmn_b200.so.  Ops:
+
+  mmn_b200::winattn_fwd / winattn_bwd   fused shift + window gather + attention + scatter
+  mmn_b200::mha_fwd / mha_bwd           (T,B,E) multi-head attention core
+  mmn_b200::mha_avg_weights             head-averaged probabilities
+
+Window attention takes its q/k/v in one of two packings so that the backward can write one
+packed gradient tensor (no slice-backward copies):
+  a = qkv (..., 3C), b = None            self attention   (swin_v2 / swinfusion self)
+  a = q   (..., C),  b = kv (..., 2C)    cross attention  (swinfusion Cross_WindowAttention)
+All tensors are in the un-windowed, un-shifted (B, *grid, channels) order.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import MhaDesc, WinAttnDesc
+
+Tensor = torch.Tensor
+
+_DT = {torch.float32: _lib.DT_F32, torch.bfloat16: _lib.DT_BF16}
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("multimodal_neuroimage_b200 ops run on CUDA tensors only (there is no CPU path); "
+                               f"got a tensor on {t.device}")
+
+
+def _ptr(t: Optional[Tensor], elem_offset: int = 0):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr() + elem_offset * t.element_size())
+
+
+def _row_stride(t: Tensor) -> int:
+    """Element stride between consecutive tokens of a (..., channels) tensor whose leading
+    dims collapse to one uniform stride (true for contiguous tensors and channel slices)."""
+    if t.stride(-1) != 1:
+        raise RuntimeError("channel dimension must be contiguous")
+    rs = t.stride(-2)
+    exp = rs
+    for i in range(t.dim() - 2, -1, -1):
+        if t.shape[i] != 1 and t.stride(i) != exp:
+            raise RuntimeError(f"token rows are not uniformly strided: shape {tuple(t.shape)} strides {t.stride()}")
+        exp *= t.shape[i]
+    return rs
+
+
+def _stream(t: Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _win_desc(a: Tensor, b: Optional[Tensor], grid, window, shift, num_heads, score_kind, mask_kind, mask_windows,
+              scale, dropout_p, seed, offset, path) -> Tuple[WinAttnDesc, int]:
+    n = len(grid)
+    if a.dtype not in _DT:
+        raise RuntimeError(f"unsupported dtype {a.dtype}: the window-attention kernels take float32 or bfloat16")
+    Cc = a.shape[-1] // 3 if b is None else a.shape[-1]
+    if Cc % num_heads:
+        raise RuntimeError("channels not divisible by heads")
+    d = WinAttnDesc()
+    d.ndim, d.batch = n, a.shape[0]
+    for i in range(n):
+        d.grid[i], d.window[i], d.shift[i] = int(grid[i]), int(window[i]), int(shift[i])
+    d.num_heads, d.head_dim = num_heads, Cc // num_heads
+    d.score_kind, d.mask_kind, d.mask_windows = score_kind, mask_kind, mask_windows
+    d.io_dtype, d.path = _DT[a.dtype], path
+    d.scale, d.dropout_p, d.seed, d.offset = scale, dropout_p, seed, offset
+    return d, Cc
+
+
+@torch.library.custom_op("mmn_b200::winattn_fwd", mutates_args=())
+def winattn_fwd(a: Tensor, b: Optional[Tensor], bias: Optional[Tensor], head_scale: Optional[Tensor],
+                mask: Optional[Tensor], grid: List[int], window: List[int], shift: List[int], num_heads: int,
+                score_kind: int, mask_kind: int, scale: float, dropout_p: float, seed: int, offset: int,
+                path: int) -> Tuple[Tensor, Tensor]:
+    _require_cuda(a, b, bias, head_scale, mask)
+    lib = _lib.load()
+    d, Cc = _win_desc(a, b, grid, window, shift, num_heads, score_kind, mask_kind,
+                      mask.shape[0] if mask is not None else 0, scale, dropout_p, seed, offset, path)
+    if tuple(a.shape[1:-1]) != tuple(grid):
+        raise RuntimeError(f"tensor grid {tuple(a.shape[1:-1])} != geometry {tuple(grid)}")
+    out = torch.empty(*a.shape[:-1], Cc, dtype=a.dtype, device=a.device)
+    N = 1
+    nW = 1
+    for g, w in zip(grid, window):
+        N *= w
+        nW *= g // w
+    lse = torch.empty(a.shape[0] * nW, num_heads, N, dtype=torch.float32, device=a.device)
+    if b is None:
+        q, k, v = _ptr(a), _ptr(a, Cc), _ptr(a, 2 * Cc)
+        d.q_row_stride = d.k_row_stride = d.v_row_stride = _row_stride(a)
+    else:
+        q, k, v = _ptr(a), _ptr(b), _ptr(b, Cc)
+        d.q_row_stride = _row_stride(a)
+        d.k_row_stride = d.v_row_stride = _row_stride(b)
+    d.o_row_stride = Cc
+    for t in (bias, head_scale, mask):
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+            raise RuntimeError("bias / head_scale / mask must be contiguous float32")
+    _lib.check(lib.mmn_winattn_fwd(C.byref(d), q, k, v, _ptr(bias), _ptr(head_scale), _ptr(mask), _ptr(out), _ptr(lse),
+                                   a.device.index, _stream(a)), "mmn_winattn_fwd")
+    return out, lse
+
+
+@winattn_fwd.register_fake
+def _(a, b, bias, head_scale, mask, grid, window, shift, num_heads, score_kind, mask_kind, scale, dropout_p, seed,
+      offset, path):
+    Cc = a.shape[-1] // 3 if b is None else a.shape[-1]
+    N = nW = 1
+    for g, w in zip(grid, window):
+        N *= w
+        nW *= g // w
+    return a.new_empty(*a.shape[:-1], Cc), a.new_empty(a.shape[0] * nW, num_heads, N, dtype=torch.float32)
+
+
+@torch.library.custom_op("mmn_b200::winattn_bwd", mutates_args=())
+def winattn_bwd(dout: Tensor, a: Tensor, b: Optional[Tensor], bias: Optional[Tensor], head_scale: Optional[Tensor],
+                mask: Optional[Tensor], out: Tensor, lse: Tensor, grid: List[int], window: List[int], shift: List[int],
+                num_heads: int, score_kind: int, mask_kind: int, scale: float, dropout_p: float, seed: int,
+                offset: int, path: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Returns (da, db, dbias, dhead_scale); unused ones are empty tensors."""
+    _require_cuda(dout, a, b, bias, head_scale, mask, out, lse)
+    lib = _lib.load()
+    d, Cc = _win_desc(a, b, grid, window, shift, num_heads, score_kind, mask_kind,
+                      mask.shape[0] if mask is not None else 0, scale, dropout_p, seed, offset, path)
+    dout = dout.contiguous()
+    da = torch.empty(a.shape, dtype=a.dtype, device=a.device)
+    db = torch.empty(b.shape, dtype=b.dtype, device=b.device) if b is not None else a.new_empty(0)
+    if b is None:
+        q, k, v = _ptr(a), _ptr(a, Cc), _ptr(a, 2 * Cc)
+        dq, dk, dv = _ptr(da), _ptr(da, Cc), _ptr(da, 2 * Cc)
+        d.q_row_stride = d.k_row_stride = d.v_row_stride = _row_stride(a)
+        d.dq_row_stride = d.dk_row_stride = d.dv_row_stride = 3 * Cc
+    else:
+        q, k, v = _ptr(a), _ptr(b), _ptr(b, Cc)
+        dq, dk, dv = _ptr(da), _ptr(db), _ptr(db, Cc)
+        d.q_row_stride = _row_stride(a)
+        d.k_row_stride = d.v_row_stride = _row_stride(b)
+        d.dq_row_stride = Cc
+        d.dk_row_stride = d.dv_row_stride = 2 * Cc
+    d.o_row_stride = _row_stride(out)
+    d.do_row_stride = Cc
+    dbias = torch.zeros_like(bias) if bias is not None else a.new_empty(0, dtype=torch.float32)
+    dhs = torch.zeros_like(head_scale) if head_scale is not None else a.new_empty(0, dtype=torch.float32)
+    _lib.check(lib.mmn_winattn_bwd(C.byref(d), q, k, v, _ptr(bias), _ptr(head_scale), _ptr(mask), _ptr(out), _ptr(lse),
+                                   _ptr(dout), dq, dk, dv, _ptr(dbias) if bias is not None else None,
+                                   _ptr(dhs) if head_scale is not None else None, a.device.index, _stream(a)),
+               "mmn_winattn_bwd")
+    return da, db, dbias, dhs
+
+
+@winattn_bwd.register_fake
+def _(dout, a, b, bias, head_scale, mask, out, lse, grid, window, shift, num_heads, score_kind, mask_kind, scale,
+      dropout_p, seed, offset, path):
+    return (torch.empty_like(a), torch.empty_like(b) if b is not None else a.new_empty(0),
+            torch.empty_like(bias) if bias is not None else a.new_empty(0, dtype=torch.float32),
+            torch.empty_like(head_scale) if head_scale is not None else a.new_empty(0, dtype=torch.float32))
+
+
+def _winattn_setup(ctx, inputs, output):
+    (a, b, bias, head_scale, mask, grid, window, shift, num_heads, score_kind, mask_kind, scale, dropout_p, seed,
+     offset, path) = inputs
+    out, lse = output
+    ctx.save_for_backward(a, b, bias, head_scale, mask, out, lse)
+    ctx.cfg = (grid, window, shift, num_heads, score_kind, mask_kind, scale, dropout_p, seed, offset, path)
+
+
+def _winattn_backward(ctx, dout, dlse):
+    a, b, bias, head_scale, mask, out, lse = ctx.saved_tensors
+    da, db, dbias, dhs = torch.ops.mmn_b200.winattn_bwd(dout, a, b, bias, head_scale, mask, out, lse, *ctx.cfg)
+    return (da, db if b is not None else None, dbias if bias is not None else None,
+            dhs if head_scale is not None else None, None) + (None,) * 11
+
+
+torch.library.register_autograd("mmn_b200::winattn_fwd", _winattn_backward, setup_context=_winattn_setup)
+
+
+# ------------------------------------------------------------------------------------------
+# multi-head attention
+# ------------------------------------------------------------------------------------------
+def _tb_strides(t: Tensor) -> Tuple[int, int]:
+    if t.dim() != 3 or t.stride(2) != 1:
+        raise RuntimeError("expected a (len, batch, embed) tensor with contiguous embed dimension")
+    return t.stride(0), t.stride(1)
+
+
+def _mha_desc(q, k, num_heads, mask_kind, mask_diag, scale, dropout_p, seed, offset) -> MhaDesc:
+    if q.dtype not in _DT:
+        raise RuntimeError(f"unsupported dtype {q.dtype}: the attention kernels take float32 or bfloat16")
+    d = MhaDesc()
+    d.tgt_len, d.batch, E = q.shape
+    d.src_len = k.shape[0]
+    if E % num_heads:
+        raise RuntimeError("embed_dim not divisible by heads")
+    d.num_heads, d.head_dim = num_heads, E // num_heads
+    d.mask_kind, d.mask_diagonal = mask_kind, mask_diag
+    d.io_dtype, d.path = _DT[q.dtype], _lib.PATH_AUTO
+    d.scale, d.dropout_p, d.seed, d.offset = scale, dropout_p, seed, offset
+    return d
+
+
+@torch.library.custom_op("mmn_b200::mha_fwd", mutates_args=())
+def mha_fwd(q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor], num_heads: int, mask_kind: int, mask_diag: int,
+            scale: float, dropout_p: float, seed: int, offset: int) -> Tuple[Tensor, Tensor]:
+    _require_cuda(q, k, v, mask)
+    lib = _lib.load()
+    d = _mha_desc(q, k, num_heads, mask_kind, mask_diag, scale, dropout_p, seed, offset)
+    out = torch.empty(q.shape, dtype=q.dtype, device=q.device)
+    lse = torch.empty(q.shape[1] * num_heads, q.shape[0], dtype=torch.float32, device=q.device)
+    d.q_stride_t, d.q_stride_b = _tb_strides(q)
+    d.k_stride_t, d.k_stride_b = _tb_strides(k)
+    d.v_stride_t, d.v_stride_b = _tb_strides(v)
+    d.o_stride_t, d.o_stride_b = _tb_strides(out)
+    if mask is not None and (mask.dtype != torch.float32 or not mask.is_contiguous()):
+        raise RuntimeError("attn_mask must be contiguous float32")
+    _lib.check(lib.mmn_mha_fwd(C.byref(d), _ptr(q), _ptr(k), _ptr(v), _ptr(mask), _ptr(out), _ptr(lse), q.device.index,
+                               _stream(q)), "mmn_mha_fwd")
+    return out, lse
+
+
+@mha_fwd.register_fake
+def _(q, k, v, mask, num_heads, mask_kind, mask_diag, scale, dropout_p, seed, offset):
+    return torch.empty_like(q, memory_format=torch.contiguous_format), q.new_empty(q.shape[1] * num_heads, q.shape[0],
+                                                                                    dtype=torch.float32)
+
+
+@torch.library.custom_op("mmn_b200::mha_bwd", mutates_args=())
+def mha_bwd(dout: Tensor, q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor], out: Tensor, lse: Tensor,
+            num_heads: int, mask_kind: int, mask_diag: int, scale: float, dropout_p: float, seed: int,
+            offset: int) -> Tuple[Tensor, Tensor, Tensor]:
+    _require_cuda(dout, q, k, v, mask, out, lse)
+    lib = _lib.load()
+    d = _mha_desc(q, k, num_heads, mask_kind, mask_diag, scale, dropout_p, seed, offset)
+    dout = dout.contiguous()
+    dq = torch.empty(q.shape, dtype=q.dtype, device=q.device)
+    dk = torch.empty(k.shape, dtype=k.dtype, device=k.device)
+    dv = torch.empty(v.shape, dtype=v.dtype, device=v.device)
+    d.q_stride_t, d.q_stride_b = _tb_strides(q)
+    d.k_stride_t, d.k_stride_b = _tb_strides(k)
+    d.v_stride_t, d.v_stride_b = _tb_strides(v)
+    d.o_stride_t, d.o_stride_b = _tb_strides(out)
+    d.do_stride_t, d.do_stride_b = _tb_strides(dout)
+    d.dq_stride_t, d.dq_stride_b = _tb_strides(dq)
+    d.dk_stride_t, d.dk_stride_b = _tb_strides(dk)
+    d.dv_stride_t, d.dv_stride_b = _tb_strides(dv)
+    _lib.check(lib.mmn_mha_bwd(C.byref(d), _ptr(q), _ptr(k), _ptr(v), _ptr(mask), _ptr(out), _ptr(lse), _ptr(dout),
+                               _ptr(dq), _ptr(dk), _ptr(dv), q.device.index, _stream(q)), "mmn_mha_bwd")
+    return dq, dk, dv
+
+
+@mha_bwd.register_fake
+def _(dout, q, k, v, mask, out, lse, num_heads, mask_kind, mask_diag, scale, dropout_p, seed, offset):
+    c = torch.contiguous_format
+    return torch.empty_like(q, memory_format=c), torch.empty_like(k, memory_format=c), torch.empty_like(v, memory_format=c)
+
+
+def _mha_setup(ctx, inputs, output):
+    q, k, v, mask, num_heads, mask_kind, mask_diag, scale, dropout_p, seed, offset = inputs
+    out, lse = output
+    ctx.save_for_backward(q, k, v, mask, out, lse)
+    ctx.cfg = (num_heads, mask_kind, mask_diag, scale, dropout_p, seed, offset)
+
+
+def _mha_backward(ctx, dout, dlse):
+    q, k, v, mask, out, lse = ctx.saved_tensors
+    dq, dk, dv = torch.ops.mmn_b200.mha_bwd(dout, q, k, v, mask, out, lse, *ctx.cfg)
+    return (dq, dk, dv, None) + (None,) * 7
+
+
+torch.library.register_autograd("mmn_b200::mha_fwd", _mha_backward, setup_context=_mha_setup)
+
+
+@torch.library.custom_op("mmn_b200::mha_avg_weights", mutates_args=())
+def mha_avg_weights(q: Tensor, k: Tensor, mask: Optional[Tensor], lse: Tensor, num_heads: int, mask_kind: int,
+                    mask_diag: int, scale: float, dropout_p: float, seed: int, offset: int) -> Tensor:
+    _require_cuda(q, k, mask, lse)
+    lib = _lib.load()
+    d = _mha_desc(q, k, num_heads, mask_kind, mask_diag, scale, dropout_p, seed, offset)
+    d.q_stride_t, d.q_stride_b = _tb_strides(q)
+    d.k_stride_t, d.k_stride_b = _tb_strides(k)
+    avg = torch.empty(q.shape[1], q.shape[0], k.shape[0], dtype=torch.float32, device=q.device)
+    _lib.check(lib.mmn_mha_avg_weights(C.byref(d), _ptr(q), _ptr(k), _ptr(mask), _ptr(lse), _ptr(avg), q.device.index,
+                                       _stream(q)), "mmn_mha_avg_weights")
+    return avg
+
+
+@mha_avg_weights.register_fake
+def _(q, k, mask, lse, num_heads, mask_kind, mask_diag, scale, dropout_p, seed, offset):
+    return q.new_empty(q.shape[1], q.shape[0], k.shape[0], dtype=torch.float32)
+
+
+def next_dropout_stream(p: float, training: bool, device) -> Tuple[float, int, int]:
+    """(p, seed, offset) for one attention call: a fresh Philox offset drawn from torch's
+    generator so `torch.manual_seed` controls it; p = 0 outside training."""
+    if not training or p <= 0.0:
+        return 0.0, 0, 0
+    s = torch.randint(0, 2 ** 62, (2,), dtype=torch.int64)
+    return float(p), int(s[0]), int(s[1])
+
+
+def winattn_path_name(a: Tensor, b: Optional[Tensor], grid, window, shift, num_heads, score_kind, mask_kind) -> str:
+    d, _ = _win_desc(a, b, grid, window, shift, num_heads, score_kind, mask_kind, 1, 1.0, 0.0, 0, 0, _lib.PATH_AUTO)
+    return _lib.load().mmn_winattn_path(C.byref(d)).decode()

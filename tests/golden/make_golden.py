@@ -50,7 +50,7 @@ def randomise(module, gen):
                 p.copy_(torch.empty_like(p).normal_(0, 0.3, generator=gen))
 
 
-def record(out, case, module, inputs, outputs, grads_wrt):
+def record(out, case, module, inputs, outputs, grads_wrt, loss_outs=None):
     """Store state_dict, inputs, outputs and d(sum(outputs * cot))/d(inputs, params)."""
     for k, v in module.state_dict().items():
         out[f"{case}/sd/{k}"] = npy(v)
@@ -63,7 +63,9 @@ def record(out, case, module, inputs, outputs, grads_wrt):
         cot = torch.randn(o.shape, generator=gen, dtype=o.dtype)
         out[f"{case}/out/{i}"] = npy(o)
         out[f"{case}/cot/{i}"] = npy(cot)
-        loss = loss + (o * cot).sum()
+        if loss_outs is None or i in loss_outs:
+            loss = loss + (o * cot).sum()
+    out[f"{case}/loss_outs"] = np.array(list(range(len(outs))) if loss_outs is None else list(loss_outs), np.int64)
     module.zero_grad()
     loss.backward()
     for k, v in grads_wrt.items():
@@ -213,7 +215,9 @@ def crossmodal():
             v = torch.randn(S, B, E, generator=gen, requires_grad=True)
             a, w = m(q, k, v, attn_mask=mask)
             ins, gw = {"q": q, "k": k, "v": v}, {"q": q, "k": k, "v": v}
-        record(out, case, m, ins, (a, w), gw)
+        # the head-averaged weights (output 1) are returned but every caller discards them
+        # (crossmodal_transformer.py:148,152): gradients are taken through output 0 only
+        record(out, case, m, ins, (a, w), gw, loss_outs=(0,))
         out[f"{case}/cfg"] = np.array([E, nH, T, S, B, int(mask is not None)], np.int64)
     # Encoder: self and cross streams, mask on/off; a zero in channel 0 exercises the padding position
     for case, (E, nH, L, T, B, use_mask, cross) in {"enc_self": (28, 4, 2, 20, 2, True, False), "enc_cross": (84, 12, 2, 16, 2, True, True),

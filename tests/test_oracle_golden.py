@@ -91,7 +91,8 @@ def _check_case(G, case, fn, in_names):
         close(o, G.t(f"{case}/out/{i}"))
     gsd = G.group(f"{case}/gsd/")
     wrt = [ins[k] for k in in_names] + [sd[k] for k in gsd]
-    got = _grads(outs, cots, wrt)
+    used = G.arr(f"{case}/loss_outs").tolist()
+    got = _grads([outs[i] for i in used], [cots[i] for i in used], wrt)
     for k, g in zip(in_names, got[:len(in_names)]):
         close(g, G.t(f"{case}/gin/{k}"), 1e-4, 1e-5)
     for k, g in zip(gsd, got[len(in_names):]):
