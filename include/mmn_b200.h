@@ -101,11 +101,13 @@ int mmn_winattn_fwd(const mmn_winattn_desc* desc, const void* q, const void* k, 
                     void* out, float* lse, int device, void* stream);
 
 /* dbias (num_heads,N,N) fp32 and dhead_scale (num_heads) fp32 are ACCUMULATED into (the
- * caller zeroes them); either may be NULL to skip. */
+ * caller zeroes them); either may be NULL to skip.  `out` is the forward output (may be NULL:
+ * the kernels recompute rowsum(P o dP) instead of reading it).  `workspace`: scratch of
+ * TWICE the extent of lse (2*batch*nW*num_heads*N floats), contents undefined on return. */
 int mmn_winattn_bwd(const mmn_winattn_desc* desc, const void* q, const void* k, const void* v,
                     const float* bias, const float* head_scale, const float* mask,
                     const void* out, const float* lse, const void* dout,
-                    void* dq, void* dk, void* dv, float* dbias, float* dhead_scale,
+                    void* dq, void* dk, void* dv, float* dbias, float* dhead_scale, float* workspace,
                     int device, void* stream);
 
 /* mask (T,S) fp32, TENSOR only; out (T,B,E)-addressed rows; lse (batch*num_heads*T) fp32. */
@@ -114,7 +116,8 @@ int mmn_mha_fwd(const mmn_mha_desc* desc, const void* q, const void* k, const vo
 
 int mmn_mha_bwd(const mmn_mha_desc* desc, const void* q, const void* k, const void* v,
                 const float* mask, const void* out, const float* lse, const void* dout,
-                void* dq, void* dk, void* dv, int device, void* stream);
+                void* dq, void* dk, void* dv, float* workspace /* 2*batch*num_heads*T floats */,
+                int device, void* stream);
 
 /* avg (batch,T,S) fp32 = mean over heads of the (dropped-out) attention probabilities. */
 int mmn_mha_avg_weights(const mmn_mha_desc* desc, const void* q, const void* k, const float* mask,

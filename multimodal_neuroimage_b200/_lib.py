@@ -101,12 +101,12 @@ def load() -> C.CDLL:
         lib.mmn_winattn_fwd.restype = C.c_int
         lib.mmn_winattn_fwd.argtypes = [C.POINTER(WinAttnDesc), vp, vp, vp, fp, fp, fp, vp, fp, C.c_int, vp]
         lib.mmn_winattn_bwd.restype = C.c_int
-        lib.mmn_winattn_bwd.argtypes = [C.POINTER(WinAttnDesc), vp, vp, vp, fp, fp, fp, vp, fp, vp, vp, vp, vp, fp, fp,
+        lib.mmn_winattn_bwd.argtypes = [C.POINTER(WinAttnDesc), vp, vp, vp, fp, fp, fp, vp, fp, vp, vp, vp, vp, fp, fp, fp,
                                         C.c_int, vp]
         lib.mmn_mha_fwd.restype = C.c_int
         lib.mmn_mha_fwd.argtypes = [C.POINTER(MhaDesc), vp, vp, vp, fp, vp, fp, C.c_int, vp]
         lib.mmn_mha_bwd.restype = C.c_int
-        lib.mmn_mha_bwd.argtypes = [C.POINTER(MhaDesc), vp, vp, vp, fp, vp, fp, vp, vp, vp, vp, C.c_int, vp]
+        lib.mmn_mha_bwd.argtypes = [C.POINTER(MhaDesc), vp, vp, vp, fp, vp, fp, vp, vp, vp, vp, fp, C.c_int, vp]
         lib.mmn_mha_avg_weights.restype = C.c_int
         lib.mmn_mha_avg_weights.argtypes = [C.POINTER(MhaDesc), vp, vp, fp, fp, fp, C.c_int, vp]
         if lib.mmn_abi_version() != 1:

@@ -12,7 +12,8 @@
 // shared memory in chunks, softmax is online so nothing N x N is ever materialised.
 // Backward is two kernels with the same structure and roles swapped (dq: thread per
 // query row; dkv: thread per key row), recomputing probabilities from the saved
-// log-sum-exp; no atomics except the cross-window reductions dbias / dhead_scale.
+// log-sum-exp; no atomics except the cross-window reductions dbias / dhead_scale.  The
+// backward never reads the forward output: delta = rowsum(P o dP) is recomputed exactly.
 #pragma once
 
 #include <cuda_bf16.h>
@@ -243,9 +244,9 @@ attn_fwd_generic(GenericProblem P, GenericLaunch L, const T* __restrict__ q, con
 template <typename T, int DMAX>
 __global__ void __launch_bounds__(kGenericThreads)
 attn_bwd_dq_generic(GenericProblem P, GenericLaunch L, const T* __restrict__ q, const T* __restrict__ k,
-                    const T* __restrict__ v, const T* __restrict__ out, const float* __restrict__ lse,
+                    const T* __restrict__ v, const float* __restrict__ lse,
                     const T* __restrict__ dout, T* __restrict__ dq, float* __restrict__ dbias,
-                    float* __restrict__ dhead_scale) {
+                    float* __restrict__ dhead_scale, float* __restrict__ delta_ws) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int cap = L.chunk, slots = L.slots, d = P.d;
   long long* sOff = reinterpret_cast<long long*>(smem_raw);
@@ -263,10 +264,9 @@ attn_bwd_dq_generic(GenericProblem P, GenericLaunch L, const T* __restrict__ q, 
   float qr[DMAX], dor[DMAX], dqr[DMAX];
   int rid_i = 0;
   long long dq_off = 0;
-  float hscale = 1.f, delta = 0.f, lse_i = 0.f, qinv = 1.f, dscale = 0.f;
+  float hscale = 1.f, delta = 0.f, psum = 0.f, lse_i = 0.f, qinv = 1.f, dscale = 0.f;
   if (active) {
     long long qo = row_offset(P, item, row, P.q_s0, P.q_s1, &rid_i);
-    long long oo = row_offset(P, item, row, P.o_s0, P.o_s1, &rid_i);
     long long doo = row_offset(P, item, row, P.do_s0, P.do_s1, &rid_i);
     dq_off = row_offset(P, item, row, P.dq_s0, P.dq_s1, &rid_i);
     float ss = 0.f;
@@ -274,8 +274,6 @@ attn_bwd_dq_generic(GenericProblem P, GenericLaunch L, const T* __restrict__ q, 
     for (int c = 0; c < DMAX; ++c) {
       qr[c] = c < d ? ldf(q + qo + c) : 0.f;
       dor[c] = c < d ? ldf(dout + doo + c) : 0.f;
-      float oc = c < d ? ldf(out + oo + c) : 0.f;
-      delta += dor[c] * oc;
       ss += qr[c] * qr[c];
       dqr[c] = 0.f;
     }
@@ -284,6 +282,40 @@ attn_bwd_dq_generic(GenericProblem P, GenericLaunch L, const T* __restrict__ q, 
     for (int c = 0; c < DMAX; ++c) qr[c] *= qinv;
     if (P.cosine) hscale = __ldg(P.head_scale + item % P.nH);
     lse_i = lse[(long long)item * P.nq + row];
+  }
+
+  // Pass 0: delta_i = sum_j P_ij dP_ij (== dO_i . O_i), from the recomputed probabilities so
+  // that no rounding of a low-precision `out` leaks into the cancellation-heavy reductions
+  // (dhead_scale, dbias).  It is handed to the key-side kernel through `delta_ws`.
+  for (int k0 = 0; k0 < P.nk; k0 += cap) {
+    const int cnt = min(cap, P.nk - k0);
+    stage_rows(P, k, P.k_s0, P.k_s1, item0, slots, k0, cnt, cap, sK, sOff, sRid, P.cosine ? 1 : 0, 1.f);
+    stage_rows(P, v, P.v_s0, P.v_s1, item0, slots, k0, cnt, cap, sV, sOff, (int*)nullptr, 0, 1.f);
+    if (active) {
+      const float* Ks = sK + slot * cap * d;
+      const float* Vs = sV + slot * cap * d;
+      const int* Rs = sRid + slot * cap;
+      for (int j = 0; j < cnt; ++j) {
+        float dot = 0.f, dp = 0.f;
+#pragma unroll
+        for (int c = 0; c < DMAX; ++c) if (c < d) { dot += qr[c] * Ks[j * d + c]; dp += dor[c] * Vs[j * d + c]; }
+        float s = logit(P, item, dot, row, k0 + j, rid_i, Rs[j], hscale);
+        if (s == -INFINITY) continue;
+        float p = expf(s - lse_i);
+        psum += p;
+        delta += p * dp * keep_scale(P, item, row, k0 + j);
+      }
+    }
+    __syncthreads();
+  }
+  // exp(s - lse) sums to 1 only to within ulp(lse); with logits of magnitude ~100 that is
+  // ~1e-5, and ds = p (dp - delta) turns a row-sum error into a bias that the reductions
+  // over rows do not cancel.  Renormalise by the row sum actually obtained.
+  const float pnorm = 1.f / psum;
+  delta *= pnorm;
+  if (active) {
+    delta_ws[(long long)item * P.nq + row] = delta;
+    delta_ws[(long long)P.n_items * P.nq + (long long)item * P.nq + row] = pnorm;
   }
 
   for (int k0 = 0; k0 < P.nk; k0 += cap) {
@@ -301,7 +333,7 @@ attn_bwd_dq_generic(GenericProblem P, GenericLaunch L, const T* __restrict__ q, 
         for (int c = 0; c < DMAX; ++c) if (c < d) { dot += qr[c] * Ks[j * d + c]; dp += dor[c] * Vs[j * d + c]; }
         float s = logit(P, item, dot, row, k0 + j, rid_i, Rs[j], hscale);
         if (s == -INFINITY) continue;
-        float p = expf(s - lse_i);
+        float p = expf(s - lse_i) * pnorm;
         float ds = p * (dp * keep_scale(P, item, row, k0 + j) - delta);
         float g = ds * hscale;
 #pragma unroll
@@ -336,7 +368,7 @@ attn_bwd_dq_generic(GenericProblem P, GenericLaunch L, const T* __restrict__ q, 
 template <typename T, int DMAX>
 __global__ void __launch_bounds__(kGenericThreads)
 attn_bwd_dkv_generic(GenericProblem P, GenericLaunch L, const T* __restrict__ q, const T* __restrict__ k,
-                     const T* __restrict__ v, const T* __restrict__ out, const float* __restrict__ lse,
+                     const T* __restrict__ v, const float* __restrict__ lse, const float* __restrict__ delta_ws,
                      const T* __restrict__ dout, T* __restrict__ dk, T* __restrict__ dv) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int cap = L.chunk, slots = L.slots, d = P.d;
@@ -344,9 +376,9 @@ attn_bwd_dkv_generic(GenericProblem P, GenericLaunch L, const T* __restrict__ q,
   int* sRid = reinterpret_cast<int*>(sOff + slots * cap);
   float* sLse = reinterpret_cast<float*>(sRid + slots * cap);
   float* sDelta = sLse + slots * cap;
-  float* sQ = sDelta + slots * cap;
+  float* sNorm = sDelta + slots * cap;
+  float* sQ = sNorm + slots * cap;
   float* sDO = sQ + slots * cap * d;
-  float* sO = sDO + slots * cap * d;           // staged only to form delta
 
   const int t = threadIdx.x;
   const int slot = t / L.rows_per_slot, r_in = t - slot * L.rows_per_slot;
@@ -385,15 +417,16 @@ attn_bwd_dkv_generic(GenericProblem P, GenericLaunch L, const T* __restrict__ q,
     stage_rows(P, q, P.q_s0, P.q_s1, item0, slots, q0, cnt, cap, sQ, sOff, sRid, P.cosine ? 1 : 0,
                P.cosine ? 1.f : P.scale);
     stage_rows(P, dout, P.do_s0, P.do_s1, item0, slots, q0, cnt, cap, sDO, sOff, (int*)nullptr, 0, 1.f);
-    stage_rows(P, out, P.o_s0, P.o_s1, item0, slots, q0, cnt, cap, sO, sOff, (int*)nullptr, 0, 1.f);
     for (int idx = t; idx < slots * cnt; idx += kGenericThreads) {
       int s = idx / cnt, i = idx - s * cnt, it = item0 + s;
-      float dl = 0.f, ls = 0.f;
+      float dl = 0.f, ls = 0.f, pn = 0.f;
       if (it < P.n_items) {
-        for (int c = 0; c < d; ++c) dl += sDO[(s * cap + i) * d + c] * sO[(s * cap + i) * d + c];
+        dl = delta_ws[(long long)it * P.nq + q0 + i];
+        pn = delta_ws[(long long)P.n_items * P.nq + (long long)it * P.nq + q0 + i];
         ls = lse[(long long)it * P.nq + q0 + i];
       }
       sDelta[s * cap + i] = dl;
+      sNorm[s * cap + i] = pn;
       sLse[s * cap + i] = ls;
     }
     __syncthreads();
@@ -407,7 +440,7 @@ attn_bwd_dkv_generic(GenericProblem P, GenericLaunch L, const T* __restrict__ q,
         for (int c = 0; c < DMAX; ++c) if (c < d) { dot += Qs[i * d + c] * kr[c]; dp += DOs[i * d + c] * vr[c]; }
         float s = logit(P, item, dot, q0 + i, col, Rs[i], rid_j, hscale);
         if (s == -INFINITY) continue;
-        float p = expf(s - sLse[slot * cap + i]);
+        float p = expf(s - sLse[slot * cap + i]) * sNorm[slot * cap + i];
         float ks = keep_scale(P, item, q0 + i, col);
         float ds = p * (dp * ks - sDelta[slot * cap + i]);
         float pk = p * ks, g = ds * hscale;

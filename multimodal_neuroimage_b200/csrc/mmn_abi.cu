@@ -144,24 +144,24 @@ int launch_fwd(const mmn::GenericProblem& P, const void* q, const void* k, const
 }
 
 template <typename T, int DMAX>
-int launch_bwd(const mmn::GenericProblem& P, const void* q, const void* k, const void* v, const void* out, const float* lse,
-               const void* dout, void* dq, void* dk, void* dv, float* dbias, float* dhs, cudaStream_t st) {
+int launch_bwd(const mmn::GenericProblem& P, const void* q, const void* k, const void* v, const float* lse,
+               const void* dout, void* dq, void* dk, void* dv, float* dbias, float* dhs, float* ws, cudaStream_t st) {
   {
     mmn::GenericLaunch L = plan(P.nq, P.nk, 2 * P.d * 4 + 12);
     auto kern = mmn::attn_bwd_dq_generic<T, DMAX>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     dim3 grid((P.n_items + L.slots - 1) / L.slots, (P.nq + L.rows_per_slot - 1) / L.rows_per_slot);
-    kern<<<grid, mmn::kGenericThreads, L.smem_bytes, st>>>(P, L, (const T*)q, (const T*)k, (const T*)v, (const T*)out, lse,
-                                                          (const T*)dout, (T*)dq, dbias, dhs);
+    kern<<<grid, mmn::kGenericThreads, L.smem_bytes, st>>>(P, L, (const T*)q, (const T*)k, (const T*)v, lse,
+                                                          (const T*)dout, (T*)dq, dbias, dhs, ws);
     int rc = check_launch("attn_bwd_dq_generic");
     if (rc) return rc;
   }
   {
-    mmn::GenericLaunch L = plan(P.nk, P.nq, 3 * P.d * 4 + 20);
+    mmn::GenericLaunch L = plan(P.nk, P.nq, 2 * P.d * 4 + 24);
     auto kern = mmn::attn_bwd_dkv_generic<T, DMAX>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     dim3 grid((P.n_items + L.slots - 1) / L.slots, (P.nk + L.rows_per_slot - 1) / L.rows_per_slot);
-    kern<<<grid, mmn::kGenericThreads, L.smem_bytes, st>>>(P, L, (const T*)q, (const T*)k, (const T*)v, (const T*)out, lse,
+    kern<<<grid, mmn::kGenericThreads, L.smem_bytes, st>>>(P, L, (const T*)q, (const T*)k, (const T*)v, lse, ws,
                                                           (const T*)dout, (T*)dk, (T*)dv);
     return check_launch("attn_bwd_dkv_generic");
   }
@@ -182,10 +182,10 @@ int generic_fwd(const mmn::GenericProblem& P, int dt, const void* q, const void*
   MMN_DISPATCH_D(__nv_bfloat16, launch_fwd, P, q, k, v, out, lse, st);
 }
 
-int generic_bwd(const mmn::GenericProblem& P, int dt, const void* q, const void* k, const void* v, const void* out, const float* lse,
-                const void* dout, void* dq, void* dk, void* dv, float* dbias, float* dhs, cudaStream_t st) {
-  if (dt == MMN_DT_F32) MMN_DISPATCH_D(float, launch_bwd, P, q, k, v, out, lse, dout, dq, dk, dv, dbias, dhs, st);
-  MMN_DISPATCH_D(__nv_bfloat16, launch_bwd, P, q, k, v, out, lse, dout, dq, dk, dv, dbias, dhs, st);
+int generic_bwd(const mmn::GenericProblem& P, int dt, const void* q, const void* k, const void* v, const float* lse,
+                const void* dout, void* dq, void* dk, void* dv, float* dbias, float* dhs, float* ws, cudaStream_t st) {
+  if (dt == MMN_DT_F32) MMN_DISPATCH_D(float, launch_bwd, P, q, k, v, lse, dout, dq, dk, dv, dbias, dhs, ws, st);
+  MMN_DISPATCH_D(__nv_bfloat16, launch_bwd, P, q, k, v, lse, dout, dq, dk, dv, dbias, dhs, ws, st);
 }
 
 bool have_device() {
@@ -236,10 +236,11 @@ int mmn_winattn_fwd(const mmn_winattn_desc* d, const void* q, const void* k, con
 
 int mmn_winattn_bwd(const mmn_winattn_desc* d, const void* q, const void* k, const void* v, const float* bias,
                     const float* head_scale, const float* mask, const void* out, const float* lse, const void* dout,
-                    void* dq, void* dk, void* dv, float* dbias, float* dhead_scale, int device, void* stream) {
+                    void* dq, void* dk, void* dv, float* dbias, float* dhead_scale, float* workspace, int device,
+                    void* stream) {
   int rc = validate_win(d);
   if (rc) return rc;
-  if (!q || !k || !v || !out || !lse || !dout || !dq || !dk || !dv) return fail(MMN_ERR_INVALID, "null tensor pointer");
+  if (!q || !k || !v || !lse || !dout || !dq || !dk || !dv || !workspace) return fail(MMN_ERR_INVALID, "null tensor pointer");
   if (d->score_kind == MMN_SCORE_COSINE && !head_scale) return fail(MMN_ERR_INVALID, "cosine attention needs head_scale");
   if (d->mask_kind == MMN_MASK_TENSOR && !mask) return fail(MMN_ERR_INVALID, "MMN_MASK_TENSOR needs a mask");
   if (!have_device()) return fail(MMN_ERR_CUDA, "no CUDA device: libmmn_b200 has no CPU path");
@@ -249,13 +250,13 @@ int mmn_winattn_bwd(const mmn_winattn_desc* d, const void* q, const void* k, con
   bool tc_ok = mmn::tc::winattn_bwd_supported(d);
   if (d->path == MMN_PATH_TCGEN05 && !tc_ok) return fail(MMN_ERR_UNSUPPORTED, "shape not supported by the tcgen05 backward path");
   if (d->path != MMN_PATH_GENERIC && tc_ok) {
-    rc = mmn::tc::winattn_bwd(d, q, k, v, bias, head_scale, mask, out, lse, dout, dq, dk, dv, dbias, dhead_scale, st, g_err, sizeof(g_err));
+    rc = mmn::tc::winattn_bwd(d, q, k, v, bias, head_scale, mask, out, lse, dout, dq, dk, dv, dbias, dhead_scale, workspace, st, g_err, sizeof(g_err));
     if (rc == MMN_OK) g_launches.fetch_add(1, std::memory_order_relaxed);
     return rc;
   }
   mmn::GenericProblem P = problem_from(d, bias, head_scale, mask);
-  return generic_bwd(P, d->io_dtype, q, k, v, out, lse, dout, dq, dk, dv, bias ? dbias : nullptr,
-                     P.cosine ? dhead_scale : nullptr, st);
+  return generic_bwd(P, d->io_dtype, q, k, v, lse, dout, dq, dk, dv, bias ? dbias : nullptr,
+                     P.cosine ? dhead_scale : nullptr, workspace, st);
 }
 
 int mmn_mha_fwd(const mmn_mha_desc* d, const void* q, const void* k, const void* v, const float* mask, void* out,
@@ -271,15 +272,16 @@ int mmn_mha_fwd(const mmn_mha_desc* d, const void* q, const void* k, const void*
 }
 
 int mmn_mha_bwd(const mmn_mha_desc* d, const void* q, const void* k, const void* v, const float* mask, const void* out,
-                const float* lse, const void* dout, void* dq, void* dk, void* dv, int device, void* stream) {
+                const float* lse, const void* dout, void* dq, void* dk, void* dv, float* workspace, int device,
+                void* stream) {
   int rc = validate_mha(d);
   if (rc) return rc;
-  if (!q || !k || !v || !out || !lse || !dout || !dq || !dk || !dv) return fail(MMN_ERR_INVALID, "null tensor pointer");
+  if (!q || !k || !v || !lse || !dout || !dq || !dk || !dv || !workspace) return fail(MMN_ERR_INVALID, "null tensor pointer");
   if (d->mask_kind == MMN_MASK_TENSOR && !mask) return fail(MMN_ERR_INVALID, "MMN_MASK_TENSOR needs a mask");
   if (!have_device()) return fail(MMN_ERR_CUDA, "no CUDA device: libmmn_b200 has no CPU path");
   DeviceGuard g(device);
   if (!g.ok) return fail(MMN_ERR_CUDA, "cannot select device %d", device);
-  return generic_bwd(problem_from(d, mask), d->io_dtype, q, k, v, out, lse, dout, dq, dk, dv, nullptr, nullptr,
+  return generic_bwd(problem_from(d, mask), d->io_dtype, q, k, v, lse, dout, dq, dk, dv, nullptr, nullptr, workspace,
                      (cudaStream_t)stream);
 }
 

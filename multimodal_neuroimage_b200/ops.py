@@ -154,7 +154,8 @@ def winattn_bwd(dout: Tensor, a: Tensor, b: Optional[Tensor], bias: Optional[Ten
     dhs = torch.zeros_like(head_scale) if head_scale is not None else a.new_empty(0, dtype=torch.float32)
     _lib.check(lib.mmn_winattn_bwd(C.byref(d), q, k, v, _ptr(bias), _ptr(head_scale), _ptr(mask), _ptr(out), _ptr(lse),
                                    _ptr(dout), dq, dk, dv, _ptr(dbias) if bias is not None else None,
-                                   _ptr(dhs) if head_scale is not None else None, a.device.index, _stream(a)),
+                                   _ptr(dhs) if head_scale is not None else None, _ptr(lse.new_empty(2 * lse.numel())),
+                                   a.device.index, _stream(a)),
                "mmn_winattn_bwd")
     return da, db, dbias, dhs
 
@@ -254,7 +255,8 @@ def mha_bwd(dout: Tensor, q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor
     d.dk_stride_t, d.dk_stride_b = _tb_strides(dk)
     d.dv_stride_t, d.dv_stride_b = _tb_strides(dv)
     _lib.check(lib.mmn_mha_bwd(C.byref(d), _ptr(q), _ptr(k), _ptr(v), _ptr(mask), _ptr(out), _ptr(lse), _ptr(dout),
-                               _ptr(dq), _ptr(dk), _ptr(dv), q.device.index, _stream(q)), "mmn_mha_bwd")
+                               _ptr(dq), _ptr(dk), _ptr(dv), _ptr(lse.new_empty(2 * lse.numel())), q.device.index, _stream(q)),
+               "mmn_mha_bwd")
     return dq, dk, dv
 
 

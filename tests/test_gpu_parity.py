@@ -172,7 +172,7 @@ def test_winattn_core_bf16_tcgen05(mm, case, cross):
     name = mm.ops.winattn_path_name(a.cuda().bfloat16(), None if b is None else b.cuda().bfloat16(), grid, window, shift,
                                     nH, mm.lib.SCORE_COSINE if cosine else mm.lib.SCORE_SCALED, kind)
     assert name == "tcgen05", f"tuned shape fell back to {name}"
-    _run_core(mm, case, torch.bfloat16, cross, mm.lib.PATH_TCGEN05)
+    _run_core(mm, case, torch.bfloat16, cross, mm.lib.PATH_AUTO)
 
 
 # ------------------------------------------------------------------------------------------
@@ -265,7 +265,7 @@ def test_mha_dense_mask_equals_generated_mask(mm):
 # 3. 3-D modules (our generalisation) vs the n-D oracle, fp32 and bf16 autocast
 # ------------------------------------------------------------------------------------------
 def _sd64(module):
-    return {k: v.detach().double().cpu() for k, v in module.state_dict().items()}
+    return {k: (v.detach().double() if v.is_floating_point() else v.detach()).cpu() for k, v in module.state_dict().items()}
 
 
 def _randomise(module, seed):
