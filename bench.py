@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the attention hot path (BASELINE.json, configs[1]).
+
+Workload "cfg2": the SwinV2 3-D shifted-window attention module (x -> qkv projection ->
+cosine window attention with CPB bias and shift mask -> output projection), 4x4x4 windows
+shifted by 2, 3 heads x 32, on synthetic bf16 volumes of 32^3 tokens x 96 channels,
+forward + backward.  A "step" is one forward+backward pass over one per-GPU batch.
+
+metric  window_attn_fwd_bwd, unit TFLOP/s: ALGORITHMIC flops of the fused module,
+        3*(4 N^2 C + 8 N C^2) = 18.87 MFLOP per window, summed over all ranks,
+        divided by the device-timed step (CUDA events, max over ranks).
+value   inputs resident in HBM.            e2e   same call, inputs in pinned host memory,
+        H2D of x and dy and D2H of y and dx inside the timed region.
+roofline  the dominant kernel of the step, timed live with CUDA events on its stream.
+cpu_baseline / --impl reference  the CPU oracle port of the reference module (the reference
+        is PyTorch/Python and is not on the GPU box) on a bounded sample, all host threads.
+
+  python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--batch B]
+  torchrun ... bench.py --gpus N ...        (one rank per GPU, NCCL; weak scaling)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GRID, WINDOW, SHIFT, HEADS, HEAD_DIM = (32, 32, 32), 4, 2, 3, 32
+C = HEADS * HEAD_DIM
+N = WINDOW ** 3
+WINDOWS_PER_SAMPLE = math.prod(GRID) // N
+FLOP_PER_WINDOW = 3 * (4 * N * N * C + 8 * N * C * C)            # fused-module fwd+bwd, 18.87 MFLOP
+CORE_FWD_BYTES_PER_WINDOW = 4 * N * C * 2 + HEADS * N * 4        # read q,k,v + write o (bf16) + lse
+CORE_BWD_BYTES_PER_WINDOW = 8 * N * C * 2 + 2 * HEADS * N * 4    # read q,k,v,o,do; write dq,dk,dv; lse
+METRIC, UNIT = "window_attn_fwd_bwd", "TFLOP/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.th.join(timeout=2)
+        return False
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference module (swin_v2_module.py:138-178 + 277-297)
+# ------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, samples=1, threads=None):
+    """fwd+bwd of the reference algorithm (oracle/ref_nd.py) on `samples` volumes per step.
+    Returns (TFLOP/s, ms/step, cores, description)."""
+    from oracle import ref_nd as R
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(0)
+    from multimodal_neuroimage_b200 import geometry
+    w3 = (WINDOW,) * 3
+    p = {
+        "qkv.weight": torch.randn(3 * C, C, generator=g) * C ** -0.5, "q_bias": torch.randn(C, generator=g) * 0.1,
+        "v_bias": torch.randn(C, generator=g) * 0.1, "logit_scale": torch.log(10 * torch.ones(HEADS, 1, 1)),
+        "cpb_mlp.0.weight": torch.randn(512, 3, generator=g) * 0.5, "cpb_mlp.0.bias": torch.randn(512, generator=g) * 0.1,
+        "cpb_mlp.2.weight": torch.randn(HEADS, 512, generator=g) * 0.05,
+        "proj.weight": torch.randn(C, C, generator=g) * C ** -0.5, "proj.bias": torch.zeros(C),
+        "relative_coords_table": geometry.cpb_coords_table(w3), "relative_position_index": geometry.relative_position_index(w3),
+    }
+    for k in list(p):
+        if p[k].is_floating_point() and "relative" not in k:
+            p[k].requires_grad_(True)
+    mask = R.shift_mask_nd(GRID, w3, (SHIFT,) * 3)
+    x = torch.randn(samples, math.prod(GRID), C, generator=g, requires_grad=True)
+    dy = torch.randn(samples, math.prod(GRID), C, generator=g)
+
+    def step():
+        xs = R.cyclic_shift_nd(x.view(samples, *GRID, C), (SHIFT,) * 3)
+        xw = R.window_partition_nd(xs, w3).view(-1, N, C)
+        aw = R.window_attention_cosine(xw, p, w3, HEADS, mask)
+        y = R.cyclic_shift_nd(R.window_reverse_nd(aw.view(-1, *w3, C), w3, GRID), (SHIFT,) * 3, inverse=True)
+        wrt = [x] + [t for t in p.values() if t.requires_grad]
+        torch.autograd.grad((y.reshape(samples, -1, C) * dy).sum(), wrt)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    tflops = samples * WINDOWS_PER_SAMPLE * FLOP_PER_WINDOW / dt / 1e12
+    return tflops, dt * 1e3, threads, f"{samples} volume(s) of 32^3 tokens ({samples * WINDOWS_PER_SAMPLE} windows) per step, fp32, torch CPU"
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    tflops, ms, cores, sample = cpu_reference_run(args.steps, args.warmup, samples=1)
+    line = {"impl": "reference", "metric": METRIC, "value": tflops, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.batch, world),
+            "cpu_baseline": {"value": tflops, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": tflops, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(batch, world):
+    return {"workload": "cfg2: SwinV2 3-D shifted-window attention module fwd+bwd, 4x4x4 windows shift 2, 3 heads x 32, "
+                        "32^3 tokens x 96 ch per sample",
+            "per_gpu_batch": batch, "global_batch": batch * world, "windows_per_step": batch * world * WINDOWS_PER_SAMPLE,
+            "flop_per_window": FLOP_PER_WINDOW, "l2_policy": "inputs larger than L2 (x, qkv, grads >> 126 MB)",
+            "parallelism": f"dp{world}"}
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="volumes per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from multimodal_neuroimage_b200 import _lib, ops
+    from multimodal_neuroimage_b200.modules import swin_v2_module as v2
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    B = args.batch
+    torch.manual_seed(1234 + rank)
+    attn = v2.WindowAttention(C, (WINDOW,) * 3, HEADS).to(dev)
+    with torch.no_grad():
+        attn.q_bias.normal_(0, 0.1)
+        attn.v_bias.normal_(0, 0.1)
+    if world > 1:      # same weights everywhere, gradients all-reduced over NCCL like trainer.py's DDP
+        for p in attn.parameters():
+            dist.broadcast(p.data, 0)
+
+    class Wrapped(torch.nn.Module):
+        def __init__(self, a):
+            super().__init__()
+            self.a = a
+
+        def forward(self, x):
+            return self.a.forward_grid(x, GRID, (SHIFT,) * 3)
+
+    model = Wrapped(attn)
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+
+    L = math.prod(GRID)
+    x = torch.randn(B, L, C, device=dev, dtype=torch.bfloat16, requires_grad=True)
+    dy = torch.randn(B, L, C, device=dev, dtype=torch.bfloat16)
+    x_host = torch.randn(B, L, C, dtype=torch.bfloat16).pin_memory()
+    dy_host = torch.randn(B, L, C, dtype=torch.bfloat16).pin_memory()
+    y_host = torch.empty(B, L, C, dtype=torch.bfloat16).pin_memory()
+    dx_host = torch.empty(B, L, C, dtype=torch.bfloat16).pin_memory()
+
+    def step_resident():
+        for p in model.parameters():
+            p.grad = None
+        x.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = model(x)
+        y.backward(dy)
+        return y
+
+    def step_e2e():
+        for p in model.parameters():
+            p.grad = None
+        xd = x_host.to(dev, non_blocking=True).requires_grad_(True)
+        dyd = dy_host.to(dev, non_blocking=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = model(xd)
+        y.backward(dyd)
+        y_host.copy_(y.detach(), non_blocking=True)
+        dx_host.copy_(xd.grad, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, record_kernels=False):
+        barrier()
+        launches0 = _lib.launch_count()
+        ops.KERNEL_EVENTS = {} if record_kernels else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        kern = {}
+        if record_kernels:
+            for name, evs in ops.KERNEL_EVENTS.items():
+                kern[name] = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+            ops.KERNEL_EVENTS = None
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), kern, (_lib.launch_count() - launches0) // max(steps, 1)
+
+    for _ in range(args.warmup):
+        step_resident()
+    with ClockSampler(local) as clk:
+        ms, kern, launches = timed(step_resident, args.steps, record_kernels=True)
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _, _ = timed(step_e2e, max(3, args.steps // 4))
+
+    windows = B * world * WINDOWS_PER_SAMPLE
+    value = windows * FLOP_PER_WINDOW / (ms * 1e-3) / 1e12
+    e2e = windows * FLOP_PER_WINDOW / (ms_e2e * 1e-3) / 1e12
+
+    pk = peaks()
+    # dominant kernel of the step = the longer of the two attention-core launches
+    per_launch_windows = B * WINDOWS_PER_SAMPLE
+    cand = {"winattn_fwd": CORE_FWD_BYTES_PER_WINDOW, "winattn_bwd": CORE_BWD_BYTES_PER_WINDOW}
+    dom = max((k for k in cand if k in kern), key=lambda k: kern[k], default=None)
+    roofline = None
+    if dom is not None:
+        gbs = per_launch_windows * cand[dom] / (kern[dom] * 1e-3) / 1e9
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": gbs / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                    "algorithmic_bytes_per_window": cand[dom], "ms_per_launch": kern[dom],
+                    "kernels_ms": kern,
+                    "all": {k: {"GB/s": per_launch_windows * cand[k] / (kern[k] * 1e-3) / 1e9,
+                                "frac": per_launch_windows * cand[k] / (kern[k] * 1e-3) / 1e9 / pk["hbm_gbs"]}
+                            for k in kern if k in cand},
+                    "module_tflops_frac_of_bf16_peak": value / world / pk["bf16_tflops"]}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            tf, cms, cores, sample = cpu_reference_run(steps=3, warmup=1, samples=1)
+            cpu = {"value": tf, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_step": cms}
+        elem = 2
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic", "config": workload_config(B, world),
+                "samples_per_s": B * world / (ms * 1e-3),
+                "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": 2 * B * L * C * elem,
+                        "d2h_bytes_per_step": 2 * B * L * C * elem},
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary(),
+                "paths": {"fwd": ops.winattn_path_name(torch.empty(1, *GRID, 3 * C, device=dev, dtype=torch.bfloat16), None, GRID,
+                                                       (WINDOW,) * 3, (SHIFT,) * 3, HEADS, _lib.SCORE_COSINE, _lib.MASK_SHIFT)}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -59,6 +59,28 @@ def _stream(t: Tensor):
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
+# Optional live kernel timing (bench.py): when KERNEL_EVENTS is a dict, every C call is
+# bracketed by CUDA events recorded on the launching stream and appended under its name.
+KERNEL_EVENTS = None
+
+
+class _timed:
+    def __init__(self, name, t):
+        self.name, self.t = name, t
+
+    def __enter__(self):
+        if KERNEL_EVENTS is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record(torch.cuda.current_stream(self.t.device))
+
+    def __exit__(self, *exc):
+        if KERNEL_EVENTS is not None:
+            self.e1.record(torch.cuda.current_stream(self.t.device))
+            KERNEL_EVENTS.setdefault(self.name, []).append((self.e0, self.e1))
+        return False
+
+
 def _win_desc(a: Tensor, b: Optional[Tensor], grid, window, shift, num_heads, score_kind, mask_kind, mask_windows,
               scale, dropout_p, seed, offset, path) -> Tuple[WinAttnDesc, int]:
     n = len(grid)
@@ -107,8 +129,9 @@ def winattn_fwd(a: Tensor, b: Optional[Tensor], bias: Optional[Tensor], head_sca
     for t in (bias, head_scale, mask):
         if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
             raise RuntimeError("bias / head_scale / mask must be contiguous float32")
-    _lib.check(lib.mmn_winattn_fwd(C.byref(d), q, k, v, _ptr(bias), _ptr(head_scale), _ptr(mask), _ptr(out), _ptr(lse),
-                                   a.device.index, _stream(a)), "mmn_winattn_fwd")
+    with _timed("winattn_fwd", a):
+        _lib.check(lib.mmn_winattn_fwd(C.byref(d), q, k, v, _ptr(bias), _ptr(head_scale), _ptr(mask), _ptr(out),
+                                       _ptr(lse), a.device.index, _stream(a)), "mmn_winattn_fwd")
     return out, lse
 
 
@@ -152,11 +175,12 @@ def winattn_bwd(dout: Tensor, a: Tensor, b: Optional[Tensor], bias: Optional[Ten
     d.do_row_stride = Cc
     dbias = torch.zeros_like(bias) if bias is not None else a.new_empty(0, dtype=torch.float32)
     dhs = torch.zeros_like(head_scale) if head_scale is not None else a.new_empty(0, dtype=torch.float32)
-    _lib.check(lib.mmn_winattn_bwd(C.byref(d), q, k, v, _ptr(bias), _ptr(head_scale), _ptr(mask), _ptr(out), _ptr(lse),
-                                   _ptr(dout), dq, dk, dv, _ptr(dbias) if bias is not None else None,
-                                   _ptr(dhs) if head_scale is not None else None, _ptr(lse.new_empty(2 * lse.numel())),
-                                   a.device.index, _stream(a)),
-               "mmn_winattn_bwd")
+    ws = lse.new_empty(2 * lse.numel())
+    with _timed("winattn_bwd", a):
+        _lib.check(lib.mmn_winattn_bwd(C.byref(d), q, k, v, _ptr(bias), _ptr(head_scale), _ptr(mask), _ptr(out), _ptr(lse),
+                                       _ptr(dout), dq, dk, dv, _ptr(dbias) if bias is not None else None,
+                                       _ptr(dhs) if head_scale is not None else None, _ptr(ws), a.device.index,
+                                       _stream(a)), "mmn_winattn_bwd")
     return da, db, dbias, dhs
 
 
