@@ -15,10 +15,11 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libmmn_b200.so")
-SOURCES = ["mmn_abi.cu"]
-HEADERS = ["attn_generic.cuh", "winattn_tc.cuh", "tc_common.cuh"]
+# translation unit -> headers it depends on (besides include/mmn_b200.h)
+SOURCES = {"mmn_abi.cu": ["generic_launch.h", "attn_generic.cuh", "winattn_tc.cuh", "tc_common.cuh"],
+           "generic_launch.cu": ["generic_launch.h", "attn_generic.cuh"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
 
 # enums of include/mmn_b200.h
 DT_F32, DT_BF16 = 0, 1
@@ -53,26 +54,42 @@ class MhaDesc(C.Structure):
                [(f"{t}_stride_{a}", C.c_int64) for t in ("q", "k", "v", "o", "do", "dq", "dk", "dv") for a in ("t", "b")]
 
 
-def source_stamp() -> float:
-    files = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(ROOT, "include", "mmn_b200.h")]
+def _stamp(files) -> float:
     return max(os.path.getmtime(f) for f in files if os.path.exists(f))
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu for sm_100a into PKG_DIR/libmmn_b200.so (nvcc cross-compiles
-    without a GPU).  Skips when the library is newer than every source."""
-    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= source_stamp():
-        return LIB_PATH
+    """Compile csrc/*.cu for sm_100a (one object per translation unit, rebuilt only when it
+    or one of its headers changed) and link PKG_DIR/libmmn_b200.so.  nvcc cross-compiles
+    without a GPU."""
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libmmn_b200.so")
-    cmd = [nvcc] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH + ".tmp"]
-    if verbose:
-        print(" ".join(cmd), flush=True)
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    objdir = os.path.join(PKG_DIR, "build")
+    os.makedirs(objdir, exist_ok=True)
+    header = os.path.join(ROOT, "include", "mmn_b200.h")
+    objs, procs = [], []
+    for src, deps in SOURCES.items():
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        stamp = _stamp([os.path.join(CSRC, src), header] + [os.path.join(CSRC, d) for d in deps])
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < stamp:
+            cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+            if verbose:
+                print(" ".join(cmd), flush=True)
+            procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
+    if procs or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < _stamp(objs):
+        cmd = [nvcc, "-shared", "-o", LIB_PATH + ".tmp"] + objs
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
+        os.replace(LIB_PATH + ".tmp", LIB_PATH)
     return LIB_PATH
 
 

@@ -1,0 +1,16 @@
+// generic_launch.h -- host entry points of the shape-generic kernels (attn_generic.cuh),
+// compiled in their own translation unit so that the tensor-core kernels rebuild quickly.
+#pragma once
+#include <cuda_runtime.h>
+#include "attn_generic.cuh"
+
+namespace mmn {
+// Each returns cudaSuccess or the launch error; `*launches` is incremented per kernel launched.
+cudaError_t generic_fwd(const GenericProblem& P, int io_dtype, const void* q, const void* k, const void* v, void* out,
+                        float* lse, cudaStream_t st, int* launches);
+cudaError_t generic_bwd(const GenericProblem& P, int io_dtype, const void* q, const void* k, const void* v, const float* lse,
+                        const void* dout, void* dq, void* dk, void* dv, float* dbias, float* dhs, float* ws,
+                        cudaStream_t st, int* launches);
+cudaError_t generic_avg_weights(const GenericProblem& P, int io_dtype, int batch, const void* q, const void* k,
+                                const float* lse, float* avg, cudaStream_t st, int* launches);
+}  // namespace mmn

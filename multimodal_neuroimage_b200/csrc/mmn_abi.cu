@@ -8,7 +8,7 @@
 #include <cstring>
 
 #include "../../include/mmn_b200.h"
-#include "attn_generic.cuh"
+#include "generic_launch.h"
 #include "winattn_tc.cuh"
 
 namespace {
@@ -35,14 +35,11 @@ struct DeviceGuard {
   ~DeviceGuard() { if (ok && prev >= 0) cudaSetDevice(prev); }
 };
 
-int check_launch(const char* what) {
-  cudaError_t e = cudaGetLastError();
+int finish(cudaError_t e, int launches, const char* what) {
+  g_launches.fetch_add((uint64_t)launches, std::memory_order_relaxed);
   if (e != cudaSuccess) return fail(MMN_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
-  g_launches.fetch_add(1, std::memory_order_relaxed);
   return MMN_OK;
 }
-
-int prod3(const int32_t* a, int n) { int p = 1; for (int i = 0; i < n; ++i) p *= a[i]; return p; }
 
 int validate_win(const mmn_winattn_desc* d) {
   if (!d) return fail(MMN_ERR_INVALID, "null descriptor");
@@ -115,79 +112,6 @@ mmn::GenericProblem problem_from(const mmn_mha_desc* d, const float* mask) {
   return P;
 }
 
-// rows: extent of the thread-per-row side; other: extent of the staged side;
-// floats_per_staged_row: shared floats per staged row excluding the 12-byte offset/rid.
-mmn::GenericLaunch plan(int rows, int other, int bytes_per_staged_row) {
-  mmn::GenericLaunch L{};
-  L.rows_per_slot = rows < mmn::kGenericThreads ? rows : mmn::kGenericThreads;
-  L.slots = mmn::kGenericThreads / L.rows_per_slot;
-  const size_t budget = 96 * 1024;
-  int cap = (int)(budget / ((size_t)L.slots * bytes_per_staged_row));
-  if (cap > other) cap = other;
-  if (cap > 256) cap = 256;
-  if (cap < 1) cap = 1;
-  L.chunk = cap;
-  L.smem_bytes = (size_t)L.slots * cap * bytes_per_staged_row;
-  return L;
-}
-
-constexpr int kMaxSmem = 100 * 1024;
-
-template <typename T, int DMAX>
-int launch_fwd(const mmn::GenericProblem& P, const void* q, const void* k, const void* v, void* out, float* lse, cudaStream_t st) {
-  mmn::GenericLaunch L = plan(P.nq, P.nk, 2 * P.d * 4 + 12);
-  auto kern = mmn::attn_fwd_generic<T, DMAX>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-  dim3 grid((P.n_items + L.slots - 1) / L.slots, (P.nq + L.rows_per_slot - 1) / L.rows_per_slot);
-  kern<<<grid, mmn::kGenericThreads, L.smem_bytes, st>>>(P, L, (const T*)q, (const T*)k, (const T*)v, (T*)out, lse);
-  return check_launch("attn_fwd_generic");
-}
-
-template <typename T, int DMAX>
-int launch_bwd(const mmn::GenericProblem& P, const void* q, const void* k, const void* v, const float* lse,
-               const void* dout, void* dq, void* dk, void* dv, float* dbias, float* dhs, float* ws, cudaStream_t st) {
-  {
-    mmn::GenericLaunch L = plan(P.nq, P.nk, 2 * P.d * 4 + 12);
-    auto kern = mmn::attn_bwd_dq_generic<T, DMAX>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    dim3 grid((P.n_items + L.slots - 1) / L.slots, (P.nq + L.rows_per_slot - 1) / L.rows_per_slot);
-    kern<<<grid, mmn::kGenericThreads, L.smem_bytes, st>>>(P, L, (const T*)q, (const T*)k, (const T*)v, lse,
-                                                          (const T*)dout, (T*)dq, dbias, dhs, ws);
-    int rc = check_launch("attn_bwd_dq_generic");
-    if (rc) return rc;
-  }
-  {
-    mmn::GenericLaunch L = plan(P.nk, P.nq, 2 * P.d * 4 + 24);
-    auto kern = mmn::attn_bwd_dkv_generic<T, DMAX>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    dim3 grid((P.n_items + L.slots - 1) / L.slots, (P.nk + L.rows_per_slot - 1) / L.rows_per_slot);
-    kern<<<grid, mmn::kGenericThreads, L.smem_bytes, st>>>(P, L, (const T*)q, (const T*)k, (const T*)v, lse, ws,
-                                                          (const T*)dout, (T*)dk, (T*)dv);
-    return check_launch("attn_bwd_dkv_generic");
-  }
-}
-
-#define MMN_DISPATCH_D(T, FN, ...)                                            \
-  do {                                                                         \
-    if (P.d <= 4) return FN<T, 4>(__VA_ARGS__);                                \
-    if (P.d <= 8) return FN<T, 8>(__VA_ARGS__);                                \
-    if (P.d <= 16) return FN<T, 16>(__VA_ARGS__);                              \
-    if (P.d <= 32) return FN<T, 32>(__VA_ARGS__);                              \
-    if (P.d <= 64) return FN<T, 64>(__VA_ARGS__);                              \
-    return FN<T, 128>(__VA_ARGS__);                                            \
-  } while (0)
-
-int generic_fwd(const mmn::GenericProblem& P, int dt, const void* q, const void* k, const void* v, void* out, float* lse, cudaStream_t st) {
-  if (dt == MMN_DT_F32) MMN_DISPATCH_D(float, launch_fwd, P, q, k, v, out, lse, st);
-  MMN_DISPATCH_D(__nv_bfloat16, launch_fwd, P, q, k, v, out, lse, st);
-}
-
-int generic_bwd(const mmn::GenericProblem& P, int dt, const void* q, const void* k, const void* v, const float* lse,
-                const void* dout, void* dq, void* dk, void* dv, float* dbias, float* dhs, float* ws, cudaStream_t st) {
-  if (dt == MMN_DT_F32) MMN_DISPATCH_D(float, launch_bwd, P, q, k, v, lse, dout, dq, dk, dv, dbias, dhs, ws, st);
-  MMN_DISPATCH_D(__nv_bfloat16, launch_bwd, P, q, k, v, lse, dout, dq, dk, dv, dbias, dhs, ws, st);
-}
-
 bool have_device() {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -231,7 +155,8 @@ int mmn_winattn_fwd(const mmn_winattn_desc* d, const void* q, const void* k, con
     if (rc == MMN_OK) g_launches.fetch_add(1, std::memory_order_relaxed);
     return rc;
   }
-  return generic_fwd(problem_from(d, bias, head_scale, mask), d->io_dtype, q, k, v, out, lse, st);
+  int n = 0;
+  return finish(mmn::generic_fwd(problem_from(d, bias, head_scale, mask), d->io_dtype, q, k, v, out, lse, st, &n), n, "attn_fwd_generic");
 }
 
 int mmn_winattn_bwd(const mmn_winattn_desc* d, const void* q, const void* k, const void* v, const float* bias,
@@ -255,8 +180,9 @@ int mmn_winattn_bwd(const mmn_winattn_desc* d, const void* q, const void* k, con
     return rc;
   }
   mmn::GenericProblem P = problem_from(d, bias, head_scale, mask);
-  return generic_bwd(P, d->io_dtype, q, k, v, lse, dout, dq, dk, dv, bias ? dbias : nullptr,
-                     P.cosine ? dhead_scale : nullptr, workspace, st);
+  int n = 0;
+  return finish(mmn::generic_bwd(P, d->io_dtype, q, k, v, lse, dout, dq, dk, dv, bias ? dbias : nullptr,
+                                 P.cosine ? dhead_scale : nullptr, workspace, st, &n), n, "attn_bwd_generic");
 }
 
 int mmn_mha_fwd(const mmn_mha_desc* d, const void* q, const void* k, const void* v, const float* mask, void* out,
@@ -268,7 +194,8 @@ int mmn_mha_fwd(const mmn_mha_desc* d, const void* q, const void* k, const void*
   if (!have_device()) return fail(MMN_ERR_CUDA, "no CUDA device: libmmn_b200 has no CPU path");
   DeviceGuard g(device);
   if (!g.ok) return fail(MMN_ERR_CUDA, "cannot select device %d", device);
-  return generic_fwd(problem_from(d, mask), d->io_dtype, q, k, v, out, lse, (cudaStream_t)stream);
+  int n = 0;
+  return finish(mmn::generic_fwd(problem_from(d, mask), d->io_dtype, q, k, v, out, lse, (cudaStream_t)stream, &n), n, "attn_fwd_generic");
 }
 
 int mmn_mha_bwd(const mmn_mha_desc* d, const void* q, const void* k, const void* v, const float* mask, const void* out,
@@ -281,8 +208,9 @@ int mmn_mha_bwd(const mmn_mha_desc* d, const void* q, const void* k, const void*
   if (!have_device()) return fail(MMN_ERR_CUDA, "no CUDA device: libmmn_b200 has no CPU path");
   DeviceGuard g(device);
   if (!g.ok) return fail(MMN_ERR_CUDA, "cannot select device %d", device);
-  return generic_bwd(problem_from(d, mask), d->io_dtype, q, k, v, lse, dout, dq, dk, dv, nullptr, nullptr, workspace,
-                     (cudaStream_t)stream);
+  int n = 0;
+  return finish(mmn::generic_bwd(problem_from(d, mask), d->io_dtype, q, k, v, lse, dout, dq, dk, dv, nullptr, nullptr, workspace,
+                                 (cudaStream_t)stream, &n), n, "attn_bwd_generic");
 }
 
 int mmn_mha_avg_weights(const mmn_mha_desc* d, const void* q, const void* k, const float* mask, const float* lse,
@@ -293,15 +221,9 @@ int mmn_mha_avg_weights(const mmn_mha_desc* d, const void* q, const void* k, con
   if (!have_device()) return fail(MMN_ERR_CUDA, "no CUDA device: libmmn_b200 has no CPU path");
   DeviceGuard g(device);
   if (!g.ok) return fail(MMN_ERR_CUDA, "cannot select device %d", device);
-  mmn::GenericProblem P = problem_from(d, mask);
-  long long total = (long long)d->batch * d->tgt_len * d->src_len;
-  int blocks = (int)((total + 255) / 256);
-  if (d->io_dtype == MMN_DT_F32)
-    mmn::mha_avg_weights_generic<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(P, d->batch, (const float*)q, (const float*)k, lse, avg);
-  else
-    mmn::mha_avg_weights_generic<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(P, d->batch, (const __nv_bfloat16*)q,
-                                                                                         (const __nv_bfloat16*)k, lse, avg);
-  return check_launch("mha_avg_weights_generic");
+  int n = 0;
+  return finish(mmn::generic_avg_weights(problem_from(d, mask), d->io_dtype, d->batch, q, k, lse, avg, (cudaStream_t)stream, &n), n,
+                "mha_avg_weights_generic");
 }
 
 }  // extern "C"

@@ -4,14 +4,14 @@
 // Tuned shape: 64-token windows (4x4x4, 8x8, or 64 pre-windowed tokens), head_dim 32.
 // A CTA tile is a PAIR of windows x one head: 128 query rows = the 128 TMEM lanes.
 //
-//   warp 4   TMA producer   q/k/v tiles of the pair, gathered straight out of the un-windowed,
+//   warp 8   TMA producer   q/k/v tiles of the pair, gathered straight out of the un-windowed,
 //                           un-shifted (B,D,H,W,3C) tensor with 5-D tensor maps.  The cyclic
 //                           shift is a coordinate offset; a window that wraps around the volume
 //                           edge is fetched as 2 / 2*w0 / 2*w0*w1 boxes (split along the
 //                           innermost wrapping axis), each landing at its window-order rows.
-//   warp 5   MMA issuer     S = Q K^T  (M128 N128 K32, block diagonal = the two windows),
+//   warp 9   MMA issuer     S = Q K^T  (M128 N128 K32, block diagonal = the two windows),
 //                           O = P V    (M128 N32 K128); accumulators in TMEM.
-//   warps 0-3 softmax       one thread per query row: tcgen05.ld its 64 logits, apply
+//   warps 0-7 softmax       two threads per query row (32 keys each): tcgen05.ld the logits, apply
 //                           cosine normalisation / logit scale (or q scale), relative position
 //                           bias, shift mask (region ids computed from coordinates), softmax in
 //                           fp32, write P (bf16, 128B-swizzled K-major) for the second MMA,
@@ -37,7 +37,10 @@ constexpr int kD = 32;            // head_dim
 constexpr int kStages = 3;
 constexpr int kTile = 128 * 64;   // bytes of one operand tile: 2 windows x 64 rows x 64 B
 constexpr int kWinBytes = 64 * 64;
-constexpr int kFwdThreads = 192;
+constexpr int kSoftmaxThreads = 256;   // warps 0-7: two threads per query row (32 keys each)
+constexpr int kProducerWarp = 8, kMmaWarp = 9;
+constexpr int kFwdThreads = 320;
+constexpr int kBiasLd = 68;             // padded row of the shared bias table (conflict-free float4 rows)
 constexpr int kTmemCols = 256;    // S: columns [0,128), O: columns [128,160)
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -119,8 +122,12 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
   uint8_t* sQKV = smem;                                  // kStages x 3 x kTile
   uint8_t* sP = sQKV + kStages * 3 * kTile;              // 2 x 16 KB (key halves)
   uint8_t* sO = sP + 2 * 16384;                          // 8 KB
-  float* sRk = reinterpret_cast<float*>(sO + kTile);     // 128 floats
-  int* sRid = reinterpret_cast<int*>(sRk + 128);         // 128 ints
+  float* sBias = reinterpret_cast<float*>(sO + kTile);   // [64][kBiasLd] fp32: this CTA's head
+  float* sRq = sBias + kN * kBiasLd;                     // 128: per-row logit multiplier
+  float* sRk = sRq + 128;                                // 128: per-key 1/||k||
+  float* sMax = sRk + 128;                               // [2][128] partial row maxima
+  float* sSum = sMax + 256;                              // [2][128] partial row sums
+  int* sRid = reinterpret_cast<int*>(sSum + 256);        // 128 region ids
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRid + 128);
   uint64_t* full = bars;                                 // [kStages]
   uint64_t* empty = bars + kStages;                      // [kStages]
@@ -131,31 +138,34 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_items = P.n_pairs * P.nH;
+  // A CTA serves ONE head (its bias table stays in shared memory) and strides over window pairs.
+  const int h = blockIdx.x % P.nH;
+  const int pair0 = blockIdx.x / P.nH, pair_step = gridDim.x / P.nH;
 
   // ---- one-time setup
   for (int i = tid; i < 2 * 16384 / 16; i += kFwdThreads) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0, 0, 0, 0);
+  if (P.bias)
+    for (int i = tid; i < kN * kN; i += kFwdThreads) sBias[(i >> 6) * kBiasLd + (i & 63)] = __ldg(P.bias + (size_t)h * kN * kN + i);
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(s_full, 1); mbar_init(s_empty, 128); mbar_init(p_full, 128); mbar_init(o_full, 1);
+    mbar_init(s_full, 1); mbar_init(s_empty, kSoftmaxThreads); mbar_init(p_full, kSoftmaxThreads); mbar_init(o_full, 1);
     fence_barrier_init();
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     for (int i = 0; i < 4; ++i) { tma_prefetch_desc(&P.q[i]); tma_prefetch_desc(&P.k[i]); tma_prefetch_desc(&P.v[i]); tma_prefetch_desc(&P.o[i]); }
   }
-  if (warp == 5) tmem_alloc<kTmemCols>(tmem_slot);
+  if (warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_slot);
   fence_proxy_async_smem();            // zeroed P must be visible to the tensor-core (async) proxy
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == kProducerWarp) {
     // ============================== TMA producer ==============================
     int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    for (int pair = pair0; pair < P.n_pairs; pair += pair_step, ++it) {
       const int stage = it % kStages, phase = (it / kStages) & 1;
-      const int pair = item / P.nH, h = item - pair * P.nH;
       mbar_wait(&empty[stage], phase ^ 1);
       if (lane == 0) mbar_arrive_expect_tx(&full[stage], 3 * kTile);
       __syncwarp();
@@ -168,14 +178,14 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
         issue_boxes<true>(P, P.v, g, h * kD, base + 2 * kTile + slot * kWinBytes, &full[stage], lane);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     // ============================== MMA issuer ==============================
     constexpr uint32_t idescS = umma_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
     constexpr uint32_t idescO = umma_idesc_bf16(128, 32, 0, 1);    // P (K-major) x V (MN-major)
     const uint32_t tS = tmem, tO = tmem + 128;
     const uint32_t pAddr = smem_u32(sP);
     int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    for (int pair = pair0; pair < P.n_pairs; pair += pair_step, ++it) {
       const int stage = it % kStages, phase = (it / kStages) & 1;
       const uint32_t qAddr = smem_u32(sQKV + stage * 3 * kTile), kAddr = qAddr + kTile, vAddr = qAddr + 2 * kTile;
       mbar_wait(&full[stage], phase);
@@ -202,119 +212,118 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
       __syncwarp();
     }
   } else {
-    // ============================== softmax / epilogue (threads 0..127) ==============================
-    const int r = tid, slot = r >> 6, i = r & 63;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    // ============================== softmax / epilogue (256 threads: 2 per query row) ==============================
+    const int r = tid & 127, half = tid >> 7;            // row of the pair tile; which 32 of its 64 keys
+    const int slot = r >> 6, i = r & 63;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const float hscale = P.cosine ? __ldg(P.head_scale + h) : 1.f;
     int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    for (int pair = pair0; pair < P.n_pairs; pair += pair_step, ++it) {
       const int stage = it % kStages, phase = (it / kStages) & 1;
-      const int pair = item / P.nH, h = item - pair * P.nH;
       const int w = pair * 2 + slot;
       const WinGeom g = decode_window(P, w);
-      const bool masked = P.mask_kind == MMN_MASK_SHIFT && g.aw >= 0;   // uniform over the 64 threads of a window
+      const bool masked = P.mask_kind == MMN_MASK_SHIFT && g.aw >= 0;   // uniform over the threads of a window
       const uint8_t* base = sQKV + stage * 3 * kTile;
 
       mbar_wait(&full[stage], phase);
-      float a_i = P.scale;
       if (P.cosine) {
-        // row norms of this thread's q row and k row (sum over the 64-byte row; the swizzle
-        // only permutes 16-byte chunks inside the row)
-        float sq = 0.f, sk = 0.f;
-        const uint4* qrow = reinterpret_cast<const uint4*>(base + r * 64);
-        const uint4* krow = reinterpret_cast<const uint4*>(base + kTile + r * 64);
+        // half 0 owns ||q_r||, half 1 owns ||k_r|| (the swizzle only permutes 16-byte chunks inside the 64-byte row)
+        const uint4* row = reinterpret_cast<const uint4*>(base + half * kTile + r * 64);
+        float ss = 0.f;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          uint4 a = qrow[c], b = krow[c];
+          uint4 a = row[c];
           const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
-          const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float2 fa = __bfloat1622float2(pa[e]), fb = __bfloat1622float2(pb[e]);
-            sq += fa.x * fa.x + fa.y * fa.y;
-            sk += fb.x * fb.x + fb.y * fb.y;
-          }
+          for (int e = 0; e < 4; ++e) { float2 f = __bfloat1622float2(pa[e]); ss += f.x * f.x + f.y * f.y; }
         }
-        a_i = __ldg(P.head_scale + h) / fmaxf(sqrtf(sq), 1e-12f);
-        sRk[r] = 1.f / fmaxf(sqrtf(sk), 1e-12f);
+        const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+        if (half == 0) sRq[r] = inv * hscale; else sRk[r] = inv;
       }
       int rid_i = 0;
-      if (masked) { rid_i = region_id(P, g, i); sRid[r] = rid_i; }
-      named_bar_sync(1, 128);
+      if (masked) { rid_i = region_id(P, g, i); if (half == 0) sRid[r] = rid_i; }
+      named_bar_sync(1, kSoftmaxThreads);
 
-      // ---- logits
+      // ---- logits of this thread's 32 keys
       mbar_wait(s_full, it & 1);
       tcgen05_fence_after();
-      uint32_t raw[2][32];
-      tmem_ld_32x32b_x32(tmem + lane_base + slot * 64, raw[0]);
-      tmem_ld_32x32b_x32(tmem + lane_base + slot * 64 + 32, raw[1]);
+      uint32_t raw[32];
+      tmem_ld_32x32b_x32(tmem + lane_base + slot * 64 + half * 32, raw);
       tmem_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(s_empty);
 
-      float s[64];
-      const float4* brow = P.bias ? reinterpret_cast<const float4*>(P.bias + ((size_t)h * kN + i) * kN) : nullptr;
+      float s[32];
+      const float a_i = P.cosine ? sRq[r] : P.scale;
+      const float4* brow = reinterpret_cast<const float4*>(sBias + i * kBiasLd + half * 32);
+      const float4* krow = reinterpret_cast<const float4*>(sRk + slot * 64 + half * 32);
       const float4* mrow = P.mask_kind == MMN_MASK_TENSOR
-                               ? reinterpret_cast<const float4*>(P.mask + ((size_t)(w % P.mask_windows) * kN + i) * kN)
+                               ? reinterpret_cast<const float4*>(P.mask + ((size_t)(w % P.mask_windows) * kN + i) * kN + half * 32)
                                : nullptr;
       float mx = -INFINITY;
 #pragma unroll
-      for (int j4 = 0; j4 < 16; ++j4) {
-        float4 bb = brow ? __ldg(brow + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j4 = 0; j4 < 8; ++j4) {
+        float4 bb = P.bias ? brow[j4] : make_float4(0.f, 0.f, 0.f, 0.f);
         if (mrow) { float4 mm = __ldg(mrow + j4); bb.x += mm.x; bb.y += mm.y; bb.z += mm.z; bb.w += mm.w; }
-        float add[4] = {bb.x, bb.y, bb.z, bb.w};
+        float4 kk = P.cosine ? krow[j4] : make_float4(1.f, 1.f, 1.f, 1.f);
+        const float add[4] = {bb.x, bb.y, bb.z, bb.w};
+        const float rk[4] = {kk.x, kk.y, kk.z, kk.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int j = j4 * 4 + e;
-          float acc = __uint_as_float(raw[j >> 5][j & 31]);
-          float sc = P.cosine ? a_i * sRk[slot * 64 + j] : a_i;
-          float v = fmaf(acc, sc, add[e]);
-          if (masked && sRid[slot * 64 + j] != rid_i) v -= 100.f;
+          float v = fmaf(__uint_as_float(raw[j]) * rk[e], a_i, add[e]);
+          if (masked && sRid[slot * 64 + half * 32 + j] != rid_i) v -= 100.f;
           s[j] = v;
           mx = fmaxf(mx, v);
         }
       }
+      sMax[half * 128 + r] = mx;
+      named_bar_sync(2, kSoftmaxThreads);
+      mx = fmaxf(mx, sMax[(half ^ 1) * 128 + r]);
       float l = 0.f;
       const float mneg = -mx * kLog2e;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) { s[j] = fast_exp2(fmaf(s[j], kLog2e, mneg)); l += s[j]; }
+      for (int j = 0; j < 32; ++j) { s[j] = fast_exp2(fmaf(s[j], kLog2e, mneg)); l += s[j]; }
+      sSum[half * 128 + r] = l;
 
       // ---- P (bf16) into the 128B-swizzled K-major tile of this window's key half
       {
         uint8_t* prow = sP + slot * 16384 + r * 128;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 4; ++c) {
           uint4 v4 = make_uint4(pack_bf16x2(s[c * 8 + 0], s[c * 8 + 1]), pack_bf16x2(s[c * 8 + 2], s[c * 8 + 3]),
                                 pack_bf16x2(s[c * 8 + 4], s[c * 8 + 5]), pack_bf16x2(s[c * 8 + 6], s[c * 8 + 7]));
-          *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = v4;
+          *reinterpret_cast<uint4*>(prow + (((half * 4 + c) ^ (r & 7)) << 4)) = v4;
         }
       }
       fence_proxy_async_smem();
       mbar_arrive(p_full);
-      P.lse[((size_t)w * P.nH + h) * kN + i] = mx + __logf(l);
 
-      // ---- O epilogue
-      if (warp == 0) tma_store_wait_read<0>();        // previous item's stores have drained sO
+      // ---- O epilogue: half 0 takes output channels [0,16), half 1 [16,32)
+      if (warp == 0) tma_store_wait_read<0>();        // previous pair's stores have drained sO
       mbar_wait(o_full, it & 1);
       tcgen05_fence_after();
-      uint32_t oraw[32];
-      tmem_ld_32x32b_x32(tmem + lane_base + 128, oraw);
+      uint32_t oraw[16];
+      tmem_ld_32x32b_x16(tmem + lane_base + 128 + half * 16, oraw);
       tmem_ld_wait();
       tcgen05_fence_before();
-      named_bar_sync(2, 128);                         // sO free (warp 0 waited) before anyone writes it
+      named_bar_sync(3, kSoftmaxThreads);             // sO free (warp 0 waited) and sSum complete
       {
+        l = sSum[r] + sSum[128 + r];
+        if (half == 0) P.lse[((size_t)w * P.nH + h) * kN + i] = mx + __logf(l);
         const float inv = 1.f / l;
         uint8_t* orow = sO + r * 64;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           uint4 v4 = make_uint4(pack_bf16x2(__uint_as_float(oraw[c * 8 + 0]) * inv, __uint_as_float(oraw[c * 8 + 1]) * inv),
                                 pack_bf16x2(__uint_as_float(oraw[c * 8 + 2]) * inv, __uint_as_float(oraw[c * 8 + 3]) * inv),
                                 pack_bf16x2(__uint_as_float(oraw[c * 8 + 4]) * inv, __uint_as_float(oraw[c * 8 + 5]) * inv),
                                 pack_bf16x2(__uint_as_float(oraw[c * 8 + 6]) * inv, __uint_as_float(oraw[c * 8 + 7]) * inv));
-          *reinterpret_cast<uint4*>(orow + ((c ^ ((r >> 1) & 3)) << 4)) = v4;
+          *reinterpret_cast<uint4*>(orow + (((half * 2 + c) ^ ((r >> 1) & 3)) << 4)) = v4;
         }
       }
       fence_proxy_async_smem();
-      named_bar_sync(3, 128);
+      named_bar_sync(4, kSoftmaxThreads);
       if (warp == 0) {
 #pragma unroll
         for (int sl = 0; sl < 2; ++sl) {
@@ -329,10 +338,11 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<kTmemCols>(tmem);
+  if (warp == kMmaWarp) tmem_dealloc<kTmemCols>(tmem);
 }
 
-constexpr size_t kFwdSmemBytes = 1024 /*align slack*/ + kStages * 3 * kTile + 2 * 16384 + kTile + 128 * 4 + 128 * 4 + 16 * 8;
+constexpr size_t kFwdSmemBytes = 1024 /*align slack*/ + kStages * 3 * kTile + 2 * 16384 + kTile + kN * kBiasLd * 4 +
+                                 (128 + 128 + 256 + 256 + 128) * 4 + 16 * 8;
 
 // ------------------------------------------------------------------------------------------
 // Host side
@@ -440,8 +450,10 @@ inline int winattn_fwd(const mmn_winattn_desc* d, const void* q, const void* k, 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   });
-  const int n_items = P.n_pairs * P.nH;
-  const int grid = n_items < num_sms ? n_items : num_sms;
+  int per_head = num_sms / P.nH;                 // CTAs per head (each CTA keeps one head's bias table resident)
+  if (per_head < 1) per_head = 1;
+  if (per_head > P.n_pairs) per_head = P.n_pairs;
+  const int grid = per_head * P.nH;
   winattn_fwd_tc_kernel<<<grid, kFwdThreads, kFwdSmemBytes, st>>>(P);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
