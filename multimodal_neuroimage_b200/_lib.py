@@ -16,8 +16,9 @@ ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libmmn_b200.so")
 # translation unit -> headers it depends on (besides include/mmn_b200.h)
-SOURCES = {"mmn_abi.cu": ["generic_launch.h", "attn_generic.cuh", "winattn_tc.cuh", "tc_common.cuh"],
-           "generic_launch.cu": ["generic_launch.h", "attn_generic.cuh"]}
+SOURCES = {"mmn_abi.cu": ["generic_launch.h", "attn_generic.cuh", "winattn_tc.h"],
+           "generic_launch.cu": ["generic_launch.h", "attn_generic.cuh"],
+           "winattn_tc.cu": ["winattn_tc.h", "winattn_tc_fwd.cuh", "winattn_tc_bwd.cuh", "tc_window.cuh", "tc_common.cuh"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

@@ -9,7 +9,7 @@
 
 #include "../../include/mmn_b200.h"
 #include "generic_launch.h"
-#include "winattn_tc.cuh"
+#include "winattn_tc.h"
 
 namespace {
 
@@ -129,7 +129,7 @@ uint64_t mmn_launch_count(void) { return g_launches.load(std::memory_order_relax
 const char* mmn_winattn_path(const mmn_winattn_desc* d) {
   if (validate_win(d) != MMN_OK) return "invalid";
   if (d->path == MMN_PATH_GENERIC) return "generic";
-  return mmn::tc::winattn_supported(d) ? "tcgen05" : "generic";
+  return mmn::tc::fwd_why_not(d) == nullptr ? "tcgen05" : "generic";
 }
 
 const char* mmn_mha_path(const mmn_mha_desc* d) {
@@ -148,8 +148,9 @@ int mmn_winattn_fwd(const mmn_winattn_desc* d, const void* q, const void* k, con
   DeviceGuard g(device);
   if (!g.ok) return fail(MMN_ERR_CUDA, "cannot select device %d", device);
   cudaStream_t st = (cudaStream_t)stream;
-  bool tc_ok = mmn::tc::winattn_supported(d);
-  if (d->path == MMN_PATH_TCGEN05 && !tc_ok) return fail(MMN_ERR_UNSUPPORTED, "shape not supported by the tcgen05 path: %s", mmn::tc::why_not(d));
+  const char* why = mmn::tc::fwd_why_not(d);
+  bool tc_ok = why == nullptr;
+  if (d->path == MMN_PATH_TCGEN05 && !tc_ok) return fail(MMN_ERR_UNSUPPORTED, "shape not supported by the tcgen05 path: %s", why);
   if (d->path != MMN_PATH_GENERIC && tc_ok) {
     rc = mmn::tc::winattn_fwd(d, q, k, v, bias, head_scale, mask, out, lse, st, g_err, sizeof(g_err));
     if (rc == MMN_OK) g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -172,11 +173,13 @@ int mmn_winattn_bwd(const mmn_winattn_desc* d, const void* q, const void* k, con
   DeviceGuard g(device);
   if (!g.ok) return fail(MMN_ERR_CUDA, "cannot select device %d", device);
   cudaStream_t st = (cudaStream_t)stream;
-  bool tc_ok = mmn::tc::winattn_bwd_supported(d);
-  if (d->path == MMN_PATH_TCGEN05 && !tc_ok) return fail(MMN_ERR_UNSUPPORTED, "shape not supported by the tcgen05 backward path");
+  const char* why = mmn::tc::bwd_why_not(d);
+  bool tc_ok = why == nullptr;
+  if (d->path == MMN_PATH_TCGEN05 && !tc_ok) return fail(MMN_ERR_UNSUPPORTED, "shape not supported by the tcgen05 backward path: %s", why);
   if (d->path != MMN_PATH_GENERIC && tc_ok) {
-    rc = mmn::tc::winattn_bwd(d, q, k, v, bias, head_scale, mask, out, lse, dout, dq, dk, dv, dbias, dhead_scale, workspace, st, g_err, sizeof(g_err));
-    if (rc == MMN_OK) g_launches.fetch_add(1, std::memory_order_relaxed);
+    int n = 0;
+    rc = mmn::tc::winattn_bwd(d, q, k, v, bias, head_scale, mask, out, lse, dout, dq, dk, dv, dbias, dhead_scale, workspace, st, g_err, sizeof(g_err), &n);
+    g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed);
     return rc;
   }
   mmn::GenericProblem P = problem_from(d, bias, head_scale, mask);

@@ -1,0 +1,145 @@
+// tc_window.cuh -- window geometry shared by the tensor-core forward and backward kernels:
+// a div/mod-free cursor over windows, the decomposition of a (possibly wrapped) shifted
+// window into contiguous TMA boxes, the piece-major token permutation that goes with it,
+// and the shift-mask region ids.  All closed forms restate SURVEY.md 8a (a1-a4).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mmn_b200.h"
+#include "tc_common.cuh"
+
+namespace mmn { namespace tc {
+
+constexpr int kN = 64;            // tokens per window (tuned path)
+constexpr int kD = 32;            // head_dim (tuned path)
+
+struct WinShape {                 // right-aligned geometry: unused leading axes have extent 1
+  int grid[3], win[3], shift[3], nwin[3];
+  int nW;                         // windows per sample
+  int n_windows;                  // batch * nW
+};
+
+// Mixed-radix position (batch, i0, i1, i2) of a window; advancing by a fixed stride is a
+// handful of adds with carries instead of the six div/mod a decode costs.
+struct WinCursor {
+  int b, i0, i1, i2;
+  __device__ __forceinline__ void init(const WinShape& S, int w) {
+    b = w / S.nW;
+    int wl = w - b * S.nW;
+    i2 = wl % S.nwin[2];
+    int t = wl / S.nwin[2];
+    i1 = t % S.nwin[1];
+    i0 = t / S.nwin[1];
+  }
+  __device__ __forceinline__ void advance(const WinShape& S, const WinCursor& step) {
+    i2 += step.i2; int c = i2 >= S.nwin[2]; i2 -= c ? S.nwin[2] : 0;
+    i1 += step.i1 + c; c = i1 >= S.nwin[1]; i1 -= c ? S.nwin[1] : 0;
+    i0 += step.i0 + c; c = i0 >= S.nwin[0]; i0 -= c ? S.nwin[0] : 0;
+    b += step.b + c;
+  }
+};
+
+struct WinGeom {
+  int b, start[3], idx[3];
+  int cls;       // wrap class: bit x set if the window wraps around the volume edge along axis x
+};
+
+__device__ __forceinline__ WinGeom window_geom(const WinShape& S, const WinCursor& c) {
+  WinGeom g;
+  g.b = c.b;
+  g.idx[0] = c.i0; g.idx[1] = c.i1; g.idx[2] = c.i2;
+  g.cls = 0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    g.start[a] = g.idx[a] * S.win[a] + S.shift[a];
+    if (g.start[a] + S.win[a] > S.grid[a]) g.cls |= 1 << a;
+  }
+  return g;
+}
+
+// A window that wraps along k axes is 2^k contiguous pieces of the source volume.  Piece q is
+// one TMA box and lands at rows [q*psize, (q+1)*psize) of the window's 64-row tile, so the
+// tile holds the window's tokens in PIECE-MAJOR order.  Attention is equivariant to that
+// permutation as long as bias / mask / lse are addressed through it (piece_position) and the
+// outputs are stored through the same boxes.  Axis 2 is the least significant wrapped axis.
+// `maps` has one tensor map per wrap class (box = half extent along every wrapped axis).
+template <bool LOAD>
+__device__ __forceinline__ void issue_window_boxes(const WinShape& S, const CUtensorMap* maps, const WinGeom& g, int chan,
+                                                   uint8_t* tile, uint64_t* bar) {
+  const int npieces = 1 << __popc(g.cls);
+  const int psize_bytes = (kN >> __popc(g.cls)) * 64;
+  const CUtensorMap* m = &maps[g.cls];
+  for (int q = 0; q < npieces; ++q) {
+    int c[3], qq = q;
+#pragma unroll
+    for (int a = 2; a >= 0; --a) {
+      int bit = (g.cls >> a) & 1;
+      c[a] = g.start[a] + (bit ? (qq & 1) * (S.win[a] >> 1) : 0);
+      if (bit) qq >>= 1;
+      if (c[a] >= S.grid[a]) c[a] -= S.grid[a];
+    }
+    uint8_t* p = tile + q * psize_bytes;
+    if (LOAD) tma_load_5d(m, bar, p, chan, c[2], c[1], c[0], g.b);
+    else tma_store_5d(m, p, chan, c[2], c[1], c[0], g.b);
+  }
+}
+
+// Window position (row-major over the window) of tile row `row` for wrap class `cls`.
+__device__ __forceinline__ int piece_position(const WinShape& S, int cls, int row) {
+  int seg[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) seg[a] = (cls >> a) & 1 ? S.win[a] >> 1 : S.win[a];
+  const int psize = seg[0] * seg[1] * seg[2];
+  int q = row / psize, rem = row - q * psize;
+  int b2 = rem % seg[2]; rem /= seg[2];
+  int b1 = rem % seg[1]; int b0 = rem / seg[1];
+  int a2 = b2, a1 = b1, a0 = b0;
+  if (cls & 4) { a2 += (q & 1) * seg[2]; q >>= 1; }
+  if (cls & 2) { a1 += (q & 1) * seg[1]; q >>= 1; }
+  if (cls & 1) { a0 += (q & 1) * seg[0]; }
+  return (a0 * S.win[1] + a1) * S.win[2] + a2;
+}
+
+// Region id of in-window position p in the shifted frame (swin_v2_module.py:247-258).
+__device__ __forceinline__ int region_id(const WinShape& S, const WinGeom& g, int p) {
+  int a2 = p % S.win[2]; int t = p / S.win[2];
+  int a1 = t % S.win[1]; int a0 = t / S.win[1];
+  int a[3] = {a0, a1, a2};
+  int rid = 0;
+#pragma unroll
+  for (int x = 0; x < 3; ++x) {
+    int v = g.idx[x] * S.win[x] + a[x];
+    int r = S.shift[x] == 0 ? 0 : (v < S.grid[x] - S.win[x] ? 0 : (v < S.grid[x] - S.shift[x] ? 1 : 2));
+    rid = rid * 3 + r;
+  }
+  return rid;
+}
+
+// ------------------------------------------------------------------------------------------
+// Host helpers
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn();
+
+inline WinShape shape_from(const mmn_winattn_desc* d) {
+  WinShape g;
+  for (int a = 0; a < 3; ++a) { g.grid[a] = 1; g.win[a] = 1; g.shift[a] = 0; g.nwin[a] = 1; }
+  for (int a = 0; a < d->ndim; ++a) {
+    int t = 3 - d->ndim + a;
+    g.grid[t] = d->grid[a]; g.win[t] = d->window[a]; g.shift[t] = d->shift[a]; g.nwin[t] = d->grid[a] / d->window[a];
+  }
+  g.nW = g.nwin[0] * g.nwin[1] * g.nwin[2];
+  g.n_windows = d->batch * g.nW;
+  return g;
+}
+
+// Eight tensor maps (one box shape per wrap class) over a (B, g0, g1, g2, channels) bf16 tensor
+// whose tokens are `row_stride` elements apart; boxes are 32 channels (one head) wide, 64B-swizzled.
+bool make_window_maps(CUtensorMap* out, const void* ptr, long long row_stride, int batch, int channels, const WinShape& g);
+
+}}  // namespace mmn::tc

@@ -1,0 +1,58 @@
+// winattn_tc.cu -- translation unit of the tcgen05 / TMEM / TMA window-attention kernels.
+#include "winattn_tc.h"
+
+#include "winattn_tc_fwd.cuh"
+
+namespace mmn { namespace tc {
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      cudaGetLastError();
+  });
+  return fn;
+}
+
+bool make_window_maps(CUtensorMap* out, const void* ptr, long long row_stride, int batch, int channels, const WinShape& g) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  if (reinterpret_cast<uintptr_t>(ptr) % 16) return false;
+  cuuint64_t dims[5] = {(cuuint64_t)channels, (cuuint64_t)g.grid[2], (cuuint64_t)g.grid[1], (cuuint64_t)g.grid[0], (cuuint64_t)batch};
+  cuuint64_t rs = (cuuint64_t)row_stride * 2;
+  cuuint64_t strides[4] = {rs, rs * g.grid[2], rs * g.grid[2] * g.grid[1], rs * g.grid[2] * g.grid[1] * g.grid[0]};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  for (int cls = 0; cls < 8; ++cls) {
+    cuuint32_t box[5] = {kD, (cuuint32_t)(cls & 4 ? g.win[2] / 2 : g.win[2]), (cuuint32_t)(cls & 2 ? g.win[1] / 2 : g.win[1]),
+                         (cuuint32_t)(cls & 1 ? g.win[0] / 2 : g.win[0]), 1};
+    for (int i = 1; i < 4; ++i) if (box[i] < 1) box[i] = 1;      // class unused for this geometry (unit extent)
+    CUresult r = enc(&out[cls], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+  }
+  return true;
+}
+
+const char* fwd_why_not(const mmn_winattn_desc* d) { return fwd_why_not_impl(d); }
+const char* bwd_why_not(const mmn_winattn_desc*) { return "tcgen05 backward not built"; }
+
+int winattn_fwd(const mmn_winattn_desc* d, const void* q, const void* k, const void* v, const float* bias,
+                const float* head_scale, const float* mask, void* out, float* lse, cudaStream_t st, char* err, size_t errlen) {
+  return winattn_fwd_launch(d, q, k, v, bias, head_scale, mask, out, lse, st, err, errlen);
+}
+
+int winattn_bwd(const mmn_winattn_desc*, const void*, const void*, const void*, const float*, const float*, const float*,
+                const void*, const float*, const void*, void*, void*, void*, float*, float*, float*, cudaStream_t, char* err,
+                size_t errlen, int*) {
+  snprintf(err, errlen, "tcgen05 backward not built");
+  return MMN_ERR_UNSUPPORTED;
+}
+
+}}  // namespace mmn::tc

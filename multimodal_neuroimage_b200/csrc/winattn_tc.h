@@ -1,0 +1,18 @@
+// winattn_tc.h -- host entry points of the tcgen05 window-attention kernels (winattn_tc.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include "../../include/mmn_b200.h"
+
+namespace mmn { namespace tc {
+// nullptr when the descriptor qualifies for the tensor-core path, else the reason it does not.
+const char* fwd_why_not(const mmn_winattn_desc* d);
+const char* bwd_why_not(const mmn_winattn_desc* d);
+int winattn_fwd(const mmn_winattn_desc* d, const void* q, const void* k, const void* v, const float* bias,
+                const float* head_scale, const float* mask, void* out, float* lse, cudaStream_t st, char* err, size_t errlen);
+int winattn_bwd(const mmn_winattn_desc* d, const void* q, const void* k, const void* v, const float* bias,
+                const float* head_scale, const float* mask, const void* out, const float* lse, const void* dout, void* dq,
+                void* dk, void* dv, float* dbias, float* dhead_scale, float* workspace, cudaStream_t st, char* err,
+                size_t errlen, int* launches);
+}}  // namespace mmn::tc
