@@ -1,7 +1,7 @@
 // winattn_tc.cu -- translation unit of the tcgen05 / TMEM / TMA window-attention kernels.
 #include "winattn_tc.h"
 
-#include "winattn_tc_fwd.cuh"
+#include "winattn_tc_bwd.cuh"
 
 namespace mmn { namespace tc {
 
@@ -41,18 +41,20 @@ bool make_window_maps(CUtensorMap* out, const void* ptr, long long row_stride, i
 }
 
 const char* fwd_why_not(const mmn_winattn_desc* d) { return fwd_why_not_impl(d); }
-const char* bwd_why_not(const mmn_winattn_desc*) { return "tcgen05 backward not built"; }
+const char* bwd_why_not(const mmn_winattn_desc* d) { return bwd_why_not_impl(d); }
 
 int winattn_fwd(const mmn_winattn_desc* d, const void* q, const void* k, const void* v, const float* bias,
                 const float* head_scale, const float* mask, void* out, float* lse, cudaStream_t st, char* err, size_t errlen) {
   return winattn_fwd_launch(d, q, k, v, bias, head_scale, mask, out, lse, st, err, errlen);
 }
 
-int winattn_bwd(const mmn_winattn_desc*, const void*, const void*, const void*, const float*, const float*, const float*,
-                const void*, const float*, const void*, void*, void*, void*, float*, float*, float*, cudaStream_t, char* err,
-                size_t errlen, int*) {
-  snprintf(err, errlen, "tcgen05 backward not built");
-  return MMN_ERR_UNSUPPORTED;
+int winattn_bwd(const mmn_winattn_desc* d, const void* q, const void* k, const void* v, const float* bias,
+                const float* head_scale, const float* mask, const void* /*out*/, const float* lse, const void* dout, void* dq,
+                void* dk, void* dv, float* dbias, float* dhead_scale, float* /*workspace*/, cudaStream_t st, char* err,
+                size_t errlen, int* launches) {
+  int rc = winattn_bwd_launch(d, q, k, v, bias, head_scale, mask, lse, dout, dq, dk, dv, dbias, dhead_scale, st, err, errlen);
+  if (rc == MMN_OK) ++*launches;
+  return rc;
 }
 
 }}  // namespace mmn::tc
