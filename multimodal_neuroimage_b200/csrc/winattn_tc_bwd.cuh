@@ -42,6 +42,9 @@ struct BwdParams {
   float* dhead_scale;   // (nH) accumulated, may be null
 };
 
+// COS: cosine attention (else scaled dot product); MASK: MMN_MASK_NONE / _SHIFT / _TENSOR.  Compile-time so that
+// each variant carries only its own code (the kernel is instruction-cache sensitive).
+template <bool COS, int MASK>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -204,7 +207,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
     const int r = tid & 127, half = tid >> 7;
     const int slot = r >> 6, i = r & 63;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const float hscale = P.cosine ? __ldg(P.head_scale + h) : 1.f;
+    const float hscale = COS ? __ldg(P.head_scale + h) : 1.f;
     const int rsw = (r >> 1) & 3;                       // 64B-swizzle phase of this thread's tile row
     float dbacc[32];                                    // dbias[i][32*half + j] over window-ordered tiles
 #pragma unroll
@@ -218,8 +221,8 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       const int stage = it % kBwdStages, phase = (it / kBwdStages) & 1;
       const int w = pair * 2 + slot;
       const WinGeom g = window_geom(S, cur);
-      const bool masked = P.mask_kind == MMN_MASK_SHIFT && g.cls != 0;
-      const bool permuted = (g.cls & 6) != 0;
+      const bool masked = (MASK == MMN_MASK_SHIFT) && g.cls != 0;
+      const bool permuted = (MASK == MMN_MASK_SHIFT) && (g.cls & 6) != 0;
       const uint8_t* pos = sPos + g.cls * 64;
       const int ipos = permuted ? pos[i] : i;
       const uint8_t* base = sIn + stage * 4 * kTile;
@@ -239,8 +242,8 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) { float2 f = __bfloat1622float2(pa[e]); ss += f.x * f.x + f.y * f.y; }
         }
-        if (P.cosine) rinv = rsqrtf(fmaxf(ss, 1e-24f));
-        const float mul = P.cosine ? rinv * hscale : P.scale;
+        if (COS) rinv = rsqrtf(fmaxf(ss, 1e-24f));
+        const float mul = COS ? rinv * hscale : P.scale;
         uint8_t* dst = (half == 0 ? sQs : sKs) + r * 64;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -249,7 +252,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
           *reinterpret_cast<uint4*>(dst + (c << 4)) = make_uint4(pack_bf16x2(f0.x * mul, f0.y * mul), pack_bf16x2(f1.x * mul, f1.y * mul),
                                                                  pack_bf16x2(f2.x * mul, f2.y * mul), pack_bf16x2(f3.x * mul, f3.y * mul));
         }
-        if (P.cosine) { if (half == 0) sRq[r] = rinv * hscale; else sRk[r] = rinv; }
+        if (COS) { if (half == 0) sRq[r] = rinv * hscale; else sRk[r] = rinv; }
       }
       int rid_i = 0;
       if (masked) { rid_i = region_id(S, g, ipos); if (half == 0) sRid[r] = rid_i; }
@@ -257,7 +260,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
 
       // ---- (b) additive terms of this thread's 32 logits (bias, mask) while S / dP finish
       float p[32];
-      const float* mtile = P.mask_kind == MMN_MASK_TENSOR ? P.mask + (size_t)(w % P.mask_windows) * kN * kN : nullptr;
+      const float* mtile = (MASK == MMN_MASK_TENSOR) ? P.mask + (size_t)(w % P.mask_windows) * kN * kN : nullptr;
       if (!permuted) {
         const float4* brow = reinterpret_cast<const float4*>(sBias + ipos * kBiasLd + half * 32);
         const float4* mrow = mtile ? reinterpret_cast<const float4*>(mtile + ipos * kN + half * 32) : nullptr;
@@ -296,13 +299,13 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       tmem_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(sdp_empty);
-      const float a_i = P.cosine ? sRq[r] : P.scale;
+      const float a_i = COS ? sRq[r] : P.scale;
       const float4* krow = reinterpret_cast<const float4*>(sRk + slot * 64 + half * 32);
       const float lneg = -lse_i * kLog2e;
       float delta = 0.f, acc_pdt = 0.f, acc_pt = 0.f;   // sum p dp, sum p dp t, sum p t   (t = raw * rk)
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4) {
-        float4 kk = P.cosine ? krow[j4] : make_float4(1.f, 1.f, 1.f, 1.f);
+        float4 kk = COS ? krow[j4] : make_float4(1.f, 1.f, 1.f, 1.f);
         const float rk[4] = {kk.x, kk.y, kk.z, kk.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -332,7 +335,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       // ---- (d) dS = P o (dP - delta), in place of P; dbias and d(logit scale) reductions
 #pragma unroll
       for (int j = 0; j < 32; ++j) p[j] *= __uint_as_float(dpr[j]) - delta;
-      if (P.cosine) dscale_acc += (acc_pdt - delta * acc_pt) * (a_i / hscale);   // sum_j dS_ij cos_ij, cos = raw rk_j rq_i
+      if (COS) dscale_acc += (acc_pdt - delta * acc_pt) * (a_i / hscale);   // sum_j dS_ij cos_ij, cos = raw rk_j rq_i
       if (P.dbias) {
         if (!permuted) {
 #pragma unroll
@@ -369,7 +372,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       tmem_ld_wait();
       tcgen05_fence_before();
       float outv[32];
-      if (P.cosine) {
+      if (COS) {
         // d/dx of x / max(||x||, eps): (g - xhat (xhat . g)) / ||x||, xhat = x * rinv; x re-read from the stage tile
         float xrow[32];
         const uint8_t* rowp = base + half * kTile + r * 64;
@@ -420,7 +423,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
         if (v != 0.f) atomicAdd(gdb + e, v);
       }
     }
-    if (P.cosine && P.dhead_scale) {
+    if (COS && P.dhead_scale) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) dscale_acc += __shfl_xor_sync(0xffffffffu, dscale_acc, o);
       if (lane == 0) sRed[warp] = dscale_acc;
@@ -472,18 +475,24 @@ inline int winattn_bwd_launch(const mmn_winattn_desc* d, const void* q, const vo
   P.dbias = bias ? dbias : nullptr;
   P.dhead_scale = P.cosine ? dhead_scale : nullptr;
 
+  using Kern = void (*)(const BwdParams);
+  static const Kern kernels[2][3] = {
+      {winattn_bwd_tc_kernel<false, MMN_MASK_NONE>, winattn_bwd_tc_kernel<false, MMN_MASK_SHIFT>, winattn_bwd_tc_kernel<false, MMN_MASK_TENSOR>},
+      {winattn_bwd_tc_kernel<true, MMN_MASK_NONE>, winattn_bwd_tc_kernel<true, MMN_MASK_SHIFT>, winattn_bwd_tc_kernel<true, MMN_MASK_TENSOR>}};
   static std::once_flag once;
   static int num_sms = 148;
   std::call_once(once, [] {
-    cudaFuncSetAttribute(winattn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes);
+    for (int c = 0; c < 2; ++c)
+      for (int m = 0; m < 3; ++m) cudaFuncSetAttribute(kernels[c][m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   });
+  const Kern kern = kernels[P.cosine ? 1 : 0][P.mask_kind];
   int per_head = num_sms / P.nH;
   if (per_head < 1) per_head = 1;
   if (per_head > P.n_pairs) per_head = P.n_pairs;
-  winattn_bwd_tc_kernel<<<per_head * P.nH, kFwdThreads, kBwdSmemBytes, st>>>(P);
+  kern<<<per_head * P.nH, kFwdThreads, kBwdSmemBytes, st>>>(P);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(err, errlen, "winattn_bwd_tc_kernel: %s", cudaGetErrorString(e));

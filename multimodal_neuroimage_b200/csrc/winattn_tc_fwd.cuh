@@ -58,6 +58,9 @@ __device__ __forceinline__ void trace_ev(const FwdParams& P, int role, int item,
   if (P.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && item < 32) P.trace[(role * 32 + item) * 16 + ev] = clock64();
 }
 
+// COS: cosine attention (else scaled dot product); MASK: MMN_MASK_NONE / _SHIFT / _TENSOR.  Compile-time so that
+// each variant carries only its own code (the kernel is instruction-cache sensitive).
+template <bool COS, int MASK>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -214,7 +217,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
     const int r = tid & 127, half = tid >> 7;            // row of the pair tile; which 32 of its 64 keys
     const int slot = r >> 6, i = r & 63;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const float hscale = P.cosine ? __ldg(P.head_scale + h) : 1.f;
+    const float hscale = COS ? __ldg(P.head_scale + h) : 1.f;
     const int trole = warp == 0 ? 0 : (warp == 7 ? 1 : -1);
 #define TR(item, ev) do { if (trole >= 0) trace_ev(P, trole, item, ev); } while (0)
 
@@ -257,8 +260,8 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
       const int stage = it % kStages, phase = (it / kStages) & 1;
       const int w = pair * 2 + slot;
       const WinGeom g = window_geom(S, cur);
-      const bool masked = P.mask_kind == MMN_MASK_SHIFT && g.cls != 0;  // uniform over the threads of a window
-      const bool permuted = (g.cls & 6) != 0;         // splitting the slowest axis only keeps window order
+      const bool masked = (MASK == MMN_MASK_SHIFT) && g.cls != 0;  // uniform over the threads of a window
+      const bool permuted = (MASK == MMN_MASK_SHIFT) && (g.cls & 6) != 0;         // splitting the slowest axis only keeps window order
       const uint8_t* pos = sPos + g.cls * 64;
       const int ipos = permuted ? pos[i] : i;         // window position of this thread's query row
       const uint8_t* base = sQKV + stage * 3 * kTile;
@@ -266,7 +269,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
       TR(it, 0);
       mbar_wait(&full[stage], phase);
       TR(it, 1);
-      if (P.cosine) {
+      if (COS) {
         // half 0 owns ||q_r||, half 1 owns ||k_r|| (the swizzle only permutes 16-byte chunks inside the 64-byte row)
         const uint4* row = reinterpret_cast<const uint4*>(base + half * kTile + r * 64);
         float ss = 0.f;
@@ -297,9 +300,9 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
       TR(it, 4);
 
       float s[32];
-      const float a_i = P.cosine ? sRq[r] : P.scale;
+      const float a_i = COS ? sRq[r] : P.scale;
       const float4* krow = reinterpret_cast<const float4*>(sRk + slot * 64 + half * 32);
-      const float* mtile = P.mask_kind == MMN_MASK_TENSOR ? P.mask + (size_t)(w % P.mask_windows) * kN * kN : nullptr;
+      const float* mtile = (MASK == MMN_MASK_TENSOR) ? P.mask + (size_t)(w % P.mask_windows) * kN * kN : nullptr;
       if (!permuted) {
         const float4* brow = reinterpret_cast<const float4*>(sBias + ipos * kBiasLd + half * 32);
         const float4* mrow = mtile ? reinterpret_cast<const float4*>(mtile + ipos * kN + half * 32) : nullptr;
@@ -307,7 +310,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
         for (int j4 = 0; j4 < 8; ++j4) {
           float4 bb = P.bias ? brow[j4] : make_float4(0.f, 0.f, 0.f, 0.f);
           if (mrow) { float4 mm = __ldg(mrow + j4); bb.x += mm.x; bb.y += mm.y; bb.z += mm.z; bb.w += mm.w; }
-          float4 kk = P.cosine ? krow[j4] : make_float4(1.f, 1.f, 1.f, 1.f);
+          float4 kk = COS ? krow[j4] : make_float4(1.f, 1.f, 1.f, 1.f);
           const float add[4] = {bb.x, bb.y, bb.z, bb.w};
           const float rk[4] = {kk.x, kk.y, kk.z, kk.w};
 #pragma unroll
@@ -322,7 +325,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const uint32_t pk = pj4[j4];
-          float4 kk = P.cosine ? krow[j4] : make_float4(1.f, 1.f, 1.f, 1.f);
+          float4 kk = COS ? krow[j4] : make_float4(1.f, 1.f, 1.f, 1.f);
           const float rk[4] = {kk.x, kk.y, kk.z, kk.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -434,19 +437,25 @@ inline int winattn_fwd_launch(const mmn_winattn_desc* d, const void* q, const vo
     cudaMemsetAsync(P.trace, 0, 5 * 32 * 16 * sizeof(long long), st);
   }
 
+  using Kern = void (*)(const FwdParams);
+  static const Kern kernels[2][3] = {
+      {winattn_fwd_tc_kernel<false, MMN_MASK_NONE>, winattn_fwd_tc_kernel<false, MMN_MASK_SHIFT>, winattn_fwd_tc_kernel<false, MMN_MASK_TENSOR>},
+      {winattn_fwd_tc_kernel<true, MMN_MASK_NONE>, winattn_fwd_tc_kernel<true, MMN_MASK_SHIFT>, winattn_fwd_tc_kernel<true, MMN_MASK_TENSOR>}};
   static std::once_flag once;
   static int num_sms = 148;
   std::call_once(once, [] {
-    cudaFuncSetAttribute(winattn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemBytes);
+    for (int c = 0; c < 2; ++c)
+      for (int m = 0; m < 3; ++m) cudaFuncSetAttribute(kernels[c][m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemBytes);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   });
+  const Kern kern = kernels[P.cosine ? 1 : 0][P.mask_kind];
   int per_head = num_sms / P.nH;                 // CTAs per head (each CTA keeps one head's bias table resident)
   if (per_head < 1) per_head = 1;
   if (per_head > P.n_pairs) per_head = P.n_pairs;
   const int grid = per_head * P.nH;
-  winattn_fwd_tc_kernel<<<grid, kFwdThreads, kFwdSmemBytes, st>>>(P);
+  kern<<<grid, kFwdThreads, kFwdSmemBytes, st>>>(P);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(err, errlen, "winattn_fwd_tc_kernel: %s", cudaGetErrorString(e));
