@@ -205,7 +205,7 @@ def main():
     with torch.no_grad():
         attn.q_bias.normal_(0, 0.1)
         attn.v_bias.normal_(0, 0.1)
-    if world > 1:      # same weights everywhere, gradients all-reduced over NCCL like trainer.py's DDP
+    if world > 1:      # same weights everywhere
         for p in attn.parameters():
             dist.broadcast(p.data, 0)
 
@@ -218,8 +218,28 @@ def main():
             return self.a.forward_grid(x, GRID, (SHIFT,) * 3)
 
     model = Wrapped(attn)
-    if world > 1:
-        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+    params = [p for p in model.parameters() if p.requires_grad]
+    flat = torch.zeros(sum(p.numel() for p in params), device=dev, dtype=torch.float32)
+
+    def allreduce_grads():
+        """The path's one exchange: average the weight gradients over ranks.  Same
+        collective as trainer.py's DDP (NCCL all-reduce over NVLink), issued once on a flat buffer
+        after backward -- the module has ~47 K parameters, so bucketing/overlap has nothing to hide."""
+        if world == 1:
+            return
+        off = 0
+        for p in params:
+            n = p.numel()
+            flat[off:off + n].copy_(p.grad.reshape(-1) if p.grad is not None else torch.zeros(n, device=dev))
+            off += n
+        dist.all_reduce(flat)
+        flat.div_(world)
+        off = 0
+        for p in params:
+            n = p.numel()
+            if p.grad is not None:
+                p.grad.copy_(flat[off:off + n].view_as(p.grad))
+            off += n
 
     L = math.prod(GRID)
     x = torch.randn(B, L, C, device=dev, dtype=torch.bfloat16, requires_grad=True)
@@ -236,6 +256,7 @@ def main():
         with torch.autocast("cuda", dtype=torch.bfloat16):
             y = model(x)
         y.backward(dy)
+        allreduce_grads()
         return y
 
     def step_e2e():
@@ -246,6 +267,7 @@ def main():
         with torch.autocast("cuda", dtype=torch.bfloat16):
             y = model(xd)
         y.backward(dyd)
+        allreduce_grads()
         y_host.copy_(y.detach(), non_blocking=True)
         dx_host.copy_(xd.grad, non_blocking=True)
 

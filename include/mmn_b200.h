@@ -102,13 +102,16 @@ int mmn_winattn_fwd(const mmn_winattn_desc* desc, const void* q, const void* k, 
 
 /* dbias (num_heads,N,N) fp32 and dhead_scale (num_heads) fp32 are ACCUMULATED into (the
  * caller zeroes them); either may be NULL to skip.  `out` is the forward output (may be NULL:
- * the kernels recompute rowsum(P o dP) instead of reading it).  `workspace`: scratch of
+ * the kernels recompute rowsum(P o dP) instead of reading it).  dcolsum (3, num_heads*head_dim) fp32,
+ * ACCUMULATED, may be NULL: column sums over all tokens of dq, dk, dv -- the bias gradients of the
+ * projections that produced q, k, v (replaces the reductions autograd does for F.linear's bias,
+ * swin_v2_module.py:147-148, swinfusion_module.py:121,221-222).  `workspace`: scratch of
  * TWICE the extent of lse (2*batch*nW*num_heads*N floats), contents undefined on return. */
 int mmn_winattn_bwd(const mmn_winattn_desc* desc, const void* q, const void* k, const void* v,
                     const float* bias, const float* head_scale, const float* mask,
                     const void* out, const float* lse, const void* dout,
-                    void* dq, void* dk, void* dv, float* dbias, float* dhead_scale, float* workspace,
-                    int device, void* stream);
+                    void* dq, void* dk, void* dv, float* dbias, float* dhead_scale, float* dcolsum,
+                    float* workspace, int device, void* stream);
 
 /* mask (T,S) fp32, TENSOR only; out (T,B,E)-addressed rows; lse (batch*num_heads*T) fp32. */
 int mmn_mha_fwd(const mmn_mha_desc* desc, const void* q, const void* k, const void* v,
@@ -122,6 +125,11 @@ int mmn_mha_bwd(const mmn_mha_desc* desc, const void* q, const void* k, const vo
 /* avg (batch,T,S) fp32 = mean over heads of the (dropped-out) attention probabilities. */
 int mmn_mha_avg_weights(const mmn_mha_desc* desc, const void* q, const void* k, const float* mask,
                         const float* lse, float* avg, int device, void* stream);
+
+/* out[c] += sum over rows of x[r*row_stride + c]: the bias gradient of the output projection
+ * (F.linear backward, swin_v2_module.py:176) at memory speed.  cols % 8 == 0, cols <= 2048. */
+int mmn_colsum(const void* x, int io_dtype, int64_t rows, int32_t cols, int64_t row_stride, float* out,
+               int device, void* stream);
 
 #ifdef __cplusplus
 }

@@ -29,7 +29,7 @@ MASK_NONE, MASK_SHIFT, MASK_TENSOR, MASK_FUTURE = 0, 1, 2, 3
 PATH_AUTO, PATH_GENERIC, PATH_TCGEN05 = 0, 1, 2
 
 EXPORTS = ["mmn_abi_version", "mmn_last_error", "mmn_winattn_path", "mmn_mha_path", "mmn_launch_count",
-           "mmn_winattn_fwd", "mmn_winattn_bwd", "mmn_mha_fwd", "mmn_mha_bwd", "mmn_mha_avg_weights"]
+           "mmn_winattn_fwd", "mmn_winattn_bwd", "mmn_mha_fwd", "mmn_mha_bwd", "mmn_mha_avg_weights", "mmn_colsum"]
 
 
 class WinAttnDesc(C.Structure):
@@ -119,7 +119,7 @@ def load() -> C.CDLL:
         lib.mmn_winattn_fwd.restype = C.c_int
         lib.mmn_winattn_fwd.argtypes = [C.POINTER(WinAttnDesc), vp, vp, vp, fp, fp, fp, vp, fp, C.c_int, vp]
         lib.mmn_winattn_bwd.restype = C.c_int
-        lib.mmn_winattn_bwd.argtypes = [C.POINTER(WinAttnDesc), vp, vp, vp, fp, fp, fp, vp, fp, vp, vp, vp, vp, fp, fp, fp,
+        lib.mmn_winattn_bwd.argtypes = [C.POINTER(WinAttnDesc), vp, vp, vp, fp, fp, fp, vp, fp, vp, vp, vp, vp, fp, fp, fp, fp,
                                         C.c_int, vp]
         lib.mmn_mha_fwd.restype = C.c_int
         lib.mmn_mha_fwd.argtypes = [C.POINTER(MhaDesc), vp, vp, vp, fp, vp, fp, C.c_int, vp]
@@ -127,6 +127,8 @@ def load() -> C.CDLL:
         lib.mmn_mha_bwd.argtypes = [C.POINTER(MhaDesc), vp, vp, vp, fp, vp, fp, vp, vp, vp, vp, fp, C.c_int, vp]
         lib.mmn_mha_avg_weights.restype = C.c_int
         lib.mmn_mha_avg_weights.argtypes = [C.POINTER(MhaDesc), vp, vp, fp, fp, fp, C.c_int, vp]
+        lib.mmn_colsum.restype = C.c_int
+        lib.mmn_colsum.argtypes = [vp, C.c_int, C.c_int64, C.c_int32, C.c_int64, fp, C.c_int, vp]
         if lib.mmn_abi_version() != 1:
             raise RuntimeError("libmmn_b200.so ABI version mismatch")
         _lib = lib

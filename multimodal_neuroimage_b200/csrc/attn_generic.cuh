@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kGenericThreads)
 attn_bwd_dq_generic(GenericProblem P, GenericLaunch L, const T* __restrict__ q, const T* __restrict__ k,
                     const T* __restrict__ v, const float* __restrict__ lse,
                     const T* __restrict__ dout, T* __restrict__ dq, float* __restrict__ dbias,
-                    float* __restrict__ dhead_scale, float* __restrict__ delta_ws) {
+                    float* __restrict__ dhead_scale, float* __restrict__ delta_ws, float* __restrict__ dcolsum) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int cap = L.chunk, slots = L.slots, d = P.d;
   long long* sOff = reinterpret_cast<long long*>(smem_raw);
@@ -352,11 +352,16 @@ attn_bwd_dq_generic(GenericProblem P, GenericLaunch L, const T* __restrict__ q, 
       for (int c = 0; c < DMAX; ++c) proj += qr[c] * dqr[c];
       bool tiny = qinv >= 1e12f;                         // ||q|| < eps: qhat = q / eps, linear
 #pragma unroll
-      for (int c = 0; c < DMAX; ++c) if (c < d) stf(dq + dq_off + c, (dqr[c] - (tiny ? 0.f : qr[c] * proj)) * qinv);
+      for (int c = 0; c < DMAX; ++c) dqr[c] = (dqr[c] - (tiny ? 0.f : qr[c] * proj)) * qinv;
       if (dhead_scale) atomicAdd(dhead_scale + item % P.nH, dscale);
     } else {
 #pragma unroll
-      for (int c = 0; c < DMAX; ++c) if (c < d) stf(dq + dq_off + c, dqr[c] * P.scale);
+      for (int c = 0; c < DMAX; ++c) dqr[c] *= P.scale;
+    }
+#pragma unroll
+    for (int c = 0; c < DMAX; ++c) if (c < d) {
+      stf(dq + dq_off + c, dqr[c]);
+      if (dcolsum) atomicAdd(dcolsum + (item % P.nH) * d + c, dqr[c]);
     }
   }
 }
@@ -369,7 +374,7 @@ template <typename T, int DMAX>
 __global__ void __launch_bounds__(kGenericThreads)
 attn_bwd_dkv_generic(GenericProblem P, GenericLaunch L, const T* __restrict__ q, const T* __restrict__ k,
                      const T* __restrict__ v, const float* __restrict__ lse, const float* __restrict__ delta_ws,
-                     const T* __restrict__ dout, T* __restrict__ dk, T* __restrict__ dv) {
+                     const T* __restrict__ dout, T* __restrict__ dk, T* __restrict__ dv, float* __restrict__ dcolsum) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int cap = L.chunk, slots = L.slots, d = P.d;
   long long* sOff = reinterpret_cast<long long*>(smem_raw);
@@ -459,8 +464,14 @@ attn_bwd_dkv_generic(GenericProblem P, GenericLaunch L, const T* __restrict__ q,
     }
 #pragma unroll
     for (int c = 0; c < DMAX; ++c) if (c < d) {
-      stf(dk + dk_off + c, P.cosine ? (dkr[c] - kr[c] * proj) * kinv : dkr[c]);
+      const float dkc = P.cosine ? (dkr[c] - kr[c] * proj) * kinv : dkr[c];
+      stf(dk + dk_off + c, dkc);
       stf(dv + dv_off + c, dvr[c]);
+      if (dcolsum) {
+        const int C = P.nH * d, hc = (item % P.nH) * d + c;
+        atomicAdd(dcolsum + C + hc, dkc);
+        atomicAdd(dcolsum + 2 * C + hc, dvr[c]);
+      }
     }
   }
 }
@@ -489,6 +500,40 @@ mha_avg_weights_generic(GenericProblem P, int B, const T* __restrict__ q, const 
     if (s != -INFINITY) sum += expf(s - lse[(long long)item * P.nq + i]) * keep_scale(P, item, i, j);
   }
   avg[idx] = sum / (float)P.nH;
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Column sums of a (rows, cols) matrix into fp32 (accumulated): the bias gradient of a
+// projection, at memory speed.  Thread = 8 consecutive columns; a block strides over rows.
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ x, long long rows, int cols, long long row_stride, float* __restrict__ out) {
+  constexpr int V = 8;
+  const int vcols = cols / V;
+  const int rpb = 256 / vcols;                        // rows handled in parallel by a block
+  const int tx = threadIdx.x % vcols, ty = threadIdx.x / vcols;
+  float acc[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) acc[e] = 0.f;
+  if (ty < rpb) {
+    for (long long r = (long long)blockIdx.x * rpb + ty; r < rows; r += (long long)gridDim.x * rpb) {
+      const T* p = x + r * row_stride + tx * V;
+#pragma unroll
+      for (int e = 0; e < V; ++e) acc[e] += ldf(p + e);
+    }
+  }
+  __shared__ float red[256 * V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) red[threadIdx.x * V + e] = ty < rpb ? acc[e] : 0.f;
+  __syncthreads();
+  if (threadIdx.x < vcols * V) {
+    const int c = threadIdx.x;                        // column
+    float s = 0.f;
+    for (int y = 0; y < rpb; ++y) s += red[(y * vcols + c / V) * V + c % V];
+    atomicAdd(out + c, s);
+  }
 }
 
 }  // namespace mmn

@@ -38,14 +38,14 @@ cudaError_t launch_fwd(const mmn::GenericProblem& P, const void* q, const void* 
 
 template <typename T, int DMAX>
 cudaError_t launch_bwd(const mmn::GenericProblem& P, const void* q, const void* k, const void* v, const float* lse,
-               const void* dout, void* dq, void* dk, void* dv, float* dbias, float* dhs, float* ws, cudaStream_t st, int* launches) {
+               const void* dout, void* dq, void* dk, void* dv, float* dbias, float* dhs, float* ws, float* dcs, cudaStream_t st, int* launches) {
   {
     mmn::GenericLaunch L = plan(P.nq, P.nk, 2 * P.d * 4 + 12);
     auto kern = mmn::attn_bwd_dq_generic<T, DMAX>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     dim3 grid((P.n_items + L.slots - 1) / L.slots, (P.nq + L.rows_per_slot - 1) / L.rows_per_slot);
     kern<<<grid, mmn::kGenericThreads, L.smem_bytes, st>>>(P, L, (const T*)q, (const T*)k, (const T*)v, lse,
-                                                          (const T*)dout, (T*)dq, dbias, dhs, ws);
+                                                          (const T*)dout, (T*)dq, dbias, dhs, ws, dcs);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     ++*launches;
@@ -56,7 +56,7 @@ cudaError_t launch_bwd(const mmn::GenericProblem& P, const void* q, const void* 
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     dim3 grid((P.n_items + L.slots - 1) / L.slots, (P.nk + L.rows_per_slot - 1) / L.rows_per_slot);
     kern<<<grid, mmn::kGenericThreads, L.smem_bytes, st>>>(P, L, (const T*)q, (const T*)k, (const T*)v, lse, ws,
-                                                          (const T*)dout, (T*)dk, (T*)dv);
+                                                          (const T*)dout, (T*)dk, (T*)dv, dcs);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) ++*launches;
     return e;
@@ -82,10 +82,10 @@ cudaError_t generic_fwd(const GenericProblem& P, int dt, const void* q, const vo
 }
 
 cudaError_t generic_bwd(const GenericProblem& P, int dt, const void* q, const void* k, const void* v, const float* lse,
-                        const void* dout, void* dq, void* dk, void* dv, float* dbias, float* dhs, float* ws, cudaStream_t st,
+                        const void* dout, void* dq, void* dk, void* dv, float* dbias, float* dhs, float* ws, float* dcs, cudaStream_t st,
                         int* launches) {
-  if (dt == MMN_DT_F32) MMN_DISPATCH_D(float, launch_bwd, P, q, k, v, lse, dout, dq, dk, dv, dbias, dhs, ws, st, launches);
-  MMN_DISPATCH_D(__nv_bfloat16, launch_bwd, P, q, k, v, lse, dout, dq, dk, dv, dbias, dhs, ws, st, launches);
+  if (dt == MMN_DT_F32) MMN_DISPATCH_D(float, launch_bwd, P, q, k, v, lse, dout, dq, dk, dv, dbias, dhs, ws, dcs, st, launches);
+  MMN_DISPATCH_D(__nv_bfloat16, launch_bwd, P, q, k, v, lse, dout, dq, dk, dv, dbias, dhs, ws, dcs, st, launches);
 }
 
 cudaError_t generic_avg_weights(const GenericProblem& P, int dt, int batch, const void* q, const void* k, const float* lse,
@@ -96,6 +96,18 @@ cudaError_t generic_avg_weights(const GenericProblem& P, int dt, int batch, cons
     mha_avg_weights_generic<float><<<blocks, 256, 0, st>>>(P, batch, (const float*)q, (const float*)k, lse, avg);
   else
     mha_avg_weights_generic<__nv_bfloat16><<<blocks, 256, 0, st>>>(P, batch, (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, lse, avg);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) ++*launches;
+  return e;
+}
+
+cudaError_t colsum(int dt, const void* x, long long rows, int cols, long long row_stride, float* out, cudaStream_t st, int* launches) {
+  const int vcols = cols / 8;
+  const int rpb = 256 / vcols;
+  long long want = (rows + rpb - 1) / rpb;
+  int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
+  if (dt == MMN_DT_F32) colsum_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, rows, cols, row_stride, out);
+  else colsum_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, rows, cols, row_stride, out);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) ++*launches;
   return e;

@@ -9,8 +9,10 @@ namespace mmn {
 cudaError_t generic_fwd(const GenericProblem& P, int io_dtype, const void* q, const void* k, const void* v, void* out,
                         float* lse, cudaStream_t st, int* launches);
 cudaError_t generic_bwd(const GenericProblem& P, int io_dtype, const void* q, const void* k, const void* v, const float* lse,
-                        const void* dout, void* dq, void* dk, void* dv, float* dbias, float* dhs, float* ws,
+                        const void* dout, void* dq, void* dk, void* dv, float* dbias, float* dhs, float* ws, float* dcolsum,
                         cudaStream_t st, int* launches);
 cudaError_t generic_avg_weights(const GenericProblem& P, int io_dtype, int batch, const void* q, const void* k,
                                 const float* lse, float* avg, cudaStream_t st, int* launches);
+cudaError_t colsum(int io_dtype, const void* x, long long rows, int cols, long long row_stride, float* out, cudaStream_t st,
+                   int* launches);
 }  // namespace mmn

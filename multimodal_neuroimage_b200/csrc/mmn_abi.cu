@@ -157,13 +157,14 @@ int mmn_winattn_fwd(const mmn_winattn_desc* d, const void* q, const void* k, con
     return rc;
   }
   int n = 0;
-  return finish(mmn::generic_fwd(problem_from(d, bias, head_scale, mask), d->io_dtype, q, k, v, out, lse, st, &n), n, "attn_fwd_generic");
+  cudaError_t e = mmn::generic_fwd(problem_from(d, bias, head_scale, mask), d->io_dtype, q, k, v, out, lse, st, &n);
+  return finish(e, n, "attn_fwd_generic");
 }
 
 int mmn_winattn_bwd(const mmn_winattn_desc* d, const void* q, const void* k, const void* v, const float* bias,
                     const float* head_scale, const float* mask, const void* out, const float* lse, const void* dout,
-                    void* dq, void* dk, void* dv, float* dbias, float* dhead_scale, float* workspace, int device,
-                    void* stream) {
+                    void* dq, void* dk, void* dv, float* dbias, float* dhead_scale, float* dcolsum, float* workspace,
+                    int device, void* stream) {
   int rc = validate_win(d);
   if (rc) return rc;
   if (!q || !k || !v || !lse || !dout || !dq || !dk || !dv || !workspace) return fail(MMN_ERR_INVALID, "null tensor pointer");
@@ -178,14 +179,15 @@ int mmn_winattn_bwd(const mmn_winattn_desc* d, const void* q, const void* k, con
   if (d->path == MMN_PATH_TCGEN05 && !tc_ok) return fail(MMN_ERR_UNSUPPORTED, "shape not supported by the tcgen05 backward path: %s", why);
   if (d->path != MMN_PATH_GENERIC && tc_ok) {
     int n = 0;
-    rc = mmn::tc::winattn_bwd(d, q, k, v, bias, head_scale, mask, out, lse, dout, dq, dk, dv, dbias, dhead_scale, workspace, st, g_err, sizeof(g_err), &n);
+    rc = mmn::tc::winattn_bwd(d, q, k, v, bias, head_scale, mask, out, lse, dout, dq, dk, dv, dbias, dhead_scale, dcolsum, workspace, st, g_err, sizeof(g_err), &n);
     g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed);
     return rc;
   }
   mmn::GenericProblem P = problem_from(d, bias, head_scale, mask);
   int n = 0;
-  return finish(mmn::generic_bwd(P, d->io_dtype, q, k, v, lse, dout, dq, dk, dv, bias ? dbias : nullptr,
-                                 P.cosine ? dhead_scale : nullptr, workspace, st, &n), n, "attn_bwd_generic");
+  cudaError_t e = mmn::generic_bwd(P, d->io_dtype, q, k, v, lse, dout, dq, dk, dv, bias ? dbias : nullptr,
+                                 P.cosine ? dhead_scale : nullptr, workspace, dcolsum, st, &n);
+  return finish(e, n, "attn_bwd_generic");
 }
 
 int mmn_mha_fwd(const mmn_mha_desc* d, const void* q, const void* k, const void* v, const float* mask, void* out,
@@ -198,7 +200,8 @@ int mmn_mha_fwd(const mmn_mha_desc* d, const void* q, const void* k, const void*
   DeviceGuard g(device);
   if (!g.ok) return fail(MMN_ERR_CUDA, "cannot select device %d", device);
   int n = 0;
-  return finish(mmn::generic_fwd(problem_from(d, mask), d->io_dtype, q, k, v, out, lse, (cudaStream_t)stream, &n), n, "attn_fwd_generic");
+  cudaError_t e = mmn::generic_fwd(problem_from(d, mask), d->io_dtype, q, k, v, out, lse, (cudaStream_t)stream, &n);
+  return finish(e, n, "attn_fwd_generic");
 }
 
 int mmn_mha_bwd(const mmn_mha_desc* d, const void* q, const void* k, const void* v, const float* mask, const void* out,
@@ -212,8 +215,9 @@ int mmn_mha_bwd(const mmn_mha_desc* d, const void* q, const void* k, const void*
   DeviceGuard g(device);
   if (!g.ok) return fail(MMN_ERR_CUDA, "cannot select device %d", device);
   int n = 0;
-  return finish(mmn::generic_bwd(problem_from(d, mask), d->io_dtype, q, k, v, lse, dout, dq, dk, dv, nullptr, nullptr, workspace,
-                                 (cudaStream_t)stream, &n), n, "attn_bwd_generic");
+  cudaError_t e = mmn::generic_bwd(problem_from(d, mask), d->io_dtype, q, k, v, lse, dout, dq, dk, dv, nullptr, nullptr, workspace,
+                                 nullptr, (cudaStream_t)stream, &n);
+  return finish(e, n, "attn_bwd_generic");
 }
 
 int mmn_mha_avg_weights(const mmn_mha_desc* d, const void* q, const void* k, const float* mask, const float* lse,
@@ -225,8 +229,21 @@ int mmn_mha_avg_weights(const mmn_mha_desc* d, const void* q, const void* k, con
   DeviceGuard g(device);
   if (!g.ok) return fail(MMN_ERR_CUDA, "cannot select device %d", device);
   int n = 0;
-  return finish(mmn::generic_avg_weights(problem_from(d, mask), d->io_dtype, d->batch, q, k, lse, avg, (cudaStream_t)stream, &n), n,
-                "mha_avg_weights_generic");
+  cudaError_t e = mmn::generic_avg_weights(problem_from(d, mask), d->io_dtype, d->batch, q, k, lse, avg, (cudaStream_t)stream, &n);
+  return finish(e, n, "mha_avg_weights_generic");
+}
+
+int mmn_colsum(const void* x, int io_dtype, int64_t rows, int32_t cols, int64_t row_stride, float* out, int device, void* stream) {
+  if (!x || !out || rows < 0 || cols < 1) return fail(MMN_ERR_INVALID, "bad colsum arguments");
+  if (io_dtype != MMN_DT_F32 && io_dtype != MMN_DT_BF16) return fail(MMN_ERR_INVALID, "bad io_dtype");
+  if (cols % 8 != 0 || cols > 2048) return fail(MMN_ERR_UNSUPPORTED, "colsum needs cols %% 8 == 0 and cols <= 2048 (got %d)", cols);
+  if (!have_device()) return fail(MMN_ERR_CUDA, "no CUDA device: libmmn_b200 has no CPU path");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(MMN_ERR_CUDA, "cannot select device %d", device);
+  if (rows == 0) return MMN_OK;
+  int n = 0;
+  cudaError_t e = mmn::colsum(io_dtype, x, rows, cols, row_stride, out, (cudaStream_t)stream, &n);
+  return finish(e, n, "colsum_kernel");
 }
 
 }  // extern "C"

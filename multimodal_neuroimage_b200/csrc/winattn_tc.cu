@@ -50,9 +50,9 @@ int winattn_fwd(const mmn_winattn_desc* d, const void* q, const void* k, const v
 
 int winattn_bwd(const mmn_winattn_desc* d, const void* q, const void* k, const void* v, const float* bias,
                 const float* head_scale, const float* mask, const void* /*out*/, const float* lse, const void* dout, void* dq,
-                void* dk, void* dv, float* dbias, float* dhead_scale, float* /*workspace*/, cudaStream_t st, char* err,
-                size_t errlen, int* launches) {
-  int rc = winattn_bwd_launch(d, q, k, v, bias, head_scale, mask, lse, dout, dq, dk, dv, dbias, dhead_scale, st, err, errlen);
+                void* dk, void* dv, float* dbias, float* dhead_scale, float* dcolsum, float* /*workspace*/, cudaStream_t st,
+                char* err, size_t errlen, int* launches) {
+  int rc = winattn_bwd_launch(d, q, k, v, bias, head_scale, mask, lse, dout, dq, dk, dv, dbias, dhead_scale, dcolsum, st, err, errlen);
   if (rc == MMN_OK) ++*launches;
   return rc;
 }

@@ -13,6 +13,6 @@ int winattn_fwd(const mmn_winattn_desc* d, const void* q, const void* k, const v
                 const float* head_scale, const float* mask, void* out, float* lse, cudaStream_t st, char* err, size_t errlen);
 int winattn_bwd(const mmn_winattn_desc* d, const void* q, const void* k, const void* v, const float* bias,
                 const float* head_scale, const float* mask, const void* out, const float* lse, const void* dout, void* dq,
-                void* dk, void* dv, float* dbias, float* dhead_scale, float* workspace, cudaStream_t st, char* err,
-                size_t errlen, int* launches);
+                void* dk, void* dv, float* dbias, float* dhead_scale, float* dcolsum, float* workspace, cudaStream_t st,
+                char* err, size_t errlen, int* launches);
 }}  // namespace mmn::tc

@@ -40,6 +40,7 @@ struct BwdParams {
   const float* lse;
   float* dbias;         // (nH, 64, 64) accumulated, may be null
   float* dhead_scale;   // (nH) accumulated, may be null
+  float* dcolsum;       // (3, nH*32) accumulated column sums of dq, dk, dv (= projection bias grads), may be null
 };
 
 // COS: cosine attention (else scaled dot product); MASK: MMN_MASK_NONE / _SHIFT / _TENSOR.  Compile-time so that
@@ -180,27 +181,65 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       if (pair + pair_step < P.n_pairs) issue_sdp(it + 1);
     }
   } else if (warp == kStoreWarp) {
-    // ============================== TMA store ==============================
-    if (lane == 0) {
+    // ============================== TMA store (+ projection-bias gradients) ==============================
+    // Lane 0 issues the stores; meanwhile all 32 lanes sum the columns of the three staging tiles
+    // (dq, dk, dv over all tokens = the bias gradients of the q/k/v projections).  Lane l owns the
+    // 8 channels of logical 16-byte chunk l%4 for rows == l/4 (mod 8).
+    {
       WinCursor c0;
       c0.init(S, 2 * pair0);
+      float cs[3][8];
+#pragma unroll
+      for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) cs[t][e] = 0.f;
       int it = 0;
       for (int pair = pair0; pair < P.n_pairs; pair += pair_step, ++it, c0.advance(S, step)) {
         mbar_wait(so_ready, it & 1);
-        WinCursor c = c0;
+        if (lane == 0) {
+          WinCursor c = c0;
 #pragma unroll
-        for (int slot = 0; slot < 2; ++slot) {
-          const WinGeom g = window_geom(S, c);
-          issue_window_boxes<false>(S, P.dq, g, h * kD, sOut + slot * kWinBytes, nullptr);
-          issue_window_boxes<false>(S, P.dk, g, h * kD, sOut + kTile + slot * kWinBytes, nullptr);
-          issue_window_boxes<false>(S, P.dv, g, h * kD, sOut + 2 * kTile + slot * kWinBytes, nullptr);
-          c.advance(S, one);
+          for (int slot = 0; slot < 2; ++slot) {
+            const WinGeom g = window_geom(S, c);
+            issue_window_boxes<false>(S, P.dq, g, h * kD, sOut + slot * kWinBytes, nullptr);
+            issue_window_boxes<false>(S, P.dk, g, h * kD, sOut + kTile + slot * kWinBytes, nullptr);
+            issue_window_boxes<false>(S, P.dv, g, h * kD, sOut + 2 * kTile + slot * kWinBytes, nullptr);
+            c.advance(S, one);
+          }
+          tma_store_commit();
         }
-        tma_store_commit();
-        tma_store_wait_read<0>();
-        mbar_arrive(so_free);
+        if (P.dcolsum) {
+#pragma unroll
+          for (int t = 0; t < 3; ++t)
+#pragma unroll 4
+            for (int r0 = 0; r0 < 128; r0 += 8) {
+              const int row = r0 + (lane >> 2);
+              const uint4 a = *reinterpret_cast<const uint4*>(sOut + t * kTile + row * 64 + (((lane & 3) ^ ((row >> 1) & 3)) << 4));
+              const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { float2 f = __bfloat1622float2(pa[e]); cs[t][2 * e] += f.x; cs[t][2 * e + 1] += f.y; }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_wait_read<0>();
+          mbar_arrive(so_free);
+        }
       }
-      tma_store_wait_all<0>();
+      if (lane == 0) tma_store_wait_all<0>();
+      if (P.dcolsum) {
+        const int C = P.nH * kD;
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float v = cs[t][e];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (lane < 4) atomicAdd(P.dcolsum + t * C + h * kD + lane * 8 + e, v);
+          }
+      }
     }
   } else {
     // ============================== softmax / epilogue (256 threads: 2 per row) ==============================
@@ -453,7 +492,7 @@ inline const char* bwd_why_not_impl(const mmn_winattn_desc* d) {
 
 inline int winattn_bwd_launch(const mmn_winattn_desc* d, const void* q, const void* k, const void* v, const float* bias,
                               const float* head_scale, const float* mask, const float* lse, const void* dout, void* dq, void* dk,
-                              void* dv, float* dbias, float* dhead_scale, cudaStream_t st, char* err, size_t errlen) {
+                              void* dv, float* dbias, float* dhead_scale, float* dcolsum, cudaStream_t st, char* err, size_t errlen) {
   BwdParams P;
   P.S = shape_from(d);
   const int C = d->num_heads * d->head_dim;
@@ -474,6 +513,7 @@ inline int winattn_bwd_launch(const mmn_winattn_desc* d, const void* q, const vo
   P.bias = bias; P.head_scale = head_scale; P.mask = mask; P.lse = lse;
   P.dbias = bias ? dbias : nullptr;
   P.dhead_scale = P.cosine ? dhead_scale : nullptr;
+  P.dcolsum = dcolsum;
 
   using Kern = void (*)(const BwdParams);
   static const Kern kernels[2][3] = {

@@ -20,7 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 import torch.utils.checkpoint as checkpoint
 
-from .. import _lib, geometry, ops
+from .. import _lib, fused, geometry, ops
 
 _LOGIT_MAX = math.log(1.0 / 0.01)
 
@@ -162,11 +162,16 @@ class WindowAttention(nn.Module):
     def forward_grid(self, x, grid, shift):
         """x: (B, prod(grid), C) in the natural token order; the cyclic shift, the window
         gather/scatter and the shift mask all happen inside the kernel."""
-        B, L, C = x.shape
-        qkv = self._qkv(x).view(B, *grid, 3 * C)
         shifted = any(int(s) > 0 for s in shift)
-        out = self._core(qkv, grid, self.window_size, shift, _lib.MASK_SHIFT if shifted else _lib.MASK_NONE, None)
-        return self.proj_drop(self.proj(out.view(B, L, C)))
+        bias = None
+        if self.q_bias is not None:
+            bias = torch.cat((self.q_bias, torch.zeros_like(self.v_bias, requires_grad=False), self.v_bias))
+        y = fused.window_attention_module(x, None, self.qkv.weight, bias, None, None, self.proj.weight, self.proj.bias,
+                                          self.position_bias(), self.head_scale(), grid, self.window_size, shift,
+                                          self.num_heads_swin, _lib.SCORE_COSINE,
+                                          _lib.MASK_SHIFT if shifted else _lib.MASK_NONE, 1.0,
+                                          ops.next_dropout_stream(self.attn_drop.p, self.training, x.device), self.kernel_path)
+        return self.proj_drop(y)
 
     def extra_repr(self) -> str:
         return (f"dim={self.dim}, window_size={self.window_size}, "

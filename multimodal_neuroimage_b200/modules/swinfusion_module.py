@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 import torch.utils.checkpoint as checkpoint
 
-from .. import _lib, geometry, ops
+from .. import _lib, fused, geometry, ops
 from .swin_v2_module import DropPath, to_2tuple, to_ntuple, window_partition, window_reverse
 
 window_partition_fusion = window_partition
@@ -102,11 +102,13 @@ class WindowAttention_fusion(_TableBiasAttention):
         return self.proj_drop(self.proj(out))
 
     def forward_grid(self, x, grid, shift):
-        B, L, C = x.shape
         shifted = any(int(s) > 0 for s in shift)
-        out = self._core(self.qkv(x).view(B, *grid, 3 * C), None, grid, self.window_size, shift,
-                         _lib.MASK_SHIFT if shifted else _lib.MASK_NONE, None)
-        return self.proj_drop(self.proj(out.view(B, L, C)))
+        y = fused.window_attention_module(x, None, self.qkv.weight, self.qkv.bias, None, None, self.proj.weight,
+                                          self.proj.bias, self.position_bias(), None, grid, self.window_size, shift,
+                                          self.num_heads, _lib.SCORE_SCALED, _lib.MASK_SHIFT if shifted else _lib.MASK_NONE,
+                                          float(self.scale), ops.next_dropout_stream(self.attn_drop.p, self.training, x.device),
+                                          self.kernel_path)
+        return self.proj_drop(y)
 
 
 class Cross_WindowAttention(_TableBiasAttention):
@@ -131,11 +133,14 @@ class Cross_WindowAttention(_TableBiasAttention):
         return self.proj_drop(self.proj(out))
 
     def forward_grid(self, x, y, grid, shift):
-        B, L, C = x.shape
         shifted = any(int(s) > 0 for s in shift)
-        out = self._core(self.q(x).view(B, *grid, C), self.kv(y).view(B, *grid, 2 * C), grid, self.window_size, shift,
-                         _lib.MASK_SHIFT if shifted else _lib.MASK_NONE, None)
-        return self.proj_drop(self.proj(out.view(B, L, C)))
+        out = fused.window_attention_module(x, y, self.q.weight, self.q.bias, self.kv.weight, self.kv.bias, self.proj.weight,
+                                            self.proj.bias, self.position_bias(), None, grid, self.window_size, shift,
+                                            self.num_heads, _lib.SCORE_SCALED,
+                                            _lib.MASK_SHIFT if shifted else _lib.MASK_NONE, float(self.scale),
+                                            ops.next_dropout_stream(self.attn_drop.p, self.training, x.device),
+                                            self.kernel_path)
+        return self.proj_drop(out)
 
 
 class _FusionBlockBase(nn.Module):

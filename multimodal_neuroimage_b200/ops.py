@@ -150,8 +150,9 @@ def _(a, b, bias, head_scale, mask, grid, window, shift, num_heads, score_kind, 
 def winattn_bwd(dout: Tensor, a: Tensor, b: Optional[Tensor], bias: Optional[Tensor], head_scale: Optional[Tensor],
                 mask: Optional[Tensor], out: Tensor, lse: Tensor, grid: List[int], window: List[int], shift: List[int],
                 num_heads: int, score_kind: int, mask_kind: int, scale: float, dropout_p: float, seed: int,
-                offset: int, path: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
-    """Returns (da, db, dbias, dhead_scale); unused ones are empty tensors."""
+                offset: int, path: int, want_colsum: bool = False) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """Returns (da, db, dbias, dhead_scale, dcolsum); unused ones are empty tensors.  dcolsum (3, C) fp32 =
+    column sums over all tokens of dq, dk, dv, i.e. the bias gradients of the q/k/v projections."""
     _require_cuda(dout, a, b, bias, head_scale, mask, out, lse)
     lib = _lib.load()
     d, Cc = _win_desc(a, b, grid, window, shift, num_heads, score_kind, mask_kind,
@@ -176,20 +177,23 @@ def winattn_bwd(dout: Tensor, a: Tensor, b: Optional[Tensor], bias: Optional[Ten
     dbias = torch.zeros_like(bias) if bias is not None else a.new_empty(0, dtype=torch.float32)
     dhs = torch.zeros_like(head_scale) if head_scale is not None else a.new_empty(0, dtype=torch.float32)
     ws = lse.new_empty(2 * lse.numel())
+    dcs = torch.zeros(3, Cc, dtype=torch.float32, device=a.device) if want_colsum else a.new_empty(0, dtype=torch.float32)
     with _timed("winattn_bwd", a):
         _lib.check(lib.mmn_winattn_bwd(C.byref(d), q, k, v, _ptr(bias), _ptr(head_scale), _ptr(mask), _ptr(out), _ptr(lse),
                                        _ptr(dout), dq, dk, dv, _ptr(dbias) if bias is not None else None,
-                                       _ptr(dhs) if head_scale is not None else None, _ptr(ws), a.device.index,
-                                       _stream(a)), "mmn_winattn_bwd")
-    return da, db, dbias, dhs
+                                       _ptr(dhs) if head_scale is not None else None, _ptr(dcs) if want_colsum else None,
+                                       _ptr(ws), a.device.index, _stream(a)), "mmn_winattn_bwd")
+    return da, db, dbias, dhs, dcs
 
 
 @winattn_bwd.register_fake
 def _(dout, a, b, bias, head_scale, mask, out, lse, grid, window, shift, num_heads, score_kind, mask_kind, scale,
-      dropout_p, seed, offset, path):
+      dropout_p, seed, offset, path, want_colsum=False):
+    Cc = a.shape[-1] // 3 if b is None else a.shape[-1]
     return (torch.empty_like(a), torch.empty_like(b) if b is not None else a.new_empty(0),
             torch.empty_like(bias) if bias is not None else a.new_empty(0, dtype=torch.float32),
-            torch.empty_like(head_scale) if head_scale is not None else a.new_empty(0, dtype=torch.float32))
+            torch.empty_like(head_scale) if head_scale is not None else a.new_empty(0, dtype=torch.float32),
+            a.new_empty((3, Cc) if want_colsum else (0,), dtype=torch.float32))
 
 
 def _winattn_setup(ctx, inputs, output):
@@ -202,7 +206,7 @@ def _winattn_setup(ctx, inputs, output):
 
 def _winattn_backward(ctx, dout, dlse):
     a, b, bias, head_scale, mask, out, lse = ctx.saved_tensors
-    da, db, dbias, dhs = torch.ops.mmn_b200.winattn_bwd(dout, a, b, bias, head_scale, mask, out, lse, *ctx.cfg)
+    da, db, dbias, dhs, _ = torch.ops.mmn_b200.winattn_bwd(dout, a, b, bias, head_scale, mask, out, lse, *ctx.cfg)
     return (da, db if b is not None else None, dbias if bias is not None else None,
             dhs if head_scale is not None else None, None) + (None,) * 11
 
@@ -323,6 +327,24 @@ def mha_avg_weights(q: Tensor, k: Tensor, mask: Optional[Tensor], lse: Tensor, n
 @mha_avg_weights.register_fake
 def _(q, k, mask, lse, num_heads, mask_kind, mask_diag, scale, dropout_p, seed, offset):
     return q.new_empty(q.shape[1], q.shape[0], k.shape[0], dtype=torch.float32)
+
+
+@torch.library.custom_op("mmn_b200::colsum", mutates_args=())
+def colsum(x: Tensor) -> Tensor:
+    """(rows, cols) -> (cols,) fp32 column sums (a projection's bias gradient) at memory speed."""
+    _require_cuda(x)
+    if x.dim() != 2 or x.stride(1) != 1 or x.dtype not in _DT:
+        raise RuntimeError("colsum expects a 2-D float32/bfloat16 tensor with contiguous columns")
+    out = torch.zeros(x.shape[1], dtype=torch.float32, device=x.device)
+    with _timed("colsum", x):
+        _lib.check(_lib.load().mmn_colsum(_ptr(x), _DT[x.dtype], x.shape[0], x.shape[1], x.stride(0), _ptr(out),
+                                          x.device.index, _stream(x)), "mmn_colsum")
+    return out
+
+
+@colsum.register_fake
+def _(x):
+    return x.new_empty(x.shape[1], dtype=torch.float32)
 
 
 def next_dropout_stream(p: float, training: bool, device) -> Tuple[float, int, int]:
