@@ -41,7 +41,12 @@ struct BwdParams {
   float* dbias;         // (nH, 64, 64) accumulated, may be null
   float* dhead_scale;   // (nH) accumulated, may be null
   float* dcolsum;       // (3, nH*32) accumulated column sums of dq, dk, dv (= projection bias grads), may be null
+  long long* trace;     // debug: clock64 stamps of CTA 0 (MMN_TC_TRACE_BWD=<file>)
 };
+
+__device__ __forceinline__ void trace_evb(const BwdParams& P, int role, int item, int ev) {
+  if (P.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && item < 32) P.trace[(role * 32 + item) * 16 + ev] = clock64();
+}
 
 // COS: cosine attention (else scaled dot product); MASK: MMN_MASK_NONE / _SHIFT / _TENSOR.  Compile-time so that
 // each variant carries only its own code (the kernel is instruction-cache sensitive).
@@ -252,6 +257,9 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) dbacc[j] = 0.f;
     float dscale_acc = 0.f;
+    float* const gdb_head = P.dbias ? P.dbias + (size_t)h * kN * kN : nullptr;
+    const int trole = warp == 0 ? 0 : (warp == 7 ? 1 : -1);
+#define TRB(item, ev) do { if (trole >= 0) trace_evb(P, trole, item, ev); } while (0)
 
     WinCursor cur;
     cur.init(S, 2 * pair0 + slot);
@@ -268,7 +276,9 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       const float lse_i = __ldg(P.lse + ((size_t)w * P.nH + h) * kN + ipos);
 
       // ---- (a) row norm; scaled copy of this thread's q row (half 0) / k row (half 1)
+      TRB(it, 0);
       mbar_wait(&full[stage], phase);
+      TRB(it, 1);
       float rinv = 1.f;                                 // 1 / max(||row||, eps)
       {
         const uint8_t* rowp = base + half * kTile + r * 64;
@@ -296,6 +306,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       int rid_i = 0;
       if (masked) { rid_i = region_id(S, g, ipos); if (half == 0) sRid[r] = rid_i; }
       named_bar_sync(1, kSoftmaxThreads);
+      TRB(it, 2);
 
       // ---- (b) additive terms of this thread's 32 logits (bias, mask) while S / dP finish
       float p[32];
@@ -330,14 +341,17 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       }
 
       // ---- (c) S and dP from TMEM; P = exp(S - lse); partial delta and d(logit scale) sums
+      TRB(it, 3);
       mbar_wait(sdp_full, it & 1);
       tcgen05_fence_after();
+      TRB(it, 4);
       uint32_t raw[32], dpr[32];
       tmem_ld_32x32b_x32(tmem + lane_base + slot * 64 + half * 32, raw);
       tmem_ld_32x32b_x32(tmem + lane_base + 128 + slot * 64 + half * 32, dpr);
       tmem_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(sdp_empty);
+      TRB(it, 5);
       const float a_i = COS ? sRq[r] : P.scale;
       const float4* krow = reinterpret_cast<const float4*>(sRk + slot * 64 + half * 32);
       const float lneg = -lse_i * kLog2e;
@@ -368,7 +382,9 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
               make_uint4(pack_bf16x2(p[c * 8 + 0], p[c * 8 + 1]), pack_bf16x2(p[c * 8 + 2], p[c * 8 + 3]),
                          pack_bf16x2(p[c * 8 + 4], p[c * 8 + 5]), pack_bf16x2(p[c * 8 + 6], p[c * 8 + 7]));
       }
+      TRB(it, 6);
       named_bar_sync(2, kSoftmaxThreads);
+      TRB(it, 7);
       delta += sDelta[(half ^ 1) * 128 + r];
 
       // ---- (d) dS = P o (dP - delta), in place of P; dbias and d(logit scale) reductions
@@ -401,10 +417,12 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       }
       fence_proxy_async_smem();
       mbar_arrive(pds_full);
+      TRB(it, 8);
 
       // ---- (f) epilogue: half 0 -> dQ row r and dV channels [0,16); half 1 -> dK row r and dV channels [16,32)
       mbar_wait(out_full, it & 1);
       tcgen05_fence_after();
+      TRB(it, 9);
       uint32_t g32[32], gv[16];
       tmem_ld_32x32b_x32(tmem + lane_base + (half == 0 ? 288 : 320), g32);
       tmem_ld_32x32b_x16(tmem + lane_base + 256 + half * 16, gv);
@@ -433,7 +451,9 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
         for (int c = 0; c < 32; ++c) outv[c] = __uint_as_float(g32[c]);
       }
       mbar_arrive(&empty[stage]);                       // this thread is done with the stage's tiles
-      mbar_wait(so_free, (it & 1) ^ 1);                 // previous pair's stores have drained the staging tiles
+      TRB(it, 10);
+      mbar_wait(so_free, (it & 1) ^ 1);
+      TRB(it, 11);                 // previous pair's stores have drained the staging tiles
       {
         uint8_t* orow = sOut + half * kTile + r * 64;   // dQ tile (half 0) or dK tile (half 1)
 #pragma unroll
@@ -449,17 +469,18 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       }
       fence_proxy_async_smem();
       mbar_arrive(so_ready);
+      TRB(it, 12);
     }
+#undef TRB
 
     // ---- cross-window reductions: dbias (registers + shared table) and d(logit scale)
     if (P.dbias) {
-      float* gdb = P.dbias + (size_t)h * kN * kN;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) atomicAdd(gdb + i * kN + half * 32 + j, dbacc[j]);
+      for (int j = 0; j < 32; ++j) atomicAdd(gdb_head + i * kN + half * 32 + j, dbacc[j]);
       named_bar_sync(1, kSoftmaxThreads);               // all shared-memory atomics done
       for (int e = tid; e < kN * kN; e += kSoftmaxThreads) {
         float v = sDb[(e >> 6) * kBiasLd + (e & 63)];
-        if (v != 0.f) atomicAdd(gdb + e, v);
+        if (v != 0.f) atomicAdd(gdb_head + e, v);
       }
     }
     if (COS && P.dhead_scale) {
@@ -514,6 +535,12 @@ inline int winattn_bwd_launch(const mmn_winattn_desc* d, const void* q, const vo
   P.dbias = bias ? dbias : nullptr;
   P.dhead_scale = P.cosine ? dhead_scale : nullptr;
   P.dcolsum = dcolsum;
+  P.trace = nullptr;
+  const char* trace_path = getenv("MMN_TC_TRACE_BWD");
+  if (trace_path && *trace_path) {
+    cudaMalloc(&P.trace, 5 * 32 * 16 * sizeof(long long));
+    cudaMemsetAsync(P.trace, 0, 5 * 32 * 16 * sizeof(long long), st);
+  }
 
   using Kern = void (*)(const BwdParams);
   static const Kern kernels[2][3] = {
@@ -537,6 +564,21 @@ inline int winattn_bwd_launch(const mmn_winattn_desc* d, const void* q, const vo
   if (e != cudaSuccess) {
     snprintf(err, errlen, "winattn_bwd_tc_kernel: %s", cudaGetErrorString(e));
     return MMN_ERR_CUDA;
+  }
+  if (P.trace) {
+    static long long host[5 * 32 * 16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(host, P.trace, sizeof(host), cudaMemcpyDeviceToHost);
+    cudaFree(P.trace);
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (int role = 0; role < 5; ++role)
+        for (int item = 0; item < 32; ++item) {
+          fprintf(f, "%d %d", role, item);
+          for (int ev = 0; ev < 16; ++ev) fprintf(f, " %lld", host[(role * 32 + item) * 16 + ev]);
+          fprintf(f, "\n");
+        }
+      fclose(f);
+    }
   }
   return MMN_OK;
 }
