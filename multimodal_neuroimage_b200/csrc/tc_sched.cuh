@@ -1,0 +1,196 @@
+// tc_sched.cuh -- work schedule of the tensor-core window-attention kernels.
+//
+// Windows are enumerated CLASS-SORTED: all windows that do not wrap around the volume edge first,
+// then the seven wrap classes (tc_window.cuh: bit a of the class = the shifted window wraps along
+// axis a, which happens exactly for the last window index of a shifted axis).  Inside a class the
+// windows form a dense (batch, j0, j1, j2) lattice.  A work ITEM is a pair of consecutive windows
+// of one class (the last item of an odd class has one window), so that everything that depends
+// on the class -- TMA box shape, piece-major token permutation, shift mask -- is uniform over an
+// item, and a CTA, which owns a contiguous (cost-weighted) range of items, sees a class change at
+// most seven times.  That is what lets the kernels keep a per-class, pre-permuted, pre-masked
+// bias table in shared memory and accumulate the bias gradient in registers without atomics.
+#pragma once
+
+#include "tc_window.cuh"
+
+namespace mmn { namespace tc {
+
+struct Sched {
+  int cnt[8];        // windows per wrap class
+  int dim[8][4];     // lattice extents (batch, j0, j1, j2) of the class
+  int wt[8];         // relative cost of one item of the class (partitioning only)
+  int n_items;       // sum over classes of ceil(cnt / 2)
+  long long total_wt;
+};
+
+inline Sched make_sched(const WinShape& S, int batch) {
+  Sched sc;
+  sc.n_items = 0;
+  sc.total_wt = 0;
+  for (int c = 0; c < 8; ++c) {
+    long long n = batch;
+    sc.dim[c][0] = batch;
+    for (int a = 0; a < 3; ++a) {
+      const int bit = (c >> a) & 1;
+      const int d = S.shift[a] ? (bit ? 1 : S.nwin[a] - 1) : (bit ? 0 : S.nwin[a]);
+      sc.dim[c][1 + a] = d;
+      n *= d;
+    }
+    sc.cnt[c] = (int)n;
+    sc.wt[c] = 16 + 2 * __builtin_popcount(c);      // wrapped windows: more, smaller TMA boxes
+    sc.n_items += (sc.cnt[c] + 1) / 2;
+    sc.total_wt += (long long)((sc.cnt[c] + 1) / 2) * sc.wt[c];
+  }
+  return sc;
+}
+
+// First item of the k-th of G cost-balanced contiguous ranges (k = G gives n_items).
+__device__ __forceinline__ int sched_range_begin(const Sched& sc, int k, int G) {
+  if (k >= G) return sc.n_items;
+  long long target = sc.total_wt * k / G;
+  int base = 0;
+  for (int c = 0; c < 8; ++c) {
+    const int np = (sc.cnt[c] + 1) >> 1;
+    const long long cw = (long long)np * sc.wt[c];
+    if (target < cw) return base + (int)(target / sc.wt[c]);
+    target -= cw;
+    base += np;
+  }
+  return sc.n_items;
+}
+
+struct ItemCursor {
+  int cls, b, j0, j1, j2;
+  int d0, d1, d2;    // lattice extents of the current class (cached: sc.dim[cls] is a dynamically indexed constant load)
+  int left;          // windows of this class not yet consumed, including the current item's
+
+  __device__ __forceinline__ void load_dims(const Sched& sc) {
+    d0 = sc.dim[cls][1]; d1 = sc.dim[cls][2]; d2 = sc.dim[cls][3];
+  }
+  __device__ __forceinline__ void seek(const Sched& sc, int item) {
+    cls = 0;
+    while (cls < 8) {
+      const int np = (sc.cnt[cls] + 1) >> 1;
+      if (item < np) break;
+      item -= np;
+      ++cls;
+    }
+    if (cls == 8) { left = 0; b = j0 = j1 = j2 = 0; d0 = d1 = d2 = 1; return; }
+    load_dims(sc);
+    int w = 2 * item;
+    left = sc.cnt[cls] - w;
+    j2 = w % d2; w /= d2;
+    j1 = w % d1; w /= d1;
+    j0 = w % d0;
+    b = w / d0;
+  }
+  __device__ __forceinline__ void step_window() {
+    if (++j2 == d2) {
+      j2 = 0;
+      if (++j1 == d1) {
+        j1 = 0;
+        if (++j0 == d0) { j0 = 0; ++b; }
+      }
+    }
+  }
+  __device__ __forceinline__ void next_item(const Sched& sc) {
+    if (left <= 2) {
+      do { ++cls; } while (cls < 8 && sc.cnt[cls] == 0);
+      b = j0 = j1 = j2 = 0;
+      if (cls < 8) { left = sc.cnt[cls]; load_dims(sc); } else { left = 0; d0 = d1 = d2 = 1; }
+    } else {
+      step_window();
+      step_window();
+      left -= 2;
+    }
+  }
+  __device__ __forceinline__ bool slot_valid(int slot) const { return slot == 0 || left >= 2; }
+};
+
+struct ItemGeom : WinGeom {
+  int w;             // linear window index (b * nW + row-major window position): addresses lse
+};
+
+// Geometry of window `slot` (0 / 1) of the cursor's item.
+__device__ __forceinline__ ItemGeom item_geom(const WinShape& S, const Sched& sc, const ItemCursor& c, int slot) {
+  ItemCursor t = c;
+  if (slot) t.step_window();
+  ItemGeom g;
+  g.b = t.b;
+  g.cls = t.cls;
+  const int j[3] = {t.j0, t.j1, t.j2};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    g.idx[a] = (t.cls >> a) & 1 ? S.nwin[a] - 1 : j[a];
+    g.start[a] = g.idx[a] * S.win[a] + S.shift[a];
+  }
+  g.w = t.b * S.nW + (g.idx[0] * S.nwin[1] + g.idx[1]) * S.nwin[2] + g.idx[2];
+  return g;
+}
+
+// Shift-mask region id of in-window position p for a window of wrap class `cls`
+// (swin_v2_module.py:247-258: along a wrapped axis the last window straddles regions 1 | 2 at
+// win - shift; every other window lies in region 0).
+__device__ __forceinline__ int class_region_id(const WinShape& S, int cls, int p) {
+  const int a2 = p % S.win[2]; const int t = p / S.win[2];
+  const int a1 = t % S.win[1]; const int a0 = t / S.win[1];
+  const int a[3] = {a0, a1, a2};
+  int rid = 0;
+#pragma unroll
+  for (int x = 0; x < 3; ++x) rid = rid * 3 + ((cls >> x) & 1 ? (a[x] < S.win[x] - S.shift[x] ? 1 : 2) : 0);
+  return rid;
+}
+
+// Per-class additive table in the item's tile order, in the log2 domain:
+//   tbl[i][j] = log2(e) * (bias[pos(i)][pos(j)] + (region(pos i) != region(pos j) ? -100 : 0)).
+// `bias` is this head's (64,64) fp32 table or null; `pos` the class's 64-entry tile-row -> window-position LUT.
+__device__ __forceinline__ void build_class_table(float* tbl, int ld, const float* bias, const uint8_t* pos, const WinShape& S,
+                                                  int cls, bool shift_mask, int t, int nthreads) {
+  for (int e = t; e < kN * kN; e += nthreads) {
+    const int i = e >> 6, j = e & 63;
+    const int pi = pos[i], pj = pos[j];
+    float v = bias ? __ldg(bias + pi * kN + pj) : 0.f;
+    if (shift_mask && cls != 0 && class_region_id(S, cls, pi) != class_region_id(S, cls, pj)) v -= 100.f;
+    tbl[i * ld + j] = v * 1.4426950408889634f;
+  }
+}
+
+// All TMA boxes of one item, one box per lane and round: box x = (slot, tensor t, piece) in piece-fastest order.
+// The coordinate arithmetic runs in parallel over the lanes; only the few instructions that feed the TMA unit
+// are serialised.  Tensor t's tile of slot s starts at dst[t] + s * slot_stride[t]; pieces land back to back
+// (piece-major token order, tc_window.cuh).  Both windows of an item have the same wrap class.
+template <bool LOAD, int T>
+__device__ __forceinline__ void issue_item_boxes(const WinShape& S, const ItemGeom& g0, const ItemGeom& g1, int nvalid, int chan,
+                                                 const CUtensorMap* const (&maps)[T], uint8_t* const (&dst)[T],
+                                                 const int (&slot_stride)[T], uint64_t* bar, int lane) {
+  const int cls = g0.cls;
+  const int lp = __popc(cls);
+  const int psize_bytes = (kN >> lp) * 64;
+  const int nbox = (nvalid * T) << lp;
+  for (int x = lane; x < nbox; x += 32) {
+    const int piece = x & ((1 << lp) - 1);
+    const int rest = x >> lp;
+    const int slot = rest / T, t = rest - slot * T;
+    const ItemGeom& g = slot ? g1 : g0;
+    int c[3], qq = piece;
+#pragma unroll
+    for (int a = 2; a >= 0; --a) {
+      const int bit = (cls >> a) & 1;
+      c[a] = g.start[a] + (bit ? (qq & 1) * (S.win[a] >> 1) : 0);
+      if (bit) qq >>= 1;
+      if (c[a] >= S.grid[a]) c[a] -= S.grid[a];
+    }
+    const CUtensorMap* m = maps[0];
+    uint8_t* p = dst[0];
+    int ss = slot_stride[0];
+#pragma unroll
+    for (int u = 1; u < T; ++u)
+      if (t == u) { m = maps[u]; p = dst[u]; ss = slot_stride[u]; }
+    m += cls;
+    p += slot * ss + piece * psize_bytes;
+    if (LOAD) tma_load_5d(m, bar, p, chan, c[2], c[1], c[0], g.b);
+    else tma_store_5d(m, p, chan, c[2], c[1], c[0], g.b);
+  }
+}
+
+}}  // namespace mmn::tc

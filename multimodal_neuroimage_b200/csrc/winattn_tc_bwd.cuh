@@ -1,38 +1,47 @@
 // winattn_tc_bwd.cuh -- shifted-window attention backward on the Blackwell tensor cores.
 //
-// Same work decomposition as the forward (winattn_tc_fwd.cuh): item = pair of 64-token
-// windows x one head, 128 rows = 128 TMEM lanes, one head per CTA, 352 threads:
+// Same tiling and schedule as the forward (winattn_tc_fwd.cuh, tc_sched.cuh): a work item is a
+// pair of 64-token windows of one wrap class x one head, operands gathered by TMA straight out of
+// the un-windowed tensors, gradients scattered back through the same boxes.  Per item, with
+// P = exp(S - lse) recomputed:
+//   S  = Q K^T, dP = dO V^T        (M128 N64 K64 each: windows stacked along M, channels along K
+//                                    against a shared zero block; S/dP double-buffered in TMEM so the
+//                                    next item's are ready when the softmax warps finish this one)
+//   dS = P o (dP - rowsum(P o dP)),  dS' = dS o c,  c_ij = d s_ij / d (q_i . k_j)
+//   dV = P^T dO, dQ~ = dS' K, dK~ = dS'^T Q   (M128 N32 K128; one bf16 dS' tile serves both)
+// Cosine attention differentiates through x / max(||x||, eps) in the epilogue:
+// dq = dQ~ - q^ (q^ . dQ~) (likewise dk), exact because c already carries 1/||q|| 1/||k|| x logit scale.
+// rowsum(P o dP) is computed in-tile, so `out` is never read.
 //
-//   warp 8    TMA producer   Q, K, V, dO tiles (piece-major boxes out of the un-windowed tensors)
-//   warp 9    MMA issuer     S  = Q K^T,  dP = dO V^T                       (M128 N128 K32)
-//                            dV = P^T dO, dQ = dS Ks, dK = dS^T Qs          (M128 N32 K128)
-//                            where P / dS are the softmax warps' bf16 tiles (block diagonal over
-//                            the two windows), read K-major for dQ and MN-major (= transposed,
-//                            same bytes) for dV / dK, and Qs / Ks are the q / k tiles pre-multiplied
-//                            by the logit scale (x 1/||.|| for cosine attention).
-//   warps 0-7 softmax        two threads per query row (32 keys each): recompute P = exp(S - lse)
-//                            from the saved log-sum-exp, delta = rowsum(P o dP) exactly (the whole
-//                            row is in the tile), dS = P o (dP - delta); accumulate dbias (registers
-//                            for window-ordered tiles, shared-memory atomics for piece-major ones)
-//                            and d(logit scale); then the epilogue: gradients through the cosine
-//                            normalisation, bf16, staging tiles.
-//   warp 10   TMA store      dQ, dK, dV staging tiles -> global through the same boxes.
-//
-// The forward output is never read (delta is recomputed), matching the generic path.
+// 512 threads, one CTA per SM:
+//   warps 0-7    softmax: two threads per query row (32 keys each); never wait for the gradient MMAs.
+//                dbias accumulates in registers in the item's tile order and is flushed through the
+//                class's permutation when the wrap class changes (at most 8 times per CTA).
+//   warps 8-11   epilogue: one thread per row, dQ~/dK~/dV out of TMEM -> normalisation Jacobian ->
+//                bf16 staging tiles.
+//   warp 12 TMA producer, warp 13 MMA issuer, warp 14 TMA store + column sums of dq/dk/dv
+//   (= the q/k/v projection bias gradients), warp 15 idle.
+// Register budget by warpgroup (setmaxnreg): softmax 160, epilogue 136, the rest 56.
 #pragma once
 
 #include "winattn_tc_fwd.cuh"
 
 namespace mmn { namespace tc {
 
-constexpr int kBwdStages = 2;
-constexpr int kBwdTmemCols = 512;   // S [0,128) dP [128,256) dV [256,288) dQ [288,320) dK [320,352)
+constexpr int kStagesB = 3;
+constexpr int kStageBytesB = 2 * kQRegion + 2 * kTile;   // Q0|Z|Q1, K0 K1, V0 V1, dO0|Z|dO1
+constexpr int kOffK = kQRegion, kOffV = kQRegion + kTile, kOffDO = kQRegion + 2 * kTile;
+constexpr int kSoftmaxThreadsB = 256, kEpiThreads = 128;
+constexpr int kEpiWarp0 = 8, kProducerWarpB = 12, kMmaWarpB = 13, kStoreWarpB = 14;
+constexpr int kBwdThreads = 512;
+constexpr int kBwdTmemCols = 512;     // S[b] at 128 b, dP[b] at 128 b + 64; dV|dQ~|dK~ [b] at 256 + 96 b
 
 struct BwdParams {
   CUtensorMap q[8], k[8], v[8], dout[8], dq[8], dk[8], dv[8];
   WinShape S;
-  int nH, n_pairs;
-  int cosine, mask_kind, mask_windows;
+  Sched sc;
+  int nH, per_head;
+  int mask_windows;
   float scale;
   const float* bias;
   const float* head_scale;
@@ -44,450 +53,480 @@ struct BwdParams {
   long long* trace;     // debug: clock64 stamps of CTA 0 (MMN_TC_TRACE_BWD=<file>)
 };
 
-__device__ __forceinline__ void trace_evb(const BwdParams& P, int role, int item, int ev) {
-  if (P.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && item < 32) P.trace[(role * 32 + item) * 16 + ev] = clock64();
-}
+template <int R> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 
-// COS: cosine attention (else scaled dot product); MASK: MMN_MASK_NONE / _SHIFT / _TENSOR.  Compile-time so that
-// each variant carries only its own code (the kernel is instruction-cache sensitive).
 template <bool COS, int MASK>
-__global__ void __launch_bounds__(kFwdThreads, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sIn = smem;                                   // kBwdStages x (Q | K | V | dO) x kTile
-  uint8_t* sP = sIn + kBwdStages * 4 * kTile;            // 2 x 16 KB (key halves)
-  uint8_t* sDS = sP + 2 * 16384;                         // 2 x 16 KB
-  uint8_t* sQs = sDS + 2 * 16384;                        // scaled q tile (64B-swizzled rows)
-  uint8_t* sKs = sQs + kTile;                            // scaled k tile
-  uint8_t* sOut = sKs + kTile;                           // dQ | dK | dV staging, 3 x kTile
-  float* sBias = reinterpret_cast<float*>(sOut + 3 * kTile);   // [64][kBiasLd]
-  float* sDb = sBias + kN * kBiasLd;                     // [64][kBiasLd] dbias accumulator (piece-major windows)
-  float* sRq = sDb + kN * kBiasLd;                       // 128: logit multiplier per row
-  float* sRk = sRq + 128;                                // 128: 1/||k|| per key
-  float* sDelta = sRk + 128;                             // [2][128] partial deltas
-  float* sRed = sDelta + 256;                            // 8 floats: dhead_scale per softmax warp
-  int* sRid = reinterpret_cast<int*>(sRed + 8);          // 128
-  uint8_t* sPos = reinterpret_cast<uint8_t*>(sRid + 128); // [8][64]
+  uint8_t* sStage = smem;                                 // kStagesB x kStageBytesB
+  uint8_t* sP = sStage + kStagesB * kStageBytesB;         // P0 | Z | P1
+  uint8_t* sDS = sP + kPRegion;                           // dS'0 | Z | dS'1
+  uint8_t* sOut = sDS + kPRegion;                         // dQ | dK | dV staging, 3 x kTile
+  float* sTbl = reinterpret_cast<float*>(sOut + 3 * kTile);   // [64][kTblLd]
+  float* sA = sTbl + kN * kTblLd;                         // [2][128] logit multiplier per query row (natural units)
+  float* sRk = sA + 256;                                  // [2][128] 1/||k|| per key
+  float* sDelta = sRk + 256;                              // [2][128] partial deltas
+  float* sRed = sDelta + 256;                             // 8 floats: dhead_scale per softmax warp
+  uint8_t* sPos = reinterpret_cast<uint8_t*>(sRed + 8);   // [8][64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sPos + 512);
-  uint64_t* full = bars;                                 // [kBwdStages]
-  uint64_t* empty = bars + kBwdStages;                   // [kBwdStages] (256 arrivals: softmax threads)
-  uint64_t* sdp_full = bars + 2 * kBwdStages;
-  uint64_t* sdp_empty = sdp_full + 1;                    // 256 arrivals
-  uint64_t* pds_full = sdp_full + 2;                     // 256 arrivals
-  uint64_t* out_full = sdp_full + 3;
-  uint64_t* so_ready = sdp_full + 4;                     // 256 arrivals
-  uint64_t* so_free = sdp_full + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdp_full + 6);
+  uint64_t* full = bars;                                  // [kStagesB]
+  uint64_t* empty = bars + kStagesB;                      // [kStagesB] (128 arrivals: epilogue threads)
+  uint64_t* sdp_full = bars + 2 * kStagesB;               // [2]
+  uint64_t* sdp_empty = sdp_full + 2;                     // [2] 256 arrivals
+  uint64_t* pds_full = sdp_full + 4;                      // 256 arrivals
+  uint64_t* out_full = sdp_full + 5;                      // [2]
+  uint64_t* out_empty = sdp_full + 7;                     // [2] 128 arrivals
+  uint64_t* so_ready = sdp_full + 9;                      // 128 arrivals
+  uint64_t* so_free = sdp_full + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdp_full + 11);
 
   const WinShape& S = P.S;
+  const Sched& sc = P.sc;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x % P.nH;
-  const int pair0 = blockIdx.x / P.nH, pair_step = gridDim.x / P.nH;
+  const int item0 = sched_range_begin(sc, blockIdx.x / P.nH, P.per_head);
+  const int cnt = sched_range_begin(sc, blockIdx.x / P.nH + 1, P.per_head) - item0;
 
   // ---- one-time setup
-  for (int i = tid; i < 4 * 16384 / 16; i += kFwdThreads) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0, 0, 0, 0);   // P and dS
-  for (int i = tid; i < kN * kBiasLd; i += kFwdThreads) sDb[i] = 0.f;
-  if (P.bias)
-    for (int i = tid; i < kN * kN; i += kFwdThreads) sBias[(i >> 6) * kBiasLd + (i & 63)] = __ldg(P.bias + (size_t)h * kN * kN + i);
-  for (int i = tid; i < 512; i += kFwdThreads) sPos[i] = (uint8_t)piece_position(S, i >> 6, i & 63);
+  for (int i = tid; i < (kStagesB * kStageBytesB + 2 * kPRegion) / 16; i += kBwdThreads)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 512; i += kBwdThreads) sPos[i] = (uint8_t)piece_position(S, i >> 6, i & 63);
   if (tid == 0) {
-    for (int s = 0; s < kBwdStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kSoftmaxThreads); }
-    mbar_init(sdp_full, 1); mbar_init(sdp_empty, kSoftmaxThreads); mbar_init(pds_full, kSoftmaxThreads);
-    mbar_init(out_full, 1); mbar_init(so_ready, kSoftmaxThreads); mbar_init(so_free, 1);
+    for (int s = 0; s < kStagesB; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kEpiThreads); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&sdp_full[b], 1); mbar_init(&sdp_empty[b], kSoftmaxThreadsB);
+      mbar_init(&out_full[b], 1); mbar_init(&out_empty[b], kEpiThreads);
+    }
+    mbar_init(pds_full, kSoftmaxThreadsB); mbar_init(so_ready, kEpiThreads); mbar_init(so_free, 1);
     fence_barrier_init();
   }
-  if (warp == kProducerWarp && lane == 0)
+  if (warp == kProducerWarpB && lane == 0)
     for (int i = 0; i < 8; ++i) { tma_prefetch_desc(&P.q[i]); tma_prefetch_desc(&P.k[i]); tma_prefetch_desc(&P.v[i]); tma_prefetch_desc(&P.dout[i]); }
-  if (warp == kStoreWarp && lane == 0)
+  if (warp == kStoreWarpB && lane == 0)
     for (int i = 0; i < 8; ++i) { tma_prefetch_desc(&P.dq[i]); tma_prefetch_desc(&P.dk[i]); tma_prefetch_desc(&P.dv[i]); }
-  if (warp == kMmaWarp) tmem_alloc<kBwdTmemCols>(tmem_slot);
+  if (warp == kMmaWarpB) tmem_alloc<kBwdTmemCols>(tmem_slot);
   fence_proxy_async_smem();
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  WinCursor step;
-  step.init(S, 2 * pair_step);
-  WinCursor one;
-  one.b = 0; one.i0 = 0; one.i1 = 0; one.i2 = 1;
-
-  if (warp == kProducerWarp) {
-    // ============================== TMA producer ==============================
-    if (lane == 0) {
-      WinCursor c0;
-      c0.init(S, 2 * pair0);
-      int it = 0;
-      for (int pair = pair0; pair < P.n_pairs; pair += pair_step, ++it, c0.advance(S, step)) {
-        const int stage = it % kBwdStages, phase = (it / kBwdStages) & 1;
+  if (warp >= kProducerWarpB) {
+    setmaxnreg_dec<56>();
+    if (warp == kProducerWarpB) {
+      // ============================== TMA producer ==============================
+      // every lane runs the loop; lane l issues boxes l, l + 32 of the item (issue_item_boxes)
+      const CUtensorMap* const maps[4] = {P.q, P.dout, P.k, P.v};
+      const int slot_stride[4] = {2 * kWinBytes, 2 * kWinBytes, kWinBytes, kWinBytes};
+      ItemCursor cur;
+      cur.seek(sc, item0);
+      for (int n = 0; n < cnt; ++n, cur.next_item(sc)) {
+        const int stage = n % kStagesB, phase = (n / kStagesB) & 1;
+        trace_ev(P.trace, 2, n, 0);
         mbar_wait(&empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full[stage], 4 * kTile);
-        uint8_t* base = sIn + stage * 4 * kTile;
-        WinCursor c = c0;
-#pragma unroll
-        for (int slot = 0; slot < 2; ++slot) {
-          const WinGeom g = window_geom(S, c);
-          issue_window_boxes<true>(S, P.q, g, h * kD, base + slot * kWinBytes, &full[stage]);
-          issue_window_boxes<true>(S, P.k, g, h * kD, base + kTile + slot * kWinBytes, &full[stage]);
-          issue_window_boxes<true>(S, P.v, g, h * kD, base + 2 * kTile + slot * kWinBytes, &full[stage]);
-          issue_window_boxes<true>(S, P.dout, g, h * kD, base + 3 * kTile + slot * kWinBytes, &full[stage]);
-          c.advance(S, one);
-        }
+        trace_ev(P.trace, 2, n, 1);
+        const int nvalid = cur.slot_valid(1) ? 2 : 1;
+        if (lane == 0) mbar_arrive_expect_tx(&full[stage], nvalid * 4 * kWinBytes);
+        __syncwarp();
+        uint8_t* base = sStage + stage * kStageBytesB;
+        uint8_t* const dst[4] = {base, base + kOffDO, base + kOffK, base + kOffV};
+        issue_item_boxes<true, 4>(S, item_geom(S, sc, cur, 0), item_geom(S, sc, cur, 1), nvalid, h * kD, maps, dst, slot_stride,
+                                  &full[stage], lane);
+        trace_ev(P.trace, 2, n, 2);
       }
-    }
-  } else if (warp == kMmaWarp) {
-    // ============================== MMA issuer ==============================
-    constexpr uint32_t idescS = umma_idesc_bf16(128, 128, 0, 0);    // A K-major, B K-major
-    constexpr uint32_t idescKM = umma_idesc_bf16(128, 32, 0, 1);    // A K-major (dS),      B MN-major (Ks)
-    constexpr uint32_t idescMM = umma_idesc_bf16(128, 32, 1, 1);    // A MN-major (P^T/dS^T), B MN-major (dO / Qs)
-    const uint32_t pAddr = smem_u32(sP), dsAddr = smem_u32(sDS), qsAddr = smem_u32(sQs), ksAddr = smem_u32(sKs);
-    auto issue_sdp = [&](int n) {
-      const int stage = n % kBwdStages, phase = (n / kBwdStages) & 1;
-      const uint32_t qAddr = smem_u32(sIn + stage * 4 * kTile), kAddr = qAddr + kTile, vAddr = qAddr + 2 * kTile, doAddr = qAddr + 3 * kTile;
-      mbar_wait(&full[stage], phase);
-      mbar_wait(sdp_empty, (n & 1) ^ 1);
-      tcgen05_fence_after();
-      if (lane == 0) {
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks)
-          umma_bf16_ss(tmem, umma_smem_desc(qAddr + ks * 32, 0, 512, kSwz64), umma_smem_desc(kAddr + ks * 32, 0, 512, kSwz64), idescS, ks);
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks)
-          umma_bf16_ss(tmem + 128, umma_smem_desc(doAddr + ks * 32, 0, 512, kSwz64), umma_smem_desc(vAddr + ks * 32, 0, 512, kSwz64), idescS, ks);
-        umma_commit(sdp_full);
-      }
-      __syncwarp();
-    };
-    int it = 0;
-    if (pair0 < P.n_pairs) issue_sdp(0);
-    for (int pair = pair0; pair < P.n_pairs; pair += pair_step, ++it) {
-      const int stage = it % kBwdStages;
-      const uint32_t doAddr = smem_u32(sIn + stage * 4 * kTile) + 3 * kTile;
-      mbar_wait(pds_full, it & 1);
-      tcgen05_fence_after();
-      if (lane == 0) {
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {   // 16 queries (dV, dK) or 16 keys (dQ) per step
-          // dV[key][d] += P[query][key]^T dO[query][d]
-          umma_bf16_ss(tmem + 256, umma_smem_desc(pAddr + ks * 2048, 16384, 1024, kSwz128),
-                       umma_smem_desc(doAddr + ks * 1024, 8192, 512, kSwz64), idescMM, ks);
-          // dQ[query][d] += dS[query][key] Ks[key][d]
-          umma_bf16_ss(tmem + 288, umma_smem_desc(dsAddr + (ks >> 2) * 16384 + (ks & 3) * 32, 0, 1024, kSwz128),
-                       umma_smem_desc(ksAddr + ks * 1024, 8192, 512, kSwz64), idescKM, ks);
-          // dK[key][d] += dS[query][key]^T Qs[query][d]
-          umma_bf16_ss(tmem + 320, umma_smem_desc(dsAddr + ks * 2048, 16384, 1024, kSwz128),
-                       umma_smem_desc(qsAddr + ks * 1024, 8192, 512, kSwz64), idescMM, ks);
-        }
-        umma_commit(out_full);
-      }
-      __syncwarp();
-      // S / dP of the next pair: their TMEM columns were read out long ago; Q,K,V,dO of the next stage are prefetched
-      if (pair + pair_step < P.n_pairs) issue_sdp(it + 1);
-    }
-  } else if (warp == kStoreWarp) {
-    // ============================== TMA store (+ projection-bias gradients) ==============================
-    // Lane 0 issues the stores; meanwhile all 32 lanes sum the columns of the three staging tiles
-    // (dq, dk, dv over all tokens = the bias gradients of the q/k/v projections).  Lane l owns the
-    // 8 channels of logical 16-byte chunk l%4 for rows == l/4 (mod 8).
-    {
-      WinCursor c0;
-      c0.init(S, 2 * pair0);
-      float cs[3][8];
-#pragma unroll
-      for (int t = 0; t < 3; ++t)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) cs[t][e] = 0.f;
-      int it = 0;
-      for (int pair = pair0; pair < P.n_pairs; pair += pair_step, ++it, c0.advance(S, step)) {
-        mbar_wait(so_ready, it & 1);
+    } else if (warp == kMmaWarpB) {
+      // ============================== MMA issuer ==============================
+      constexpr uint32_t idescS = umma_idesc_bf16(128, 64, 0, 0);     // A K-major, B K-major
+      constexpr uint32_t idescKM = umma_idesc_bf16(128, 32, 0, 1);    // A K-major (dS'),        B MN-major (K)
+      constexpr uint32_t idescMM = umma_idesc_bf16(128, 32, 1, 1);    // A MN-major (P^T, dS'^T), B MN-major (dO, Q)
+      // descriptors: everything but the 14-bit start-address field is loop-invariant, and adding (bytes >> 4)
+      // to a descriptor moves its start address -- one add per operand instead of rebuilding it
+      const uint64_t dKm = umma_smem_desc(0, 0, 512, kSwz64);         // Q, K, V, dO tiles read K-major
+      const uint64_t dMn = umma_smem_desc(0, 8192, 512, kSwz64);      // K, Q, dO tiles read MN-major
+      const uint64_t dPk = umma_smem_desc(0, 0, 1024, kSwz128);       // dS' read K-major
+      const uint64_t dPm = umma_smem_desc(0, 8192, 1024, kSwz128);    // P, dS' read MN-major (transposed)
+      const uint32_t stage0 = smem_u32(sStage) >> 4, p0 = smem_u32(sP) >> 4, ds0 = smem_u32(sDS) >> 4;
+      constexpr uint32_t W16 = kWinBytes >> 4;
+      auto issue_sdp = [&](int n) {
+        const int stage = n % kStagesB, phase = (n / kStagesB) & 1, b = n & 1;
+        mbar_wait(&full[stage], phase);
+        mbar_wait(&sdp_empty[b], ((n >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
         if (lane == 0) {
-          WinCursor c = c0;
+          const uint64_t sb = dKm + (stage0 + stage * (kStageBytesB >> 4));
+          const uint32_t tS = tmem + b * 128, tDP = tS + 64;
 #pragma unroll
-          for (int slot = 0; slot < 2; ++slot) {
-            const WinGeom g = window_geom(S, c);
-            issue_window_boxes<false>(S, P.dq, g, h * kD, sOut + slot * kWinBytes, nullptr);
-            issue_window_boxes<false>(S, P.dk, g, h * kD, sOut + kTile + slot * kWinBytes, nullptr);
-            issue_window_boxes<false>(S, P.dv, g, h * kD, sOut + 2 * kTile + slot * kWinBytes, nullptr);
-            c.advance(S, one);
-          }
-          tma_store_commit();
-        }
-        if (P.dcolsum) {
+          for (int ks = 0; ks < 4; ++ks)
+            umma_bf16_ss(tS, sb + ((ks >> 1) * W16 + (ks & 1) * 2), sb + ((kOffK >> 4) + (ks >> 1) * W16 + (ks & 1) * 2), idescS, ks);
 #pragma unroll
-          for (int t = 0; t < 3; ++t)
-#pragma unroll 4
-            for (int r0 = 0; r0 < 128; r0 += 8) {
-              const int row = r0 + (lane >> 2);
-              const uint4 a = *reinterpret_cast<const uint4*>(sOut + t * kTile + row * 64 + (((lane & 3) ^ ((row >> 1) & 3)) << 4));
-              const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) { float2 f = __bfloat1622float2(pa[e]); cs[t][2 * e] += f.x; cs[t][2 * e + 1] += f.y; }
-            }
+          for (int ks = 0; ks < 4; ++ks)
+            umma_bf16_ss(tDP, sb + ((kOffDO >> 4) + (ks >> 1) * W16 + (ks & 1) * 2), sb + ((kOffV >> 4) + (ks >> 1) * W16 + (ks & 1) * 2), idescS, ks);
+          umma_commit(&sdp_full[b]);
         }
         __syncwarp();
+      };
+      if (cnt > 0) issue_sdp(0);
+      if (cnt > 1) issue_sdp(1);
+      for (int n = 0; n < cnt; ++n) {
+        const int stage = n % kStagesB, b = n & 1;
+        trace_ev(P.trace, 3, n, 0);
+        mbar_wait(pds_full, n & 1);
+        mbar_wait(&out_empty[b], ((n >> 1) & 1) ^ 1);
+        trace_ev(P.trace, 3, n, 1);
+        tcgen05_fence_after();
         if (lane == 0) {
-          tma_store_wait_read<0>();
-          mbar_arrive(so_free);
+          const uint64_t sbm = dMn + (stage0 + stage * (kStageBytesB >> 4));
+          const uint64_t ap = dPm + p0, adk = dPk + ds0, adm = dPm + ds0;
+          const uint32_t tO = tmem + 256 + b * 96;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {   // 16 queries (dV, dK~) or 16 keys (dQ~) per step; ks < 4: window 0
+            const uint32_t wofs = (ks >> 2) * 2 * W16 + (ks & 3) * 64;     // 16 rows of window ks/4 inside a X0|Z|X1 region
+            // dV[key][d] += P[query][key]^T dO[query][d]
+            umma_bf16_ss(tO, ap + ks * 128, sbm + ((kOffDO >> 4) + wofs), idescMM, ks);
+            // dQ~[query][d] += dS'[query][key] K[key][d]
+            umma_bf16_ss(tO + 32, adk + ((ks >> 2) * 512 + (ks & 3) * 2), sbm + ((kOffK >> 4) + ks * 64), idescKM, ks);
+            // dK~[key][d] += dS'[query][key]^T Q[query][d]
+            umma_bf16_ss(tO + 64, adm + ks * 128, sbm + wofs, idescMM, ks);
+          }
+          umma_commit(&out_full[b]);
         }
+        __syncwarp();
+        trace_ev(P.trace, 3, n, 2);
+        if (n + 2 < cnt) issue_sdp(n + 2);
+        trace_ev(P.trace, 3, n, 3);
       }
-      if (lane == 0) tma_store_wait_all<0>();
+    } else if (warp == kStoreWarpB) {
+      // ============================== TMA store (+ column sums of dv) ==============================
+      // Each lane issues its share of the item's boxes; meanwhile all 32 lanes sum the columns of the dv staging
+      // tile (the v-projection bias gradient; dq / dk column sums come from the epilogue warps' registers).
+      // Lane l owns the 8 channels of logical 16-byte chunk l%4 for rows == l/4 (mod 8).
+      const CUtensorMap* const maps[3] = {P.dq, P.dk, P.dv};
+      const int slot_stride[3] = {kWinBytes, kWinBytes, kWinBytes};
+      uint8_t* const dst[3] = {sOut, sOut + kTile, sOut + 2 * kTile};
+      ItemCursor cur;
+      cur.seek(sc, item0);
+      float cs[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) cs[e] = 0.f;
+      for (int n = 0; n < cnt; ++n, cur.next_item(sc)) {
+        trace_ev(P.trace, 4, n, 0);
+        mbar_wait(so_ready, n & 1);
+        trace_ev(P.trace, 4, n, 1);
+        issue_item_boxes<false, 3>(S, item_geom(S, sc, cur, 0), item_geom(S, sc, cur, 1), cur.slot_valid(1) ? 2 : 1, h * kD, maps, dst,
+                                   slot_stride, nullptr, lane);
+        tma_store_commit();
+        if (P.dcolsum) {
+#pragma unroll 4
+          for (int r0 = 0; r0 < 128; r0 += 8) {
+            const int row = r0 + (lane >> 2);
+            const uint4 a = *reinterpret_cast<const uint4*>(sOut + 2 * kTile + row * 64 + (((lane & 3) ^ ((row >> 1) & 3)) << 4));
+            const uint32_t u[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { cs[2 * e] += __uint_as_float(u[e] << 16); cs[2 * e + 1] += __uint_as_float(u[e] & 0xffff0000u); }
+          }
+        }
+        tma_store_wait_read<0>();          // per thread: each lane waits for the smem reads of its own boxes
+        __syncwarp();
+        if (lane == 0) mbar_arrive(so_free);
+        trace_ev(P.trace, 4, n, 2);
+      }
+      tma_store_wait_all<0>();
       if (P.dcolsum) {
         const int C = P.nH * kD;
 #pragma unroll
-        for (int t = 0; t < 3; ++t)
+        for (int e = 0; e < 8; ++e) {
+          float v = cs[e];
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (lane < 4) atomicAdd(P.dcolsum + 2 * C + h * kD + lane * 8 + e, v);
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ============================== epilogue warpgroup: one thread per tile row ==============================
+    const int r = tid - kEpiWarp0 * 32;
+    const int slot = r >> 6, i = r & 63;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const int rsw = (r >> 1) & 3;                       // 64B-swizzle phase of this thread's tile row
+    setmaxnreg_inc<136>();
+    float cs[2][32];                                    // this row's share of the column sums of dq, dk (fp32, before rounding)
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float v = cs[t][e];
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            v += __shfl_xor_sync(0xffffffffu, v, 8);
-            v += __shfl_xor_sync(0xffffffffu, v, 16);
-            if (lane < 4) atomicAdd(P.dcolsum + t * C + h * kD + lane * 8 + e, v);
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int c = 0; c < 32; ++c) cs[t][c] = 0.f;
+    ItemCursor cur;
+    cur.seek(sc, item0);
+    for (int n = 0; n < cnt; ++n, cur.next_item(sc)) {
+      const int stage = n % kStagesB, b = n & 1;
+      const bool valid = cur.slot_valid(slot);
+      const uint8_t* base = sStage + stage * kStageBytesB;
+      const uint32_t tO = tmem + lane_base + 256 + b * 96;
+      if (warp == kEpiWarp0) trace_ev(P.trace, 1, n, 0);
+      mbar_wait(&out_full[b], (n >> 1) & 1);
+      tcgen05_fence_after();
+      if (warp == kEpiWarp0) trace_ev(P.trace, 1, n, 1);
+
+      mbar_wait(so_free, (n & 1) ^ 1);                  // previous item's stores have drained the staging tiles
+      if (warp == kEpiWarp0) trace_ev(P.trace, 1, n, 2);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {                     // t = 0: dQ~ with q row, t = 1: dK~ with k row
+        uint32_t g32[32];
+        tmem_ld_32x32b_x32(tO + 32 + t * 32, g32);
+        tmem_ld_wait();
+        uint8_t* orow = sOut + t * kTile + r * 64;
+        if (COS) {
+          // d/dx of x / max(||x||, eps) applied to G = dQ~ (which already carries 1/||x||): G - x^ (x^ . G)
+          const uint8_t* rowp = t == 0 ? base + slot * 2 * kWinBytes + i * 64 : base + kOffK + r * 64;
+          uint4 xq[4];
+          float ss = 0.f, dot = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            xq[c] = *reinterpret_cast<const uint4*>(rowp + ((c ^ rsw) << 4));
+            const uint32_t u[4] = {xq[c].x, xq[c].y, xq[c].z, xq[c].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float lo = __uint_as_float(u[e] << 16), hi = __uint_as_float(u[e] & 0xffff0000u);
+              ss = fmaf(lo, lo, ss); ss = fmaf(hi, hi, ss);
+              dot = fmaf(lo, __uint_as_float(g32[c * 8 + 2 * e]), dot);
+              dot = fmaf(hi, __uint_as_float(g32[c * 8 + 2 * e + 1]), dot);
+            }
           }
+          const float rinv = rsqrtf(fmaxf(ss, 1e-24f));
+          const float proj = rinv >= 1e12f ? 0.f : -dot * rinv * rinv;     // below eps the normalisation is x / eps: no projection
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t u[4] = {xq[c].x, xq[c].y, xq[c].z, xq[c].w};
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float lo = __uint_as_float(u[e] << 16), hi = __uint_as_float(u[e] & 0xffff0000u);
+              const float o0 = fmaf(lo, proj, __uint_as_float(g32[c * 8 + 2 * e])), o1 = fmaf(hi, proj, __uint_as_float(g32[c * 8 + 2 * e + 1]));
+              if (valid) { cs[t][c * 8 + 2 * e] += o0; cs[t][c * 8 + 2 * e + 1] += o1; }
+              o[e] = pack_bf16x2(o0, o1);
+            }
+            *reinterpret_cast<uint4*>(orow + ((c ^ rsw) << 4)) = valid ? make_uint4(o[0], o[1], o[2], o[3]) : make_uint4(0, 0, 0, 0);
+          }
+        } else {
+          if (valid) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) cs[t][c] += __uint_as_float(g32[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<uint4*>(orow + ((c ^ rsw) << 4)) =
+                valid ? make_uint4(pack_bf16x2(__uint_as_float(g32[c * 8 + 0]), __uint_as_float(g32[c * 8 + 1])),
+                                   pack_bf16x2(__uint_as_float(g32[c * 8 + 2]), __uint_as_float(g32[c * 8 + 3])),
+                                   pack_bf16x2(__uint_as_float(g32[c * 8 + 4]), __uint_as_float(g32[c * 8 + 5])),
+                                   pack_bf16x2(__uint_as_float(g32[c * 8 + 6]), __uint_as_float(g32[c * 8 + 7])))
+                      : make_uint4(0, 0, 0, 0);
+        }
+      }
+      {
+        uint32_t gv[32];
+        tmem_ld_32x32b_x32(tO, gv);
+        tmem_ld_wait();
+        uint8_t* orow = sOut + 2 * kTile + r * 64;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(orow + ((c ^ rsw) << 4)) =
+              valid ? make_uint4(pack_bf16x2(__uint_as_float(gv[c * 8 + 0]), __uint_as_float(gv[c * 8 + 1])),
+                                 pack_bf16x2(__uint_as_float(gv[c * 8 + 2]), __uint_as_float(gv[c * 8 + 3])),
+                                 pack_bf16x2(__uint_as_float(gv[c * 8 + 4]), __uint_as_float(gv[c * 8 + 5])),
+                                 pack_bf16x2(__uint_as_float(gv[c * 8 + 6]), __uint_as_float(gv[c * 8 + 7])))
+                    : make_uint4(0, 0, 0, 0);
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&out_empty[b]);                       // accumulators read out
+      mbar_arrive(&empty[stage]);                       // q / k rows read: the stage can be refilled
+      if (warp == kEpiWarp0) trace_ev(P.trace, 1, n, 3);
+      fence_proxy_async_smem();
+      mbar_arrive(so_ready);
+      if (warp == kEpiWarp0) trace_ev(P.trace, 1, n, 4);
+    }
+    // column sums of dq, dk over this CTA's tokens: transpose-reduce over the warp's 32 rows (lane l ends up
+    // with channel l), one atomic per lane and tensor
+    if (P.dcolsum) {
+      const int C = P.nH * kD;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+          for (int c = 0; c < off; ++c) {
+            const bool up = (lane & off) != 0;
+            const float send = up ? cs[t][c] : cs[t][c + off];
+            const float keep = up ? cs[t][c + off] : cs[t][c];
+            cs[t][c] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+        }
+        atomicAdd(P.dcolsum + t * C + h * kD + lane, cs[t][0]);
       }
     }
   } else {
-    // ============================== softmax / epilogue (256 threads: 2 per row) ==============================
+    // ============================== softmax (256 threads: 2 per row) ==============================
+    setmaxnreg_inc<160>();
     const int r = tid & 127, half = tid >> 7;
     const int slot = r >> 6, i = r & 63;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const float hscale = COS ? __ldg(P.head_scale + h) : 1.f;
-    const int rsw = (r >> 1) & 3;                       // 64B-swizzle phase of this thread's tile row
-    float dbacc[32];                                    // dbias[i][32*half + j] over window-ordered tiles
+    const float hscale = COS ? __ldg(P.head_scale + h) : P.scale;
+    const float* bias_h = P.bias ? P.bias + (size_t)h * kN * kN : nullptr;
+    float* const gdb_head = P.dbias ? P.dbias + (size_t)h * kN * kN : nullptr;
+    uint8_t* prow = sP + slot * 16384 + i * 128;
+    uint8_t* drow = sDS + slot * 16384 + i * 128;
+    float dbacc[32];                                    // dbias[tile row i][32*half + j] of the current wrap class
 #pragma unroll
     for (int j = 0; j < 32; ++j) dbacc[j] = 0.f;
     float dscale_acc = 0.f;
-    float* const gdb_head = P.dbias ? P.dbias + (size_t)h * kN * kN : nullptr;
-    const int trole = warp == 0 ? 0 : (warp == 7 ? 1 : -1);
-#define TRB(item, ev) do { if (trole >= 0) trace_evb(P, trole, item, ev); } while (0)
+    const int trole = warp == 0 ? 0 : -1;
+#define TRB(item, ev) do { if (trole >= 0) trace_ev(P.trace, trole, item, ev); } while (0)
 
-    WinCursor cur;
-    cur.init(S, 2 * pair0 + slot);
-    int it = 0;
-    for (int pair = pair0; pair < P.n_pairs; pair += pair_step, ++it, cur.advance(S, step)) {
-      const int stage = it % kBwdStages, phase = (it / kBwdStages) & 1;
-      const int w = pair * 2 + slot;
-      const WinGeom g = window_geom(S, cur);
-      const bool masked = (MASK == MMN_MASK_SHIFT) && g.cls != 0;
-      const bool permuted = (MASK == MMN_MASK_SHIFT) && (g.cls & 6) != 0;
-      const uint8_t* pos = sPos + g.cls * 64;
-      const int ipos = permuted ? pos[i] : i;
-      const uint8_t* base = sIn + stage * 4 * kTile;
-      const float lse_i = __ldg(P.lse + ((size_t)w * P.nH + h) * kN + ipos);
+    auto flush_dbias = [&](int cls) {
+      const uint8_t* pos = sPos + cls * 64;
+      float* rowp = gdb_head + (int)pos[i] * kN;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { atomicAdd(rowp + pos[half * 32 + j], dbacc[j]); dbacc[j] = 0.f; }
+    };
 
-      // ---- (a) row norm; scaled copy of this thread's q row (half 0) / k row (half 1)
-      TRB(it, 0);
+    ItemCursor cur;
+    cur.seek(sc, item0);
+    int cls_loaded = -1;
+    for (int n = 0; n < cnt; ++n, cur.next_item(sc)) {
+      const int stage = n % kStagesB, phase = (n / kStagesB) & 1, b = n & 1;
+      const ItemGeom geo = item_geom(S, sc, cur, slot);
+      const bool valid = cur.slot_valid(slot);
+      if (cur.cls != cls_loaded) {                      // rare: at most 8 times per CTA
+        if (gdb_head && cls_loaded >= 0) flush_dbias(cls_loaded);
+        named_bar_sync(3, kSoftmaxThreadsB);            // everyone is done reading the old table
+        build_class_table(sTbl, kTblLd, bias_h, sPos + cur.cls * 64, S, cur.cls, MASK == MMN_MASK_SHIFT, tid, kSoftmaxThreadsB);
+        cls_loaded = cur.cls;
+      }
+      const int ipos = sPos[cur.cls * 64 + i];
+      const uint8_t* base = sStage + stage * kStageBytesB;
+      const float lse2 = valid ? __ldg(P.lse + ((size_t)geo.w * P.nH + h) * kN + ipos) * kLog2e : 0.f;
+
+      // ---- (a) row norms: half 0 -> logit multiplier of query row r, half 1 -> 1/||k_r||
+      TRB(n, 0);
       mbar_wait(&full[stage], phase);
-      TRB(it, 1);
-      float rinv = 1.f;                                 // 1 / max(||row||, eps)
-      {
-        const uint8_t* rowp = base + half * kTile + r * 64;
-        uint4 raw4[4];
-        float ss = 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          raw4[c] = *reinterpret_cast<const uint4*>(rowp + (c << 4));   // physical chunk order: fine for a sum and a copy
-          const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&raw4[c]);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) { float2 f = __bfloat1622float2(pa[e]); ss += f.x * f.x + f.y * f.y; }
-        }
-        if (COS) rinv = rsqrtf(fmaxf(ss, 1e-24f));
-        const float mul = COS ? rinv * hscale : P.scale;
-        uint8_t* dst = (half == 0 ? sQs : sKs) + r * 64;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&raw4[c]);
-          float2 f0 = __bfloat1622float2(pa[0]), f1 = __bfloat1622float2(pa[1]), f2 = __bfloat1622float2(pa[2]), f3 = __bfloat1622float2(pa[3]);
-          *reinterpret_cast<uint4*>(dst + (c << 4)) = make_uint4(pack_bf16x2(f0.x * mul, f0.y * mul), pack_bf16x2(f1.x * mul, f1.y * mul),
-                                                                 pack_bf16x2(f2.x * mul, f2.y * mul), pack_bf16x2(f3.x * mul, f3.y * mul));
-        }
-        if (COS) { if (half == 0) sRq[r] = rinv * hscale; else sRk[r] = rinv; }
+      TRB(n, 1);
+      if (COS) {
+        const float ss = row_sumsq(half == 0 ? base + slot * 2 * kWinBytes + i * 64 : base + kOffK + r * 64);
+        const float rinv = rsqrtf(fmaxf(ss, 1e-24f));
+        if (half == 0) sA[b * 128 + r] = rinv * hscale; else sRk[b * 128 + r] = rinv;
       }
-      int rid_i = 0;
-      if (masked) { rid_i = region_id(S, g, ipos); if (half == 0) sRid[r] = rid_i; }
-      named_bar_sync(1, kSoftmaxThreads);
-      TRB(it, 2);
+      named_bar_sync(1, kSoftmaxThreadsB);
+      TRB(n, 2);
+      const float a_i = COS ? sA[b * 128 + r] : hscale;
+      const float4* krow = reinterpret_cast<const float4*>(sRk + b * 128 + slot * 64 + half * 32);
 
-      // ---- (b) additive terms of this thread's 32 logits (bias, mask) while S / dP finish
+      // ---- (b) additive terms of this thread's 32 logits (table, mask, -lse), log2 domain
       float p[32];
-      const float* mtile = (MASK == MMN_MASK_TENSOR) ? P.mask + (size_t)(w % P.mask_windows) * kN * kN : nullptr;
-      if (!permuted) {
-        const float4* brow = reinterpret_cast<const float4*>(sBias + ipos * kBiasLd + half * 32);
-        const float4* mrow = mtile ? reinterpret_cast<const float4*>(mtile + ipos * kN + half * 32) : nullptr;
+      {
+        const float4* trow = reinterpret_cast<const float4*>(sTbl + i * kTblLd + half * 32);
+        const float* mrow = (MASK == MMN_MASK_TENSOR) ? P.mask + ((size_t)(geo.w % P.mask_windows) * kN + ipos) * kN + half * 32 : nullptr;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          float4 bb = P.bias ? brow[j4] : make_float4(0.f, 0.f, 0.f, 0.f);
-          if (mrow) { float4 mm = __ldg(mrow + j4); bb.x += mm.x; bb.y += mm.y; bb.z += mm.z; bb.w += mm.w; }
-          p[j4 * 4 + 0] = bb.x; p[j4 * 4 + 1] = bb.y; p[j4 * 4 + 2] = bb.z; p[j4 * 4 + 3] = bb.w;
-        }
-      } else {
-        const uint32_t* pj4 = reinterpret_cast<const uint32_t*>(pos + half * 32);
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const uint32_t pk = pj4[j4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int jp = (pk >> (8 * e)) & 0xff;
-            float add = P.bias ? sBias[ipos * kBiasLd + jp] : 0.f;
-            if (mtile) add += __ldg(mtile + ipos * kN + jp);
-            p[j4 * 4 + e] = add;
+          float4 tt = trow[j4];
+          if (MASK == MMN_MASK_TENSOR) {
+            const float4 mm = __ldg(reinterpret_cast<const float4*>(mrow) + j4);
+            tt.x = fmaf(mm.x, kLog2e, tt.x); tt.y = fmaf(mm.y, kLog2e, tt.y); tt.z = fmaf(mm.z, kLog2e, tt.z); tt.w = fmaf(mm.w, kLog2e, tt.w);
           }
+          p[j4 * 4 + 0] = tt.x - lse2; p[j4 * 4 + 1] = tt.y - lse2; p[j4 * 4 + 2] = tt.z - lse2; p[j4 * 4 + 3] = tt.w - lse2;
         }
-      }
-      if (masked) {
-        const int* rids = sRid + slot * 64 + half * 32;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) if (rids[j] != rid_i) p[j] -= 100.f;
       }
 
       // ---- (c) S and dP from TMEM; P = exp(S - lse); partial delta and d(logit scale) sums
-      TRB(it, 3);
-      mbar_wait(sdp_full, it & 1);
+      TRB(n, 3);
+      mbar_wait(&sdp_full[b], (n >> 1) & 1);
       tcgen05_fence_after();
-      TRB(it, 4);
-      uint32_t raw[32], dpr[32];
-      tmem_ld_32x32b_x32(tmem + lane_base + slot * 64 + half * 32, raw);
-      tmem_ld_32x32b_x32(tmem + lane_base + 128 + slot * 64 + half * 32, dpr);
-      tmem_ld_wait();
-      tcgen05_fence_before();
-      mbar_arrive(sdp_empty);
-      TRB(it, 5);
-      const float a_i = COS ? sRq[r] : P.scale;
-      const float4* krow = reinterpret_cast<const float4*>(sRk + slot * 64 + half * 32);
-      const float lneg = -lse_i * kLog2e;
-      float delta = 0.f, acc_pdt = 0.f, acc_pt = 0.f;   // sum p dp, sum p dp t, sum p t   (t = raw * rk)
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        float4 kk = COS ? krow[j4] : make_float4(1.f, 1.f, 1.f, 1.f);
-        const float rk[4] = {kk.x, kk.y, kk.z, kk.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j = j4 * 4 + e;
-          const float t = __uint_as_float(raw[j]) * rk[e];
-          const float pj = fast_exp2(fmaf(fmaf(t, a_i, p[j]), kLog2e, lneg));
-          const float pd = pj * __uint_as_float(dpr[j]);
-          p[j] = pj;
-          delta += pd;
-          acc_pdt = fmaf(pd, t, acc_pdt);
-          acc_pt = fmaf(pj, t, acc_pt);
-        }
-      }
-      sDelta[half * 128 + r] = delta;
-      // P (bf16) can go out before delta is known
+      TRB(n, 4);
+      uint32_t dpr[32];
+      float delta = 0.f, acc_pdu = 0.f, acc_pu = 0.f;   // sum p dp, sum p dp u, sum p u   (u = the logit without bias / mask)
       {
-        uint8_t* prow = sP + slot * 16384 + r * 128;
+        uint32_t raw[32];
+        tmem_ld_32x32b_x32(tmem + lane_base + b * 128 + half * 32, raw);
+        tmem_ld_32x32b_x32(tmem + lane_base + b * 128 + 64 + half * 32, dpr);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        mbar_arrive(&sdp_empty[b]);
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          *reinterpret_cast<uint4*>(prow + (((half * 4 + c) ^ (r & 7)) << 4)) =
-              make_uint4(pack_bf16x2(p[c * 8 + 0], p[c * 8 + 1]), pack_bf16x2(p[c * 8 + 2], p[c * 8 + 3]),
-                         pack_bf16x2(p[c * 8 + 4], p[c * 8 + 5]), pack_bf16x2(p[c * 8 + 6], p[c * 8 + 7]));
-      }
-      TRB(it, 6);
-      named_bar_sync(2, kSoftmaxThreads);
-      TRB(it, 7);
-      delta += sDelta[(half ^ 1) * 128 + r];
-
-      // ---- (d) dS = P o (dP - delta), in place of P; dbias and d(logit scale) reductions
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 kk = COS ? krow[j4] : make_float4(1.f, 1.f, 1.f, 1.f);
+          const float rk[4] = {kk.x, kk.y, kk.z, kk.w};
 #pragma unroll
-      for (int j = 0; j < 32; ++j) p[j] *= __uint_as_float(dpr[j]) - delta;
-      if (COS) dscale_acc += (acc_pdt - delta * acc_pt) * (a_i / hscale);   // sum_j dS_ij cos_ij, cos = raw rk_j rq_i
-      if (P.dbias) {
-        if (!permuted) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) dbacc[j] += p[j];
-        } else {
-          const uint32_t* pj4 = reinterpret_cast<const uint32_t*>(pos + half * 32);
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const uint32_t pk = pj4[j4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) atomicAdd(&sDb[ipos * kBiasLd + ((pk >> (8 * e)) & 0xff)], p[j4 * 4 + e]);
+          for (int e = 0; e < 4; ++e) {
+            const int j = j4 * 4 + e;
+            const float u = __uint_as_float(raw[j]) * (COS ? rk[e] * a_i : a_i);
+            const float pj = fast_exp2(fmaf(u, kLog2e, p[j]));
+            const float dpj = __uint_as_float(dpr[j]);
+            delta = fmaf(pj, dpj, delta);
+            if (COS) {
+              acc_pdu = fmaf(pj * dpj, u, acc_pdu);
+              acc_pu = fmaf(pj, u, acc_pu);
+            }
+            p[j] = pj;
           }
         }
       }
-
-      // ---- (e) dS (bf16) into its 128B-swizzled tile
-      {
-        uint8_t* drow = sDS + slot * 16384 + r * 128;
+      sDelta[half * 128 + r] = delta;
+      TRB(n, 5);
+      // P (bf16) can go out before delta is known; the previous item's gradient MMAs must have finished reading P / dS'
+      if (n > 0) mbar_wait(&out_full[b ^ 1], ((n - 1) >> 1) & 1);
+      TRB(n, 6);
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          *reinterpret_cast<uint4*>(drow + (((half * 4 + c) ^ (r & 7)) << 4)) =
-              make_uint4(pack_bf16x2(p[c * 8 + 0], p[c * 8 + 1]), pack_bf16x2(p[c * 8 + 2], p[c * 8 + 3]),
-                         pack_bf16x2(p[c * 8 + 4], p[c * 8 + 5]), pack_bf16x2(p[c * 8 + 6], p[c * 8 + 7]));
+      for (int c = 0; c < 4; ++c) {
+        uint4 v4 = make_uint4(pack_bf16x2(p[c * 8 + 0], p[c * 8 + 1]), pack_bf16x2(p[c * 8 + 2], p[c * 8 + 3]),
+                              pack_bf16x2(p[c * 8 + 4], p[c * 8 + 5]), pack_bf16x2(p[c * 8 + 6], p[c * 8 + 7]));
+        if (!valid) v4 = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(prow + (((half * 4 + c) ^ (i & 7)) << 4)) = v4;
+      }
+      named_bar_sync(2, kSoftmaxThreadsB);
+      TRB(n, 7);
+      delta += sDelta[(half ^ 1) * 128 + r];
+
+      // ---- (d) dS = P o (dP - delta): dbias; dS' = dS o c into the MMA tile; d(logit scale)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) p[j] *= __uint_as_float(dpr[j]) - delta;
+      if (valid) {
+        if (COS) dscale_acc += acc_pdu - delta * acc_pu;      // sum_j dS_ij u_ij  (u = logit_scale x cos)
+        if (gdb_head) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dbacc[j] += p[j];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float cj[8];
+        if (COS) {
+          const float4 k0 = krow[c * 2], k1 = krow[c * 2 + 1];
+          cj[0] = k0.x * a_i; cj[1] = k0.y * a_i; cj[2] = k0.z * a_i; cj[3] = k0.w * a_i;
+          cj[4] = k1.x * a_i; cj[5] = k1.y * a_i; cj[6] = k1.z * a_i; cj[7] = k1.w * a_i;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) cj[e] = a_i;
+        }
+        uint4 v4 = make_uint4(pack_bf16x2(p[c * 8 + 0] * cj[0], p[c * 8 + 1] * cj[1]), pack_bf16x2(p[c * 8 + 2] * cj[2], p[c * 8 + 3] * cj[3]),
+                              pack_bf16x2(p[c * 8 + 4] * cj[4], p[c * 8 + 5] * cj[5]), pack_bf16x2(p[c * 8 + 6] * cj[6], p[c * 8 + 7] * cj[7]));
+        if (!valid) v4 = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(drow + (((half * 4 + c) ^ (i & 7)) << 4)) = v4;
       }
       fence_proxy_async_smem();
       mbar_arrive(pds_full);
-      TRB(it, 8);
-
-      // ---- (f) epilogue: half 0 -> dQ row r and dV channels [0,16); half 1 -> dK row r and dV channels [16,32)
-      mbar_wait(out_full, it & 1);
-      tcgen05_fence_after();
-      TRB(it, 9);
-      uint32_t g32[32], gv[16];
-      tmem_ld_32x32b_x32(tmem + lane_base + (half == 0 ? 288 : 320), g32);
-      tmem_ld_32x32b_x16(tmem + lane_base + 256 + half * 16, gv);
-      tmem_ld_wait();
-      tcgen05_fence_before();
-      float outv[32];
-      if (COS) {
-        // d/dx of x / max(||x||, eps): (g - xhat (xhat . g)) / ||x||, xhat = x * rinv; x re-read from the stage tile
-        float xrow[32];
-        const uint8_t* rowp = base + half * kTile + r * 64;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint4 a = *reinterpret_cast<const uint4*>(rowp + ((c ^ rsw) << 4));
-          const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) { float2 f = __bfloat1622float2(pa[e]); xrow[c * 8 + 2 * e] = f.x * rinv; xrow[c * 8 + 2 * e + 1] = f.y * rinv; }
-        }
-        float proj = 0.f;
-#pragma unroll
-        for (int c = 0; c < 32; ++c) proj = fmaf(xrow[c], __uint_as_float(g32[c]), proj);
-        if (rinv >= 1e12f) proj = 0.f;
-#pragma unroll
-        for (int c = 0; c < 32; ++c) outv[c] = (__uint_as_float(g32[c]) - xrow[c] * proj) * rinv;
-      } else {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) outv[c] = __uint_as_float(g32[c]);
-      }
-      mbar_arrive(&empty[stage]);                       // this thread is done with the stage's tiles
-      TRB(it, 10);
-      mbar_wait(so_free, (it & 1) ^ 1);
-      TRB(it, 11);                 // previous pair's stores have drained the staging tiles
-      {
-        uint8_t* orow = sOut + half * kTile + r * 64;   // dQ tile (half 0) or dK tile (half 1)
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          *reinterpret_cast<uint4*>(orow + ((c ^ rsw) << 4)) = make_uint4(pack_bf16x2(outv[c * 8 + 0], outv[c * 8 + 1]), pack_bf16x2(outv[c * 8 + 2], outv[c * 8 + 3]),
-                                                                          pack_bf16x2(outv[c * 8 + 4], outv[c * 8 + 5]), pack_bf16x2(outv[c * 8 + 6], outv[c * 8 + 7]));
-        uint8_t* vrow = sOut + 2 * kTile + r * 64;
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-          *reinterpret_cast<uint4*>(vrow + (((half * 2 + c) ^ rsw) << 4)) =
-              make_uint4(pack_bf16x2(__uint_as_float(gv[c * 8 + 0]), __uint_as_float(gv[c * 8 + 1])), pack_bf16x2(__uint_as_float(gv[c * 8 + 2]), __uint_as_float(gv[c * 8 + 3])),
-                         pack_bf16x2(__uint_as_float(gv[c * 8 + 4]), __uint_as_float(gv[c * 8 + 5])), pack_bf16x2(__uint_as_float(gv[c * 8 + 6]), __uint_as_float(gv[c * 8 + 7])));
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(so_ready);
-      TRB(it, 12);
+      TRB(n, 8);
     }
 #undef TRB
 
-    // ---- cross-window reductions: dbias (registers + shared table) and d(logit scale)
-    if (P.dbias) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) atomicAdd(gdb_head + i * kN + half * 32 + j, dbacc[j]);
-      named_bar_sync(1, kSoftmaxThreads);               // all shared-memory atomics done
-      for (int e = tid; e < kN * kN; e += kSoftmaxThreads) {
-        float v = sDb[(e >> 6) * kBiasLd + (e & 63)];
-        if (v != 0.f) atomicAdd(gdb_head + e, v);
-      }
-    }
+    // ---- cross-window reductions: dbias (registers) and d(logit scale)
+    if (gdb_head && cls_loaded >= 0) flush_dbias(cls_loaded);
     if (COS && P.dhead_scale) {
+      dscale_acc /= hscale;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) dscale_acc += __shfl_xor_sync(0xffffffffu, dscale_acc, o);
       if (lane == 0) sRed[warp] = dscale_acc;
-      named_bar_sync(2, kSoftmaxThreads);
+      named_bar_sync(2, kSoftmaxThreadsB);
       if (tid == 0) {
         float tot = 0.f;
         for (int x = 0; x < 8; ++x) tot += sRed[x];
@@ -498,11 +537,11 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) tmem_dealloc<kBwdTmemCols>(tmem);
+  if (warp == kMmaWarpB) tmem_dealloc<kBwdTmemCols>(tmem);
 }
 
-constexpr size_t kBwdSmemBytes = 1024 + kBwdStages * 4 * kTile + 4 * 16384 + 2 * kTile + 3 * kTile + 2 * kN * kBiasLd * 4 +
-                                 (128 + 128 + 256 + 8 + 128) * 4 + 512 + 16 * 8;
+constexpr size_t kBwdSmemBytes = 1024 + kStagesB * kStageBytesB + 2 * kPRegion + 3 * kTile + kN * kTblLd * 4 +
+                                 (256 + 256 + 256 + 8) * 4 + 512 + 24 * 8;
 
 inline const char* bwd_why_not_impl(const mmn_winattn_desc* d) {
   const char* w = fwd_why_not_impl(d);
@@ -516,6 +555,7 @@ inline int winattn_bwd_launch(const mmn_winattn_desc* d, const void* q, const vo
                               void* dv, float* dbias, float* dhead_scale, float* dcolsum, cudaStream_t st, char* err, size_t errlen) {
   BwdParams P;
   P.S = shape_from(d);
+  P.sc = make_sched(P.S, d->batch);
   const int C = d->num_heads * d->head_dim;
   const int B = d->batch;
   if (!make_window_maps(P.q, q, d->q_row_stride, B, C, P.S) || !make_window_maps(P.k, k, d->k_row_stride, B, C, P.S) ||
@@ -526,14 +566,11 @@ inline int winattn_bwd_launch(const mmn_winattn_desc* d, const void* q, const vo
     return MMN_ERR_CUDA;
   }
   P.nH = d->num_heads;
-  P.n_pairs = P.S.n_windows / 2;
-  P.cosine = d->score_kind == MMN_SCORE_COSINE;
-  P.mask_kind = d->mask_kind;
   P.mask_windows = d->mask_windows > 0 ? d->mask_windows : 1;
   P.scale = d->scale;
   P.bias = bias; P.head_scale = head_scale; P.mask = mask; P.lse = lse;
   P.dbias = bias ? dbias : nullptr;
-  P.dhead_scale = P.cosine ? dhead_scale : nullptr;
+  P.dhead_scale = d->score_kind == MMN_SCORE_COSINE ? dhead_scale : nullptr;
   P.dcolsum = dcolsum;
   P.trace = nullptr;
   const char* trace_path = getenv("MMN_TC_TRACE_BWD");
@@ -547,39 +584,22 @@ inline int winattn_bwd_launch(const mmn_winattn_desc* d, const void* q, const vo
       {winattn_bwd_tc_kernel<false, MMN_MASK_NONE>, winattn_bwd_tc_kernel<false, MMN_MASK_SHIFT>, winattn_bwd_tc_kernel<false, MMN_MASK_TENSOR>},
       {winattn_bwd_tc_kernel<true, MMN_MASK_NONE>, winattn_bwd_tc_kernel<true, MMN_MASK_SHIFT>, winattn_bwd_tc_kernel<true, MMN_MASK_TENSOR>}};
   static std::once_flag once;
-  static int num_sms = 148;
   std::call_once(once, [] {
     for (int c = 0; c < 2; ++c)
       for (int m = 0; m < 3; ++m) cudaFuncSetAttribute(kernels[c][m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   });
-  const Kern kern = kernels[P.cosine ? 1 : 0][P.mask_kind];
-  int per_head = num_sms / P.nH;
+  const Kern kern = kernels[d->score_kind == MMN_SCORE_COSINE ? 1 : 0][d->mask_kind];
+  int per_head = num_sms_cached() / P.nH;
   if (per_head < 1) per_head = 1;
-  if (per_head > P.n_pairs) per_head = P.n_pairs;
-  kern<<<per_head * P.nH, kFwdThreads, kBwdSmemBytes, st>>>(P);
+  if (per_head > P.sc.n_items) per_head = P.sc.n_items;
+  P.per_head = per_head;
+  kern<<<per_head * P.nH, kBwdThreads, kBwdSmemBytes, st>>>(P);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(err, errlen, "winattn_bwd_tc_kernel: %s", cudaGetErrorString(e));
     return MMN_ERR_CUDA;
   }
-  if (P.trace) {
-    static long long host[5 * 32 * 16];
-    cudaStreamSynchronize(st);
-    cudaMemcpy(host, P.trace, sizeof(host), cudaMemcpyDeviceToHost);
-    cudaFree(P.trace);
-    if (FILE* f = fopen(trace_path, "w")) {
-      for (int role = 0; role < 5; ++role)
-        for (int item = 0; item < 32; ++item) {
-          fprintf(f, "%d %d", role, item);
-          for (int ev = 0; ev < 16; ++ev) fprintf(f, " %lld", host[(role * 32 + item) * 16 + ev]);
-          fprintf(f, "\n");
-        }
-      fclose(f);
-    }
-  }
+  if (P.trace) dump_trace(P.trace, trace_path, st);
   return MMN_OK;
 }
 
