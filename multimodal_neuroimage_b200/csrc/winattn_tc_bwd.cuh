@@ -13,15 +13,15 @@
 // dq = dQ~ - q^ (q^ . dQ~) (likewise dk), exact because c already carries 1/||q|| 1/||k|| x logit scale.
 // rowsum(P o dP) is computed in-tile, so `out` is never read.
 //
-// 512 threads, one CTA per SM:
-//   warps 0-7    softmax: two threads per query row (32 keys each); never wait for the gradient MMAs.
+// 768 threads, one CTA per SM (the kernel is latency-bound: 4 softmax warps per scheduler hide what 2 cannot):
+//   warps 0-15   softmax: FOUR threads per query row (16 keys each); never wait for the gradient MMAs.
 //                dbias accumulates in registers in the item's tile order and is flushed through the
 //                class's permutation when the wrap class changes (at most 8 times per CTA).
-//   warps 8-11   epilogue: one thread per row, dQ~/dK~/dV out of TMEM -> normalisation Jacobian ->
-//                bf16 staging tiles.
-//   warp 12 TMA producer, warp 13 MMA issuer, warp 14 TMA store + column sums of dq/dk/dv
-//   (= the q/k/v projection bias gradients), warp 15 idle.
-// Register budget by warpgroup (setmaxnreg): softmax 160, epilogue 136, the rest 56.
+//   warps 16-19  epilogue: one thread per row, dQ~/dK~/dV out of TMEM -> normalisation Jacobian ->
+//                bf16 staging tiles; column sums of dq, dk (= q/k projection bias gradients) by a
+//                warp transpose-reduce.
+//   warp 20 TMA producer, warp 21 MMA issuer, warp 22 TMA store + column sums of dv, warp 23 idle.
+// Register budget by warpgroup (setmaxnreg): softmax 80 (= launch), epilogue 104, the rest 56: 512*80 + 128*104 + 128*56 = 768*80.
 #pragma once
 
 #include "winattn_tc_fwd.cuh"
@@ -31,9 +31,10 @@ namespace mmn { namespace tc {
 constexpr int kStagesB = 3;
 constexpr int kStageBytesB = 2 * kQRegion + 2 * kTile;   // Q0|Z|Q1, K0 K1, V0 V1, dO0|Z|dO1
 constexpr int kOffK = kQRegion, kOffV = kQRegion + kTile, kOffDO = kQRegion + 2 * kTile;
-constexpr int kSoftmaxThreadsB = 256, kEpiThreads = 128;
-constexpr int kEpiWarp0 = 8, kProducerWarpB = 12, kMmaWarpB = 13, kStoreWarpB = 14;
-constexpr int kBwdThreads = 512;
+constexpr int kSoftmaxThreadsB = 512, kEpiThreads = 128;
+constexpr int kKeysPerThread = 16;                  // 64 keys / 4 threads per row
+constexpr int kEpiWarp0 = 16, kProducerWarpB = 20, kMmaWarpB = 21, kStoreWarpB = 22;
+constexpr int kBwdThreads = 768;
 constexpr int kBwdTmemCols = 512;     // S[b] at 128 b, dP[b] at 128 b + 64; dV|dQ~|dK~ [b] at 256 + 96 b
 
 struct BwdParams {
@@ -68,10 +69,11 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
   float* sTbl = reinterpret_cast<float*>(sOut + 3 * kTile);   // [64][kTblLd]
   float* sA = sTbl + kN * kTblLd;                         // [2][128] logit multiplier per query row (natural units)
   float* sRk = sA + 256;                                  // [2][128] 1/||k|| per key
-  float* sDelta = sRk + 256;                              // [2][128] partial deltas
-  float* sRed = sDelta + 256;                             // 8 floats: dhead_scale per softmax warp
-  uint8_t* sPos = reinterpret_cast<uint8_t*>(sRed + 8);   // [8][64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sPos + 512);
+  float* sDelta = sRk + 256;                              // [4][128] partial deltas
+  float* sRed = sDelta + 512;                             // 16 floats: dhead_scale per softmax warp
+  uint8_t* sPos = reinterpret_cast<uint8_t*>(sRed + 16);  // [8][64]
+  int4* sItem = reinterpret_cast<int4*>(sPos + 512);      // [8] ring: {wrap class, window index of slot 0, of slot 1, valid slots} of item n & 7
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sItem + 8);
   uint64_t* full = bars;                                  // [kStagesB]
   uint64_t* empty = bars + kStagesB;                      // [kStagesB] (128 arrivals: epilogue threads)
   uint64_t* sdp_full = bars + 2 * kStagesB;               // [2]
@@ -79,9 +81,9 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
   uint64_t* pds_full = sdp_full + 4;                      // 256 arrivals
   uint64_t* out_full = sdp_full + 5;                      // [2]
   uint64_t* out_empty = sdp_full + 7;                     // [2] 128 arrivals
-  uint64_t* so_ready = sdp_full + 9;                      // 128 arrivals
-  uint64_t* so_free = sdp_full + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdp_full + 11);
+  uint64_t* so_ready = sdp_full + 9;                      // [3] one per staging tile (dq, dk, dv), 128 arrivals
+  uint64_t* so_free = sdp_full + 12;                      // [3]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdp_full + 15);
 
   const WinShape& S = P.S;
   const Sched& sc = P.sc;
@@ -100,7 +102,8 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       mbar_init(&sdp_full[b], 1); mbar_init(&sdp_empty[b], kSoftmaxThreadsB);
       mbar_init(&out_full[b], 1); mbar_init(&out_empty[b], kEpiThreads);
     }
-    mbar_init(pds_full, kSoftmaxThreadsB); mbar_init(so_ready, kEpiThreads); mbar_init(so_free, 1);
+    mbar_init(pds_full, kSoftmaxThreadsB);
+    for (int t = 0; t < 3; ++t) { mbar_init(&so_ready[t], kEpiThreads); mbar_init(&so_free[t], 1); }
     fence_barrier_init();
   }
   if (warp == kProducerWarpB && lane == 0)
@@ -129,12 +132,15 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
         mbar_wait(&empty[stage], phase ^ 1);
         trace_ev(P.trace, 2, n, 1);
         const int nvalid = cur.slot_valid(1) ? 2 : 1;
-        if (lane == 0) mbar_arrive_expect_tx(&full[stage], nvalid * 4 * kWinBytes);
+        const ItemGeom g0 = item_geom(S, sc, cur, 0), g1 = item_geom(S, sc, cur, 1);
+        if (lane == 0) {
+          sItem[n & 7] = make_int4(cur.cls, g0.w, g1.w, nvalid);      // published by the arrive below
+          mbar_arrive_expect_tx(&full[stage], nvalid * 4 * kWinBytes);
+        }
         __syncwarp();
         uint8_t* base = sStage + stage * kStageBytesB;
         uint8_t* const dst[4] = {base, base + kOffDO, base + kOffK, base + kOffV};
-        issue_item_boxes<true, 4>(S, item_geom(S, sc, cur, 0), item_geom(S, sc, cur, 1), nvalid, h * kD, maps, dst, slot_stride,
-                                  &full[stage], lane);
+        issue_item_boxes<true, 4>(S, g0, g1, nvalid, h * kD, maps, dst, slot_stride, &full[stage], lane);
         trace_ev(P.trace, 2, n, 2);
       }
     } else if (warp == kMmaWarpB) {
@@ -155,7 +161,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
         mbar_wait(&full[stage], phase);
         mbar_wait(&sdp_empty[b], ((n >> 1) & 1) ^ 1);
         tcgen05_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint64_t sb = dKm + (stage0 + stage * (kStageBytesB >> 4));
           const uint32_t tS = tmem + b * 128, tDP = tS + 64;
 #pragma unroll
@@ -177,7 +183,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
         mbar_wait(&out_empty[b], ((n >> 1) & 1) ^ 1);
         trace_ev(P.trace, 3, n, 1);
         tcgen05_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint64_t sbm = dMn + (stage0 + stage * (kStageBytesB >> 4));
           const uint64_t ap = dPm + p0, adk = dPk + ds0, adm = dPm + ds0;
           const uint32_t tO = tmem + 256 + b * 96;
@@ -199,52 +205,33 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
         trace_ev(P.trace, 3, n, 3);
       }
     } else if (warp == kStoreWarpB) {
-      // ============================== TMA store (+ column sums of dv) ==============================
-      // Each lane issues its share of the item's boxes; meanwhile all 32 lanes sum the columns of the dv staging
-      // tile (the v-projection bias gradient; dq / dk column sums come from the epilogue warps' registers).
-      // Lane l owns the 8 channels of logical 16-byte chunk l%4 for rows == l/4 (mod 8).
-      const CUtensorMap* const maps[3] = {P.dq, P.dk, P.dv};
-      const int slot_stride[3] = {kWinBytes, kWinBytes, kWinBytes};
-      uint8_t* const dst[3] = {sOut, sOut + kTile, sOut + 2 * kTile};
+      // ============================== TMA store ==============================
+      // The three staging tiles (dq, dk, dv) are handed over one by one, so the epilogue warps fill the next
+      // tile while this one drains.  Each lane issues its share of a tile's boxes; a tile is returned to the
+      // epilogue once the bulk group two behind has finished reading shared memory.
       ItemCursor cur;
       cur.seek(sc, item0);
-      float cs[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) cs[e] = 0.f;
+      int grp = 0;
       for (int n = 0; n < cnt; ++n, cur.next_item(sc)) {
-        trace_ev(P.trace, 4, n, 0);
-        mbar_wait(so_ready, n & 1);
-        trace_ev(P.trace, 4, n, 1);
-        issue_item_boxes<false, 3>(S, item_geom(S, sc, cur, 0), item_geom(S, sc, cur, 1), cur.slot_valid(1) ? 2 : 1, h * kD, maps, dst,
-                                   slot_stride, nullptr, lane);
-        tma_store_commit();
-        if (P.dcolsum) {
-#pragma unroll 4
-          for (int r0 = 0; r0 < 128; r0 += 8) {
-            const int row = r0 + (lane >> 2);
-            const uint4 a = *reinterpret_cast<const uint4*>(sOut + 2 * kTile + row * 64 + (((lane & 3) ^ ((row >> 1) & 3)) << 4));
-            const uint32_t u[4] = {a.x, a.y, a.z, a.w};
+        const ItemGeom g0 = item_geom(S, sc, cur, 0), g1 = item_geom(S, sc, cur, 1);
+        const int nvalid = cur.slot_valid(1) ? 2 : 1;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { cs[2 * e] += __uint_as_float(u[e] << 16); cs[2 * e + 1] += __uint_as_float(u[e] & 0xffff0000u); }
-          }
+        for (int t = 0; t < 3; ++t, ++grp) {
+          const CUtensorMap* const maps[1] = {t == 0 ? P.dq : (t == 1 ? P.dk : P.dv)};
+          const int slot_stride[1] = {kWinBytes};
+          uint8_t* const dst[1] = {sOut + t * kTile};
+          if (t == 0) trace_ev(P.trace, 4, n, 0);
+          mbar_wait(&so_ready[t], n & 1);
+          if (t == 0) trace_ev(P.trace, 4, n, 1);
+          issue_item_boxes<false, 1>(S, g0, g1, nvalid, h * kD, maps, dst, slot_stride, nullptr, lane);
+          tma_store_commit();
+          tma_store_wait_read<2>();        // per thread: the group two behind (tile (t + 1) % 3) has been read out
+          __syncwarp();
+          if (lane == 0 && grp >= 2) mbar_arrive(&so_free[(t + 1) % 3]);
         }
-        tma_store_wait_read<0>();          // per thread: each lane waits for the smem reads of its own boxes
-        __syncwarp();
-        if (lane == 0) mbar_arrive(so_free);
         trace_ev(P.trace, 4, n, 2);
       }
       tma_store_wait_all<0>();
-      if (P.dcolsum) {
-        const int C = P.nH * kD;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float v = cs[e];
-          v += __shfl_xor_sync(0xffffffffu, v, 4);
-          v += __shfl_xor_sync(0xffffffffu, v, 8);
-          v += __shfl_xor_sync(0xffffffffu, v, 16);
-          if (lane < 4) atomicAdd(P.dcolsum + 2 * C + h * kD + lane * 8 + e, v);
-        }
-      }
     }
   } else if (warp >= kEpiWarp0) {
     // ============================== epilogue warpgroup: one thread per tile row ==============================
@@ -252,37 +239,33 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
     const int slot = r >> 6, i = r & 63;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int rsw = (r >> 1) & 3;                       // 64B-swizzle phase of this thread's tile row
-    setmaxnreg_inc<136>();
-    float cs[2][32];                                    // this row's share of the column sums of dq, dk (fp32, before rounding)
-#pragma unroll
-    for (int t = 0; t < 2; ++t)
-#pragma unroll
-      for (int c = 0; c < 32; ++c) cs[t][c] = 0.f;
-    ItemCursor cur;
-    cur.seek(sc, item0);
-    for (int n = 0; n < cnt; ++n, cur.next_item(sc)) {
+    setmaxnreg_inc<104>();
+    float cs[3] = {0.f, 0.f, 0.f};                      // lane l: column sums of dq, dk, dv channel l over this warp's rows
+    for (int n = 0; n < cnt; ++n) {
       const int stage = n % kStagesB, b = n & 1;
-      const bool valid = cur.slot_valid(slot);
       const uint8_t* base = sStage + stage * kStageBytesB;
       const uint32_t tO = tmem + lane_base + 256 + b * 96;
       if (warp == kEpiWarp0) trace_ev(P.trace, 1, n, 0);
       mbar_wait(&out_full[b], (n >> 1) & 1);
       tcgen05_fence_after();
+      const bool valid = slot < sItem[n & 7].w;
       if (warp == kEpiWarp0) trace_ev(P.trace, 1, n, 1);
 
-      mbar_wait(so_free, (n & 1) ^ 1);                  // previous item's stores have drained the staging tiles
-      if (warp == kEpiWarp0) trace_ev(P.trace, 1, n, 2);
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {                     // t = 0: dQ~ with q row, t = 1: dK~ with k row
+      for (int t = 0; t < 3; ++t) {                     // t = 0: dQ~ with the q row, 1: dK~ with the k row, 2: dV
         uint32_t g32[32];
-        tmem_ld_32x32b_x32(tO + 32 + t * 32, g32);
+        tmem_ld_32x32b_x32(tO + (t == 2 ? 0 : 32 + t * 32), g32);
         tmem_ld_wait();
-        uint8_t* orow = sOut + t * kTile + r * 64;
-        if (COS) {
+        if (t == 2) {
+          tcgen05_fence_before();
+          mbar_arrive(&out_empty[b]);                   // accumulators read out
+        }
+        uint32_t o[16];
+        if (COS && t < 2) {
           // d/dx of x / max(||x||, eps) applied to G = dQ~ (which already carries 1/||x||): G - x^ (x^ . G)
           const uint8_t* rowp = t == 0 ? base + slot * 2 * kWinBytes + i * 64 : base + kOffK + r * 64;
           uint4 xq[4];
-          float ss = 0.f, dot = 0.f;
+          float ss[2] = {0.f, 0.f}, dot[2] = {0.f, 0.f};
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             xq[c] = *reinterpret_cast<const uint4*>(rowp + ((c ^ rsw) << 4));
@@ -290,86 +273,69 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float lo = __uint_as_float(u[e] << 16), hi = __uint_as_float(u[e] & 0xffff0000u);
-              ss = fmaf(lo, lo, ss); ss = fmaf(hi, hi, ss);
-              dot = fmaf(lo, __uint_as_float(g32[c * 8 + 2 * e]), dot);
-              dot = fmaf(hi, __uint_as_float(g32[c * 8 + 2 * e + 1]), dot);
+              ss[0] = fmaf(lo, lo, ss[0]); ss[1] = fmaf(hi, hi, ss[1]);
+              dot[0] = fmaf(lo, __uint_as_float(g32[c * 8 + 2 * e]), dot[0]);
+              dot[1] = fmaf(hi, __uint_as_float(g32[c * 8 + 2 * e + 1]), dot[1]);
             }
           }
-          const float rinv = rsqrtf(fmaxf(ss, 1e-24f));
-          const float proj = rinv >= 1e12f ? 0.f : -dot * rinv * rinv;     // below eps the normalisation is x / eps: no projection
+          if (t == 1) mbar_arrive(&empty[stage]);       // q and k rows read: the stage can be refilled
+          const float rinv = rsqrtf(fmaxf(ss[0] + ss[1], 1e-24f));
+          const float proj = rinv >= 1e12f ? 0.f : -(dot[0] + dot[1]) * rinv * rinv;     // below eps the normalisation is x / eps: no projection
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const uint32_t u[4] = {xq[c].x, xq[c].y, xq[c].z, xq[c].w};
-            uint32_t o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float lo = __uint_as_float(u[e] << 16), hi = __uint_as_float(u[e] & 0xffff0000u);
               const float o0 = fmaf(lo, proj, __uint_as_float(g32[c * 8 + 2 * e])), o1 = fmaf(hi, proj, __uint_as_float(g32[c * 8 + 2 * e + 1]));
-              if (valid) { cs[t][c * 8 + 2 * e] += o0; cs[t][c * 8 + 2 * e + 1] += o1; }
-              o[e] = pack_bf16x2(o0, o1);
+              g32[c * 8 + 2 * e] = __float_as_uint(o0); g32[c * 8 + 2 * e + 1] = __float_as_uint(o1);
+              o[c * 4 + e] = pack_bf16x2(o0, o1);
             }
-            *reinterpret_cast<uint4*>(orow + ((c ^ rsw) << 4)) = valid ? make_uint4(o[0], o[1], o[2], o[3]) : make_uint4(0, 0, 0, 0);
           }
         } else {
-          if (valid) {
+          if (t == 1) mbar_arrive(&empty[stage]);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) cs[t][c] += __uint_as_float(g32[c]);
-          }
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            *reinterpret_cast<uint4*>(orow + ((c ^ rsw) << 4)) =
-                valid ? make_uint4(pack_bf16x2(__uint_as_float(g32[c * 8 + 0]), __uint_as_float(g32[c * 8 + 1])),
-                                   pack_bf16x2(__uint_as_float(g32[c * 8 + 2]), __uint_as_float(g32[c * 8 + 3])),
-                                   pack_bf16x2(__uint_as_float(g32[c * 8 + 4]), __uint_as_float(g32[c * 8 + 5])),
-                                   pack_bf16x2(__uint_as_float(g32[c * 8 + 6]), __uint_as_float(g32[c * 8 + 7])))
-                      : make_uint4(0, 0, 0, 0);
+          for (int c = 0; c < 16; ++c) o[c] = pack_bf16x2(__uint_as_float(g32[2 * c]), __uint_as_float(g32[2 * c + 1]));
         }
-      }
-      {
-        uint32_t gv[32];
-        tmem_ld_32x32b_x32(tO, gv);
-        tmem_ld_wait();
-        uint8_t* orow = sOut + 2 * kTile + r * 64;
+        mbar_wait(&so_free[t], (n & 1) ^ 1);            // the previous item's stores have drained this staging tile
+        uint8_t* orow = sOut + t * kTile + r * 64;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           *reinterpret_cast<uint4*>(orow + ((c ^ rsw) << 4)) =
-              valid ? make_uint4(pack_bf16x2(__uint_as_float(gv[c * 8 + 0]), __uint_as_float(gv[c * 8 + 1])),
-                                 pack_bf16x2(__uint_as_float(gv[c * 8 + 2]), __uint_as_float(gv[c * 8 + 3])),
-                                 pack_bf16x2(__uint_as_float(gv[c * 8 + 4]), __uint_as_float(gv[c * 8 + 5])),
-                                 pack_bf16x2(__uint_as_float(gv[c * 8 + 6]), __uint_as_float(gv[c * 8 + 7])))
-                    : make_uint4(0, 0, 0, 0);
+              valid ? make_uint4(o[c * 4 + 0], o[c * 4 + 1], o[c * 4 + 2], o[c * 4 + 3]) : make_uint4(0, 0, 0, 0);
+        fence_proxy_async_smem();
+        mbar_arrive(&so_ready[t]);
+        if (warp == kEpiWarp0) trace_ev(P.trace, 1, n, 2 + t);
+        if (P.dcolsum) {
+          // transpose-reduce the warp's 32 rows x 32 channels (fp32, before rounding): lane l ends up with channel l
+          if (!valid) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) g32[c] = 0u;
+          }
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int c = 0; c < off; ++c) {
+              const float lo = __uint_as_float(g32[c]), hi = __uint_as_float(g32[c + off]);
+              const float keep = up ? hi : lo, send = up ? lo : hi;
+              g32[c] = __float_as_uint(keep + __shfl_xor_sync(0xffffffffu, send, off));
+            }
+          }
+          cs[t] += __uint_as_float(g32[0]);
+        }
       }
-      tcgen05_fence_before();
-      mbar_arrive(&out_empty[b]);                       // accumulators read out
-      mbar_arrive(&empty[stage]);                       // q / k rows read: the stage can be refilled
-      if (warp == kEpiWarp0) trace_ev(P.trace, 1, n, 3);
-      fence_proxy_async_smem();
-      mbar_arrive(so_ready);
-      if (warp == kEpiWarp0) trace_ev(P.trace, 1, n, 4);
     }
-    // column sums of dq, dk over this CTA's tokens: transpose-reduce over the warp's 32 rows (lane l ends up
-    // with channel l), one atomic per lane and tensor
     if (P.dcolsum) {
       const int C = P.nH * kD;
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-#pragma unroll
-          for (int c = 0; c < off; ++c) {
-            const bool up = (lane & off) != 0;
-            const float send = up ? cs[t][c] : cs[t][c + off];
-            const float keep = up ? cs[t][c + off] : cs[t][c];
-            cs[t][c] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-          }
-        }
-        atomicAdd(P.dcolsum + t * C + h * kD + lane, cs[t][0]);
-      }
+      for (int t = 0; t < 3; ++t) atomicAdd(P.dcolsum + t * C + h * kD + lane, cs[t]);
     }
   } else {
-    // ============================== softmax (256 threads: 2 per row) ==============================
-    setmaxnreg_inc<160>();
-    const int r = tid & 127, half = tid >> 7;
+    // ============================== softmax (512 threads: 4 per row, 16 keys each) ==============================
+    // (softmax warps stay at the launch allocation: setmaxnreg only moves registers freed by the CTA's own warps)
+    constexpr int KP = kKeysPerThread;
+    const int r = tid & 127, qt = tid >> 7;             // tile row; which quarter of its 64 keys
     const int slot = r >> 6, i = r & 63;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const float hscale = COS ? __ldg(P.head_scale + h) : P.scale;
@@ -377,9 +343,9 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
     float* const gdb_head = P.dbias ? P.dbias + (size_t)h * kN * kN : nullptr;
     uint8_t* prow = sP + slot * 16384 + i * 128;
     uint8_t* drow = sDS + slot * 16384 + i * 128;
-    float dbacc[32];                                    // dbias[tile row i][32*half + j] of the current wrap class
+    float dbacc[KP];                                    // dbias[tile row i][KP*qt + j] of the current wrap class
 #pragma unroll
-    for (int j = 0; j < 32; ++j) dbacc[j] = 0.f;
+    for (int j = 0; j < KP; ++j) dbacc[j] = 0.f;
     float dscale_acc = 0.f;
     const int trole = warp == 0 ? 0 : -1;
 #define TRB(item, ev) do { if (trole >= 0) trace_ev(P.trace, trole, item, ev); } while (0)
@@ -388,47 +354,46 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       const uint8_t* pos = sPos + cls * 64;
       float* rowp = gdb_head + (int)pos[i] * kN;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) { atomicAdd(rowp + pos[half * 32 + j], dbacc[j]); dbacc[j] = 0.f; }
+      for (int j = 0; j < KP; ++j) { atomicAdd(rowp + pos[qt * KP + j], dbacc[j]); dbacc[j] = 0.f; }
     };
 
-    ItemCursor cur;
-    cur.seek(sc, item0);
     int cls_loaded = -1;
-    for (int n = 0; n < cnt; ++n, cur.next_item(sc)) {
+    for (int n = 0; n < cnt; ++n) {
       const int stage = n % kStagesB, phase = (n / kStagesB) & 1, b = n & 1;
-      const ItemGeom geo = item_geom(S, sc, cur, slot);
-      const bool valid = cur.slot_valid(slot);
-      if (cur.cls != cls_loaded) {                      // rare: at most 8 times per CTA
-        if (gdb_head && cls_loaded >= 0) flush_dbias(cls_loaded);
-        named_bar_sync(3, kSoftmaxThreadsB);            // everyone is done reading the old table
-        build_class_table(sTbl, kTblLd, bias_h, sPos + cur.cls * 64, S, cur.cls, MASK == MMN_MASK_SHIFT, tid, kSoftmaxThreadsB);
-        cls_loaded = cur.cls;
-      }
-      const int ipos = sPos[cur.cls * 64 + i];
-      const uint8_t* base = sStage + stage * kStageBytesB;
-      const float lse2 = valid ? __ldg(P.lse + ((size_t)geo.w * P.nH + h) * kN + ipos) * kLog2e : 0.f;
-
-      // ---- (a) row norms: half 0 -> logit multiplier of query row r, half 1 -> 1/||k_r||
       TRB(n, 0);
       mbar_wait(&full[stage], phase);
       TRB(n, 1);
-      if (COS) {
-        const float ss = row_sumsq(half == 0 ? base + slot * 2 * kWinBytes + i * 64 : base + kOffK + r * 64);
+      const int4 item = sItem[n & 7];                   // written by the producer before it armed full[stage]
+      const int cls = item.x, gw = slot ? item.z : item.y;
+      const bool valid = slot < item.w;
+      if (cls != cls_loaded) {                          // rare: at most 8 times per CTA
+        if (gdb_head && cls_loaded >= 0) flush_dbias(cls_loaded);
+        named_bar_sync(3, kSoftmaxThreadsB);            // everyone is done reading the old table
+        build_class_table(sTbl, kTblLd, bias_h, sPos + cls * 64, S, cls, MASK == MMN_MASK_SHIFT, tid, kSoftmaxThreadsB);
+        cls_loaded = cls;
+      }
+      const int ipos = sPos[cls * 64 + i];
+      const uint8_t* base = sStage + stage * kStageBytesB;
+      const float lse2 = valid ? __ldg(P.lse + ((size_t)gw * P.nH + h) * kN + ipos) * kLog2e : 0.f;
+
+      // ---- (a) row norms: quarter 0 -> logit multiplier of query row r, quarter 1 -> 1/||k_r||
+      if (COS && qt < 2) {
+        const float ss = row_sumsq(qt == 0 ? base + slot * 2 * kWinBytes + i * 64 : base + kOffK + r * 64, i);
         const float rinv = rsqrtf(fmaxf(ss, 1e-24f));
-        if (half == 0) sA[b * 128 + r] = rinv * hscale; else sRk[b * 128 + r] = rinv;
+        if (qt == 0) sA[b * 128 + r] = rinv * hscale; else sRk[b * 128 + r] = rinv;
       }
       named_bar_sync(1, kSoftmaxThreadsB);
       TRB(n, 2);
       const float a_i = COS ? sA[b * 128 + r] : hscale;
-      const float4* krow = reinterpret_cast<const float4*>(sRk + b * 128 + slot * 64 + half * 32);
+      const float4* krow = reinterpret_cast<const float4*>(sRk + b * 128 + slot * 64 + qt * KP);
 
-      // ---- (b) additive terms of this thread's 32 logits (table, mask, -lse), log2 domain
-      float p[32];
+      // ---- (b) additive terms of this thread's logits (table, mask, -lse), log2 domain
+      float p[KP];
       {
-        const float4* trow = reinterpret_cast<const float4*>(sTbl + i * kTblLd + half * 32);
-        const float* mrow = (MASK == MMN_MASK_TENSOR) ? P.mask + ((size_t)(geo.w % P.mask_windows) * kN + ipos) * kN + half * 32 : nullptr;
+        const float4* trow = reinterpret_cast<const float4*>(sTbl + i * kTblLd + qt * KP);
+        const float* mrow = (MASK == MMN_MASK_TENSOR) ? P.mask + ((size_t)(gw % P.mask_windows) * kN + ipos) * kN + qt * KP : nullptr;
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
+        for (int j4 = 0; j4 < KP / 4; ++j4) {
           float4 tt = trow[j4];
           if (MASK == MMN_MASK_TENSOR) {
             const float4 mm = __ldg(reinterpret_cast<const float4*>(mrow) + j4);
@@ -443,17 +408,17 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       mbar_wait(&sdp_full[b], (n >> 1) & 1);
       tcgen05_fence_after();
       TRB(n, 4);
-      uint32_t dpr[32];
+      uint32_t dpr[KP];
       float delta = 0.f, acc_pdu = 0.f, acc_pu = 0.f;   // sum p dp, sum p dp u, sum p u   (u = the logit without bias / mask)
       {
-        uint32_t raw[32];
-        tmem_ld_32x32b_x32(tmem + lane_base + b * 128 + half * 32, raw);
-        tmem_ld_32x32b_x32(tmem + lane_base + b * 128 + 64 + half * 32, dpr);
+        uint32_t raw[KP];
+        tmem_ld_32x32b_x16(tmem + lane_base + b * 128 + qt * KP, raw);
+        tmem_ld_32x32b_x16(tmem + lane_base + b * 128 + 64 + qt * KP, dpr);
         tmem_ld_wait();
         tcgen05_fence_before();
         mbar_arrive(&sdp_empty[b]);
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
+        for (int j4 = 0; j4 < KP / 4; ++j4) {
           const float4 kk = COS ? krow[j4] : make_float4(1.f, 1.f, 1.f, 1.f);
           const float rk[4] = {kk.x, kk.y, kk.z, kk.w};
 #pragma unroll
@@ -471,34 +436,34 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
           }
         }
       }
-      sDelta[half * 128 + r] = delta;
+      sDelta[qt * 128 + r] = delta;
       TRB(n, 5);
       // P (bf16) can go out before delta is known; the previous item's gradient MMAs must have finished reading P / dS'
       if (n > 0) mbar_wait(&out_full[b ^ 1], ((n - 1) >> 1) & 1);
       TRB(n, 6);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < KP / 8; ++c) {
         uint4 v4 = make_uint4(pack_bf16x2(p[c * 8 + 0], p[c * 8 + 1]), pack_bf16x2(p[c * 8 + 2], p[c * 8 + 3]),
                               pack_bf16x2(p[c * 8 + 4], p[c * 8 + 5]), pack_bf16x2(p[c * 8 + 6], p[c * 8 + 7]));
         if (!valid) v4 = make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(prow + (((half * 4 + c) ^ (i & 7)) << 4)) = v4;
+        *reinterpret_cast<uint4*>(prow + (((qt * (KP / 8) + c) ^ (i & 7)) << 4)) = v4;
       }
       named_bar_sync(2, kSoftmaxThreadsB);
       TRB(n, 7);
-      delta += sDelta[(half ^ 1) * 128 + r];
+      delta = (sDelta[r] + sDelta[128 + r]) + (sDelta[256 + r] + sDelta[384 + r]);
 
       // ---- (d) dS = P o (dP - delta): dbias; dS' = dS o c into the MMA tile; d(logit scale)
 #pragma unroll
-      for (int j = 0; j < 32; ++j) p[j] *= __uint_as_float(dpr[j]) - delta;
+      for (int j = 0; j < KP; ++j) p[j] *= __uint_as_float(dpr[j]) - delta;
       if (valid) {
         if (COS) dscale_acc += acc_pdu - delta * acc_pu;      // sum_j dS_ij u_ij  (u = logit_scale x cos)
         if (gdb_head) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dbacc[j] += p[j];
+          for (int j = 0; j < KP; ++j) dbacc[j] += p[j];
         }
       }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < KP / 8; ++c) {
         float cj[8];
         if (COS) {
           const float4 k0 = krow[c * 2], k1 = krow[c * 2 + 1];
@@ -511,7 +476,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
         uint4 v4 = make_uint4(pack_bf16x2(p[c * 8 + 0] * cj[0], p[c * 8 + 1] * cj[1]), pack_bf16x2(p[c * 8 + 2] * cj[2], p[c * 8 + 3] * cj[3]),
                               pack_bf16x2(p[c * 8 + 4] * cj[4], p[c * 8 + 5] * cj[5]), pack_bf16x2(p[c * 8 + 6] * cj[6], p[c * 8 + 7] * cj[7]));
         if (!valid) v4 = make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(drow + (((half * 4 + c) ^ (i & 7)) << 4)) = v4;
+        *reinterpret_cast<uint4*>(drow + (((qt * (KP / 8) + c) ^ (i & 7)) << 4)) = v4;
       }
       fence_proxy_async_smem();
       mbar_arrive(pds_full);
@@ -529,7 +494,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       named_bar_sync(2, kSoftmaxThreadsB);
       if (tid == 0) {
         float tot = 0.f;
-        for (int x = 0; x < 8; ++x) tot += sRed[x];
+        for (int x = 0; x < kSoftmaxThreadsB / 32; ++x) tot += sRed[x];
         atomicAdd(P.dhead_scale + h, tot);
       }
     }
@@ -541,7 +506,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
 }
 
 constexpr size_t kBwdSmemBytes = 1024 + kStagesB * kStageBytesB + 2 * kPRegion + 3 * kTile + kN * kTblLd * 4 +
-                                 (256 + 256 + 256 + 8) * 4 + 512 + 24 * 8;
+                                 (256 + 256 + 512 + 16) * 4 + 512 + 8 * 16 + 24 * 8;
 
 inline const char* bwd_why_not_impl(const mmn_winattn_desc* d) {
   const char* w = fwd_why_not_impl(d);

@@ -66,12 +66,14 @@ __device__ __forceinline__ void trace_ev(long long* trace, int role, int item, i
   if (trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && item < 32) trace[(role * 32 + item) * 16 + ev] = clock64();
 }
 
-// sum of squares of one 64-byte bf16 row (any chunk order)
-__device__ __forceinline__ float row_sumsq(const uint8_t* rowp) {
+// sum of squares of one 64-byte bf16 row.  `row` = the row's index in its tile: chunk c is read at its
+// swizzled place, which also spreads the lanes of a warp over all banks (plain order is a 4-way conflict).
+__device__ __forceinline__ float row_sumsq(const uint8_t* rowp, int row) {
+  const int sw = (row >> 1) & 3;
   float ss[4] = {0.f, 0.f, 0.f, 0.f};                      // one chain per 16-byte chunk
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    const uint4 a = *reinterpret_cast<const uint4*>(rowp + (c << 4));
+    const uint4 a = *reinterpret_cast<const uint4*>(rowp + ((c ^ sw) << 4));
     const uint32_t u[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -171,7 +173,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
       const int stage = n % kStagesF, phase = (n / kStagesF) & 1;
       mbar_wait(&full[stage], phase);
       tcgen05_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint64_t aq = dQK + (stage0 + stage * (kStageBytesF >> 4)), bk = aq + (kQRegion >> 4);
         const uint32_t tS = tmem + (n & 1) * 64;
 #pragma unroll
@@ -189,7 +191,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
       mbar_wait(&p_full[g], kk & 1);
       trace_ev(P.trace, 3, n, 1);
       tcgen05_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint64_t ap = dP + (p0 + g * (kPRegion >> 4));
         const uint64_t bv = dV + (stage0 + stage * (kStageBytesF >> 4) + ((kQRegion + kTile) >> 4));
         const uint32_t tO = tmem + 128 + (g * 2 + (kk & 1)) * 32;
@@ -284,8 +286,8 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
       TR(n, 1);
       float a_i = hscale;
       if (COS) {
-        const float ssq = row_sumsq(base + slot * 2 * kWinBytes + i * 64);
-        const float ssk = row_sumsq(base + kQRegion + r * 64);
+        const float ssq = row_sumsq(base + slot * 2 * kWinBytes + i * 64, i);
+        const float ssk = row_sumsq(base + kQRegion + r * 64, i);
         a_i *= rsqrtf(fmaxf(ssq, 1e-24f));               // 1 / max(||q||, 1e-12) x logit scale x log2(e)
         rkbuf[r] = rsqrtf(fmaxf(ssk, 1e-24f));
       }
