@@ -259,17 +259,47 @@ def main():
         allreduce_grads()
         return y
 
+    # End-to-end step: inputs start in pinned host memory, results end there.  The batch is cut into chunks that
+    # flow through three streams (H2D copy -> forward+backward -> D2H copy), so the PCIe transfers of one chunk
+    # overlap the kernels of another; weight gradients accumulate over the chunks exactly as over one batch.
+    E2E_CHUNKS = 8 if B % 8 == 0 else (4 if B % 4 == 0 else 1)
+    cb = B // E2E_CHUNKS
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    xd_buf = torch.empty(B, L, C, device=dev, dtype=torch.bfloat16)
+    dyd_buf = torch.empty(B, L, C, device=dev, dtype=torch.bfloat16)
+
     def step_e2e():
         for p in model.parameters():
             p.grad = None
-        xd = x_host.to(dev, non_blocking=True).requires_grad_(True)
-        dyd = dy_host.to(dev, non_blocking=True)
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            y = model(xd)
-        y.backward(dyd)
+        cur = torch.cuda.current_stream(dev)
+        s_in.wait_stream(cur)          # the previous step's kernels are done with the device buffers
+        ev_in = []
+        with torch.cuda.stream(s_in):
+            for c in range(E2E_CHUNKS):
+                sl = slice(c * cb, (c + 1) * cb)
+                xd_buf[sl].copy_(x_host[sl], non_blocking=True)
+                dyd_buf[sl].copy_(dy_host[sl], non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(s_in)
+                ev_in.append(e)
+        for c in range(E2E_CHUNKS):
+            sl = slice(c * cb, (c + 1) * cb)
+            cur.wait_event(ev_in[c])
+            xc = xd_buf[sl].detach().requires_grad_(True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y = model(xc)
+            y.backward(dyd_buf[sl])
+            e = torch.cuda.Event()
+            e.record(cur)
+            yd, dxd = y.detach(), xc.grad
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(e)
+                y_host[sl].copy_(yd, non_blocking=True)
+                dx_host[sl].copy_(dxd, non_blocking=True)
+                yd.record_stream(s_out)
+                dxd.record_stream(s_out)
         allreduce_grads()
-        y_host.copy_(y.detach(), non_blocking=True)
-        dx_host.copy_(xd.grad, non_blocking=True)
+        cur.wait_stream(s_out)         # the step ends when its results are in host memory
 
     def barrier():
         if world > 1:
@@ -337,7 +367,9 @@ def main():
                 "data": "synthetic", "config": workload_config(B, world),
                 "samples_per_s": B * world / (ms * 1e-3),
                 "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": 2 * B * L * C * elem,
-                        "d2h_bytes_per_step": 2 * B * L * C * elem},
+                        "d2h_bytes_per_step": 2 * B * L * C * elem, "chunks": E2E_CHUNKS,
+                        "note": "x, dy from pinned host memory; y, dx back to pinned host memory; copies of one chunk overlap "
+                                "the kernels of another (3 streams)"},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary(),
                 "paths": {"fwd": ops.winattn_path_name(torch.empty(1, *GRID, 3 * C, device=dev, dtype=torch.bfloat16), None, GRID,
                                                        (WINDOW,) * 3, (SHIFT,) * 3, HEADS, _lib.SCORE_COSINE, _lib.MASK_SHIFT)}}

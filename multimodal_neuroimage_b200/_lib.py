@@ -18,9 +18,13 @@ LIB_PATH = os.path.join(PKG_DIR, "libmmn_b200.so")
 # translation unit -> headers it depends on (besides include/mmn_b200.h)
 SOURCES = {"mmn_abi.cu": ["generic_launch.h", "attn_generic.cuh", "winattn_tc.h"],
            "generic_launch.cu": ["generic_launch.h", "attn_generic.cuh"],
-           "winattn_tc.cu": ["winattn_tc.h", "winattn_tc_fwd.cuh", "winattn_tc_bwd.cuh", "tc_window.cuh", "tc_common.cuh"]}
+           "winattn_tc.cu": ["winattn_tc.h", "winattn_tc_fwd.cuh", "winattn_tc_bwd.cuh", "tc_window.cuh", "tc_sched.cuh", "tc_common.cuh"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
+# MMN_BUILD_TRACE=1 compiles the per-phase clock tracing into the tensor-core kernels (tools/trace_*.py);
+# production builds leave it out (it costs ~8 % of the softmax warps' instructions).
+if os.environ.get("MMN_BUILD_TRACE"):
+    NVCC_FLAGS.append("-DMMN_TC_TRACING")
 
 # enums of include/mmn_b200.h
 DT_F32, DT_BF16 = 0, 1
@@ -74,7 +78,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(obj)
         stamp = _stamp([os.path.join(CSRC, src), header] + [os.path.join(CSRC, d) for d in deps])
-        if force or not os.path.exists(obj) or os.path.getmtime(obj) < stamp:
+        if force or os.environ.get("MMN_BUILD_TRACE") or not os.path.exists(obj) or os.path.getmtime(obj) < stamp:
             cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
             if verbose:
                 print(" ".join(cmd), flush=True)

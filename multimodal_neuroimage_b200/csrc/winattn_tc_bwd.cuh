@@ -67,21 +67,21 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
   uint8_t* sDS = sP + kPRegion;                           // dS'0 | Z | dS'1
   uint8_t* sOut = sDS + kPRegion;                         // dQ | dK | dV staging, 3 x kTile
   float* sTbl = reinterpret_cast<float*>(sOut + 3 * kTile);   // [64][kTblLd]
-  float* sA = sTbl + kN * kTblLd;                         // [2][128] logit multiplier per query row (natural units)
-  float* sRk = sA + 256;                                  // [2][128] 1/||k|| per key
-  float* sDelta = sRk + 256;                              // [4][128] partial deltas
+  float* sA = sTbl + kN * kTblLd;                         // [3][128] logit multiplier per query row (natural units), ring over items
+  float* sRk = sA + 384;                                  // [3][128] 1/||k|| per key
+  float* sDelta = sRk + 384;                              // [4][128] partial deltas
   float* sRed = sDelta + 512;                             // 16 floats: dhead_scale per softmax warp
   uint8_t* sPos = reinterpret_cast<uint8_t*>(sRed + 16);  // [8][64]
   int4* sItem = reinterpret_cast<int4*>(sPos + 512);      // [8] ring: {wrap class, window index of slot 0, of slot 1, valid slots} of item n & 7
   uint64_t* bars = reinterpret_cast<uint64_t*>(sItem + 8);
   uint64_t* full = bars;                                  // [kStagesB]
-  uint64_t* empty = bars + kStagesB;                      // [kStagesB] (128 arrivals: epilogue threads)
+  uint64_t* empty = bars + kStagesB;                      // [kStagesB] (one arrival per warp: epilogue threads)
   uint64_t* sdp_full = bars + 2 * kStagesB;               // [2]
-  uint64_t* sdp_empty = sdp_full + 2;                     // [2] 256 arrivals
-  uint64_t* pds_full = sdp_full + 4;                      // 256 arrivals
+  uint64_t* sdp_empty = sdp_full + 2;                     // [2] one arrival per warp
+  uint64_t* pds_full = sdp_full + 4;                      // one arrival per warp
   uint64_t* out_full = sdp_full + 5;                      // [2]
-  uint64_t* out_empty = sdp_full + 7;                     // [2] 128 arrivals
-  uint64_t* so_ready = sdp_full + 9;                      // [3] one per staging tile (dq, dk, dv), 128 arrivals
+  uint64_t* out_empty = sdp_full + 7;                     // [2] one arrival per warp
+  uint64_t* so_ready = sdp_full + 9;                      // [3] one per staging tile (dq, dk, dv), one arrival per warp
   uint64_t* so_free = sdp_full + 12;                      // [3]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdp_full + 15);
 
@@ -97,13 +97,13 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
     reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < 512; i += kBwdThreads) sPos[i] = (uint8_t)piece_position(S, i >> 6, i & 63);
   if (tid == 0) {
-    for (int s = 0; s < kStagesB; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kEpiThreads); }
+    for (int s = 0; s < kStagesB; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kEpiThreads / 32); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&sdp_full[b], 1); mbar_init(&sdp_empty[b], kSoftmaxThreadsB);
-      mbar_init(&out_full[b], 1); mbar_init(&out_empty[b], kEpiThreads);
+      mbar_init(&sdp_full[b], 1); mbar_init(&sdp_empty[b], kSoftmaxThreadsB / 32);
+      mbar_init(&out_full[b], 1); mbar_init(&out_empty[b], kEpiThreads / 32);
     }
-    mbar_init(pds_full, kSoftmaxThreadsB);
-    for (int t = 0; t < 3; ++t) { mbar_init(&so_ready[t], kEpiThreads); mbar_init(&so_free[t], 1); }
+    mbar_init(pds_full, kSoftmaxThreadsB / 32);
+    for (int t = 0; t < 3; ++t) { mbar_init(&so_ready[t], kEpiThreads / 32); mbar_init(&so_free[t], 1); }
     fence_barrier_init();
   }
   if (warp == kProducerWarpB && lane == 0)
@@ -241,6 +241,8 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
     const int rsw = (r >> 1) & 3;                       // 64B-swizzle phase of this thread's tile row
     setmaxnreg_inc<104>();
     float cs[3] = {0.f, 0.f, 0.f};                      // lane l: column sums of dq, dk, dv channel l over this warp's rows
+    float dscale_acc = 0.f;                             // sum over rows of q_i . dQ~_i = sum_ij dS_ij (s_ij - bias_ij)
+    const float inv_hscale = COS ? 1.f / __ldg(P.head_scale + h) : 1.f;
     for (int n = 0; n < cnt; ++n) {
       const int stage = n % kStagesB, b = n & 1;
       const uint8_t* base = sStage + stage * kStageBytesB;
@@ -258,14 +260,14 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
         tmem_ld_wait();
         if (t == 2) {
           tcgen05_fence_before();
-          mbar_arrive(&out_empty[b]);                   // accumulators read out
+          mbar_arrive_warp(&out_empty[b]);                   // accumulators read out
         }
         uint32_t o[16];
         if (COS && t < 2) {
           // d/dx of x / max(||x||, eps) applied to G = dQ~ (which already carries 1/||x||): G - x^ (x^ . G)
           const uint8_t* rowp = t == 0 ? base + slot * 2 * kWinBytes + i * 64 : base + kOffK + r * 64;
           uint4 xq[4];
-          float ss[2] = {0.f, 0.f}, dot[2] = {0.f, 0.f};
+          float dot[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             xq[c] = *reinterpret_cast<const uint4*>(rowp + ((c ^ rsw) << 4));
@@ -273,14 +275,16 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float lo = __uint_as_float(u[e] << 16), hi = __uint_as_float(u[e] & 0xffff0000u);
-              ss[0] = fmaf(lo, lo, ss[0]); ss[1] = fmaf(hi, hi, ss[1]);
-              dot[0] = fmaf(lo, __uint_as_float(g32[c * 8 + 2 * e]), dot[0]);
-              dot[1] = fmaf(hi, __uint_as_float(g32[c * 8 + 2 * e + 1]), dot[1]);
+              dot[e] = fmaf(lo, __uint_as_float(g32[c * 8 + 2 * e]), dot[e]);
+              dot[e] = fmaf(hi, __uint_as_float(g32[c * 8 + 2 * e + 1]), dot[e]);
             }
           }
-          if (t == 1) mbar_arrive(&empty[stage]);       // q and k rows read: the stage can be refilled
-          const float rinv = rsqrtf(fmaxf(ss[0] + ss[1], 1e-24f));
-          const float proj = rinv >= 1e12f ? 0.f : -(dot[0] + dot[1]) * rinv * rinv;     // below eps the normalisation is x / eps: no projection
+          // 1 / max(||x||, eps) was computed by the softmax warps when they prepared this item (ring slot n % 3)
+          const float rinv = t == 0 ? sA[(n % 3) * 128 + r] * inv_hscale : sRk[(n % 3) * 128 + r];
+          if (t == 1) mbar_arrive_warp(&empty[stage]);       // q and k rows (and their norms) read: the stage can be refilled
+          const float xg = (dot[0] + dot[1]) + (dot[2] + dot[3]);
+          if (t == 0 && valid) dscale_acc += xg;
+          const float proj = rinv >= 1e12f ? 0.f : -xg * rinv * rinv;     // below eps the normalisation is x / eps: no projection
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const uint32_t u[4] = {xq[c].x, xq[c].y, xq[c].z, xq[c].w};
@@ -293,7 +297,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
             }
           }
         } else {
-          if (t == 1) mbar_arrive(&empty[stage]);
+          if (t == 1) mbar_arrive_warp(&empty[stage]);
 #pragma unroll
           for (int c = 0; c < 16; ++c) o[c] = pack_bf16x2(__uint_as_float(g32[2 * c]), __uint_as_float(g32[2 * c + 1]));
         }
@@ -304,7 +308,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
           *reinterpret_cast<uint4*>(orow + ((c ^ rsw) << 4)) =
               valid ? make_uint4(o[c * 4 + 0], o[c * 4 + 1], o[c * 4 + 2], o[c * 4 + 3]) : make_uint4(0, 0, 0, 0);
         fence_proxy_async_smem();
-        mbar_arrive(&so_ready[t]);
+        mbar_arrive_warp(&so_ready[t]);
         if (warp == kEpiWarp0) trace_ev(P.trace, 1, n, 2 + t);
         if (P.dcolsum) {
           // transpose-reduce the warp's 32 rows x 32 channels (fp32, before rounding): lane l ends up with channel l
@@ -331,6 +335,11 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
 #pragma unroll
       for (int t = 0; t < 3; ++t) atomicAdd(P.dcolsum + t * C + h * kD + lane, cs[t]);
     }
+    if (COS && P.dhead_scale) {                          // d s_ij / d(logit scale) = cos_ij = (s_ij - bias_ij) / logit scale
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dscale_acc += __shfl_xor_sync(0xffffffffu, dscale_acc, o);
+      if (lane == 0) atomicAdd(P.dhead_scale + h, dscale_acc * inv_hscale);
+    }
   } else {
     // ============================== softmax (512 threads: 4 per row, 16 keys each) ==============================
     // (softmax warps stay at the launch allocation: setmaxnreg only moves registers freed by the CTA's own warps)
@@ -346,7 +355,6 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
     float dbacc[KP];                                    // dbias[tile row i][KP*qt + j] of the current wrap class
 #pragma unroll
     for (int j = 0; j < KP; ++j) dbacc[j] = 0.f;
-    float dscale_acc = 0.f;
     const int trole = warp == 0 ? 0 : -1;
 #define TRB(item, ev) do { if (trole >= 0) trace_ev(P.trace, trole, item, ev); } while (0)
 
@@ -357,35 +365,47 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       for (int j = 0; j < KP; ++j) { atomicAdd(rowp + pos[qt * KP + j], dbacc[j]); dbacc[j] = 0.f; }
     };
 
+    // Everything item n needs before its logits arrive -- its descriptor, the lse of this thread's row (a global
+    // load) and the row norms -- is prepared one item ahead, inside item n-1, so that the latencies hide under
+    // item n-1's arithmetic and the norms are published by item n-1's delta barrier (no barrier of their own).
+    int nx_cls = 0, nx_gw = 0, nx_ipos = 0;
+    bool nx_valid = false;
+    float nx_lse = 0.f;
+    auto prep = [&](int n) {
+      const int stage = n % kStagesB, phase = (n / kStagesB) & 1;
+      mbar_wait(&full[stage], phase);
+      const int4 item = sItem[n & 7];                   // written by the producer before it armed full[stage]
+      nx_cls = item.x; nx_gw = slot ? item.z : item.y;
+      nx_valid = slot < item.w;
+      nx_ipos = sPos[nx_cls * 64 + i];
+      nx_lse = nx_valid ? __ldg(P.lse + ((size_t)nx_gw * P.nH + h) * kN + nx_ipos) : 0.f;
+      if (COS && qt < 2) {
+        const uint8_t* base = sStage + stage * kStageBytesB;
+        const float ss = row_sumsq(qt == 0 ? base + slot * 2 * kWinBytes + i * 64 : base + kOffK + r * 64, i);
+        const float rinv = rsqrtf(fmaxf(ss, 1e-24f));
+        if (qt == 0) sA[(n % 3) * 128 + r] = rinv * hscale; else sRk[(n % 3) * 128 + r] = rinv;
+      }
+    };
+    if (cnt > 0) prep(0);
+    named_bar_sync(1, kSoftmaxThreadsB);
+
     int cls_loaded = -1;
     for (int n = 0; n < cnt; ++n) {
-      const int stage = n % kStagesB, phase = (n / kStagesB) & 1, b = n & 1;
+      const int b = n & 1;
       TRB(n, 0);
-      mbar_wait(&full[stage], phase);
-      TRB(n, 1);
-      const int4 item = sItem[n & 7];                   // written by the producer before it armed full[stage]
-      const int cls = item.x, gw = slot ? item.z : item.y;
-      const bool valid = slot < item.w;
+      const int cls = nx_cls, gw = nx_gw, ipos = nx_ipos;
+      const bool valid = nx_valid;
+      const float lse2 = nx_lse * kLog2e;
       if (cls != cls_loaded) {                          // rare: at most 8 times per CTA
         if (gdb_head && cls_loaded >= 0) flush_dbias(cls_loaded);
         named_bar_sync(3, kSoftmaxThreadsB);            // everyone is done reading the old table
         build_class_table(sTbl, kTblLd, bias_h, sPos + cls * 64, S, cls, MASK == MMN_MASK_SHIFT, tid, kSoftmaxThreadsB);
         cls_loaded = cls;
+        named_bar_sync(3, kSoftmaxThreadsB);
       }
-      const int ipos = sPos[cls * 64 + i];
-      const uint8_t* base = sStage + stage * kStageBytesB;
-      const float lse2 = valid ? __ldg(P.lse + ((size_t)gw * P.nH + h) * kN + ipos) * kLog2e : 0.f;
-
-      // ---- (a) row norms: quarter 0 -> logit multiplier of query row r, quarter 1 -> 1/||k_r||
-      if (COS && qt < 2) {
-        const float ss = row_sumsq(qt == 0 ? base + slot * 2 * kWinBytes + i * 64 : base + kOffK + r * 64, i);
-        const float rinv = rsqrtf(fmaxf(ss, 1e-24f));
-        if (qt == 0) sA[b * 128 + r] = rinv * hscale; else sRk[b * 128 + r] = rinv;
-      }
-      named_bar_sync(1, kSoftmaxThreadsB);
       TRB(n, 2);
-      const float a_i = COS ? sA[b * 128 + r] : hscale;
-      const float4* krow = reinterpret_cast<const float4*>(sRk + b * 128 + slot * 64 + qt * KP);
+      const float a_i = COS ? sA[(n % 3) * 128 + r] : hscale;
+      const float4* krow = reinterpret_cast<const float4*>(sRk + (n % 3) * 128 + slot * 64 + qt * KP);
 
       // ---- (b) additive terms of this thread's logits (table, mask, -lse), log2 domain
       float p[KP];
@@ -409,14 +429,14 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       tcgen05_fence_after();
       TRB(n, 4);
       uint32_t dpr[KP];
-      float delta = 0.f, acc_pdu = 0.f, acc_pu = 0.f;   // sum p dp, sum p dp u, sum p u   (u = the logit without bias / mask)
+      float delta = 0.f;                                // sum_j p_j dp_j over this thread's keys
       {
         uint32_t raw[KP];
         tmem_ld_32x32b_x16(tmem + lane_base + b * 128 + qt * KP, raw);
         tmem_ld_32x32b_x16(tmem + lane_base + b * 128 + 64 + qt * KP, dpr);
         tmem_ld_wait();
         tcgen05_fence_before();
-        mbar_arrive(&sdp_empty[b]);
+        mbar_arrive_warp(&sdp_empty[b]);
 #pragma unroll
         for (int j4 = 0; j4 < KP / 4; ++j4) {
           const float4 kk = COS ? krow[j4] : make_float4(1.f, 1.f, 1.f, 1.f);
@@ -428,14 +448,11 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
             const float pj = fast_exp2(fmaf(u, kLog2e, p[j]));
             const float dpj = __uint_as_float(dpr[j]);
             delta = fmaf(pj, dpj, delta);
-            if (COS) {
-              acc_pdu = fmaf(pj * dpj, u, acc_pdu);
-              acc_pu = fmaf(pj, u, acc_pu);
-            }
             p[j] = pj;
           }
         }
       }
+      if (n + 1 < cnt) prep(n + 1);                     // published by the delta barrier below
       sDelta[qt * 128 + r] = delta;
       TRB(n, 5);
       // P (bf16) can go out before delta is known; the previous item's gradient MMAs must have finished reading P / dS'
@@ -455,12 +472,9 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       // ---- (d) dS = P o (dP - delta): dbias; dS' = dS o c into the MMA tile; d(logit scale)
 #pragma unroll
       for (int j = 0; j < KP; ++j) p[j] *= __uint_as_float(dpr[j]) - delta;
-      if (valid) {
-        if (COS) dscale_acc += acc_pdu - delta * acc_pu;      // sum_j dS_ij u_ij  (u = logit_scale x cos)
-        if (gdb_head) {
+      if (valid && gdb_head) {
 #pragma unroll
-          for (int j = 0; j < KP; ++j) dbacc[j] += p[j];
-        }
+        for (int j = 0; j < KP; ++j) dbacc[j] += p[j];
       }
 #pragma unroll
       for (int c = 0; c < KP / 8; ++c) {
@@ -479,25 +493,13 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
         *reinterpret_cast<uint4*>(drow + (((qt * (KP / 8) + c) ^ (i & 7)) << 4)) = v4;
       }
       fence_proxy_async_smem();
-      mbar_arrive(pds_full);
+      mbar_arrive_warp(pds_full);
       TRB(n, 8);
     }
 #undef TRB
 
-    // ---- cross-window reductions: dbias (registers) and d(logit scale)
+    // ---- cross-window reduction: dbias (registers)
     if (gdb_head && cls_loaded >= 0) flush_dbias(cls_loaded);
-    if (COS && P.dhead_scale) {
-      dscale_acc /= hscale;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) dscale_acc += __shfl_xor_sync(0xffffffffu, dscale_acc, o);
-      if (lane == 0) sRed[warp] = dscale_acc;
-      named_bar_sync(2, kSoftmaxThreadsB);
-      if (tid == 0) {
-        float tot = 0.f;
-        for (int x = 0; x < kSoftmaxThreadsB / 32; ++x) tot += sRed[x];
-        atomicAdd(P.dhead_scale + h, tot);
-      }
-    }
   }
 
   tcgen05_fence_before();
@@ -506,7 +508,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
 }
 
 constexpr size_t kBwdSmemBytes = 1024 + kStagesB * kStageBytesB + 2 * kPRegion + 3 * kTile + kN * kTblLd * 4 +
-                                 (256 + 256 + 512 + 16) * 4 + 512 + 8 * 16 + 24 * 8;
+                                 (384 + 384 + 512 + 16) * 4 + 512 + 8 * 16 + 24 * 8;
 
 inline const char* bwd_why_not_impl(const mmn_winattn_desc* d) {
   const char* w = fwd_why_not_impl(d);
@@ -540,8 +542,11 @@ inline int winattn_bwd_launch(const mmn_winattn_desc* d, const void* q, const vo
   P.trace = nullptr;
   const char* trace_path = getenv("MMN_TC_TRACE_BWD");
   if (trace_path && *trace_path) {
-    cudaMalloc(&P.trace, 5 * 32 * 16 * sizeof(long long));
-    cudaMemsetAsync(P.trace, 0, 5 * 32 * 16 * sizeof(long long), st);
+    cudaMalloc(&P.trace, (5 * 32 * 16 + 1) * sizeof(long long));
+    cudaMemsetAsync(P.trace, 0, (5 * 32 * 16 + 1) * sizeof(long long), st);
+    const char* cta = getenv("MMN_TC_TRACE_CTA");        // which CTA to trace (default 0); slot [5*32*16] of the buffer
+    const long long cta_id = cta ? atoll(cta) : 0;
+    cudaMemcpyAsync(P.trace + 5 * 32 * 16, &cta_id, sizeof(cta_id), cudaMemcpyHostToDevice, st);
   }
 
   using Kern = void (*)(const BwdParams);

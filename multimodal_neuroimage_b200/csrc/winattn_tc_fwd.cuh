@@ -62,9 +62,19 @@ struct FwdParams {
 };
 
 // trace[(role*32 + item)*16 + ev]; roles: 0 group A warp 0, 1 group B warp 4, 2 producer, 3 MMA, 4 store
-__device__ __forceinline__ void trace_ev(long long* trace, int role, int item, int ev) {
-  if (trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && item < 32) trace[(role * 32 + item) * 16 + ev] = clock64();
+__device__ __forceinline__ void trace_stamp(long long* trace, int role, int item, int ev) {
+  if (trace && (int)blockIdx.x == (int)trace[5 * 32 * 16] && (threadIdx.x & 31) == 0 && item < 32) trace[(role * 32 + item) * 16 + ev] = clock64();
 }
+// Backward kernel: compiled in only with -DMMN_TC_TRACING (MMN_BUILD_TRACE=1); it costs that kernel 20 %.
+__device__ __forceinline__ void trace_ev(long long* trace, int role, int item, int ev) {
+#ifdef MMN_TC_TRACING
+  trace_stamp(trace, role, item, ev);
+#endif
+}
+// Forward kernel: always compiled in.  The (never taken, when not tracing) branches are phase boundaries that
+// keep ptxas from interleaving the softmax phases; measured on B200 at BASELINE cfg2, the forward runs
+// 0.30 ms with them and 0.37 ms without.
+__device__ __forceinline__ void trace_evf(long long* trace, int role, int item, int ev) { trace_stamp(trace, role, item, ev); }
 
 // sum of squares of one 64-byte bf16 row.  `row` = the row's index in its tile: chunk c is read at its
 // swizzled place, which also spreads the lanes of a warp over all banks (plain order is a 4-way conflict).
@@ -101,9 +111,9 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
   uint64_t* full = bars;                                  // [kStagesF] TMA -> MMA, softmax
   uint64_t* empty = bars + kStagesF;                      // [kStagesF] MMA -> TMA
   uint64_t* s_full = bars + 2 * kStagesF;                 // [2] S in TMEM
-  uint64_t* p_full = s_full + 2;                          // [2] P in smem (128 arrivals)
+  uint64_t* p_full = s_full + 2;                          // [2] P in smem (one arrival per warp)
   uint64_t* o_full = s_full + 4;                          // [2] O in TMEM / P consumed
-  uint64_t* so_ready = s_full + 6;                        // [2] staging tile written (128 arrivals)
+  uint64_t* so_ready = s_full + 6;                        // [2] staging tile written (one arrival per warp)
   uint64_t* so_free = s_full + 8;                         // [2] staging tile drained by the store warp
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 10);
 
@@ -122,8 +132,8 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
   if (tid == 0) {
     for (int s = 0; s < kStagesF; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int g = 0; g < 2; ++g) {
-      mbar_init(&s_full[g], 1); mbar_init(&p_full[g], kGroupThreads); mbar_init(&o_full[g], 1);
-      mbar_init(&so_ready[g], kGroupThreads); mbar_init(&so_free[g], 1);
+      mbar_init(&s_full[g], 1); mbar_init(&p_full[g], kGroupThreads / 32); mbar_init(&o_full[g], 1);
+      mbar_init(&so_ready[g], kGroupThreads / 32); mbar_init(&so_free[g], 1);
     }
     fence_barrier_init();
   }
@@ -147,9 +157,9 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
     cur.seek(sc, item0);
     for (int n = 0; n < cnt; ++n, cur.next_item(sc)) {
       const int stage = n % kStagesF, phase = (n / kStagesF) & 1;
-      trace_ev(P.trace, 2, n, 0);
+      trace_evf(P.trace, 2, n, 0);
       mbar_wait(&empty[stage], phase ^ 1);
-      trace_ev(P.trace, 2, n, 1);
+      trace_evf(P.trace, 2, n, 1);
       const int nvalid = cur.slot_valid(1) ? 2 : 1;
       if (lane == 0) mbar_arrive_expect_tx(&full[stage], nvalid * 3 * kWinBytes);
       __syncwarp();
@@ -157,7 +167,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
       uint8_t* const dst[3] = {base, base + kQRegion, base + kQRegion + kTile};
       issue_item_boxes<true, 3>(S, item_geom(S, sc, cur, 0), item_geom(S, sc, cur, 1), nvalid, h * kD, maps, dst, slot_stride,
                                 &full[stage], lane);
-      trace_ev(P.trace, 2, n, 2);
+      trace_evf(P.trace, 2, n, 2);
     }
   } else if (warp == kMmaWarp) {
     // ============================== MMA issuer ==============================
@@ -187,9 +197,9 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
     if (cnt > 1) issue_s(1);
     for (int n = 0; n < cnt; ++n) {
       const int g = n & 1, kk = n >> 1, stage = n % kStagesF;
-      trace_ev(P.trace, 3, n, 0);
+      trace_evf(P.trace, 3, n, 0);
       mbar_wait(&p_full[g], kk & 1);
-      trace_ev(P.trace, 3, n, 1);
+      trace_evf(P.trace, 3, n, 1);
       tcgen05_fence_after();
       if (elect_one()) {
         const uint64_t ap = dP + (p0 + g * (kPRegion >> 4));
@@ -203,7 +213,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
       }
       __syncwarp();
       if (n + 2 < cnt) issue_s(n + 2);
-      trace_ev(P.trace, 3, n, 2);
+      trace_evf(P.trace, 3, n, 2);
     }
   } else if (warp == kStoreWarp) {
     // ============================== TMA store ==============================
@@ -213,9 +223,9 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
     cur.seek(sc, item0);
     for (int n = 0; n < cnt; ++n, cur.next_item(sc)) {
       const int g = n & 1, kk = n >> 1;
-      trace_ev(P.trace, 4, n, 0);
+      trace_evf(P.trace, 4, n, 0);
       mbar_wait(&so_ready[g], kk & 1);
-      trace_ev(P.trace, 4, n, 1);
+      trace_evf(P.trace, 4, n, 1);
       uint8_t* const dst[1] = {sO + g * kTile};
       issue_item_boxes<false, 1>(S, item_geom(S, sc, cur, 0), item_geom(S, sc, cur, 1), cur.slot_valid(1) ? 2 : 1, h * kD, maps, dst,
                                  slot_stride, nullptr, lane);
@@ -223,7 +233,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
       tma_store_wait_read<0>();          // per thread: each lane waits for the smem reads of its own boxes
       __syncwarp();
       if (lane == 0) mbar_arrive(&so_free[g]);
-      trace_ev(P.trace, 4, n, 2);
+      trace_evf(P.trace, 4, n, 2);
     }
     tma_store_wait_all<0>();
   } else {
@@ -238,7 +248,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
     uint8_t* obuf = sO + g * kTile + r * 64;                          // this thread's staging row
     const float* bias_h = P.bias ? P.bias + (size_t)h * kN * kN : nullptr;
     const int trole = (warp & 3) == 0 ? g : -1;
-#define TR(item, ev) do { if (trole >= 0) trace_ev(P.trace, trole, item, ev); } while (0)
+#define TR(item, ev) do { if (trole >= 0) trace_evf(P.trace, trole, item, ev); } while (0)
 
     // O epilogue of this group's item number ke: deferred behind the next item's softmax so that the PV MMA
     // runs under useful work.  o_full of that item has already been waited for.
@@ -258,7 +268,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
         *reinterpret_cast<uint4*>(obuf + ((c ^ ((r >> 1) & 3)) << 4)) = v4;
       }
       fence_proxy_async_smem();
-      mbar_arrive(&so_ready[g]);
+      mbar_arrive_warp(&so_ready[g]);
     };
 
     ItemCursor cur;
@@ -364,7 +374,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
         *reinterpret_cast<uint4*>(pbuf + ((c ^ (i & 7)) << 4)) = v4;
       }
       fence_proxy_async_smem();
-      mbar_arrive(&p_full[g]);
+      mbar_arrive_warp(&p_full[g]);
       TR(n, 7);
 
       if (have_prev) epilogue(kk - 1, prev_inv, prev_lse, prev_idx, prev_valid);
@@ -455,8 +465,11 @@ inline int winattn_fwd_launch(const mmn_winattn_desc* d, const void* q, const vo
   P.trace = nullptr;
   const char* trace_path = getenv("MMN_TC_TRACE");
   if (trace_path && *trace_path) {
-    cudaMalloc(&P.trace, 5 * 32 * 16 * sizeof(long long));
-    cudaMemsetAsync(P.trace, 0, 5 * 32 * 16 * sizeof(long long), st);
+    cudaMalloc(&P.trace, (5 * 32 * 16 + 1) * sizeof(long long));
+    cudaMemsetAsync(P.trace, 0, (5 * 32 * 16 + 1) * sizeof(long long), st);
+    const char* cta = getenv("MMN_TC_TRACE_CTA");        // which CTA to trace (default 0); slot [5*32*16] of the buffer
+    const long long cta_id = cta ? atoll(cta) : 0;
+    cudaMemcpyAsync(P.trace + 5 * 32 * 16, &cta_id, sizeof(cta_id), cudaMemcpyHostToDevice, st);
   }
 
   using Kern = void (*)(const FwdParams);
