@@ -25,6 +25,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 # production builds leave it out (it costs ~8 % of the softmax warps' instructions).
 if os.environ.get("MMN_BUILD_TRACE"):
     NVCC_FLAGS.append("-DMMN_TC_TRACING")
+# MMN_NVCC_DEFINES="-DMMN_BWD_KEYS_PER_THREAD=32 ...": tuning experiments (forces a rebuild)
+NVCC_FLAGS += os.environ.get("MMN_NVCC_DEFINES", "").split()
 
 # enums of include/mmn_b200.h
 DT_F32, DT_BF16 = 0, 1
@@ -78,7 +80,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(obj)
         stamp = _stamp([os.path.join(CSRC, src), header] + [os.path.join(CSRC, d) for d in deps])
-        if force or os.environ.get("MMN_BUILD_TRACE") or not os.path.exists(obj) or os.path.getmtime(obj) < stamp:
+        if force or os.environ.get("MMN_BUILD_TRACE") or os.environ.get("MMN_NVCC_DEFINES") or not os.path.exists(obj) or os.path.getmtime(obj) < stamp:
             cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
             if verbose:
                 print(" ".join(cmd), flush=True)

@@ -133,6 +133,9 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x32b(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_32x32b_x16(taddr, r); }
+__device__ __forceinline__ void tmem_ld_32x32b(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32b_x32(taddr, r); }
+
 // ---------------------------------------------------------------- UMMA (tcgen05.mma, kind::f16)
 // Shared-memory matrix descriptor (64 bit):
 //   [0,14)  start address >> 4        [16,30) leading-dim byte offset >> 4

@@ -31,10 +31,19 @@ namespace mmn { namespace tc {
 constexpr int kStagesB = 3;
 constexpr int kStageBytesB = 2 * kQRegion + 2 * kTile;   // Q0|Z|Q1, K0 K1, V0 V1, dO0|Z|dO1
 constexpr int kOffK = kQRegion, kOffV = kQRegion + kTile, kOffDO = kQRegion + 2 * kTile;
-constexpr int kSoftmaxThreadsB = 512, kEpiThreads = 128;
-constexpr int kKeysPerThread = 16;                  // 64 keys / 4 threads per row
-constexpr int kEpiWarp0 = 16, kProducerWarpB = 20, kMmaWarpB = 21, kStoreWarpB = 22;
-constexpr int kBwdThreads = 768;
+#ifndef MMN_BWD_KEYS_PER_THREAD
+#define MMN_BWD_KEYS_PER_THREAD 16
+#endif
+constexpr int kKeysPerThread = MMN_BWD_KEYS_PER_THREAD;     // 16: four threads per query row; 32: two
+constexpr int kRowSplit = kN / kKeysPerThread;
+constexpr int kSoftmaxThreadsB = 128 * kRowSplit, kEpiThreads = 128;
+constexpr int kEpiWarp0 = kSoftmaxThreadsB / 32, kProducerWarpB = kEpiWarp0 + 4, kMmaWarpB = kEpiWarp0 + 5, kStoreWarpB = kEpiWarp0 + 6;
+constexpr int kBwdThreads = kSoftmaxThreadsB + 256;
+// register budget by warpgroup (setmaxnreg only moves registers inside the CTA's launch allocation):
+//   4 threads/row: launch 80 -> softmax 80, epilogue 104, the rest 56     (512*80 + 128*104 + 128*56 = 768*80)
+//   2 threads/row: launch 128 -> softmax 168, epilogue 112, the rest 64   (256*168 + 128*112 + 128*64 = 512*128)
+constexpr int kRegLaunch = kRowSplit == 4 ? 80 : 128;
+constexpr int kRegSoftmax = kRowSplit == 4 ? 80 : 168, kRegEpi = kRowSplit == 4 ? 104 : 112, kRegAux = kRowSplit == 4 ? 56 : 64;
 constexpr int kBwdTmemCols = 512;     // S[b] at 128 b, dP[b] at 128 b + 64; dV|dQ~|dK~ [b] at 256 + 96 b
 
 struct BwdParams {
@@ -118,7 +127,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
   const uint32_t tmem = *tmem_slot;
 
   if (warp >= kProducerWarpB) {
-    setmaxnreg_dec<56>();
+    setmaxnreg_dec<kRegAux>();
     if (warp == kProducerWarpB) {
       // ============================== TMA producer ==============================
       // every lane runs the loop; lane l issues boxes l, l + 32 of the item (issue_item_boxes)
@@ -239,7 +248,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
     const int slot = r >> 6, i = r & 63;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int rsw = (r >> 1) & 3;                       // 64B-swizzle phase of this thread's tile row
-    setmaxnreg_inc<104>();
+    if (kRegEpi > kRegLaunch) setmaxnreg_inc<kRegEpi>(); else if (kRegEpi < kRegLaunch) setmaxnreg_dec<kRegEpi>();
     float cs[3] = {0.f, 0.f, 0.f};                      // lane l: column sums of dq, dk, dv channel l over this warp's rows
     float dscale_acc = 0.f;                             // sum over rows of q_i . dQ~_i = sum_ij dS_ij (s_ij - bias_ij)
     const float inv_hscale = COS ? 1.f / __ldg(P.head_scale + h) : 1.f;
@@ -342,7 +351,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
     }
   } else {
     // ============================== softmax (512 threads: 4 per row, 16 keys each) ==============================
-    // (softmax warps stay at the launch allocation: setmaxnreg only moves registers freed by the CTA's own warps)
+    if (kRegSoftmax > kRegLaunch) setmaxnreg_inc<kRegSoftmax>();
     constexpr int KP = kKeysPerThread;
     const int r = tid & 127, qt = tid >> 7;             // tile row; which quarter of its 64 keys
     const int slot = r >> 6, i = r & 63;
@@ -432,8 +441,8 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       float delta = 0.f;                                // sum_j p_j dp_j over this thread's keys
       {
         uint32_t raw[KP];
-        tmem_ld_32x32b_x16(tmem + lane_base + b * 128 + qt * KP, raw);
-        tmem_ld_32x32b_x16(tmem + lane_base + b * 128 + 64 + qt * KP, dpr);
+        tmem_ld_32x32b(tmem + lane_base + b * 128 + qt * KP, raw);
+        tmem_ld_32x32b(tmem + lane_base + b * 128 + 64 + qt * KP, dpr);
         tmem_ld_wait();
         tcgen05_fence_before();
         mbar_arrive_warp(&sdp_empty[b]);
@@ -467,7 +476,8 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       }
       named_bar_sync(2, kSoftmaxThreadsB);
       TRB(n, 7);
-      delta = (sDelta[r] + sDelta[128 + r]) + (sDelta[256 + r] + sDelta[384 + r]);
+      delta = sDelta[r] + sDelta[128 + r];
+      if (kRowSplit == 4) delta += sDelta[256 + r] + sDelta[384 + r];
 
       // ---- (d) dS = P o (dP - delta): dbias; dS' = dS o c into the MMA tile; d(logit scale)
 #pragma unroll

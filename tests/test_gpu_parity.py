@@ -70,6 +70,12 @@ CORE_CASES = [
     ((16, 16), (8, 8), (4, 4), 1, 64, True, "shift", 1),         # d=64
     ((8, 8, 8), (8, 8, 8), (0, 0, 0), 2, 16, False, "none", 1),  # N=512 (key chunking)
     ((14, 14), (7, 7), (3, 3), 2, 7, False, "shift", 1),         # odd head_dim, N=49
+    # class-sorted item schedule of the tensor-core path (tc_sched.cuh): all eight wrap classes, odd class
+    # counts (single-window items), class changes inside a CTA's item range
+    ((12, 12, 12), (4, 4, 4), (2, 2, 2), 3, 32, True, "shift", 1),
+    ((12, 8, 16), (4, 4, 4), (2, 2, 2), 2, 32, False, "shift", 3),
+    ((16, 16, 16), (4, 4, 4), (2, 2, 2), 3, 32, True, "shift", 2),
+    ((24, 40), (8, 8), (4, 4), 3, 32, True, "shift", 3),         # 2-D, odd batch
 ]
 
 
@@ -360,6 +366,31 @@ def test_full_size_properties(mm):
     # (e) batch independence (the sharding property of SURVEY.md 8e): sample 1 alone == sample 1 of the batch
     o_s, _ = torch.ops.mmn_b200.winattn_fwd(qkv[1:2].contiguous(), None, bias, hs, None, *args, mm.lib.PATH_AUTO)
     assert torch.equal(o_s, out[1:2])
+
+
+def test_full_size_backward_properties(mm):
+    """cfg2 size, backward: tcgen05 gradients == generic-path gradients (all of them), column sums of the
+    packed gradient == the kernel's dcolsum, and batch independence of the input gradient."""
+    B, grid, window, shift, nH, d = 2, (32, 32, 32), (4, 4, 4), (2, 2, 2), 3, 32
+    C, N = nH * d, 64
+    g = torch.Generator(device="cuda").manual_seed(1)
+    qkv = torch.randn(B, *grid, 3 * C, generator=g, device="cuda", dtype=torch.bfloat16)
+    dout = torch.randn(B, *grid, C, generator=g, device="cuda", dtype=torch.bfloat16)
+    bias = torch.randn(nH, N, N, generator=g, device="cuda")
+    hs = torch.rand(nH, generator=g, device="cuda") * 10 + 1
+    args = (list(grid), list(window), list(shift), nH, mm.lib.SCORE_COSINE, mm.lib.MASK_SHIFT, 1.0, 0.0, 0, 0)
+    res = {}
+    for name, path in (("tc", mm.lib.PATH_AUTO), ("gen", mm.lib.PATH_GENERIC)):
+        out, lse = torch.ops.mmn_b200.winattn_fwd(qkv, None, bias, hs, None, *args, path)
+        res[name] = torch.ops.mmn_b200.winattn_bwd(dout, qkv, None, bias, hs, None, out, lse, *args, path, True)
+    for i, n in ((0, "dqkv"), (2, "dbias"), (3, "dhead_scale"), (4, "dcolsum")):
+        assert rel_err(res["tc"][i], res["gen"][i]) < BF16_TOL, n
+    dqkv, dcs = res["tc"][0], res["tc"][4]
+    assert rel_err(dcs.reshape(-1), dqkv.float().sum((0, 1, 2, 3))) < 1e-2
+    out, lse = torch.ops.mmn_b200.winattn_fwd(qkv[1:2].contiguous(), None, bias, hs, None, *args, mm.lib.PATH_AUTO)
+    one = torch.ops.mmn_b200.winattn_bwd(dout[1:2].contiguous(), qkv[1:2].contiguous(), None, bias, hs, None, out, lse, *args,
+                                         mm.lib.PATH_AUTO, True)
+    assert torch.equal(one[0], dqkv[1:2])
 
 
 def test_dropout_statistics_and_backward_consistency(mm):
