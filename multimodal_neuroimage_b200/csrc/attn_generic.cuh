@@ -518,10 +518,33 @@ colsum_kernel(const T* __restrict__ x, long long rows, int cols, long long row_s
 #pragma unroll
   for (int e = 0; e < V; ++e) acc[e] = 0.f;
   if (ty < rpb) {
-    for (long long r = (long long)blockIdx.x * rpb + ty; r < rows; r += (long long)gridDim.x * rpb) {
-      const T* p = x + r * row_stride + tx * V;
+    const long long r0 = (long long)blockIdx.x * rpb + ty, step = (long long)gridDim.x * rpb;
+    if (sizeof(T) == 2 && row_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+      // bf16 rows: one 16-byte load per row and thread, four rows in flight
+      long long r = r0;
+      for (; r + 3 * step < rows; r += 4 * step) {
+        uint4 v[4];
 #pragma unroll
-      for (int e = 0; e < V; ++e) acc[e] += ldf(p + e);
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(x + (r + u * step) * row_stride + tx * V));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { acc[2 * e] += __uint_as_float(w[e] << 16); acc[2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u); }
+        }
+      }
+      for (; r < rows; r += step) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + r * row_stride + tx * V));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { acc[2 * e] += __uint_as_float(w[e] << 16); acc[2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u); }
+      }
+    } else {
+      for (long long r = r0; r < rows; r += step) {
+        const T* p = x + r * row_stride + tx * V;
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] += ldf(p + e);
+      }
     }
   }
   __shared__ float red[256 * V];
