@@ -131,6 +131,19 @@ int mmn_mha_avg_weights(const mmn_mha_desc* desc, const void* q, const void* k, 
 int mmn_colsum(const void* x, int io_dtype, int64_t rows, int32_t cols, int64_t row_stride, float* out,
                int device, void* stream);
 
+/* Fused backward of a projection y = x W^T + b (F.linear: swin_v2_module.py:148,176, swinfusion_module.py:121,143,
+ * 221-222,244) in one pass over dy and x:  dx = dy W (rows x in),  dw = dy^T x (out x in, fp32, OVERWRITTEN),
+ * db = colsum(dy) (out, fp32, OVERWRITTEN; may be NULL).  w is (out, in) row-major contiguous; dy, x, dx have the
+ * given leading dimensions (elements).  Tensor-core path only: bf16, in = 96, out in {96, 192, 288}
+ * (mmn_linear_bwd_supported tells; other shapes are plain library GEMMs on the caller's side).
+ * workspace: mmn_linear_bwd_workspace_bytes(out) bytes, contents undefined on return. */
+int mmn_linear_bwd_supported(int io_dtype, int64_t rows, int32_t in_features, int32_t out_features,
+                             int64_t ld_dy, int64_t ld_x, int64_t ld_dx);
+size_t mmn_linear_bwd_workspace_bytes(int32_t out_features);
+int mmn_linear_bwd(const void* dy, const void* x, const void* w, void* dx, float* dw, float* db, void* workspace,
+                   int io_dtype, int64_t rows, int32_t in_features, int32_t out_features,
+                   int64_t ld_dy, int64_t ld_x, int64_t ld_dx, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

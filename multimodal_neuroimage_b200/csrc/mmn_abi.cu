@@ -246,4 +246,27 @@ int mmn_colsum(const void* x, int io_dtype, int64_t rows, int32_t cols, int64_t 
   return finish(e, n, "colsum_kernel");
 }
 
+int mmn_linear_bwd_supported(int io_dtype, int64_t rows, int32_t in_features, int32_t out_features, int64_t ld_dy, int64_t ld_x,
+                             int64_t ld_dx) {
+  return have_device() && mmn::tc::linbwd_why_not(io_dtype, rows, in_features, out_features, ld_dy, ld_x, ld_dx) == nullptr;
+}
+
+size_t mmn_linear_bwd_workspace_bytes(int32_t out_features) { return mmn::tc::linbwd_workspace_bytes(out_features); }
+
+int mmn_linear_bwd(const void* dy, const void* x, const void* w, void* dx, float* dw, float* db, void* workspace, int io_dtype,
+                   int64_t rows, int32_t in_features, int32_t out_features, int64_t ld_dy, int64_t ld_x, int64_t ld_dx, int device,
+                   void* stream) {
+  if (!dy || !x || !w || !dx || !dw || !workspace) return fail(MMN_ERR_INVALID, "null tensor pointer");
+  if (!have_device()) return fail(MMN_ERR_CUDA, "no CUDA device: libmmn_b200 has no CPU path");
+  const char* why = mmn::tc::linbwd_why_not(io_dtype, rows, in_features, out_features, ld_dy, ld_x, ld_dx);
+  if (why) return fail(MMN_ERR_UNSUPPORTED, "shape not supported by the fused projection backward: %s", why);
+  DeviceGuard g(device);
+  if (!g.ok) return fail(MMN_ERR_CUDA, "cannot select device %d", device);
+  int n = 0;
+  int rc = mmn::tc::linbwd(dy, x, w, dx, dw, db, (float*)workspace, rows, in_features, out_features, ld_dy, ld_x, ld_dx,
+                           (cudaStream_t)stream, g_err, sizeof(g_err), &n);
+  g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed);
+  return rc;
+}
+
 }  // extern "C"

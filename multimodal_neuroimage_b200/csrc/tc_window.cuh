@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "../../include/mmn_b200.h"
 #include "tc_common.cuh"
 
@@ -136,6 +138,17 @@ inline WinShape shape_from(const mmn_winattn_desc* d) {
   g.nW = g.nwin[0] * g.nwin[1] * g.nwin[2];
   g.n_windows = d->batch * g.nW;
   return g;
+}
+
+inline int num_sms_cached() {
+  static std::once_flag once;
+  static int num_sms = 148;
+  std::call_once(once, [] {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  });
+  return num_sms;
 }
 
 // Eight tensor maps (one box shape per wrap class) over a (B, g0, g1, g2, channels) bf16 tensor

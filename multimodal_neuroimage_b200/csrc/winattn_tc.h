@@ -15,4 +15,10 @@ int winattn_bwd(const mmn_winattn_desc* d, const void* q, const void* k, const v
                 const float* head_scale, const float* mask, const void* out, const float* lse, const void* dout, void* dq,
                 void* dk, void* dv, float* dbias, float* dhead_scale, float* dcolsum, float* workspace, cudaStream_t st,
                 char* err, size_t errlen, int* launches);
+// fused projection backward (linbwd_tc.cu)
+const char* linbwd_why_not(int io_dtype, long long rows, int in_features, int out_features, long long ld_dy, long long ld_x, long long ld_dx);
+size_t linbwd_workspace_bytes(int out_features);
+int linbwd(const void* dy, const void* x, const void* w, void* dx, float* dw, float* db, float* workspace, long long rows,
+           int in_features, int out_features, long long ld_dy, long long ld_x, long long ld_dx, cudaStream_t st, char* err,
+           size_t errlen, int* launches);
 }}  // namespace mmn::tc

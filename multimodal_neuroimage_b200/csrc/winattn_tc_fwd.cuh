@@ -435,17 +435,6 @@ inline void dump_trace(long long* dev, const char* path, cudaStream_t st) {
   }
 }
 
-inline int num_sms_cached() {
-  static std::once_flag once;
-  static int num_sms = 148;
-  std::call_once(once, [] {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  });
-  return num_sms;
-}
-
 inline int winattn_fwd_launch(const mmn_winattn_desc* d, const void* q, const void* k, const void* v, const float* bias,
                               const float* head_scale, const float* mask, void* out, float* lse, cudaStream_t st, char* err,
                               size_t errlen) {

@@ -65,25 +65,40 @@ class WindowAttentionModuleFn(torch.autograd.Function):
             if not dy.is_contiguous():
                 dy = dy.contiguous()
             out2 = out.view(B * L, C)
-            d_bp = None
-            if bpdt is not None:      # the column-sum kernel moves 8 columns per thread; odd widths are the reference's tiny stages
-                d_bp = (torch.ops.mmn_b200.colsum(dy) if C % 8 == 0 and C <= 2048 else dy.float().sum(0)).to(bpdt)
-            d_wp = _mm_f32(dy.t(), out2).to(wpdt)
-            dout = (dy @ wp).view(out.shape)
+            if ops.linear_bwd_supported(dy, out2, wp):
+                # one pass over dy: dout = dy Wp, dWp = dy^T out, dbp = colsum(dy)  (libmmn_b200: linbwd_tc.cu)
+                dout2, d_wp, d_bp = torch.ops.mmn_b200.linear_bwd(dy, out2, wp)
+                dout = dout2.view(out.shape)
+                d_wp = d_wp.to(wpdt)
+                d_bp = d_bp.to(bpdt) if bpdt is not None else None
+            else:
+                d_bp = None
+                if bpdt is not None:      # the column-sum kernel moves 8 columns per thread; odd widths are the reference's tiny stages
+                    d_bp = (torch.ops.mmn_b200.colsum(dy) if C % 8 == 0 and C <= 2048 else dy.float().sum(0)).to(bpdt)
+                d_wp = _mm_f32(dy.t(), out2).to(wpdt)
+                dout = (dy @ wp).view(out.shape)
             da, db, dbias, dhs, dcs = torch.ops.mmn_b200.winattn_bwd(dout, a, b, bias, head_scale, None, out, lse, *ctx.cfg,
                                                                      True)
             da2 = da.view(B * L, -1)
-            d_wa = _mm_f32(da2.t(), xc).to(wadt)
-            dx = (da2 @ wa).view(B, L, C).to(xdt)
+            if ops.linear_bwd_supported(da2, xc, wa):
+                dx, d_wa, _ = torch.ops.mmn_b200.linear_bwd(da2, xc, wa)
+                dx, d_wa = dx.view(B, L, C).to(xdt), d_wa.to(wadt)
+            else:
+                d_wa = _mm_f32(da2.t(), xc).to(wadt)
+                dx = (da2 @ wa).view(B, L, C).to(xdt)
             if b is None:
                 d_ba = dcs.reshape(-1).to(badt) if badt is not None else None
                 d_y = d_wb = d_bb = None
             else:
                 db2 = db.view(B * L, -1)
                 d_ba = dcs[0].to(badt) if badt is not None else None
-                d_wb = _mm_f32(db2.t(), yc).to(wbdt)
                 d_bb = dcs[1:].reshape(-1).to(bbdt) if bbdt is not None else None
-                d_y = (db2 @ wb).view(B, L, C).to(ydt)
+                if ops.linear_bwd_supported(db2, yc, wb):
+                    d_y, d_wb, _ = torch.ops.mmn_b200.linear_bwd(db2, yc, wb)
+                    d_y, d_wb = d_y.view(B, L, C).to(ydt), d_wb.to(wbdt)
+                else:
+                    d_wb = _mm_f32(db2.t(), yc).to(wbdt)
+                    d_y = (db2 @ wb).view(B, L, C).to(ydt)
         return (dx, d_y, d_wa, d_ba, d_wb, d_bb, d_wp, d_bp, dbias if bias is not None else None,
                 dhs if head_scale is not None else None) + (None,) * 9
 

@@ -347,6 +347,40 @@ def _(x):
     return x.new_empty(x.shape[1], dtype=torch.float32)
 
 
+def linear_bwd_supported(dy: Tensor, x: Tensor, w: Tensor) -> bool:
+    """True when the fused tensor-core projection backward takes these operands (bf16, in = 96, out in {96,192,288})."""
+    if not (dy.is_cuda and dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16):
+        return False
+    if dy.dim() != 2 or x.dim() != 2 or dy.stride(1) != 1 or x.stride(1) != 1 or not w.is_contiguous():
+        return False
+    return bool(_lib.load().mmn_linear_bwd_supported(_DT[dy.dtype], dy.shape[0], x.shape[1], dy.shape[1], dy.stride(0),
+                                                     x.stride(0), x.shape[1]))
+
+
+@torch.library.custom_op("mmn_b200::linear_bwd", mutates_args=())
+def linear_bwd(dy: Tensor, x: Tensor, w: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """Backward of y = x w^T + b in one pass over dy and x: returns (dx bf16 (rows, in), dw fp32 (out, in),
+    db fp32 (out))."""
+    _require_cuda(dy, x, w)
+    lib = _lib.load()
+    rows, n_out, n_in = dy.shape[0], dy.shape[1], x.shape[1]
+    dx = torch.empty(rows, n_in, dtype=dy.dtype, device=dy.device)
+    dw = torch.empty(n_out, n_in, dtype=torch.float32, device=dy.device)
+    db = torch.empty(n_out, dtype=torch.float32, device=dy.device)
+    ws = torch.empty(lib.mmn_linear_bwd_workspace_bytes(n_out), dtype=torch.uint8, device=dy.device)
+    with _timed("linear_bwd", dy):
+        _lib.check(lib.mmn_linear_bwd(_ptr(dy), _ptr(x), _ptr(w), _ptr(dx), _ptr(dw), _ptr(db), _ptr(ws), _DT[dy.dtype], rows,
+                                      n_in, n_out, dy.stride(0), x.stride(0), n_in, dy.device.index, _stream(dy)),
+                   "mmn_linear_bwd")
+    return dx, dw, db
+
+
+@linear_bwd.register_fake
+def _(dy, x, w):
+    return (dy.new_empty(dy.shape[0], x.shape[1]), dy.new_empty(dy.shape[1], x.shape[1], dtype=torch.float32),
+            dy.new_empty(dy.shape[1], dtype=torch.float32))
+
+
 def next_dropout_stream(p: float, training: bool, device) -> Tuple[float, int, int]:
     """(p, seed, offset) for one attention call: a fresh Philox offset drawn from torch's
     generator so `torch.manual_seed` controls it; p = 0 outside training."""
