@@ -375,9 +375,11 @@ def main():
             torch.cuda.synchronize()
             def _rel(a, b):
                 return float((a.detach().float() - b).abs().max() / b.abs().max().clamp_min(1e-20))
-            worst = max([_rel(y_static, y_eager), _rel(x.grad, dx_eager)] + [_rel(p.grad, ge) for p, ge in zip(params, g_eager)])
+            errs = {"y": _rel(y_static, y_eager), "dx": _rel(x.grad, dx_eager)}
+            errs.update({n: _rel(p.grad, ge) for (n, p), ge in zip([(n, p) for n, p in model.named_parameters() if p.requires_grad], g_eager)})
+            worst = max(errs.values())
             if not worst < 1e-2:
-                raise RuntimeError(f"graph replay differs from the eager step (rel err {worst:.2e})")
+                raise RuntimeError(f"graph replay differs from the eager step: {errs}")
             step_fn, graphed = step_graph, True
         except Exception as exc:                   # capture not possible in this environment: eager timing
             print(f"bench: CUDA graph capture failed ({type(exc).__name__}: {exc}); timing eager launches", file=sys.stderr)
