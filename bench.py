@@ -264,44 +264,84 @@ def main():
         return y
 
     # End-to-end step: inputs start in pinned host memory, results end there.  The batch is cut into chunks that
-    # flow through three streams (H2D copy -> forward+backward -> D2H copy), so the PCIe transfers of one chunk
-    # overlap the kernels of another; weight gradients accumulate over the chunks exactly as over one batch.
+    # flow through three streams (H2D copy -> forward+backward -> D2H copy) and three device slots, so the PCIe
+    # transfers of one chunk overlap the kernels of another -- within a step and across consecutive steps.  The
+    # forward+backward of a chunk is one CUDA-graph replay per slot (captured with the gradient buffers in place, so
+    # weight gradients accumulate over the chunks exactly as over one batch).
     E2E_CHUNKS = 8 if B % 8 == 0 else (4 if B % 4 == 0 else 1)
+    NSLOT = 3
     cb = B // E2E_CHUNKS
     s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-    xd_buf = torch.empty(B, L, C, device=dev, dtype=torch.bfloat16)
-    dyd_buf = torch.empty(B, L, C, device=dev, dtype=torch.bfloat16)
+    x_slot = [torch.zeros(cb, L, C, device=dev, dtype=torch.bfloat16).requires_grad_(True) for _ in range(NSLOT)]
+    dy_slot = [torch.zeros(cb, L, C, device=dev, dtype=torch.bfloat16) for _ in range(NSLOT)]
+    e2e_state = {"graphs": None, "y": [None] * NSLOT, "ev_free": [None] * NSLOT}
+
+    def chunk_fwd_bwd(j):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = model(x_slot[j])
+        y.backward(dy_slot[j])
+        return y
+
+    def e2e_prepare():
+        """Capture one graph per slot (eager per-chunk launches if capture is unavailable)."""
+        for p in model.parameters():
+            p.grad = torch.zeros_like(p)
+        for j in range(NSLOT):
+            x_slot[j].grad = torch.zeros_like(x_slot[j])
+        if args.no_graph:
+            return
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for j in range(NSLOT):
+                    chunk_fwd_bwd(j)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graphs = []
+            for j in range(NSLOT):
+                g = torch.cuda.CUDAGraph()
+                x_slot[j].grad.zero_()
+                with torch.cuda.graph(g):
+                    x_slot[j].grad.zero_()          # dx of a slot is per chunk; the weight gradients accumulate
+                    e2e_state["y"][j] = chunk_fwd_bwd(j)
+                graphs.append(g)
+            e2e_state["graphs"] = graphs
+        except Exception as exc:
+            print(f"bench: e2e CUDA graph capture failed ({type(exc).__name__}: {exc}); eager chunks", file=sys.stderr)
+            e2e_state["graphs"] = None
+            torch.cuda.synchronize()
 
     def step_e2e():
-        for p in model.parameters():
-            p.grad = None
         cur = torch.cuda.current_stream(dev)
-        s_in.wait_stream(cur)          # the previous step's kernels are done with the device buffers
-        ev_in = []
-        with torch.cuda.stream(s_in):
-            for c in range(E2E_CHUNKS):
-                sl = slice(c * cb, (c + 1) * cb)
-                xd_buf[sl].copy_(x_host[sl], non_blocking=True)
-                dyd_buf[sl].copy_(dy_host[sl], non_blocking=True)
-                e = torch.cuda.Event()
-                e.record(s_in)
-                ev_in.append(e)
+        for p in model.parameters():
+            p.grad.zero_()
         for c in range(E2E_CHUNKS):
+            j = c % NSLOT
             sl = slice(c * cb, (c + 1) * cb)
-            cur.wait_event(ev_in[c])
-            xc = xd_buf[sl].detach().requires_grad_(True)
-            with torch.autocast("cuda", dtype=torch.bfloat16):
-                y = model(xc)
-            y.backward(dyd_buf[sl])
-            e = torch.cuda.Event()
-            e.record(cur)
-            yd, dxd = y.detach(), xc.grad
+            with torch.cuda.stream(s_in):
+                if e2e_state["ev_free"][j] is not None:
+                    s_in.wait_event(e2e_state["ev_free"][j])      # the slot's previous chunk has been computed and copied out
+                with torch.no_grad():
+                    x_slot[j].copy_(x_host[sl], non_blocking=True)
+                dy_slot[j].copy_(dy_host[sl], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(s_in)
+            cur.wait_event(ev_in)
+            if e2e_state["graphs"] is not None:
+                e2e_state["graphs"][j].replay()
+                yj = e2e_state["y"][j]
+            else:
+                x_slot[j].grad.zero_()
+                yj = chunk_fwd_bwd(j)
+            ev_c = torch.cuda.Event()
+            ev_c.record(cur)
             with torch.cuda.stream(s_out):
-                s_out.wait_event(e)
-                y_host[sl].copy_(yd, non_blocking=True)
-                dx_host[sl].copy_(dxd, non_blocking=True)
-                yd.record_stream(s_out)
-                dxd.record_stream(s_out)
+                s_out.wait_event(ev_c)
+                y_host[sl].copy_(yj.detach(), non_blocking=True)
+                dx_host[sl].copy_(x_slot[j].grad, non_blocking=True)
+                ev_o = torch.cuda.Event()
+                ev_o.record(s_out)
+            e2e_state["ev_free"][j] = ev_o
         allreduce_grads()
         cur.wait_stream(s_out)         # the step ends when its results are in host memory
 
@@ -386,9 +426,17 @@ def main():
             torch.cuda.synchronize()
     with ClockSampler(local) as clk:
         ms, _, _ = timed(step_fn, args.steps)
+    e2e_prepare()
     for _ in range(2):
         step_e2e()
-    ms_e2e, _, _ = timed(step_e2e, max(3, args.steps // 4))
+    torch.cuda.synchronize()
+    # the chunked, graph-replayed pipeline must reproduce the plain module call on the same host data
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        y_chk = model(x_host[:cb].to(dev)).float().cpu()
+    chk = float((y_host[:cb].float() - y_chk).abs().max() / y_chk.abs().max())
+    if not chk < 1e-2:
+        raise RuntimeError(f"e2e pipeline output differs from the module call (rel err {chk:.2e})")
+    ms_e2e, _, _ = timed(step_e2e, max(5, args.steps // 2))
 
     LAUNCH_MODE[0] = "cuda-graph replay of forward+backward" if graphed else "eager"
     windows = B * world * WINDOWS_PER_SAMPLE
@@ -424,8 +472,9 @@ def main():
                 "samples_per_s": B * world / (ms * 1e-3),
                 "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": 2 * B * L * C * elem,
                         "d2h_bytes_per_step": 2 * B * L * C * elem, "chunks": E2E_CHUNKS,
-                        "note": "x, dy from pinned host memory; y, dx back to pinned host memory; copies of one chunk overlap "
-                                "the kernels of another (3 streams)"},
+                        "note": "x, dy from pinned host memory; y, dx back to pinned host memory; 8 chunks through 3 streams and "
+                                "3 device slots, one CUDA-graph replay per chunk: PCIe-bound (measured duplex floor of this box: "
+                                "8.7 ms for these bytes, tools/pcie_probe.py)"},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary(),
                 "paths": {"fwd": ops.winattn_path_name(torch.empty(1, *GRID, 3 * C, device=dev, dtype=torch.bfloat16), None, GRID,
                                                        (WINDOW,) * 3, (SHIFT,) * 3, HEADS, _lib.SCORE_COSINE, _lib.MASK_SHIFT)}}
