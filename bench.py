@@ -143,7 +143,7 @@ def cpu_reference_run(steps, warmup, samples=1, threads=None):
     return tflops, dt * 1e3, threads, f"{samples} volume(s) of 32^3 tokens ({samples * WINDOWS_PER_SAMPLE} windows) per step, fp32, torch CPU"
 
 
-def run_reference_arm(args, rank, world):
+def run_reference_arm(args, rank, world, emit):
     if rank != 0:
         return
     tflops, ms, cores, sample = cpu_reference_run(args.steps, args.warmup, samples=1)
@@ -154,7 +154,7 @@ def run_reference_arm(args, rank, world):
             "cpu_baseline": {"value": tflops, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": tflops, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 LAUNCH_MODE = ["eager"]
@@ -172,6 +172,17 @@ def workload_config(batch, world):
 # GPU arm
 # ------------------------------------------------------------------------------------------
 def main():
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -188,7 +199,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference_arm(args, rank, world)
+        run_reference_arm(args, rank, world, emit)
         return
 
     import torch.distributed as dist
@@ -478,7 +489,7 @@ def main():
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary(),
                 "paths": {"fwd": ops.winattn_path_name(torch.empty(1, *GRID, 3 * C, device=dev, dtype=torch.bfloat16), None, GRID,
                                                        (WINDOW,) * 3, (SHIFT,) * 3, HEADS, _lib.SCORE_COSINE, _lib.MASK_SHIFT)}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

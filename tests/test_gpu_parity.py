@@ -76,6 +76,7 @@ CORE_CASES = [
     ((12, 8, 16), (4, 4, 4), (2, 2, 2), 2, 32, False, "shift", 3),
     ((16, 16, 16), (4, 4, 4), (2, 2, 2), 3, 32, True, "shift", 2),
     ((24, 40), (8, 8), (4, 4), 3, 32, True, "shift", 3),         # 2-D, odd batch
+    ((8, 8, 16), (4, 4, 4), (2, 2, 2), 6, 32, True, "shift", 1), # cfg5 stage-1 head count (C = 192)
 ]
 
 
