@@ -11,6 +11,9 @@
 // bias table in shared memory and accumulate the bias gradient in registers without atomics.
 #pragma once
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "tc_window.cuh"
 
 namespace mmn { namespace tc {
@@ -23,7 +26,25 @@ struct Sched {
   long long total_wt;
 };
 
-inline Sched make_sched(const WinShape& S, int batch) {
+// Relative item cost by number of wrapped axes (partitioning only).  Tuned on B200 at BASELINE cfg2 by sweeping
+// MMN_SCHED_WT_FWD / MMN_SCHED_WT_BWD="w0,w1,w2,w3" (read once per process).
+inline const int* sched_weights(bool backward) {
+  static int wt[2][4] = {{16, 18, 20, 22}, {16, 18, 20, 22}};
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* names[2] = {"MMN_SCHED_WT_FWD", "MMN_SCHED_WT_BWD"};
+    for (int k = 0; k < 2; ++k)
+      if (const char* e = getenv(names[k])) {
+        int w[4];
+        if (sscanf(e, "%d,%d,%d,%d", &w[0], &w[1], &w[2], &w[3]) == 4 && w[0] > 0 && w[1] > 0 && w[2] > 0 && w[3] > 0)
+          for (int i = 0; i < 4; ++i) wt[k][i] = w[i];
+      }
+  });
+  return wt[backward ? 1 : 0];
+}
+
+inline Sched make_sched(const WinShape& S, int batch, bool backward) {
+  const int* wts = sched_weights(backward);
   Sched sc;
   sc.n_items = 0;
   sc.total_wt = 0;
@@ -37,7 +58,7 @@ inline Sched make_sched(const WinShape& S, int batch) {
       n *= d;
     }
     sc.cnt[c] = (int)n;
-    sc.wt[c] = 16 + 2 * __builtin_popcount(c);      // wrapped windows: more, smaller TMA boxes
+    sc.wt[c] = wts[__builtin_popcount(c)];
     sc.n_items += (sc.cnt[c] + 1) / 2;
     sc.total_wt += (long long)((sc.cnt[c] + 1) / 2) * sc.wt[c];
   }

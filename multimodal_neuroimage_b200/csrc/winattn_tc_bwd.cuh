@@ -532,7 +532,7 @@ inline int winattn_bwd_launch(const mmn_winattn_desc* d, const void* q, const vo
                               void* dv, float* dbias, float* dhead_scale, float* dcolsum, cudaStream_t st, char* err, size_t errlen) {
   BwdParams P;
   P.S = shape_from(d);
-  P.sc = make_sched(P.S, d->batch);
+  P.sc = make_sched(P.S, d->batch, true);
   const int C = d->num_heads * d->head_dim;
   const int B = d->batch;
   if (!make_window_maps(P.q, q, d->q_row_stride, B, C, P.S) || !make_window_maps(P.k, k, d->k_row_stride, B, C, P.S) ||

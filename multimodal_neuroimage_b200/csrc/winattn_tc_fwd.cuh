@@ -440,7 +440,7 @@ inline int winattn_fwd_launch(const mmn_winattn_desc* d, const void* q, const vo
                               size_t errlen) {
   FwdParams P;
   P.S = shape_from(d);
-  P.sc = make_sched(P.S, d->batch);
+  P.sc = make_sched(P.S, d->batch, false);
   const int C = d->num_heads * d->head_dim;
   if (!make_window_maps(P.q, q, d->q_row_stride, d->batch, C, P.S) || !make_window_maps(P.k, k, d->k_row_stride, d->batch, C, P.S) ||
       !make_window_maps(P.v, v, d->v_row_stride, d->batch, C, P.S) || !make_window_maps(P.o, out, d->o_row_stride, d->batch, C, P.S)) {

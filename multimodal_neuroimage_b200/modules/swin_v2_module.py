@@ -87,6 +87,22 @@ def window_reverse(windows, window_size, *grid):
     return out.reshape(B, *grid, -1)
 
 
+class _GatherRows(torch.autograd.Function):
+    """table[index] for a (T, H) table and a fixed int64 index; backward = index_add_."""
+
+    @staticmethod
+    def forward(ctx, table, index):
+        ctx.save_for_backward(index)
+        ctx.rows = table.shape[0]
+        return table.index_select(0, index)
+
+    @staticmethod
+    def backward(ctx, grad):
+        index, = ctx.saved_tensors
+        out = torch.zeros(ctx.rows, grad.shape[1], dtype=grad.dtype, device=grad.device)
+        return out.index_add_(0, index, grad), None
+
+
 class WindowAttention(nn.Module):
     """SwinV2 window attention: cosine similarity with a clamped learnable per-head logit
     scale and a log-spaced continuous relative position bias (swin_v2_module.py:65-195).
@@ -130,8 +146,10 @@ class WindowAttention(nn.Module):
         N = math.prod(self.window_size)
         with torch.autocast(device_type="cuda", enabled=False):
             tab = self.cpb_mlp(self.relative_coords_table.float()).view(-1, self.num_heads_swin)
-            b = tab[self.relative_position_index.view(-1)].view(N, N, -1).permute(2, 0, 1)
-            return (16 * torch.sigmoid(b)).contiguous().float()
+            # 16*sigmoid commutes with the gather: apply it on the (2w-1)^n-entry table, not on N*N entries, and
+            # scatter the gradient back with one index_add_ instead of autograd's sort-based index backward
+            b = _GatherRows.apply(16 * torch.sigmoid(tab), self.relative_position_index.view(-1))
+            return b.view(N, N, -1).permute(2, 0, 1).contiguous().float()
 
     def head_scale(self) -> torch.Tensor:
         """(nH,) fp32 = exp(min(logit_scale, ln 100)) (swin_v2_module.py:154-155)."""

@@ -17,7 +17,7 @@ import torch.nn as nn
 import torch.utils.checkpoint as checkpoint
 
 from .. import _lib, fused, geometry, ops
-from .swin_v2_module import DropPath, to_2tuple, to_ntuple, window_partition, window_reverse
+from .swin_v2_module import DropPath, _GatherRows, to_2tuple, to_ntuple, window_partition, window_reverse
 
 window_partition_fusion = window_partition
 
@@ -58,7 +58,7 @@ class _TableBiasAttention(nn.Module):
     def position_bias(self) -> torch.Tensor:
         """(nH, N, N) fp32 = table[index] (swinfusion_module.py:127-130)."""
         N = math.prod(self.window_size)
-        b = self.relative_position_bias_table.float()[self.relative_position_index.view(-1)]
+        b = _GatherRows.apply(self.relative_position_bias_table.float(), self.relative_position_index.view(-1))
         return b.view(N, N, -1).permute(2, 0, 1).contiguous()
 
     def _core(self, a, b, grid, window, shift, mask_kind, mask):
