@@ -131,6 +131,19 @@ int mmn_mha_avg_weights(const mmn_mha_desc* desc, const void* q, const void* k, 
 int mmn_colsum(const void* x, int io_dtype, int64_t rows, int32_t cols, int64_t row_stride, float* out,
                int device, void* stream);
 
+/* SwinV2 continuous relative-position bias (swin_v2_module.py:158-162), fp32:
+ *   bias[h][e] = 16 sigmoid(tab[index[e]][h]),  tab[t][h] = sum_j w2[h][j] relu(w1[j] . coords[t] + b1[j])
+ * coords (T, n_in) with n_in <= 3, w1 (J, n_in), b1 (J), w2 (nH, J) with nH <= 64, index (NN) int64 in [0, T).
+ * fwd writes tab16 (T, nH) [= 16 sigmoid(tab), kept for the backward] and bias (nH, NN).
+ * bwd: dbias (nH, NN) -> dw1 (J, n_in), db1 (J), dw2 (nH, J), all OVERWRITTEN; scratch (T, nH) floats.
+ * T * nH <= 12288 (the backward stages d tab in shared memory); MMN_ERR_UNSUPPORTED otherwise. */
+int mmn_cpb_bias_fwd(const float* coords, const float* w1, const float* b1, const float* w2, const int64_t* index,
+                     int32_t T, int32_t n_in, int32_t J, int32_t num_heads, int32_t NN,
+                     float* tab16, float* bias, int device, void* stream);
+int mmn_cpb_bias_bwd(const float* coords, const float* w1, const float* b1, const float* w2, const int64_t* index,
+                     const float* tab16, const float* dbias, int32_t T, int32_t n_in, int32_t J, int32_t num_heads, int32_t NN,
+                     float* scratch, float* dw1, float* db1, float* dw2, int device, void* stream);
+
 /* Fused backward of a projection y = x W^T + b (F.linear: swin_v2_module.py:148,176, swinfusion_module.py:121,143,
  * 221-222,244) in one pass over dy and x:  dx = dy W (rows x in),  dw = dy^T x (out x in, fp32, OVERWRITTEN),
  * db = colsum(dy) (out, fp32, OVERWRITTEN; may be NULL).  w is (out, in) row-major contiguous; dy, x, dx have the

@@ -19,7 +19,8 @@ LIB_PATH = os.path.join(PKG_DIR, "libmmn_b200.so")
 SOURCES = {"mmn_abi.cu": ["generic_launch.h", "attn_generic.cuh", "winattn_tc.h"],
            "generic_launch.cu": ["generic_launch.h", "attn_generic.cuh"],
            "winattn_tc.cu": ["winattn_tc.h", "winattn_tc_fwd.cuh", "winattn_tc_bwd.cuh", "tc_window.cuh", "tc_sched.cuh", "tc_common.cuh"],
-           "linbwd_tc.cu": ["winattn_tc.h", "tc_window.cuh", "tc_common.cuh"]}
+           "linbwd_tc.cu": ["winattn_tc.h", "tc_window.cuh", "tc_common.cuh"],
+           "cpb_bias.cu": ["generic_launch.h", "attn_generic.cuh"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 # MMN_BUILD_TRACE=1 compiles the per-phase clock tracing into the tensor-core kernels (tools/trace_*.py);
@@ -37,7 +38,7 @@ PATH_AUTO, PATH_GENERIC, PATH_TCGEN05 = 0, 1, 2
 
 EXPORTS = ["mmn_abi_version", "mmn_last_error", "mmn_winattn_path", "mmn_mha_path", "mmn_launch_count",
            "mmn_winattn_fwd", "mmn_winattn_bwd", "mmn_mha_fwd", "mmn_mha_bwd", "mmn_mha_avg_weights", "mmn_colsum",
-           "mmn_linear_bwd", "mmn_linear_bwd_supported", "mmn_linear_bwd_workspace_bytes"]
+           "mmn_linear_bwd", "mmn_linear_bwd_supported", "mmn_linear_bwd_workspace_bytes", "mmn_cpb_bias_fwd", "mmn_cpb_bias_bwd"]
 
 
 class WinAttnDesc(C.Structure):
@@ -137,6 +138,11 @@ def load() -> C.CDLL:
         lib.mmn_mha_avg_weights.argtypes = [C.POINTER(MhaDesc), vp, vp, fp, fp, fp, C.c_int, vp]
         lib.mmn_colsum.restype = C.c_int
         lib.mmn_colsum.argtypes = [vp, C.c_int, C.c_int64, C.c_int32, C.c_int64, fp, C.c_int, vp]
+        lib.mmn_cpb_bias_fwd.restype = C.c_int
+        lib.mmn_cpb_bias_fwd.argtypes = [fp, fp, fp, fp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, fp, fp, C.c_int, vp]
+        lib.mmn_cpb_bias_bwd.restype = C.c_int
+        lib.mmn_cpb_bias_bwd.argtypes = [fp, fp, fp, fp, vp, fp, fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         fp, fp, fp, fp, C.c_int, vp]
         lib.mmn_linear_bwd_supported.restype = C.c_int
         lib.mmn_linear_bwd_supported.argtypes = [C.c_int, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64]
         lib.mmn_linear_bwd_workspace_bytes.restype = C.c_size_t

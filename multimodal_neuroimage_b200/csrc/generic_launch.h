@@ -15,4 +15,10 @@ cudaError_t generic_avg_weights(const GenericProblem& P, int io_dtype, int batch
                                 const float* lse, float* avg, cudaStream_t st, int* launches);
 cudaError_t colsum(int io_dtype, const void* x, long long rows, int cols, long long row_stride, float* out, cudaStream_t st,
                    int* launches);
+// continuous relative-position bias (cpb_bias.cu)
+cudaError_t cpb_bias_fwd(const float* coords, const float* w1, const float* b1, const float* w2, const long long* index, int T,
+                         int n_in, int J, int nH, int NN, float* tab16, float* bias, cudaStream_t st, int* launches);
+cudaError_t cpb_bias_bwd(const float* coords, const float* w1, const float* b1, const float* w2, const long long* index,
+                         const float* tab16, const float* dbias, int T, int n_in, int J, int nH, int NN, float* dtab16, float* dw1,
+                         float* db1, float* dw2, cudaStream_t st, int* launches);
 }  // namespace mmn

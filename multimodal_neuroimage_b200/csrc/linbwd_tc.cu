@@ -214,15 +214,26 @@ linbwd_tc_kernel(const __grid_constant__ LinBwdParams P) {
   if (warp == 5) tmem_dealloc<kLTmemCols>(tmem);
 }
 
-// out[e] = sum over CTAs of ws[cta][e]; element e = (out-channel, 0..96): columns 0..95 -> dW, column 96 -> db
-__global__ void linbwd_reduce_kernel(const float* __restrict__ ws, int n_cta, int rows, float* __restrict__ dw, float* __restrict__ db) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= rows * 97) return;
+// out[e] = sum over CTAs of ws[cta][e]; element e = (out-channel, 0..96): columns 0..95 -> dW, column 96 -> db.
+// Block = 32 elements x 8 slices of the CTA range (a 148-long serial chain of dependent loads per thread took 10 us).
+__global__ void __launch_bounds__(256)
+linbwd_reduce_kernel(const float* __restrict__ ws, int n_cta, int rows, float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float part[8][33];
+  const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + lane;
+  const int n = rows * 97;
   float s = 0.f;
-  for (int c = 0; c < n_cta; ++c) s += ws[(size_t)c * rows * 97 + e];
-  const int o = e / 97, i = e - o * 97;
-  if (i < 96) dw[o * 96 + i] = s;
-  else if (db) db[o] = s;
+  if (e < n)
+    for (int c = sl; c < n_cta; c += 8) s += ws[(size_t)c * n + e];
+  part[sl][lane] = s;
+  __syncthreads();
+  if (sl == 0 && e < n) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) s += part[k][lane];
+    const int o = e / 97, i = e - o * 97;
+    if (i < 96) dw[o * 96 + i] = s;
+    else if (db) db[o] = s;
+  }
 }
 
 constexpr size_t kLSmemBytes = 1024 + kDyStages * kLTileBytes + kXStages * kXSlot + 3 * kWChunk + kLTileBytes + 32 * 8;
@@ -272,7 +283,7 @@ int linbwd(const void* dy, const void* x, const void* w, void* dx, float* dw, fl
   if (e != cudaSuccess) { snprintf(err, errlen, "linbwd_tc_kernel: %s", cudaGetErrorString(e)); return MMN_ERR_CUDA; }
   ++*launches;
   const int n = out_features * 97;
-  linbwd_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(workspace, grid, out_features, dw, db);
+  linbwd_reduce_kernel<<<(n + 31) / 32, 256, 0, st>>>(workspace, grid, out_features, dw, db);
   e = cudaGetLastError();
   if (e != cudaSuccess) { snprintf(err, errlen, "linbwd_reduce_kernel: %s", cudaGetErrorString(e)); return MMN_ERR_CUDA; }
   ++*launches;

@@ -246,6 +246,40 @@ int mmn_colsum(const void* x, int io_dtype, int64_t rows, int32_t cols, int64_t 
   return finish(e, n, "colsum_kernel");
 }
 
+static int cpb_check(int T, int n_in, int J, int nH, int NN) {
+  if (T < 1 || n_in < 1 || n_in > 3 || J < 1 || nH < 1 || nH > 64 || NN < 1) return fail(MMN_ERR_INVALID, "bad cpb_bias sizes");
+  if ((long long)T * nH > 12288) return fail(MMN_ERR_UNSUPPORTED, "cpb_bias: T * num_heads = %lld > 12288", (long long)T * nH);
+  if (!have_device()) return fail(MMN_ERR_CUDA, "no CUDA device: libmmn_b200 has no CPU path");
+  return MMN_OK;
+}
+
+int mmn_cpb_bias_fwd(const float* coords, const float* w1, const float* b1, const float* w2, const int64_t* index, int32_t T,
+                     int32_t n_in, int32_t J, int32_t nH, int32_t NN, float* tab16, float* bias, int device, void* stream) {
+  if (!coords || !w1 || !b1 || !w2 || !index || !tab16 || !bias) return fail(MMN_ERR_INVALID, "null tensor pointer");
+  int rc = cpb_check(T, n_in, J, nH, NN);
+  if (rc) return rc;
+  DeviceGuard g(device);
+  if (!g.ok) return fail(MMN_ERR_CUDA, "cannot select device %d", device);
+  int n = 0;
+  cudaError_t e = mmn::cpb_bias_fwd(coords, w1, b1, w2, (const long long*)index, T, n_in, J, nH, NN, tab16, bias, (cudaStream_t)stream, &n);
+  return finish(e, n, "cpb_bias_fwd");
+}
+
+int mmn_cpb_bias_bwd(const float* coords, const float* w1, const float* b1, const float* w2, const int64_t* index,
+                     const float* tab16, const float* dbias, int32_t T, int32_t n_in, int32_t J, int32_t nH, int32_t NN,
+                     float* scratch, float* dw1, float* db1, float* dw2, int device, void* stream) {
+  if (!coords || !w1 || !b1 || !w2 || !index || !tab16 || !dbias || !scratch || !dw1 || !db1 || !dw2)
+    return fail(MMN_ERR_INVALID, "null tensor pointer");
+  int rc = cpb_check(T, n_in, J, nH, NN);
+  if (rc) return rc;
+  DeviceGuard g(device);
+  if (!g.ok) return fail(MMN_ERR_CUDA, "cannot select device %d", device);
+  int n = 0;
+  cudaError_t e = mmn::cpb_bias_bwd(coords, w1, b1, w2, (const long long*)index, tab16, dbias, T, n_in, J, nH, NN, scratch, dw1, db1,
+                                    dw2, (cudaStream_t)stream, &n);
+  return finish(e, n, "cpb_bias_bwd");
+}
+
 int mmn_linear_bwd_supported(int io_dtype, int64_t rows, int32_t in_features, int32_t out_features, int64_t ld_dy, int64_t ld_x,
                              int64_t ld_dx) {
   return have_device() && mmn::tc::linbwd_why_not(io_dtype, rows, in_features, out_features, ld_dy, ld_x, ld_dx) == nullptr;

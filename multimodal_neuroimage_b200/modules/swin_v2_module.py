@@ -145,6 +145,13 @@ class WindowAttention(nn.Module):
         """(nH, N, N) fp32 = 16*sigmoid(cpb_mlp(table))[index] (swin_v2_module.py:158-162)."""
         N = math.prod(self.window_size)
         with torch.autocast(device_type="cuda", enabled=False):
+            coords = self.relative_coords_table.float().reshape(-1, self.relative_coords_table.shape[-1])
+            lin1, lin2 = self.cpb_mlp[0], self.cpb_mlp[2]
+            if lin2.bias is None and ops.cpb_bias_supported(coords, lin1.weight, lin2.weight):
+                # libmmn_b200 cpb_bias.cu: MLP + 16 sigmoid + gather in two launches, hand-written backward
+                b, _ = torch.ops.mmn_b200.cpb_bias_fwd(coords, lin1.weight, lin1.bias, lin2.weight,
+                                                       self.relative_position_index.view(-1))
+                return b.view(-1, N, N)
             tab = self.cpb_mlp(self.relative_coords_table.float()).view(-1, self.num_heads_swin)
             # 16*sigmoid commutes with the gather: apply it on the (2w-1)^n-entry table, not on N*N entries, and
             # scatter the gradient back with one index_add_ instead of autograd's sort-based index backward

@@ -347,6 +347,64 @@ def _(x):
     return x.new_empty(x.shape[1], dtype=torch.float32)
 
 
+def cpb_bias_supported(coords: Tensor, w1: Tensor, w2: Tensor) -> bool:
+    """True when the fused continuous-position-bias kernels take these operands (fp32 CUDA, <= 3 coordinates,
+    <= 64 heads, table x heads <= 12288)."""
+    ok = coords.is_cuda and all(t.dtype == torch.float32 for t in (coords, w1, w2))
+    T = coords.numel() // coords.shape[-1]
+    return bool(ok and coords.shape[-1] <= 3 and w2.shape[0] <= 64 and T * w2.shape[0] <= 12288)
+
+
+@torch.library.custom_op("mmn_b200::cpb_bias_fwd", mutates_args=())
+def cpb_bias_fwd(coords: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, index: Tensor) -> Tuple[Tensor, Tensor]:
+    """coords (T, n), w1 (J, n), b1 (J), w2 (nH, J), index (NN) int64 -> bias (nH, NN), tab16 (T, nH)."""
+    _require_cuda(coords, w1, b1, w2, index)
+    T, n_in, J, nH, NN = coords.shape[0], coords.shape[1], w1.shape[0], w2.shape[0], index.numel()
+    tab16 = torch.empty(T, nH, dtype=torch.float32, device=coords.device)
+    bias = torch.empty(nH, NN, dtype=torch.float32, device=coords.device)
+    _lib.check(_lib.load().mmn_cpb_bias_fwd(_ptr(coords), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(index), T, n_in, J, nH, NN,
+                                           _ptr(tab16), _ptr(bias), coords.device.index, _stream(coords)), "mmn_cpb_bias_fwd")
+    return bias, tab16
+
+
+@cpb_bias_fwd.register_fake
+def _(coords, w1, b1, w2, index):
+    return (coords.new_empty(w2.shape[0], index.numel()), coords.new_empty(coords.shape[0], w2.shape[0]))
+
+
+@torch.library.custom_op("mmn_b200::cpb_bias_bwd", mutates_args=())
+def cpb_bias_bwd(dbias: Tensor, coords: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, index: Tensor,
+                 tab16: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    _require_cuda(dbias, coords, w1, b1, w2, index, tab16)
+    T, n_in, J, nH, NN = coords.shape[0], coords.shape[1], w1.shape[0], w2.shape[0], index.numel()
+    dbias = dbias.contiguous()
+    dw1, db1, dw2 = torch.empty_like(w1), torch.empty_like(b1), torch.empty_like(w2)
+    scratch = torch.empty(T, nH, dtype=torch.float32, device=coords.device)
+    _lib.check(_lib.load().mmn_cpb_bias_bwd(_ptr(coords), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(index), _ptr(tab16), _ptr(dbias),
+                                           T, n_in, J, nH, NN, _ptr(scratch), _ptr(dw1), _ptr(db1), _ptr(dw2),
+                                           coords.device.index, _stream(coords)), "mmn_cpb_bias_bwd")
+    return dw1, db1, dw2
+
+
+@cpb_bias_bwd.register_fake
+def _(dbias, coords, w1, b1, w2, index, tab16):
+    return torch.empty_like(w1), torch.empty_like(b1), torch.empty_like(w2)
+
+
+def _cpb_setup(ctx, inputs, output):
+    coords, w1, b1, w2, index = inputs
+    ctx.save_for_backward(coords, w1, b1, w2, index, output[1])
+
+
+def _cpb_backward(ctx, dbias, _dtab16):
+    coords, w1, b1, w2, index, tab16 = ctx.saved_tensors
+    dw1, db1, dw2 = torch.ops.mmn_b200.cpb_bias_bwd(dbias, coords, w1, b1, w2, index, tab16)
+    return None, dw1, db1, dw2, None
+
+
+cpb_bias_fwd.register_autograd(_cpb_backward, setup_context=_cpb_setup)
+
+
 def linear_bwd_supported(dy: Tensor, x: Tensor, w: Tensor) -> bool:
     """True when the fused tensor-core projection backward takes these operands (bf16, in = 96, out in {96,192,288})."""
     if not (dy.is_cuda and dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16):

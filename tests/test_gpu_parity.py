@@ -415,6 +415,32 @@ def test_linear_bwd_fused(mm, rows, n_out):
     check(dw2, wide[:, :n_out].double().cpu().t() @ xd, 2e-3, "linear_bwd dw (strided dy)")
 
 
+@pytest.mark.parametrize("window,nH", [((4, 4, 4), 3), ((8, 8), 6), ((6, 6), 12), ((4, 4, 4), 24)])
+def test_cpb_bias_fused(mm, window, nH):
+    """cpb_bias.cu against the reference formulation 16*sigmoid(cpb_mlp(table))[index] (swin_v2_module.py:158-162) in
+    fp64, forward and all three parameter gradients."""
+    from multimodal_neuroimage_b200 import geometry
+    g = torch.Generator().manual_seed(nH)
+    n = len(window)
+    coords = geometry.cpb_coords_table(window).reshape(-1, n).float()
+    index = geometry.relative_position_index(window).reshape(-1)
+    w1 = torch.randn(512, n, generator=g) * 0.7
+    b1 = torch.randn(512, generator=g) * 0.3
+    w2 = torch.randn(nH, 512, generator=g) * 0.1
+    cot = torch.randn(nH, index.numel(), generator=g)
+    pd = [t.double().requires_grad_(True) for t in (w1, b1, w2)]
+    tab = torch.relu(coords.double() @ pd[0].t() + pd[1]) @ pd[2].t()
+    want = (16 * torch.sigmoid(tab))[index].t()
+    gw = torch.autograd.grad((want * cot.double()).sum(), pd)
+    pc = [t.cuda().requires_grad_(True) for t in (w1, b1, w2)]
+    assert mm.ops.cpb_bias_supported(coords.cuda(), pc[0], pc[2])
+    got, _ = torch.ops.mmn_b200.cpb_bias_fwd(coords.cuda(), pc[0], pc[1], pc[2], index.cuda())
+    gg = torch.autograd.grad((got * cot.cuda()).sum(), pc)
+    check(got, want, FP32_TOL, "cpb bias")
+    for a, b, nm in zip(gg, gw, ("dw1", "db1", "dw2")):
+        check(a, b, FP32_TOL * 2, "cpb " + nm)
+
+
 def test_dropout_statistics_and_backward_consistency(mm):
     """p > 0: keep-rate ~ 1-p, E[out] ~ no-dropout out, and fwd/bwd regenerate the same mask
     (checked by linearity: with probabilities frozen, out is linear in v)."""
