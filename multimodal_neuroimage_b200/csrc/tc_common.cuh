@@ -9,6 +9,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace mmn { namespace tc {
 
@@ -50,7 +51,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 20)) __trap();
+    if (++spins > (1u << 20)) {
+#ifdef MMN_DEBUG_WAIT
+      printf("mbar_wait timeout: block %d thread %d barrier smem 0x%x parity %u\n", (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
+#endif
+      __trap();
+    }
   }
 }
 
@@ -184,6 +190,41 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// Packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2 -- one issue slot for two lanes of fp32 arithmetic).  The softmax
+// warps are bound by instruction issue, not by the fp32 pipe, so every elementwise step over the logits works on
+// register pairs.  A pair lives in a 64-bit register; pk/upk are register renames, not instructions, as long as
+// ptxas can place the two halves in an aligned pair (it does for tcgen05.ld / LDS.128 results).
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(uint64_t v) {
+  float lo, hi;
+  upk2(v, lo, hi);
+  return pack_bf16x2(lo, hi);
 }
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;

@@ -149,6 +149,22 @@ __device__ __forceinline__ ItemGeom item_geom(const WinShape& S, const Sched& sc
   return g;
 }
 
+// Geometry of window w (linear index b * nW + row-major window position) of wrap class `cls`: what a warp that only
+// has the producer's item descriptor needs to address the window's TMA boxes.
+__device__ __forceinline__ ItemGeom geom_from_window(const WinShape& S, int cls, int w) {
+  ItemGeom g;
+  g.w = w;
+  g.cls = cls;
+  g.b = w / S.nW;
+  int wl = w - g.b * S.nW;
+  g.idx[2] = wl % S.nwin[2]; wl /= S.nwin[2];
+  g.idx[1] = wl % S.nwin[1];
+  g.idx[0] = wl / S.nwin[1];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) g.start[a] = g.idx[a] * S.win[a] + S.shift[a];
+  return g;
+}
+
 // Shift-mask region id of in-window position p for a window of wrap class `cls`
 // (swin_v2_module.py:247-258: along a wrapped axis the last window straddles regions 1 | 2 at
 // win - shift; every other window lies in region 0).
@@ -164,17 +180,107 @@ __device__ __forceinline__ int class_region_id(const WinShape& S, int cls, int p
 
 // Per-class additive table in the item's tile order, in the log2 domain:
 //   tbl[i][j] = log2(e) * (bias[pos(i)][pos(j)] + (region(pos i) != region(pos j) ? -100 : 0)).
-// `bias` is this head's (64,64) fp32 table or null; `pos` the class's 64-entry tile-row -> window-position LUT.
-__device__ __forceinline__ void build_class_table(float* tbl, int ld, const float* bias, const uint8_t* pos, const WinShape& S,
-                                                  int cls, bool shift_mask, int t, int nthreads) {
+// `bias` is this head's (64,64) fp32 table or null; `pos` the class's 64-entry tile-row -> window-position LUT;
+// `rid` the class's window-position -> region-id LUT (class_region_id, tabulated once per CTA).
+__device__ __forceinline__ void build_class_table(float* tbl, int ld, const float* bias, const uint8_t* pos, const uint8_t* rid,
+                                                  bool shift_mask, int t, int nthreads) {
   for (int e = t; e < kN * kN; e += nthreads) {
     const int i = e >> 6, j = e & 63;
     const int pi = pos[i], pj = pos[j];
     float v = bias ? __ldg(bias + pi * kN + pj) : 0.f;
-    if (shift_mask && cls != 0 && class_region_id(S, cls, pi) != class_region_id(S, cls, pj)) v -= 100.f;
+    if (shift_mask && rid[pi] != rid[pj]) v -= 100.f;
     tbl[i * ld + j] = v * 1.4426950408889634f;
   }
 }
+
+// ------------------------------------------------------------------------------------------
+// TMA issue: per-lane box plans.
+// An item of wrap class c is 2 windows x T tensors x 2^popc(c) pieces = up to 64 boxes; lane l owns boxes l and l + 32
+// (box x = (slot, tensor, piece), piece fastest).  Which tensor map, which piece offset and which shared-memory offset a
+// lane's boxes have depends only on the class, so they are tabulated once per class change (BoxPlan::build); per item a
+// lane adds its piece offset to its window's start coordinates and issues.  The single-warp integer arithmetic per item
+// was what bounded the producer (~1000 cycles per item before, box issue itself ~65 cycles per box).
+// ------------------------------------------------------------------------------------------
+struct WinStart {              // one window's first token (shifted frame, before the wrap) and sample
+  int b, s0, s1, s2;
+};
+
+// Start coordinates and linear window index of the cursor's window (slot 0) -- or of the next one (slot 1).
+__device__ __forceinline__ WinStart cursor_start(const WinShape& S, const ItemCursor& c, int slot, int& w) {
+  ItemCursor t = c;
+  if (slot) t.step_window();
+  const int i0 = (t.cls & 1) ? S.nwin[0] - 1 : t.j0, i1 = (t.cls & 2) ? S.nwin[1] - 1 : t.j1, i2 = (t.cls & 4) ? S.nwin[2] - 1 : t.j2;
+  w = t.b * S.nW + (i0 * S.nwin[1] + i1) * S.nwin[2] + i2;
+  WinStart r;
+  r.b = t.b;
+  r.s0 = i0 * S.win[0] + S.shift[0]; r.s1 = i1 * S.win[1] + S.shift[1]; r.s2 = i2 * S.win[2] + S.shift[2];
+  return r;
+}
+// The same from a linear window index (warps that only have the producer's item descriptor).
+__device__ __forceinline__ WinStart window_start(const WinShape& S, int w) {
+  WinStart r;
+  r.b = w / S.nW;
+  int wl = w - r.b * S.nW;
+  const int i2 = wl % S.nwin[2]; wl /= S.nwin[2];
+  const int i1 = wl % S.nwin[1], i0 = wl / S.nwin[1];
+  r.s0 = i0 * S.win[0] + S.shift[0]; r.s1 = i1 * S.win[1] + S.shift[1]; r.s2 = i2 * S.win[2] + S.shift[2];
+  return r;
+}
+
+template <int T>
+struct BoxPlan {
+  int cls = -1, nbox = 0;
+  int slot[2], o0[2], o1[2], o2[2], dst[2];
+  const CUtensorMap* map[2];
+
+  // dst_base[t] / slot_stride[t]: byte offset of tensor t's tile of slot 0 inside a stage, and the stride to slot 1
+  __device__ __forceinline__ void build(const WinShape& S, int c, int lane, const CUtensorMap* const (&maps)[T], const int (&dst_base)[T],
+                                        const int (&slot_stride)[T]) {
+    cls = c;
+    const int lp = __popc(c);
+    nbox = (2 * T) << lp;
+    const int psize_bytes = (kN >> lp) * 64;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int x = lane + 32 * r;
+      const int piece = x & ((1 << lp) - 1);
+      const int rest = x >> lp;
+      const int sl = rest / T, t = rest - sl * T;
+      int qq = piece, off[3];
+#pragma unroll
+      for (int a = 2; a >= 0; --a) {
+        const int bit = (c >> a) & 1;
+        off[a] = bit ? (qq & 1) * (S.win[a] >> 1) : 0;
+        if (bit) qq >>= 1;
+      }
+      slot[r] = sl; o0[r] = off[0]; o1[r] = off[1]; o2[r] = off[2];
+      const CUtensorMap* m = maps[0];
+      int d = dst_base[0], ss = slot_stride[0];
+#pragma unroll
+      for (int u = 1; u < T; ++u)
+        if (t == u) { m = maps[u]; d = dst_base[u]; ss = slot_stride[u]; }
+      map[r] = m + c;
+      dst[r] = d + sl * ss + piece * psize_bytes;
+    }
+  }
+
+  template <bool LOAD>
+  __device__ __forceinline__ void issue(const WinShape& S, const WinStart& w0, const WinStart& w1, int nvalid, int chan, uint8_t* stage,
+                                        uint64_t* bar, int lane) const {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      if (lane + 32 * r < nbox && slot[r] < nvalid) {
+        const WinStart& w = slot[r] ? w1 : w0;
+        int c0 = w.s0 + o0[r], c1 = w.s1 + o1[r], c2 = w.s2 + o2[r];
+        if (c0 >= S.grid[0]) c0 -= S.grid[0];
+        if (c1 >= S.grid[1]) c1 -= S.grid[1];
+        if (c2 >= S.grid[2]) c2 -= S.grid[2];
+        if (LOAD) tma_load_5d(map[r], bar, stage + dst[r], chan, c2, c1, c0, w.b);
+        else tma_store_5d(map[r], stage + dst[r], chan, c2, c1, c0, w.b);
+      }
+    }
+  }
+};
 
 // All TMA boxes of one item, one box per lane and round: box x = (slot, tensor t, piece) in piece-fastest order.
 // The coordinate arithmetic runs in parallel over the lanes; only the few instructions that feed the TMA unit

@@ -60,7 +60,7 @@ struct BwdParams {
   float* dbias;         // (nH, 64, 64) accumulated, may be null
   float* dhead_scale;   // (nH) accumulated, may be null
   float* dcolsum;       // (3, nH*32) accumulated column sums of dq, dk, dv (= projection bias grads), may be null
-  long long* trace;     // debug: clock64 stamps of CTA 0 (MMN_TC_TRACE_BWD=<file>)
+  TraceCfg trace;       // debug: clock64 stamps of one CTA (MMN_TC_TRACE_BWD=<file>)
 };
 
 template <int R> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
@@ -81,7 +81,8 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
   float* sDelta = sRk + 384;                              // [4][128] partial deltas
   float* sRed = sDelta + 512;                             // 16 floats: dhead_scale per softmax warp
   uint8_t* sPos = reinterpret_cast<uint8_t*>(sRed + 16);  // [8][64]
-  int4* sItem = reinterpret_cast<int4*>(sPos + 512);      // [8] ring: {wrap class, window index of slot 0, of slot 1, valid slots} of item n & 7
+  uint8_t* sRid = sPos + 512;                             // [8][64] window position -> shift-mask region id
+  int4* sItem = reinterpret_cast<int4*>(sRid + 512);      // [8] ring: {wrap class, window index of slot 0, of slot 1, valid slots} of item n & 7
   uint64_t* bars = reinterpret_cast<uint64_t*>(sItem + 8);
   uint64_t* full = bars;                                  // [kStagesB]
   uint64_t* empty = bars + kStagesB;                      // [kStagesB] (one arrival per warp: epilogue threads)
@@ -104,7 +105,10 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
   // ---- one-time setup
   for (int i = tid; i < (kStagesB * kStageBytesB + 2 * kPRegion) / 16; i += kBwdThreads)
     reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < 512; i += kBwdThreads) sPos[i] = (uint8_t)piece_position(S, i >> 6, i & 63);
+  for (int i = tid; i < 512; i += kBwdThreads) {
+    sPos[i] = (uint8_t)piece_position(S, i >> 6, i & 63);
+    sRid[i] = (uint8_t)class_region_id(S, i >> 6, i & 63);
+  }
   if (tid == 0) {
     for (int s = 0; s < kStagesB; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kEpiThreads / 32); }
     for (int b = 0; b < 2; ++b) {
@@ -125,6 +129,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
+  trace_cta_time(P.trace, 0);
 
   if (warp >= kProducerWarpB) {
     setmaxnreg_dec<kRegAux>();
@@ -408,7 +413,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       if (cls != cls_loaded) {                          // rare: at most 8 times per CTA
         if (gdb_head && cls_loaded >= 0) flush_dbias(cls_loaded);
         named_bar_sync(3, kSoftmaxThreadsB);            // everyone is done reading the old table
-        build_class_table(sTbl, kTblLd, bias_h, sPos + cls * 64, S, cls, MASK == MMN_MASK_SHIFT, tid, kSoftmaxThreadsB);
+        build_class_table(sTbl, kTblLd, bias_h, sPos + cls * 64, sRid + cls * 64, MASK == MMN_MASK_SHIFT && cls != 0, tid, kSoftmaxThreadsB);
         cls_loaded = cls;
         named_bar_sync(3, kSoftmaxThreadsB);
       }
@@ -514,11 +519,12 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
 
   tcgen05_fence_before();
   __syncthreads();
+  trace_cta_time(P.trace, 1);
   if (warp == kMmaWarpB) tmem_dealloc<kBwdTmemCols>(tmem);
 }
 
 constexpr size_t kBwdSmemBytes = 1024 + kStagesB * kStageBytesB + 2 * kPRegion + 3 * kTile + kN * kTblLd * 4 +
-                                 (384 + 384 + 512 + 16) * 4 + 512 + 8 * 16 + 24 * 8;
+                                 (384 + 384 + 512 + 16) * 4 + 1024 + 8 * 16 + 24 * 8;
 
 inline const char* bwd_why_not_impl(const mmn_winattn_desc* d) {
   const char* w = fwd_why_not_impl(d);
@@ -549,15 +555,8 @@ inline int winattn_bwd_launch(const mmn_winattn_desc* d, const void* q, const vo
   P.dbias = bias ? dbias : nullptr;
   P.dhead_scale = d->score_kind == MMN_SCORE_COSINE ? dhead_scale : nullptr;
   P.dcolsum = dcolsum;
-  P.trace = nullptr;
   const char* trace_path = getenv("MMN_TC_TRACE_BWD");
-  if (trace_path && *trace_path) {
-    cudaMalloc(&P.trace, (5 * 32 * 16 + 1) * sizeof(long long));
-    cudaMemsetAsync(P.trace, 0, (5 * 32 * 16 + 1) * sizeof(long long), st);
-    const char* cta = getenv("MMN_TC_TRACE_CTA");        // which CTA to trace (default 0); slot [5*32*16] of the buffer
-    const long long cta_id = cta ? atoll(cta) : 0;
-    cudaMemcpyAsync(P.trace + 5 * 32 * 16, &cta_id, sizeof(cta_id), cudaMemcpyHostToDevice, st);
-  }
+  P.trace = trace_setup(trace_path, st);
 
   using Kern = void (*)(const BwdParams);
   static const Kern kernels[2][3] = {
@@ -579,7 +578,7 @@ inline int winattn_bwd_launch(const mmn_winattn_desc* d, const void* q, const vo
     snprintf(err, errlen, "winattn_bwd_tc_kernel: %s", cudaGetErrorString(e));
     return MMN_ERR_CUDA;
   }
-  if (P.trace) dump_trace(P.trace, trace_path, st);
+  if (P.trace.buf) dump_trace(P.trace.buf, trace_path, st);
   return MMN_OK;
 }
 

@@ -44,8 +44,18 @@ constexpr int kProducerWarp = 8, kMmaWarp = 9, kStoreWarp = 10;
 constexpr int kFwdThreads = 352;
 constexpr int kTblLd = 68;                         // padded row of the shared table (conflict-free float4 rows)
 constexpr int kTmemColsF = 256;                    // S[g] at 64 g; O[g][b] at 128 + 32 (2 g + b)
+constexpr int kItemRing = 16;                      // item descriptors published by the TMA producer (see the ring-depth note there)
+constexpr int kChunkF = 8;                         // items a CTA claims per atomic
+constexpr int kWorkDone = 63, kWorkSlotInts = 64, kWorkSlots = 256;   // up to 63 heads
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
+
+// Debug tracing: buf[(role*32 + item - item0)*16 + ev] = clock64() of CTA `cta`; buf[kTraceCtaOfs + 2*cta + {0,1}] =
+// globaltimer at the start / end of every CTA (load balance).  Which CTA and which 32 items: MMN_TC_TRACE_CTA / _ITEM0.
+constexpr int kTraceCtaOfs = 5 * 32 * 16;
+constexpr int kTraceWords = kTraceCtaOfs + 2 * 1024;
+struct TraceCfg { long long* buf; int cta; int item0; };
+__device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 struct FwdParams {
   CUtensorMap q[8], k[8], v[8], o[8];   // one box shape per wrap class
@@ -58,15 +68,20 @@ struct FwdParams {
   const float* head_scale;
   const float* mask;
   float* lse;
-  long long* trace;   // debug: per-phase clock64 stamps of CTA 0 (MMN_TC_TRACE=<file>), else null
+  int* work;          // dynamic schedule: work[h] = next unclaimed item of head h, work[kWorkDone] = CTAs that ran dry (self-resetting)
+  TraceCfg trace;     // debug: per-phase clock64 stamps of one CTA (MMN_TC_TRACE=<file>), else buf == null
 };
 
 // trace[(role*32 + item)*16 + ev]; roles: 0 group A warp 0, 1 group B warp 4, 2 producer, 3 MMA, 4 store
-__device__ __forceinline__ void trace_stamp(long long* trace, int role, int item, int ev) {
-  if (trace && (int)blockIdx.x == (int)trace[5 * 32 * 16] && (threadIdx.x & 31) == 0 && item < 32) trace[(role * 32 + item) * 16 + ev] = clock64();
+__device__ __forceinline__ void trace_stamp(const TraceCfg& t, int role, int item, int ev) {
+  if (t.buf && (int)blockIdx.x == t.cta && (threadIdx.x & 31) == 0 && (unsigned)(item - t.item0) < 32u)
+    t.buf[(role * 32 + item - t.item0) * 16 + ev] = clock64();
+}
+__device__ __forceinline__ void trace_cta_time(const TraceCfg& t, int which) {
+  if (t.buf && threadIdx.x == 0 && blockIdx.x < 1024) t.buf[kTraceCtaOfs + 2 * blockIdx.x + which] = global_ns();
 }
 // Backward kernel: compiled in only with -DMMN_TC_TRACING (MMN_BUILD_TRACE=1); it costs that kernel 20 %.
-__device__ __forceinline__ void trace_ev(long long* trace, int role, int item, int ev) {
+__device__ __forceinline__ void trace_ev(const TraceCfg& trace, int role, int item, int ev) {
 #ifdef MMN_TC_TRACING
   trace_stamp(trace, role, item, ev);
 #endif
@@ -74,25 +89,26 @@ __device__ __forceinline__ void trace_ev(long long* trace, int role, int item, i
 // Forward kernel: always compiled in.  The (never taken, when not tracing) branches are phase boundaries that
 // keep ptxas from interleaving the softmax phases; measured on B200 at BASELINE cfg2, the forward runs
 // 0.30 ms with them and 0.37 ms without.
-__device__ __forceinline__ void trace_evf(long long* trace, int role, int item, int ev) { trace_stamp(trace, role, item, ev); }
+__device__ __forceinline__ void trace_evf(const TraceCfg& trace, int role, int item, int ev) { trace_stamp(trace, role, item, ev); }
 
 // sum of squares of one 64-byte bf16 row.  `row` = the row's index in its tile: chunk c is read at its
 // swizzled place, which also spreads the lanes of a warp over all banks (plain order is a 4-way conflict).
 __device__ __forceinline__ float row_sumsq(const uint8_t* rowp, int row) {
   const int sw = (row >> 1) & 3;
-  float ss[4] = {0.f, 0.f, 0.f, 0.f};                      // one chain per 16-byte chunk
+  uint64_t ss[4] = {0ull, 0ull, 0ull, 0ull};               // one chain of (low, high) element pairs per 16-byte chunk
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const uint4 a = *reinterpret_cast<const uint4*>(rowp + ((c ^ sw) << 4));
     const uint32_t u[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float lo = __uint_as_float(u[e] << 16), hi = __uint_as_float(u[e] & 0xffff0000u);
-      ss[c] = fmaf(lo, lo, ss[c]);
-      ss[c] = fmaf(hi, hi, ss[c]);
+      const uint64_t x = pk2u(u[e] << 16, u[e] & 0xffff0000u);
+      ss[c] = fma2(x, x, ss[c]);
     }
   }
-  return (ss[0] + ss[1]) + (ss[2] + ss[3]);
+  float lo, hi;
+  upk2(add2(add2(ss[0], ss[1]), add2(ss[2], ss[3])), lo, hi);
+  return lo + hi;
 }
 
 // COS: cosine attention (else scaled dot product); MASK: MMN_MASK_NONE / _SHIFT / _TENSOR.
@@ -107,7 +123,10 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
   float* sTbl = reinterpret_cast<float*>(sO + 2 * kTile); // [2 groups][64][kTblLd]
   float* sRk = sTbl + 2 * kN * kTblLd;                    // [2 groups][2][128] per-key 1/||k||
   uint8_t* sPos = reinterpret_cast<uint8_t*>(sRk + 512);  // [8 wrap classes][64]: tile row -> window position
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sPos + 512);
+  uint8_t* sRid = sPos + 512;                             // [8 wrap classes][64]: window position -> shift-mask region id
+  int4* sItem = reinterpret_cast<int4*>(sRid + 512);      // [kItemRing] {wrap class (-1: no more items), window of slot 0, of slot 1, valid slots}
+  int* sEnd = reinterpret_cast<int*>(sItem + kItemRing);  // [2] items group g has produced when it left its loop (else INT_MAX)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEnd + 4);
   uint64_t* full = bars;                                  // [kStagesF] TMA -> MMA, softmax
   uint64_t* empty = bars + kStagesF;                      // [kStagesF] MMA -> TMA
   uint64_t* s_full = bars + 2 * kStagesF;                 // [2] S in TMEM
@@ -121,15 +140,17 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
   const Sched& sc = P.sc;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x % P.nH;
-  const int item0 = sched_range_begin(sc, blockIdx.x / P.nH, P.per_head);
-  const int cnt = sched_range_begin(sc, blockIdx.x / P.nH + 1, P.per_head) - item0;
 
   // ---- one-time setup: zero the operand tiles (zero blocks stay zero for the whole kernel; the rest must
   // not hold NaN bit patterns, because cross terms multiply stale tiles by the zero blocks)
   for (int i = tid; i < (kStagesF * kStageBytesF + 2 * kPRegion) / 16; i += kFwdThreads)
     reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < 512; i += kFwdThreads) sPos[i] = (uint8_t)piece_position(S, i >> 6, i & 63);
+  for (int i = tid; i < 512; i += kFwdThreads) {
+    sPos[i] = (uint8_t)piece_position(S, i >> 6, i & 63);
+    sRid[i] = (uint8_t)class_region_id(S, i >> 6, i & 63);
+  }
   if (tid == 0) {
+    sEnd[0] = sEnd[1] = 0x7fffffff;
     for (int s = 0; s < kStagesF; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int g = 0; g < 2; ++g) {
       mbar_init(&s_full[g], 1); mbar_init(&p_full[g], kGroupThreads / 32); mbar_init(&o_full[g], 1);
@@ -147,27 +168,71 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
+  trace_cta_time(P.trace, 0);
+#ifdef MMN_DEBUG_WAIT
+  if (tid == 0 && blockIdx.x == 0) printf("fwd barriers at smem 0x%x (full 4, empty 4, s_full 2, p_full 2, o_full 2, so_ready 2, so_free 2)\n", smem_u32(bars));
+#endif
 
   if (warp == kProducerWarp) {
     // ============================== TMA producer ==============================
     // every lane runs the loop; lane l issues boxes l, l + 32 of the item (issue_item_boxes)
     const CUtensorMap* const maps[3] = {P.q, P.k, P.v};
+    const int dst_base[3] = {0, kQRegion, kQRegion + kTile};
     const int slot_stride[3] = {2 * kWinBytes, kWinBytes, kWinBytes};
-    ItemCursor cur;
-    cur.seek(sc, item0);
-    for (int n = 0; n < cnt; ++n, cur.next_item(sc)) {
+    BoxPlan<3> plan;
+    // Dynamic schedule: the class-sorted item list of this head is handed out in chunks of kChunkF items through an
+    // atomic counter, so a CTA's items ascend (it sees each wrap class at most once) and the CTAs finish together
+    // whatever the per-class costs are.  The next chunk is claimed while the current one is being issued.
+    // Every other warp learns its items from the descriptor ring sItem (published by the full[] arrival).  Ring
+    // depth: entry n + 16 is written only after PV(n + 12) has completed, i.e. after its group wrote P(n + 12), which
+    // it does after the epilogue of item n + 8, which waited for the store of item n + 6 -- so entry n has been read
+    // by every consumer, the store warp included.
+    int n = 0;
+    int claim = 0;
+    if (lane == 0) claim = atomicAdd(P.work + h, kChunkF);
+    for (;;) {
+      const int c0 = __shfl_sync(0xffffffffu, claim, 0);
+      if (c0 >= sc.n_items) break;
+      if (lane == 0) claim = atomicAdd(P.work + h, kChunkF);
+      const int m = min(kChunkF, sc.n_items - c0);
+      ItemCursor cur;
+      cur.seek(sc, c0);
+      for (int t = 0; t < m; ++t, ++n, cur.next_item(sc)) {
+        const int stage = n % kStagesF, phase = (n / kStagesF) & 1;
+        if (cur.cls != plan.cls) plan.build(S, cur.cls, lane, maps, dst_base, slot_stride);
+        const int nvalid = cur.slot_valid(1) ? 2 : 1;
+        int w0, w1;
+        const WinStart ws0 = cursor_start(S, cur, 0, w0), ws1 = cursor_start(S, cur, 1, w1);
+        trace_evf(P.trace, 2, n, 0);
+        mbar_wait(&empty[stage], phase ^ 1);
+        trace_evf(P.trace, 2, n, 1);
+        if (lane == 0) {
+          sItem[n % kItemRing] = make_int4(cur.cls, w0, w1, nvalid);     // published by the arrive below
+          mbar_arrive_expect_tx(&full[stage], nvalid * 3 * kWinBytes);
+        }
+        __syncwarp();
+        plan.issue<true>(S, ws0, ws1, nvalid, h * kD, sStage + stage * kStageBytesF, &full[stage], lane);
+        trace_evf(P.trace, 2, n, 2);
+      }
+    }
+    // two end markers (one per softmax group; the MMA warp stops at the first)
+    for (int e = 0; e < 2; ++e, ++n) {
       const int stage = n % kStagesF, phase = (n / kStagesF) & 1;
-      trace_evf(P.trace, 2, n, 0);
       mbar_wait(&empty[stage], phase ^ 1);
-      trace_evf(P.trace, 2, n, 1);
-      const int nvalid = cur.slot_valid(1) ? 2 : 1;
-      if (lane == 0) mbar_arrive_expect_tx(&full[stage], nvalid * 3 * kWinBytes);
+      if (lane == 0) {
+        sItem[n % kItemRing] = make_int4(-1, 0, 0, 0);
+        mbar_arrive(&full[stage]);
+      }
       __syncwarp();
-      uint8_t* base = sStage + stage * kStageBytesF;
-      uint8_t* const dst[3] = {base, base + kQRegion, base + kQRegion + kTile};
-      issue_item_boxes<true, 3>(S, item_geom(S, sc, cur, 0), item_geom(S, sc, cur, 1), nvalid, h * kD, maps, dst, slot_stride,
-                                &full[stage], lane);
-      trace_evf(P.trace, 2, n, 2);
+    }
+    // the last CTA to run dry re-arms the counters for the next launch that uses this slot
+    if (lane == 0) {
+      __threadfence();
+      if (atomicAdd(P.work + kWorkDone, 1) == (int)gridDim.x - 1) {
+        for (int hh = 0; hh < P.nH; ++hh) P.work[hh] = 0;
+        P.work[kWorkDone] = 0;
+        __threadfence();
+      }
     }
   } else if (warp == kMmaWarp) {
     // ============================== MMA issuer ==============================
@@ -179,9 +244,11 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
     const uint64_t dP = umma_smem_desc(0, 0, 1024, kSwz128);       // P tile, K-major
     const uint64_t dV = umma_smem_desc(0, 8192, 512, kSwz64);      // V tile, MN-major
     const uint32_t stage0 = smem_u32(sStage) >> 4, p0 = smem_u32(sP) >> 4;
+    int total = 0x7fffffff;                                        // items of this CTA: known once the end marker shows up
     auto issue_s = [&](int n) {
       const int stage = n % kStagesF, phase = (n / kStagesF) & 1;
       mbar_wait(&full[stage], phase);
+      if (sItem[n % kItemRing].x < 0) { total = n; return; }
       tcgen05_fence_after();
       if (elect_one()) {
         const uint64_t aq = dQK + (stage0 + stage * (kStageBytesF >> 4)), bk = aq + (kQRegion >> 4);
@@ -193,9 +260,9 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
       }
       __syncwarp();
     };
-    if (cnt > 0) issue_s(0);
-    if (cnt > 1) issue_s(1);
-    for (int n = 0; n < cnt; ++n) {
+    issue_s(0);
+    if (total > 1) issue_s(1);
+    for (int n = 0; n < total; ++n) {
       const int g = n & 1, kk = n >> 1, stage = n % kStagesF;
       trace_evf(P.trace, 3, n, 0);
       mbar_wait(&p_full[g], kk & 1);
@@ -212,23 +279,24 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
         umma_commit(&empty[stage]);
       }
       __syncwarp();
-      if (n + 2 < cnt) issue_s(n + 2);
+      if (total == 0x7fffffff) issue_s(n + 2);
       trace_evf(P.trace, 3, n, 2);
     }
   } else if (warp == kStoreWarp) {
     // ============================== TMA store ==============================
     const CUtensorMap* const maps[1] = {P.o};
+    const int dst_base[1] = {0};
     const int slot_stride[1] = {kWinBytes};
-    ItemCursor cur;
-    cur.seek(sc, item0);
-    for (int n = 0; n < cnt; ++n, cur.next_item(sc)) {
+    BoxPlan<1> plan;
+    for (int n = 0;; ++n) {
       const int g = n & 1, kk = n >> 1;
       trace_evf(P.trace, 4, n, 0);
       mbar_wait(&so_ready[g], kk & 1);
+      if (kk >= *reinterpret_cast<volatile int*>(&sEnd[g])) break;   // the group left its loop: that arrival was its farewell
       trace_evf(P.trace, 4, n, 1);
-      uint8_t* const dst[1] = {sO + g * kTile};
-      issue_item_boxes<false, 1>(S, item_geom(S, sc, cur, 0), item_geom(S, sc, cur, 1), cur.slot_valid(1) ? 2 : 1, h * kD, maps, dst,
-                                 slot_stride, nullptr, lane);
+      const int4 item = sItem[n % kItemRing];
+      if (item.x != plan.cls) plan.build(S, item.x, lane, maps, dst_base, slot_stride);
+      plan.issue<false>(S, window_start(S, item.y), window_start(S, item.z), item.w, h * kD, sO + g * kTile, nullptr, lane);
       tma_store_commit();
       tma_store_wait_read<0>();          // per thread: each lane waits for the smem reads of its own boxes
       __syncwarp();
@@ -259,40 +327,38 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
       tcgen05_fence_before();
       if (valid) P.lse[lse_index] = lse_val;
       mbar_wait(&so_free[g], (ke & 1) ^ 1);              // the store warp has drained this group's staging tile
+      const uint64_t inv2 = pk2(inv_l, inv_l);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint4 v4 = make_uint4(pack_bf16x2(__uint_as_float(oraw[c * 8 + 0]) * inv_l, __uint_as_float(oraw[c * 8 + 1]) * inv_l),
-                              pack_bf16x2(__uint_as_float(oraw[c * 8 + 2]) * inv_l, __uint_as_float(oraw[c * 8 + 3]) * inv_l),
-                              pack_bf16x2(__uint_as_float(oraw[c * 8 + 4]) * inv_l, __uint_as_float(oraw[c * 8 + 5]) * inv_l),
-                              pack_bf16x2(__uint_as_float(oraw[c * 8 + 6]) * inv_l, __uint_as_float(oraw[c * 8 + 7]) * inv_l));
+        uint4 v4 = make_uint4(pack_bf16x2(mul2(pk2u(oraw[c * 8 + 0], oraw[c * 8 + 1]), inv2)), pack_bf16x2(mul2(pk2u(oraw[c * 8 + 2], oraw[c * 8 + 3]), inv2)),
+                              pack_bf16x2(mul2(pk2u(oraw[c * 8 + 4], oraw[c * 8 + 5]), inv2)), pack_bf16x2(mul2(pk2u(oraw[c * 8 + 6], oraw[c * 8 + 7]), inv2)));
         *reinterpret_cast<uint4*>(obuf + ((c ^ ((r >> 1) & 3)) << 4)) = v4;
       }
       fence_proxy_async_smem();
       mbar_arrive_warp(&so_ready[g]);
     };
 
-    ItemCursor cur;
-    cur.seek(sc, item0 + g);
     int cls_loaded = -1;
     bool have_prev = false, prev_valid = false;
     float prev_inv = 0.f, prev_lse = 0.f;
     long long prev_idx = 0;
     int kk = 0;
-    for (int n = g; n < cnt; n += 2, ++kk) {
+    for (int n = g;; n += 2, ++kk) {
       const int stage = n % kStagesF, phase = (n / kStagesF) & 1;
-      const ItemGeom geo = item_geom(S, sc, cur, slot);
-      const bool valid = cur.slot_valid(slot);
-      if (cur.cls != cls_loaded) {                      // rare: at most 8 times per CTA
-        named_bar_sync(1 + g, kGroupThreads);           // everyone is done reading the old table
-        build_class_table(tbl, kTblLd, bias_h, sPos + cur.cls * 64, S, cur.cls, MASK == MMN_MASK_SHIFT, r, kGroupThreads);
-        cls_loaded = cur.cls;
-      }
-      const int ipos = sPos[cur.cls * 64 + i];          // window position of this thread's query row
-      const uint8_t* base = sStage + stage * kStageBytesF;
-      float* rkbuf = sRk + (g * 2 + (kk & 1)) * 128;
-
       TR(n, 0);
       mbar_wait(&full[stage], phase);
+      const int4 item = sItem[n % kItemRing];           // written by the producer before it armed full[stage]
+      if (item.x < 0) break;
+      const int cls = item.x, gw = slot ? item.z : item.y;
+      const bool valid = slot < item.w;
+      if (cls != cls_loaded) {                          // rare: at most 8 times per CTA
+        named_bar_sync(1 + g, kGroupThreads);           // everyone is done reading the old table
+        build_class_table(tbl, kTblLd, bias_h, sPos + cls * 64, sRid + cls * 64, MASK == MMN_MASK_SHIFT && cls != 0, r, kGroupThreads);
+        cls_loaded = cls;
+      }
+      const int ipos = sPos[cls * 64 + i];              // window position of this thread's query row
+      const uint8_t* base = sStage + stage * kStageBytesF;
+      float* rkbuf = sRk + (g * 2 + (kk & 1)) * 128;
       TR(n, 1);
       float a_i = hscale;
       if (COS) {
@@ -308,7 +374,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
       mbar_wait(&s_full[g], kk & 1);
       tcgen05_fence_after();
       TR(n, 3);
-      float s[64];
+      uint64_t s2[32];                                   // this row's 64 logits as fp32 pairs
       {
         uint32_t raw0[32], raw1[32];
         tmem_ld_32x32b_x32(tmem + lane_base + g * 64, raw0);
@@ -316,13 +382,14 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
         tmem_ld_wait();
         tcgen05_fence_before();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { s[j] = __uint_as_float(raw0[j]); s[32 + j] = __uint_as_float(raw1[j]); }
+        for (int j = 0; j < 16; ++j) { s2[j] = pk2u(raw0[2 * j], raw0[2 * j + 1]); s2[16 + j] = pk2u(raw1[2 * j], raw1[2 * j + 1]); }
       }
       TR(n, 4);
       {
         const float4* trow = reinterpret_cast<const float4*>(tbl + i * kTblLd);
         const float4* krow = reinterpret_cast<const float4*>(rkbuf + slot * 64);
-        const float* mrow = (MASK == MMN_MASK_TENSOR) ? P.mask + ((size_t)(geo.w % P.mask_windows) * kN + ipos) * kN : nullptr;
+        const float* mrow = (MASK == MMN_MASK_TENSOR) ? P.mask + ((size_t)(gw % P.mask_windows) * kN + ipos) * kN : nullptr;
+        const uint64_t a2 = pk2(a_i, a_i);
 #pragma unroll
         for (int j4 = 0; j4 < 16; ++j4) {
           float4 tt = trow[j4];
@@ -332,15 +399,11 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
           }
           if (COS) {
             const float4 kv = krow[j4];
-            s[j4 * 4 + 0] = fmaf(s[j4 * 4 + 0], kv.x * a_i, tt.x);
-            s[j4 * 4 + 1] = fmaf(s[j4 * 4 + 1], kv.y * a_i, tt.y);
-            s[j4 * 4 + 2] = fmaf(s[j4 * 4 + 2], kv.z * a_i, tt.z);
-            s[j4 * 4 + 3] = fmaf(s[j4 * 4 + 3], kv.w * a_i, tt.w);
+            s2[j4 * 2 + 0] = fma2(s2[j4 * 2 + 0], mul2(pk2(kv.x, kv.y), a2), pk2(tt.x, tt.y));
+            s2[j4 * 2 + 1] = fma2(s2[j4 * 2 + 1], mul2(pk2(kv.z, kv.w), a2), pk2(tt.z, tt.w));
           } else {
-            s[j4 * 4 + 0] = fmaf(s[j4 * 4 + 0], a_i, tt.x);
-            s[j4 * 4 + 1] = fmaf(s[j4 * 4 + 1], a_i, tt.y);
-            s[j4 * 4 + 2] = fmaf(s[j4 * 4 + 2], a_i, tt.z);
-            s[j4 * 4 + 3] = fmaf(s[j4 * 4 + 3], a_i, tt.w);
+            s2[j4 * 2 + 0] = fma2(s2[j4 * 2 + 0], a2, pk2(tt.x, tt.y));
+            s2[j4 * 2 + 1] = fma2(s2[j4 * 2 + 1], a2, pk2(tt.z, tt.w));
           }
         }
       }
@@ -348,17 +411,32 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
       {
         float m8[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) m8[j] = s[j];
+        for (int j = 0; j < 4; ++j) upk2(s2[j], m8[2 * j], m8[2 * j + 1]);
 #pragma unroll
-        for (int j = 8; j < 64; ++j) m8[j & 7] = fmaxf(m8[j & 7], s[j]);
+        for (int j = 4; j < 32; j += 2) {                // FMNMX3: two new values per instruction
+          float a, b, c, d;
+          upk2(s2[j], a, b); upk2(s2[j + 1], c, d);
+          const int ch = (j >> 1) & 7;
+          m8[ch] = fmaxf(fmaxf(m8[ch], a), b);
+          m8[(ch + 4) & 7] = fmaxf(fmaxf(m8[(ch + 4) & 7], c), d);
+        }
         mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
       }
+      float s[64];
       float l;
       {
-        float l8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const uint64_t nmx2 = pk2(-mx, -mx);
+        uint64_t l2[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
-        for (int j = 0; j < 64; ++j) { s[j] = fast_exp2(s[j] - mx); l8[j & 7] += s[j]; }
-        l = ((l8[0] + l8[1]) + (l8[2] + l8[3])) + ((l8[4] + l8[5]) + (l8[6] + l8[7]));
+        for (int j = 0; j < 32; ++j) {
+          float a, b;
+          upk2(add2(s2[j], nmx2), a, b);
+          s[2 * j] = fast_exp2(a); s[2 * j + 1] = fast_exp2(b);
+          l2[j & 3] = add2(l2[j & 3], pk2(s[2 * j], s[2 * j + 1]));
+        }
+        float la, lb;
+        upk2(add2(add2(l2[0], l2[1]), add2(l2[2], l2[3])), la, lb);
+        l = la + lb;
       }
       TR(n, 5);
 
@@ -383,25 +461,29 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
       prev_valid = valid;
       prev_inv = __frcp_rn(l);
       prev_lse = (mx + __log2f(l)) * kLn2;
-      prev_idx = ((long long)geo.w * P.nH + h) * kN + ipos;
-      cur.next_item(sc);
-      cur.next_item(sc);
+      prev_idx = ((long long)gw * P.nH + h) * kN + ipos;
     }
     if (have_prev) {
       mbar_wait(&o_full[g], (kk - 1) & 1);
       tcgen05_fence_after();
       epilogue(kk - 1, prev_inv, prev_lse, prev_idx, prev_valid);
     }
+    // farewell to the store warp: this group has produced kk tiles.  The store warp must have taken the last one
+    // first -- two so_ready phases completing back to back would alias in its parity wait.
+    if (have_prev) mbar_wait(&so_free[g], (kk - 1) & 1);
+    if (r == 0) sEnd[g] = kk;
+    mbar_arrive_warp(&so_ready[g]);
 #undef TR
   }
 
   tcgen05_fence_before();
   __syncthreads();
+  trace_cta_time(P.trace, 1);
   if (warp == kMmaWarp) tmem_dealloc<kTmemColsF>(tmem);
 }
 
 constexpr size_t kFwdSmemBytes = 1024 /*align slack*/ + kStagesF * kStageBytesF + 2 * kPRegion + 2 * kTile + 2 * kN * kTblLd * 4 +
-                                 512 * 4 + 512 + 24 * 8;
+                                 512 * 4 + 1024 + kItemRing * 16 + 16 + 24 * 8;
 
 // ------------------------------------------------------------------------------------------
 // Host side
@@ -409,6 +491,7 @@ constexpr size_t kFwdSmemBytes = 1024 /*align slack*/ + kStagesF * kStageBytesF 
 inline const char* fwd_why_not_impl(const mmn_winattn_desc* d) {
   if (d->io_dtype != MMN_DT_BF16) return "io dtype is not bf16";
   if (d->head_dim != kD) return "head_dim != 32";
+  if (d->num_heads > kWorkDone) return "more than 63 heads";
   if (d->dropout_p > 0.f) return "attention dropout is only implemented in the generic path";
   WinShape g = shape_from(d);
   if (g.win[0] * g.win[1] * g.win[2] != kN) return "window does not hold 64 tokens";
@@ -420,7 +503,7 @@ inline const char* fwd_why_not_impl(const mmn_winattn_desc* d) {
 }
 
 inline void dump_trace(long long* dev, const char* path, cudaStream_t st) {
-  static long long host[5 * 32 * 16];
+  static long long host[kTraceWords];
   cudaStreamSynchronize(st);
   cudaMemcpy(host, dev, sizeof(host), cudaMemcpyDeviceToHost);
   cudaFree(dev);
@@ -431,8 +514,45 @@ inline void dump_trace(long long* dev, const char* path, cudaStream_t st) {
         for (int ev = 0; ev < 16; ++ev) fprintf(f, " %lld", host[(role * 32 + item) * 16 + ev]);
         fprintf(f, "\n");
       }
+    for (int cta = 0; cta < 1024; ++cta)
+      if (host[kTraceCtaOfs + 2 * cta]) fprintf(f, "cta %d %lld %lld\n", cta, host[kTraceCtaOfs + 2 * cta], host[kTraceCtaOfs + 2 * cta + 1]);
     fclose(f);
   }
+}
+inline TraceCfg trace_setup(const char* path, cudaStream_t st) {
+  TraceCfg t{nullptr, 0, 0};
+  if (path && *path) {
+    cudaMalloc(&t.buf, kTraceWords * sizeof(long long));
+    cudaMemsetAsync(t.buf, 0, kTraceWords * sizeof(long long), st);
+    const char* cta = getenv("MMN_TC_TRACE_CTA");        // which CTA to trace (default 0)
+    const char* it0 = getenv("MMN_TC_TRACE_ITEM0");      // first of the 32 traced items (default 0)
+    t.cta = cta ? atoi(cta) : 0;
+    t.item0 = it0 ? atoi(it0) : 0;
+  }
+  return t;
+}
+
+// Work counters of the dynamic schedule: kWorkSlots self-resetting slots per device, handed out round-robin so that
+// launches in flight on different streams do not share one (a slot is re-armed by the last CTA of the launch using it).
+// Allocated on first use (not capturable: run the op once before capturing it in a CUDA graph, as PyTorch requires anyway).
+inline int* work_slot(char* err, size_t errlen) {
+  static std::mutex mu;
+  static int* base[64] = {};
+  static unsigned next[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!base[dev]) {
+    int* p = nullptr;
+    if (cudaMalloc(&p, kWorkSlots * kWorkSlotInts * sizeof(int)) != cudaSuccess || cudaMemset(p, 0, kWorkSlots * kWorkSlotInts * sizeof(int)) != cudaSuccess) {
+      snprintf(err, errlen, "work counters: cudaMalloc/cudaMemset failed (first call inside a stream capture?)");
+      cudaGetLastError();
+      return nullptr;
+    }
+    base[dev] = p;
+  }
+  return base[dev] + (size_t)(next[dev]++ % kWorkSlots) * kWorkSlotInts;
 }
 
 inline int winattn_fwd_launch(const mmn_winattn_desc* d, const void* q, const void* k, const void* v, const float* bias,
@@ -451,15 +571,10 @@ inline int winattn_fwd_launch(const mmn_winattn_desc* d, const void* q, const vo
   P.mask_windows = d->mask_windows > 0 ? d->mask_windows : 1;
   P.scale = d->scale;
   P.bias = bias; P.head_scale = head_scale; P.mask = mask; P.lse = lse;
-  P.trace = nullptr;
+  P.work = work_slot(err, errlen);
+  if (!P.work) return MMN_ERR_CUDA;
   const char* trace_path = getenv("MMN_TC_TRACE");
-  if (trace_path && *trace_path) {
-    cudaMalloc(&P.trace, (5 * 32 * 16 + 1) * sizeof(long long));
-    cudaMemsetAsync(P.trace, 0, (5 * 32 * 16 + 1) * sizeof(long long), st);
-    const char* cta = getenv("MMN_TC_TRACE_CTA");        // which CTA to trace (default 0); slot [5*32*16] of the buffer
-    const long long cta_id = cta ? atoll(cta) : 0;
-    cudaMemcpyAsync(P.trace + 5 * 32 * 16, &cta_id, sizeof(cta_id), cudaMemcpyHostToDevice, st);
-  }
+  P.trace = trace_setup(trace_path, st);
 
   using Kern = void (*)(const FwdParams);
   static const Kern kernels[2][3] = {
@@ -481,7 +596,7 @@ inline int winattn_fwd_launch(const mmn_winattn_desc* d, const void* q, const vo
     snprintf(err, errlen, "winattn_fwd_tc_kernel: %s", cudaGetErrorString(e));
     return MMN_ERR_CUDA;
   }
-  if (P.trace) dump_trace(P.trace, trace_path, st);      // debug only: synchronous dump of CTA 0's timeline
+  if (P.trace.buf) dump_trace(P.trace.buf, trace_path, st);      // debug only: synchronous dump of CTA 0's timeline
   return MMN_OK;
 }
 

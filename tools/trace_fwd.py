@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from multimodal_neuroimage_b200 import _lib, ops  # noqa: E402,F401
 
 out = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/trace_fwd.txt"
-B, grid, nH, d = 8, (32, 32, 32), 3, 32
+B, grid, nH, d = int(os.environ.get("MMN_TRACE_B", "32")), (32, 32, 32), 3, 32
 C = nH * d
 qkv = torch.randn(B, *grid, 3 * C, device="cuda", dtype=torch.bfloat16)
 bias = torch.randn(nH, 64, 64, device="cuda")
