@@ -14,7 +14,8 @@ import threading
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libmmn_b200.so")
+# MMN_LIB=<path>: load another build of the library (A/B timing of kernel variants on one GPU box)
+LIB_PATH = os.environ.get("MMN_LIB") or os.path.join(PKG_DIR, "libmmn_b200.so")
 # translation unit -> headers it depends on (besides include/mmn_b200.h)
 SOURCES = {"mmn_abi.cu": ["generic_launch.h", "attn_generic.cuh", "winattn_tc.h"],
            "generic_launch.cu": ["generic_launch.h", "attn_generic.cuh"],

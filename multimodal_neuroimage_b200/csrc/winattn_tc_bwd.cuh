@@ -116,7 +116,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       mbar_init(&out_full[b], 1); mbar_init(&out_empty[b], kEpiThreads / 32);
     }
     mbar_init(pds_full, kSoftmaxThreadsB / 32);
-    for (int t = 0; t < 3; ++t) { mbar_init(&so_ready[t], kEpiThreads / 32); mbar_init(&so_free[t], 1); }
+    for (int t = 0; t < 3; ++t) { mbar_init(&so_ready[t], kEpiThreads / 32); mbar_init(&so_free[t], P.dcolsum ? 2 : 1); }
     fence_barrier_init();
   }
   if (warp == kProducerWarpB && lane == 0)
@@ -246,6 +246,50 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
         trace_ev(P.trace, 4, n, 2);
       }
       tma_store_wait_all<0>();
+    } else if (P.dcolsum) {
+      // ============================== column sums of dq, dk, dv (= q / k / v projection bias gradients) ==============================
+      // One warp sums the bf16 staging tiles while the TMA store drains them: lane (r0, c) owns the 16-byte channel group
+      // c of rows r0, r0 + 8, ...; 24 running fp32 sums per lane for the whole kernel, reduced across lanes once at the
+      // end.  (In the epilogue warps this was a 32x32 transpose-reduce per tile: 40 % of their instructions.)  Rows of an
+      // invalid slot are zero in the tile.  Sums are over the bf16-rounded gradients, i.e. exactly the column sums of the
+      // dq/dk/dv tensors the kernel writes (what a bias gradient computed from them would be).
+      const int cg = lane & 3, r0 = lane >> 2;
+      float acc[3][8];
+#pragma unroll
+      for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[t][e] = 0.f;
+      for (int n = 0; n < cnt; ++n) {
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          mbar_wait(&so_ready[t], n & 1);
+          const uint8_t* tile = sOut + t * kTile;
+#pragma unroll 4
+          for (int it = 0; it < 16; ++it) {
+            const int row = r0 + 8 * it;
+            const uint4 v = *reinterpret_cast<const uint4*>(tile + row * 64 + ((cg ^ ((row >> 1) & 3)) << 4));
+            const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              acc[t][2 * e] += __uint_as_float(u[e] << 16);
+              acc[t][2 * e + 1] += __uint_as_float(u[e] & 0xffff0000u);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&so_free[t]);
+        }
+      }
+      const int C = P.nH * kD;
+#pragma unroll
+      for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float v = acc[t][e];
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (lane < 4) atomicAdd(P.dcolsum + t * C + h * kD + cg * 8 + e, v);
+        }
     }
   } else if (warp >= kEpiWarp0) {
     // ============================== epilogue warpgroup: one thread per tile row ==============================
@@ -254,7 +298,6 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int rsw = (r >> 1) & 3;                       // 64B-swizzle phase of this thread's tile row
     if (kRegEpi > kRegLaunch) setmaxnreg_inc<kRegEpi>(); else if (kRegEpi < kRegLaunch) setmaxnreg_dec<kRegEpi>();
-    float cs[3] = {0.f, 0.f, 0.f};                      // lane l: column sums of dq, dk, dv channel l over this warp's rows
     float dscale_acc = 0.f;                             // sum over rows of q_i . dQ~_i = sum_ij dS_ij (s_ij - bias_ij)
     const float inv_hscale = COS ? 1.f / __ldg(P.head_scale + h) : 1.f;
     for (int n = 0; n < cnt; ++n) {
@@ -280,35 +323,33 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
         if (COS && t < 2) {
           // d/dx of x / max(||x||, eps) applied to G = dQ~ (which already carries 1/||x||): G - x^ (x^ . G)
           const uint8_t* rowp = t == 0 ? base + slot * 2 * kWinBytes + i * 64 : base + kOffK + r * 64;
-          uint4 xq[4];
-          float dot[4] = {0.f, 0.f, 0.f, 0.f};
+          uint64_t x2[16];                              // the row's 32 channels as fp32 pairs
+          uint64_t dot2[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            xq[c] = *reinterpret_cast<const uint4*>(rowp + ((c ^ rsw) << 4));
-            const uint32_t u[4] = {xq[c].x, xq[c].y, xq[c].z, xq[c].w};
+            const uint4 xq = *reinterpret_cast<const uint4*>(rowp + ((c ^ rsw) << 4));
+            const uint32_t u[4] = {xq.x, xq.y, xq.z, xq.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float lo = __uint_as_float(u[e] << 16), hi = __uint_as_float(u[e] & 0xffff0000u);
-              dot[e] = fmaf(lo, __uint_as_float(g32[c * 8 + 2 * e]), dot[e]);
-              dot[e] = fmaf(hi, __uint_as_float(g32[c * 8 + 2 * e + 1]), dot[e]);
+              x2[c * 4 + e] = pk2u(u[e] << 16, u[e] & 0xffff0000u);
+              dot2[e] = fma2(x2[c * 4 + e], pk2u(g32[c * 8 + 2 * e], g32[c * 8 + 2 * e + 1]), dot2[e]);
             }
           }
           // 1 / max(||x||, eps) was computed by the softmax warps when they prepared this item (ring slot n % 3)
           const float rinv = t == 0 ? sA[(n % 3) * 128 + r] * inv_hscale : sRk[(n % 3) * 128 + r];
           if (t == 1) mbar_arrive_warp(&empty[stage]);       // q and k rows (and their norms) read: the stage can be refilled
-          const float xg = (dot[0] + dot[1]) + (dot[2] + dot[3]);
+          float xga, xgb;
+          upk2(add2(add2(dot2[0], dot2[1]), add2(dot2[2], dot2[3])), xga, xgb);
+          const float xg = xga + xgb;
           if (t == 0 && valid) dscale_acc += xg;
           const float proj = rinv >= 1e12f ? 0.f : -xg * rinv * rinv;     // below eps the normalisation is x / eps: no projection
+          const uint64_t proj2 = pk2(proj, proj);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint32_t u[4] = {xq[c].x, xq[c].y, xq[c].z, xq[c].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float lo = __uint_as_float(u[e] << 16), hi = __uint_as_float(u[e] & 0xffff0000u);
-              const float o0 = fmaf(lo, proj, __uint_as_float(g32[c * 8 + 2 * e])), o1 = fmaf(hi, proj, __uint_as_float(g32[c * 8 + 2 * e + 1]));
-              g32[c * 8 + 2 * e] = __float_as_uint(o0); g32[c * 8 + 2 * e + 1] = __float_as_uint(o1);
-              o[c * 4 + e] = pack_bf16x2(o0, o1);
-            }
+          for (int c = 0; c < 16; ++c) {
+            const uint64_t o2 = fma2(x2[c], proj2, pk2u(g32[2 * c], g32[2 * c + 1]));
+            float o0, o1;
+            upk2(o2, o0, o1);
+            o[c] = pack_bf16x2(o0, o1);
           }
         } else {
           if (t == 1) mbar_arrive_warp(&empty[stage]);
@@ -324,30 +365,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
         fence_proxy_async_smem();
         mbar_arrive_warp(&so_ready[t]);
         if (warp == kEpiWarp0) trace_ev(P.trace, 1, n, 2 + t);
-        if (P.dcolsum) {
-          // transpose-reduce the warp's 32 rows x 32 channels (fp32, before rounding): lane l ends up with channel l
-          if (!valid) {
-#pragma unroll
-            for (int c = 0; c < 32; ++c) g32[c] = 0u;
-          }
-#pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
-            const bool up = (lane & off) != 0;
-#pragma unroll
-            for (int c = 0; c < off; ++c) {
-              const float lo = __uint_as_float(g32[c]), hi = __uint_as_float(g32[c + off]);
-              const float keep = up ? hi : lo, send = up ? lo : hi;
-              g32[c] = __float_as_uint(keep + __shfl_xor_sync(0xffffffffu, send, off));
-            }
-          }
-          cs[t] += __uint_as_float(g32[0]);
-        }
       }
-    }
-    if (P.dcolsum) {
-      const int C = P.nH * kD;
-#pragma unroll
-      for (int t = 0; t < 3; ++t) atomicAdd(P.dcolsum + t * C + h * kD + lane, cs[t]);
     }
     if (COS && P.dhead_scale) {                          // d s_ij / d(logit scale) = cos_ij = (s_ij - bias_ij) / logit scale
 #pragma unroll
