@@ -128,6 +128,60 @@ struct ItemCursor {
   __device__ __forceinline__ bool slot_valid(int slot) const { return slot == 0 || left >= 2; }
 };
 
+// ------------------------------------------------------------------------------------------
+// Dynamic schedule.  Each head has one atomic counter per wrap class (work[cls] = next unclaimed item of the class).
+// A CTA starts in its HOME class -- the class its cost-weighted static range would start in, so CTAs are spread over
+// the classes in proportion to the work -- and claims chunks there; when a class runs dry it moves on to the next one
+// (cyclically) and helps there.  Most CTAs therefore see one or two classes (a class change costs a table rebuild and,
+// in the backward kernel, a dbias flush: ~3 us), yet all CTAs finish within one chunk of each other whatever the
+// per-class item costs are.  The next claim is always in flight while the current chunk is processed.
+// All lanes of the producer warp call next() together; lane 0 does the atomics.
+// ------------------------------------------------------------------------------------------
+constexpr int kWorkDone = 511, kWorkSlotInts = 512, kWorkSlots = 128;   // per slot: 63 heads x 8 classes, [511] = CTAs that ran dry
+struct ClassQueue {
+  int cls, pend, tried;
+  __device__ __forceinline__ void init(const Sched& sc, int home_item, int* work, int chunk, int lane) {
+    cls = 0;
+    while (cls < 7) {
+      const int np = (sc.cnt[cls] + 1) >> 1;
+      if (home_item < np) break;
+      home_item -= np;
+      ++cls;
+    }
+    tried = 0;
+    pend = 0;
+    if (lane == 0) pend = atomicAdd(work + cls, chunk);
+  }
+  // first item (index in the class-sorted list) and length of the next chunk; false when every class is exhausted
+  __device__ __forceinline__ bool next(const Sched& sc, int* work, int chunk, int lane, int& item0, int& m) {
+    for (;;) {
+      const int c0 = __shfl_sync(0xffffffffu, pend, 0);
+      const int np = (sc.cnt[cls] + 1) >> 1;
+      if (c0 < np) {
+        int base = 0;
+        for (int c = 0; c < cls; ++c) base += (sc.cnt[c] + 1) >> 1;
+        item0 = base + c0;
+        m = min(chunk, np - c0);
+        if (lane == 0) pend = atomicAdd(work + cls, chunk);
+        tried = 0;
+        return true;
+      }
+      if (++tried >= 8) return false;
+      cls = (cls + 1) & 7;
+      if (lane == 0) pend = atomicAdd(work + cls, chunk);
+    }
+  }
+  // called by lane 0 after the CTA ran dry: the last CTA re-arms the counters for the next launch that uses this slot
+  static __device__ __forceinline__ void retire(int* slot, int num_heads) {
+    __threadfence();
+    if (atomicAdd(slot + kWorkDone, 1) == (int)gridDim.x - 1) {
+      for (int i = 0; i < num_heads * 8; ++i) slot[i] = 0;
+      slot[kWorkDone] = 0;
+      __threadfence();
+    }
+  }
+};
+
 struct ItemGeom : WinGeom {
   int w;             // linear window index (b * nW + row-major window position): addresses lse
 };

@@ -44,6 +44,10 @@ constexpr int kBwdThreads = kSoftmaxThreadsB + 256;
 //   2 threads/row: launch 128 -> softmax 168, epilogue 112, the rest 64   (256*168 + 128*112 + 128*64 = 512*128)
 constexpr int kRegLaunch = kRowSplit == 4 ? 80 : 128;
 constexpr int kRegSoftmax = kRowSplit == 4 ? 80 : 168, kRegEpi = kRowSplit == 4 ? 104 : 112, kRegAux = kRowSplit == 4 ? 56 : 64;
+#ifndef MMN_BWD_CHUNK
+#define MMN_BWD_CHUNK 1
+#endif
+constexpr int kChunkB = MMN_BWD_CHUNK;  // items a CTA claims per atomic
 constexpr int kBwdTmemCols = 512;     // S[b] at 128 b, dP[b] at 128 b + 64; dV|dQ~|dK~ [b] at 256 + 96 b
 
 struct BwdParams {
@@ -60,6 +64,7 @@ struct BwdParams {
   float* dbias;         // (nH, 64, 64) accumulated, may be null
   float* dhead_scale;   // (nH) accumulated, may be null
   float* dcolsum;       // (3, nH*32) accumulated column sums of dq, dk, dv (= projection bias grads), may be null
+  int* work;            // dynamic schedule counters (winattn_tc_fwd.cuh: work_slot)
   TraceCfg trace;       // debug: clock64 stamps of one CTA (MMN_TC_TRACE_BWD=<file>)
 };
 
@@ -82,8 +87,10 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
   float* sRed = sDelta + 512;                             // 16 floats: dhead_scale per softmax warp
   uint8_t* sPos = reinterpret_cast<uint8_t*>(sRed + 16);  // [8][64]
   uint8_t* sRid = sPos + 512;                             // [8][64] window position -> shift-mask region id
-  int4* sItem = reinterpret_cast<int4*>(sRid + 512);      // [8] ring: {wrap class, window index of slot 0, of slot 1, valid slots} of item n & 7
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sItem + 8);
+  int4* sItem = reinterpret_cast<int4*>(sRid + 512);      // [8] ring: {wrap class (-1: no more items), window index of slot 0, of slot 1, valid slots} of item n & 7
+  int4* sGeo = sItem + 8;                                 // [8][2] ring: {sample, start coordinates} of the item's two windows (store warp)
+  int* sEnd = reinterpret_cast<int*>(sGeo + 16);          // [0] items of this CTA once the epilogue warps know (else INT_MAX)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEnd + 4);
   uint64_t* full = bars;                                  // [kStagesB]
   uint64_t* empty = bars + kStagesB;                      // [kStagesB] (one arrival per warp: epilogue threads)
   uint64_t* sdp_full = bars + 2 * kStagesB;               // [2]
@@ -99,8 +106,6 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
   const Sched& sc = P.sc;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x % P.nH;
-  const int item0 = sched_range_begin(sc, blockIdx.x / P.nH, P.per_head);
-  const int cnt = sched_range_begin(sc, blockIdx.x / P.nH + 1, P.per_head) - item0;
 
   // ---- one-time setup
   for (int i = tid; i < (kStagesB * kStageBytesB + 2 * kPRegion) / 16; i += kBwdThreads)
@@ -110,6 +115,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
     sRid[i] = (uint8_t)class_region_id(S, i >> 6, i & 63);
   }
   if (tid == 0) {
+    sEnd[0] = 0x7fffffff;
     for (int s = 0; s < kStagesB; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kEpiThreads / 32); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&sdp_full[b], 1); mbar_init(&sdp_empty[b], kSoftmaxThreadsB / 32);
@@ -138,25 +144,44 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       // every lane runs the loop; lane l issues boxes l, l + 32 of the item (issue_item_boxes)
       const CUtensorMap* const maps[4] = {P.q, P.dout, P.k, P.v};
       const int slot_stride[4] = {2 * kWinBytes, 2 * kWinBytes, kWinBytes, kWinBytes};
-      ItemCursor cur;
-      cur.seek(sc, item0);
-      for (int n = 0; n < cnt; ++n, cur.next_item(sc)) {
+      // Dynamic schedule (see the forward kernel's producer): chunks of kChunkB items of this head's class-sorted list
+      // through an atomic counter; every other warp follows the descriptor rings sItem / sGeo.  One end marker.
+      int n = 0;
+      ClassQueue wq;
+      wq.init(sc, sched_range_begin(sc, blockIdx.x / P.nH, P.per_head), P.work + h * 8, kChunkB, lane);
+      for (int c0, m; wq.next(sc, P.work + h * 8, kChunkB, lane, c0, m);) {
+        ItemCursor cur;
+        cur.seek(sc, c0);
+        for (int t = 0; t < m; ++t, ++n, cur.next_item(sc)) {
+          const int stage = n % kStagesB, phase = (n / kStagesB) & 1;
+          const int nvalid = cur.slot_valid(1) ? 2 : 1;
+          const ItemGeom g0 = item_geom(S, sc, cur, 0), g1 = item_geom(S, sc, cur, 1);
+          trace_ev(P.trace, 2, n, 0);
+          mbar_wait(&empty[stage], phase ^ 1);
+          trace_ev(P.trace, 2, n, 1);
+          if (lane == 0) {
+            sItem[n & 7] = make_int4(cur.cls, g0.w, g1.w, nvalid);      // published by the arrive below
+            sGeo[(n & 7) * 2] = make_int4(g0.b, g0.start[0], g0.start[1], g0.start[2]);
+            sGeo[(n & 7) * 2 + 1] = make_int4(g1.b, g1.start[0], g1.start[1], g1.start[2]);
+            mbar_arrive_expect_tx(&full[stage], nvalid * 4 * kWinBytes);
+          }
+          __syncwarp();
+          uint8_t* base = sStage + stage * kStageBytesB;
+          uint8_t* const dst[4] = {base, base + kOffDO, base + kOffK, base + kOffV};
+          issue_item_boxes<true, 4>(S, g0, g1, nvalid, h * kD, maps, dst, slot_stride, &full[stage], lane);
+          trace_ev(P.trace, 2, n, 2);
+        }
+      }
+      {   // end marker
         const int stage = n % kStagesB, phase = (n / kStagesB) & 1;
-        trace_ev(P.trace, 2, n, 0);
         mbar_wait(&empty[stage], phase ^ 1);
-        trace_ev(P.trace, 2, n, 1);
-        const int nvalid = cur.slot_valid(1) ? 2 : 1;
-        const ItemGeom g0 = item_geom(S, sc, cur, 0), g1 = item_geom(S, sc, cur, 1);
         if (lane == 0) {
-          sItem[n & 7] = make_int4(cur.cls, g0.w, g1.w, nvalid);      // published by the arrive below
-          mbar_arrive_expect_tx(&full[stage], nvalid * 4 * kWinBytes);
+          sItem[n & 7] = make_int4(-1, 0, 0, 0);
+          mbar_arrive(&full[stage]);
         }
         __syncwarp();
-        uint8_t* base = sStage + stage * kStageBytesB;
-        uint8_t* const dst[4] = {base, base + kOffDO, base + kOffK, base + kOffV};
-        issue_item_boxes<true, 4>(S, g0, g1, nvalid, h * kD, maps, dst, slot_stride, &full[stage], lane);
-        trace_ev(P.trace, 2, n, 2);
       }
+      if (lane == 0) ClassQueue::retire(P.work, P.nH);
     } else if (warp == kMmaWarpB) {
       // ============================== MMA issuer ==============================
       constexpr uint32_t idescS = umma_idesc_bf16(128, 64, 0, 0);     // A K-major, B K-major
@@ -170,9 +195,11 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       const uint64_t dPm = umma_smem_desc(0, 8192, 1024, kSwz128);    // P, dS' read MN-major (transposed)
       const uint32_t stage0 = smem_u32(sStage) >> 4, p0 = smem_u32(sP) >> 4, ds0 = smem_u32(sDS) >> 4;
       constexpr uint32_t W16 = kWinBytes >> 4;
+      int total = 0x7fffffff;                                         // items of this CTA: known once the end marker shows up
       auto issue_sdp = [&](int n) {
         const int stage = n % kStagesB, phase = (n / kStagesB) & 1, b = n & 1;
         mbar_wait(&full[stage], phase);
+        if (sItem[n & 7].x < 0) { total = n; return; }
         mbar_wait(&sdp_empty[b], ((n >> 1) & 1) ^ 1);
         tcgen05_fence_after();
         if (elect_one()) {
@@ -188,9 +215,9 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
         }
         __syncwarp();
       };
-      if (cnt > 0) issue_sdp(0);
-      if (cnt > 1) issue_sdp(1);
-      for (int n = 0; n < cnt; ++n) {
+      issue_sdp(0);
+      if (total > 1) issue_sdp(1);
+      for (int n = 0; n < total; ++n) {
         const int stage = n % kStagesB, b = n & 1;
         trace_ev(P.trace, 3, n, 0);
         mbar_wait(pds_full, n & 1);
@@ -215,20 +242,27 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
         }
         __syncwarp();
         trace_ev(P.trace, 3, n, 2);
-        if (n + 2 < cnt) issue_sdp(n + 2);
+        if (total == 0x7fffffff) issue_sdp(n + 2);
         trace_ev(P.trace, 3, n, 3);
       }
+      // farewell to the epilogue warps: an arrival on the out_full buffer item `total` would have used, once they have
+      // taken item total - 2 from it (two phases completing back to back would alias in their parity wait)
+      if (total >= 2) mbar_wait(&out_empty[total & 1], ((total - 2) >> 1) & 1);
+      if (lane == 0) {
+        sEnd[0] = total;
+        mbar_arrive(&out_full[total & 1]);
+      }
+      __syncwarp();
     } else if (warp == kStoreWarpB) {
       // ============================== TMA store ==============================
       // The three staging tiles (dq, dk, dv) are handed over one by one, so the epilogue warps fill the next
       // tile while this one drains.  Each lane issues its share of a tile's boxes; a tile is returned to the
       // epilogue once the bulk group two behind has finished reading shared memory.
-      ItemCursor cur;
-      cur.seek(sc, item0);
       int grp = 0;
-      for (int n = 0; n < cnt; ++n, cur.next_item(sc)) {
-        const ItemGeom g0 = item_geom(S, sc, cur, 0), g1 = item_geom(S, sc, cur, 1);
-        const int nvalid = cur.slot_valid(1) ? 2 : 1;
+      bool done = false;
+      for (int n = 0; !done; ++n) {
+        ItemGeom g0, g1;
+        int nvalid = 0;
 #pragma unroll
         for (int t = 0; t < 3; ++t, ++grp) {
           const CUtensorMap* const maps[1] = {t == 0 ? P.dq : (t == 1 ? P.dk : P.dv)};
@@ -236,7 +270,15 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
           uint8_t* const dst[1] = {sOut + t * kTile};
           if (t == 0) trace_ev(P.trace, 4, n, 0);
           mbar_wait(&so_ready[t], n & 1);
-          if (t == 0) trace_ev(P.trace, 4, n, 1);
+          if (t == 0) {
+            if (n >= *reinterpret_cast<volatile int*>(sEnd)) { done = true; break; }   // that arrival was the epilogue warps' farewell
+            const int4 it = sItem[n & 7], a0 = sGeo[(n & 7) * 2], a1 = sGeo[(n & 7) * 2 + 1];
+            nvalid = it.w;
+            g0.cls = g1.cls = it.x;
+            g0.b = a0.x; g0.start[0] = a0.y; g0.start[1] = a0.z; g0.start[2] = a0.w;
+            g1.b = a1.x; g1.start[0] = a1.y; g1.start[1] = a1.z; g1.start[2] = a1.w;
+            trace_ev(P.trace, 4, n, 1);
+          }
           issue_item_boxes<false, 1>(S, g0, g1, nvalid, h * kD, maps, dst, slot_stride, nullptr, lane);
           tma_store_commit();
           tma_store_wait_read<2>();        // per thread: the group two behind (tile (t + 1) % 3) has been read out
@@ -259,10 +301,12 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       for (int t = 0; t < 3; ++t)
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[t][e] = 0.f;
-      for (int n = 0; n < cnt; ++n) {
+      bool done = false;
+      for (int n = 0; !done; ++n) {
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
           mbar_wait(&so_ready[t], n & 1);
+          if (t == 0 && n >= *reinterpret_cast<volatile int*>(sEnd)) { done = true; break; }
           const uint8_t* tile = sOut + t * kTile;
 #pragma unroll 4
           for (int it = 0; it < 16; ++it) {
@@ -300,12 +344,14 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
     if (kRegEpi > kRegLaunch) setmaxnreg_inc<kRegEpi>(); else if (kRegEpi < kRegLaunch) setmaxnreg_dec<kRegEpi>();
     float dscale_acc = 0.f;                             // sum over rows of q_i . dQ~_i = sum_ij dS_ij (s_ij - bias_ij)
     const float inv_hscale = COS ? 1.f / __ldg(P.head_scale + h) : 1.f;
-    for (int n = 0; n < cnt; ++n) {
+    int n = 0;
+    for (;; ++n) {
       const int stage = n % kStagesB, b = n & 1;
       const uint8_t* base = sStage + stage * kStageBytesB;
       const uint32_t tO = tmem + lane_base + 256 + b * 96;
       if (warp == kEpiWarp0) trace_ev(P.trace, 1, n, 0);
       mbar_wait(&out_full[b], (n >> 1) & 1);
+      if (n >= *reinterpret_cast<volatile int*>(sEnd)) break;      // that arrival was the MMA warp's farewell
       tcgen05_fence_after();
       const bool valid = slot < sItem[n & 7].w;
       if (warp == kEpiWarp0) trace_ev(P.trace, 1, n, 1);
@@ -367,6 +413,9 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
         if (warp == kEpiWarp0) trace_ev(P.trace, 1, n, 2 + t);
       }
     }
+    // farewell to the store / column-sum warps through so_ready[0], once they have taken the last item's tile 0
+    if (n > 0) mbar_wait(&so_free[0], (n - 1) & 1);
+    mbar_arrive_warp(&so_ready[0]);
     if (COS && P.dhead_scale) {                          // d s_ij / d(logit scale) = cos_ij = (s_ij - bias_ij) / logit scale
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) dscale_acc += __shfl_xor_sync(0xffffffffu, dscale_acc, o);
@@ -390,11 +439,34 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
     const int trole = warp == 0 ? 0 : -1;
 #define TRB(item, ev) do { if (trole >= 0) trace_ev(P.trace, trole, item, ev); } while (0)
 
+    // dbias of a wrap class leaves the CTA through the (idle at that moment) table buffer: the two windows of the tile
+    // are summed there, then the 64x64 sums go out as atomics with consecutive threads on consecutive columns, so a
+    // warp's 32 atomics fall into one or two cache lines.  (One atomic per thread and register, rows 256 B apart, was
+    // 8192 scattered L2 transactions per CTA and flush -- ~30 us when every CTA changes class at the same time.)
+    // Called by all softmax threads; the caller has made sure nobody reads the table any more.
     auto flush_dbias = [&](int cls) {
-      const uint8_t* pos = sPos + cls * 64;
-      float* rowp = gdb_head + (int)pos[i] * kN;
+      float4* mine = reinterpret_cast<float4*>(sTbl + i * kTblLd + qt * KP);
+      if (slot == 0) {
 #pragma unroll
-      for (int j = 0; j < KP; ++j) { atomicAdd(rowp + pos[qt * KP + j], dbacc[j]); dbacc[j] = 0.f; }
+        for (int j4 = 0; j4 < KP / 4; ++j4) mine[j4] = make_float4(dbacc[j4 * 4], dbacc[j4 * 4 + 1], dbacc[j4 * 4 + 2], dbacc[j4 * 4 + 3]);
+      }
+      named_bar_sync(3, kSoftmaxThreadsB);
+      if (slot == 1) {
+#pragma unroll
+        for (int j4 = 0; j4 < KP / 4; ++j4) {
+          float4 v = mine[j4];
+          v.x += dbacc[j4 * 4]; v.y += dbacc[j4 * 4 + 1]; v.z += dbacc[j4 * 4 + 2]; v.w += dbacc[j4 * 4 + 3];
+          mine[j4] = v;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < KP; ++j) dbacc[j] = 0.f;
+      named_bar_sync(3, kSoftmaxThreadsB);
+      const uint8_t* pos = sPos + cls * 64;
+      for (int e = tid; e < kN * kN; e += kSoftmaxThreadsB) {
+        const int ti = e >> 6, tj = e & 63;
+        atomicAdd(gdb_head + (int)pos[ti] * kN + pos[tj], sTbl[ti * kTblLd + tj]);
+      }
     };
 
     // Everything item n needs before its logits arrive -- its descriptor, the lse of this thread's row (a global
@@ -403,11 +475,12 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
     int nx_cls = 0, nx_gw = 0, nx_ipos = 0;
     bool nx_valid = false;
     float nx_lse = 0.f;
-    auto prep = [&](int n) {
+    auto prep = [&](int n) -> bool {
       const int stage = n % kStagesB, phase = (n / kStagesB) & 1;
       mbar_wait(&full[stage], phase);
       const int4 item = sItem[n & 7];                   // written by the producer before it armed full[stage]
-      nx_cls = item.x; nx_gw = slot ? item.z : item.y;
+      // (an end marker, item.x < 0, runs through the same code as a harmless invalid item: no extra control flow here)
+      nx_cls = max(item.x, 0); nx_gw = slot ? item.z : item.y;
       nx_valid = slot < item.w;
       nx_ipos = sPos[nx_cls * 64 + i];
       nx_lse = nx_valid ? __ldg(P.lse + ((size_t)nx_gw * P.nH + h) * kN + nx_ipos) : 0.f;
@@ -417,20 +490,24 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
         const float rinv = rsqrtf(fmaxf(ss, 1e-24f));
         if (qt == 0) sA[(n % 3) * 128 + r] = rinv * hscale; else sRk[(n % 3) * 128 + r] = rinv;
       }
+      return item.x >= 0;
     };
-    if (cnt > 0) prep(0);
+    bool more = prep(0);
     named_bar_sync(1, kSoftmaxThreadsB);
 
     int cls_loaded = -1;
-    for (int n = 0; n < cnt; ++n) {
+    for (int n = 0; more; ++n) {
       const int b = n & 1;
       TRB(n, 0);
       const int cls = nx_cls, gw = nx_gw, ipos = nx_ipos;
       const bool valid = nx_valid;
       const float lse2 = nx_lse * kLog2e;
       if (cls != cls_loaded) {                          // rare: at most 8 times per CTA
-        if (gdb_head && cls_loaded >= 0) flush_dbias(cls_loaded);
         named_bar_sync(3, kSoftmaxThreadsB);            // everyone is done reading the old table
+        if (gdb_head && cls_loaded >= 0) {
+          flush_dbias(cls_loaded);
+          named_bar_sync(3, kSoftmaxThreadsB);          // sums read out: the buffer can take the new table
+        }
         build_class_table(sTbl, kTblLd, bias_h, sPos + cls * 64, sRid + cls * 64, MASK == MMN_MASK_SHIFT && cls != 0, tid, kSoftmaxThreadsB);
         cls_loaded = cls;
         named_bar_sync(3, kSoftmaxThreadsB);
@@ -460,15 +537,15 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       mbar_wait(&sdp_full[b], (n >> 1) & 1);
       tcgen05_fence_after();
       TRB(n, 4);
-      uint32_t dpr[KP];
       float delta = 0.f;                                // sum_j p_j dp_j over this thread's keys
       {
-        uint32_t raw[KP];
+        // dP is read twice (here for delta, after the barrier for dS) rather than kept in 16 registers across the
+        // barrier and the next item's preparation: the softmax warps run at the 80-register limit, and the S/dP buffer
+        // is not needed back before item n + 2's MMAs anyway (they are issued after this item's dS').
+        uint32_t raw[KP], dpr[KP];
         tmem_ld_32x32b(tmem + lane_base + b * 128 + qt * KP, raw);
         tmem_ld_32x32b(tmem + lane_base + b * 128 + 64 + qt * KP, dpr);
         tmem_ld_wait();
-        tcgen05_fence_before();
-        mbar_arrive_warp(&sdp_empty[b]);
 #pragma unroll
         for (int j4 = 0; j4 < KP / 4; ++j4) {
           const float4 kk = COS ? krow[j4] : make_float4(1.f, 1.f, 1.f, 1.f);
@@ -484,7 +561,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
           }
         }
       }
-      if (n + 1 < cnt) prep(n + 1);                     // published by the delta barrier below
+      more = prep(n + 1);                               // published by the delta barrier below
       sDelta[qt * 128 + r] = delta;
       TRB(n, 5);
       // P (bf16) can go out before delta is known; the previous item's gradient MMAs must have finished reading P / dS'
@@ -503,8 +580,15 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       if (kRowSplit == 4) delta += sDelta[256 + r] + sDelta[384 + r];
 
       // ---- (d) dS = P o (dP - delta): dbias; dS' = dS o c into the MMA tile; d(logit scale)
+      {
+        uint32_t dpr[KP];
+        tmem_ld_32x32b(tmem + lane_base + b * 128 + 64 + qt * KP, dpr);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        mbar_arrive_warp(&sdp_empty[b]);
 #pragma unroll
-      for (int j = 0; j < KP; ++j) p[j] *= __uint_as_float(dpr[j]) - delta;
+        for (int j = 0; j < KP; ++j) p[j] *= __uint_as_float(dpr[j]) - delta;
+      }
       if (valid && gdb_head) {
 #pragma unroll
         for (int j = 0; j < KP; ++j) dbacc[j] += p[j];
@@ -532,7 +616,10 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
 #undef TRB
 
     // ---- cross-window reduction: dbias (registers)
-    if (gdb_head && cls_loaded >= 0) flush_dbias(cls_loaded);
+    if (gdb_head && cls_loaded >= 0) {
+      named_bar_sync(3, kSoftmaxThreadsB);              // everyone is done reading the table
+      flush_dbias(cls_loaded);
+    }
   }
 
   tcgen05_fence_before();
@@ -542,7 +629,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
 }
 
 constexpr size_t kBwdSmemBytes = 1024 + kStagesB * kStageBytesB + 2 * kPRegion + 3 * kTile + kN * kTblLd * 4 +
-                                 (384 + 384 + 512 + 16) * 4 + 1024 + 8 * 16 + 24 * 8;
+                                 (384 + 384 + 512 + 16) * 4 + 1024 + 24 * 16 + 16 + 24 * 8;
 
 inline const char* bwd_why_not_impl(const mmn_winattn_desc* d) {
   const char* w = fwd_why_not_impl(d);
@@ -573,6 +660,8 @@ inline int winattn_bwd_launch(const mmn_winattn_desc* d, const void* q, const vo
   P.dbias = bias ? dbias : nullptr;
   P.dhead_scale = d->score_kind == MMN_SCORE_COSINE ? dhead_scale : nullptr;
   P.dcolsum = dcolsum;
+  P.work = work_slot(err, errlen);
+  if (!P.work) return MMN_ERR_CUDA;
   const char* trace_path = getenv("MMN_TC_TRACE_BWD");
   P.trace = trace_setup(trace_path, st);
 

@@ -46,7 +46,6 @@ constexpr int kTblLd = 68;                         // padded row of the shared t
 constexpr int kTmemColsF = 256;                    // S[g] at 64 g; O[g][b] at 128 + 32 (2 g + b)
 constexpr int kItemRing = 16;                      // item descriptors published by the TMA producer (see the ring-depth note there)
 constexpr int kChunkF = 8;                         // items a CTA claims per atomic
-constexpr int kWorkDone = 63, kWorkSlotInts = 64, kWorkSlots = 256;   // up to 63 heads
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -68,7 +67,7 @@ struct FwdParams {
   const float* head_scale;
   const float* mask;
   float* lse;
-  int* work;          // dynamic schedule: work[h] = next unclaimed item of head h, work[kWorkDone] = CTAs that ran dry (self-resetting)
+  int* work;          // dynamic schedule counters (tc_sched.cuh: ClassQueue), self-resetting
   TraceCfg trace;     // debug: per-phase clock64 stamps of one CTA (MMN_TC_TRACE=<file>), else buf == null
 };
 
@@ -180,21 +179,15 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
     const int dst_base[3] = {0, kQRegion, kQRegion + kTile};
     const int slot_stride[3] = {2 * kWinBytes, kWinBytes, kWinBytes};
     BoxPlan<3> plan;
-    // Dynamic schedule: the class-sorted item list of this head is handed out in chunks of kChunkF items through an
-    // atomic counter, so a CTA's items ascend (it sees each wrap class at most once) and the CTAs finish together
-    // whatever the per-class costs are.  The next chunk is claimed while the current one is being issued.
+    // Dynamic schedule (tc_sched.cuh: ClassQueue): chunks of kChunkF items of this head, home class first.
     // Every other warp learns its items from the descriptor ring sItem (published by the full[] arrival).  Ring
     // depth: entry n + 16 is written only after PV(n + 12) has completed, i.e. after its group wrote P(n + 12), which
     // it does after the epilogue of item n + 8, which waited for the store of item n + 6 -- so entry n has been read
     // by every consumer, the store warp included.
     int n = 0;
-    int claim = 0;
-    if (lane == 0) claim = atomicAdd(P.work + h, kChunkF);
-    for (;;) {
-      const int c0 = __shfl_sync(0xffffffffu, claim, 0);
-      if (c0 >= sc.n_items) break;
-      if (lane == 0) claim = atomicAdd(P.work + h, kChunkF);
-      const int m = min(kChunkF, sc.n_items - c0);
+    ClassQueue wq;
+    wq.init(sc, sched_range_begin(sc, blockIdx.x / P.nH, P.per_head), P.work + h * 8, kChunkF, lane);
+    for (int c0, m; wq.next(sc, P.work + h * 8, kChunkF, lane, c0, m);) {
       ItemCursor cur;
       cur.seek(sc, c0);
       for (int t = 0; t < m; ++t, ++n, cur.next_item(sc)) {
@@ -225,15 +218,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
       }
       __syncwarp();
     }
-    // the last CTA to run dry re-arms the counters for the next launch that uses this slot
-    if (lane == 0) {
-      __threadfence();
-      if (atomicAdd(P.work + kWorkDone, 1) == (int)gridDim.x - 1) {
-        for (int hh = 0; hh < P.nH; ++hh) P.work[hh] = 0;
-        P.work[kWorkDone] = 0;
-        __threadfence();
-      }
-    }
+    if (lane == 0) ClassQueue::retire(P.work, P.nH);
   } else if (warp == kMmaWarp) {
     // ============================== MMA issuer ==============================
     constexpr uint32_t idescS = umma_idesc_bf16(128, 64, 0, 0);    // [Q0;0],[0;Q1] (K-major) x K0,K1 (K-major)
@@ -491,7 +476,7 @@ constexpr size_t kFwdSmemBytes = 1024 /*align slack*/ + kStagesF * kStageBytesF 
 inline const char* fwd_why_not_impl(const mmn_winattn_desc* d) {
   if (d->io_dtype != MMN_DT_BF16) return "io dtype is not bf16";
   if (d->head_dim != kD) return "head_dim != 32";
-  if (d->num_heads > kWorkDone) return "more than 63 heads";
+  if (d->num_heads * 8 > kWorkDone) return "more than 63 heads";
   if (d->dropout_p > 0.f) return "attention dropout is only implemented in the generic path";
   WinShape g = shape_from(d);
   if (g.win[0] * g.win[1] * g.win[2] != kN) return "window does not hold 64 tokens";
