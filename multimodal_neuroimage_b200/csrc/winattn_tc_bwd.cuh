@@ -356,6 +356,25 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       const bool valid = slot < sItem[n & 7].w;
       if (warp == kEpiWarp0) trace_ev(P.trace, 1, n, 1);
 
+      // Everything this item still needs from its stage -- this thread's q and k rows and their norms (ring slot n % 3,
+      // written by the softmax warps when they prepared the item) -- is taken into registers first, and the stage is
+      // handed back to the producer at once: the refill (issue + TMA latency) then runs under the three tiles below
+      // instead of after two of them, which is what the softmax warps were waiting for at the next-but-one item.
+      uint4 xrow[2][4];
+      float rinv2[2] = {1.f, 1.f};
+      if (COS) {
+        const uint8_t* qrow = base + slot * 2 * kWinBytes + i * 64;
+        const uint8_t* krow_ = base + kOffK + r * 64;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          xrow[0][c] = *reinterpret_cast<const uint4*>(qrow + ((c ^ rsw) << 4));
+          xrow[1][c] = *reinterpret_cast<const uint4*>(krow_ + ((c ^ rsw) << 4));
+        }
+        rinv2[0] = sA[(n % 3) * 128 + r] * inv_hscale;
+        rinv2[1] = sRk[(n % 3) * 128 + r];
+      }
+      mbar_arrive_warp(&empty[stage]);
+
 #pragma unroll
       for (int t = 0; t < 3; ++t) {                     // t = 0: dQ~ with the q row, 1: dK~ with the k row, 2: dV
         uint32_t g32[32];
@@ -368,12 +387,11 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
         uint32_t o[16];
         if (COS && t < 2) {
           // d/dx of x / max(||x||, eps) applied to G = dQ~ (which already carries 1/||x||): G - x^ (x^ . G)
-          const uint8_t* rowp = t == 0 ? base + slot * 2 * kWinBytes + i * 64 : base + kOffK + r * 64;
           uint64_t x2[16];                              // the row's 32 channels as fp32 pairs
           uint64_t dot2[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const uint4 xq = *reinterpret_cast<const uint4*>(rowp + ((c ^ rsw) << 4));
+            const uint4 xq = xrow[t][c];
             const uint32_t u[4] = {xq.x, xq.y, xq.z, xq.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -381,9 +399,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
               dot2[e] = fma2(x2[c * 4 + e], pk2u(g32[c * 8 + 2 * e], g32[c * 8 + 2 * e + 1]), dot2[e]);
             }
           }
-          // 1 / max(||x||, eps) was computed by the softmax warps when they prepared this item (ring slot n % 3)
-          const float rinv = t == 0 ? sA[(n % 3) * 128 + r] * inv_hscale : sRk[(n % 3) * 128 + r];
-          if (t == 1) mbar_arrive_warp(&empty[stage]);       // q and k rows (and their norms) read: the stage can be refilled
+          const float rinv = rinv2[t];                  // 1 / max(||x||, eps)
           float xga, xgb;
           upk2(add2(add2(dot2[0], dot2[1]), add2(dot2[2], dot2[3])), xga, xgb);
           const float xg = xga + xgb;
@@ -398,7 +414,6 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
             o[c] = pack_bf16x2(o0, o1);
           }
         } else {
-          if (t == 1) mbar_arrive_warp(&empty[stage]);
 #pragma unroll
           for (int c = 0; c < 16; ++c) o[c] = pack_bf16x2(__uint_as_float(g32[2 * c]), __uint_as_float(g32[2 * c + 1]));
         }
@@ -478,6 +493,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
     auto prep = [&](int n) -> bool {
       const int stage = n % kStagesB, phase = (n / kStagesB) & 1;
       mbar_wait(&full[stage], phase);
+      TRB(n - 1, 10);
       const int4 item = sItem[n & 7];                   // written by the producer before it armed full[stage]
       // (an end marker, item.x < 0, runs through the same code as a harmless invalid item: no extra control flow here)
       nx_cls = max(item.x, 0); nx_gw = slot ? item.z : item.y;
@@ -561,6 +577,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
           }
         }
       }
+      TRB(n, 9);
       more = prep(n + 1);                               // published by the delta barrier below
       sDelta[qt * 128 + r] = delta;
       TRB(n, 5);

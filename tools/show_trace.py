@@ -19,11 +19,12 @@ for role in range(5):
         e = ev.get((role, item))
         if not e or not any(e):
             continue
-        st = [x for x in e if x > 0]
-        deltas = [b - a for a, b in zip(st, st[1:])]
+        pairs = sorted((x, k) for k, x in enumerate(e) if x > 0)
+        st = [x for x, _ in pairs]
+        deltas = [f"{k}:{b - a}" for (a, _), (b, k) in zip(pairs, pairs[1:])]
         gap = st[0] - prev_last if prev_last else 0
         prev_last = st[-1]
-        print(f"  item {item:3d} start {st[0] - t0:7d} gap {gap:5d} phases {deltas} total {st[-1] - st[0]}")
+        print(f"  item {item:3d} start {st[0] - t0:7d} gap {gap:5d} phases {" ".join(deltas)} total {st[-1] - st[0]}")
 if ctas:
     durs = sorted(b - a for _, a, b in ctas)
     s0 = min(a for _, a, _ in ctas)
