@@ -68,52 +68,94 @@ __global__ void cpb_scatter_kernel(const float* __restrict__ dbias, const long l
   for (int h = 0; h < nH; ++h) atomicAdd(dtab16 + t * nH + h, __ldg(dbias + (size_t)h * NN + e));
 }
 
-// One thread per hidden unit j: walks the T table entries, recomputes its activation, and accumulates
-// dW2[:, j], dW1[j, :], db1[j] in registers (no atomics: deterministic).  g[t][h] = d tab[t][h] is staged in
-// shared memory by the block: d/dx 16 sigmoid(x) = tab16 (1 - tab16 / 16).
-__global__ void __launch_bounds__(128)
+// Backward of the MLP.  A block owns 32 hidden units; its 16 warps split the T table entries (warp w takes
+// t = w, w + 16, ...), every thread recomputes its unit's activation and accumulates dW2[:, j], dW1[j, :], db1[j] for
+// its slice in registers; the 16 slices are then summed through shared memory in a fixed order (no atomics:
+// deterministic).  g[t][h] = d tab[t][h] is staged in shared memory eight heads at a time:
+// d/dx 16 sigmoid(x) = tab16 (1 - tab16 / 16).  (One thread per hidden unit walking all T entries alone -- four blocks
+// on four SMs -- took 58 us at BASELINE cfg2, 4 % of the whole fused-module step.)
+constexpr int kCpbBwdUnits = 32, kCpbBwdSlices = 16;
+__global__ void __launch_bounds__(kCpbBwdUnits * kCpbBwdSlices)
 cpb_mlp_bwd_kernel(const float* __restrict__ coords, const float* __restrict__ w1, const float* __restrict__ b1,
                    const float* __restrict__ w2, const float* __restrict__ tab16, const float* __restrict__ dtab16, int T, int n_in,
                    int J, int nH, float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dw2) {
-  extern __shared__ float g[];                 // [T][nH]
-  for (int i = threadIdx.x; i < T * nH; i += blockDim.x) {
-    const float s16 = __ldg(tab16 + i);
-    g[i] = __ldg(dtab16 + i) * s16 * (1.f - s16 * (1.f / 16.f));
+  extern __shared__ float sm[];
+  float* sc = sm;                              // [T][3] coordinates (zero-padded to 3)
+  float* g = sc + ((T * kCpbMaxIn + 3) & ~3);  // [T][8] (16-byte aligned) gradient w.r.t. the pre-sigmoid table, current head group
+  float* red = g + T * 8;                      // [slices][8][units]
+  const int tid = threadIdx.x, js = tid & (kCpbBwdUnits - 1), ts = tid / kCpbBwdUnits;
+  const int j = blockIdx.x * kCpbBwdUnits + js;
+  const bool live = j < J;
+  for (int i = tid; i < T * kCpbMaxIn; i += blockDim.x) {
+    const int t = i / kCpbMaxIn, a = i - t * kCpbMaxIn;
+    sc[i] = a < n_in ? __ldg(coords + t * n_in + a) : 0.f;
   }
-  __syncthreads();
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= J) return;
   float wj[kCpbMaxIn], dwj[kCpbMaxIn] = {0.f, 0.f, 0.f};
-  for (int a = 0; a < kCpbMaxIn; ++a) wj[a] = a < n_in ? __ldg(w1 + j * n_in + a) : 0.f;
-  const float bj = __ldg(b1 + j);
+  for (int a = 0; a < kCpbMaxIn; ++a) wj[a] = (live && a < n_in) ? __ldg(w1 + j * n_in + a) : 0.f;
+  const float bj = live ? __ldg(b1 + j) : 0.f;
   float dbj = 0.f;
-  for (int h0 = 0; h0 < nH; h0 += 8) {         // heads in groups of 8 register accumulators
-    float w2j[8], dw2j[8];
+  // sum `v` over the slices (fixed order); valid in the threads of slice 0
+  auto reduce8 = [&](const float (&v)[8], float (&out)[8]) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { w2j[k] = h0 + k < nH ? __ldg(w2 + (h0 + k) * J + j) : 0.f; dw2j[k] = 0.f; }
-    for (int t = 0; t < T; ++t) {
-      float c[kCpbMaxIn], z = bj;
-      for (int a = 0; a < kCpbMaxIn; ++a) { c[a] = a < n_in ? __ldg(coords + t * n_in + a) : 0.f; z = fmaf(wj[a], c[a], z); }
-      const float act = fmaxf(z, 0.f);
-      float dh = 0.f;
+    for (int k = 0; k < 8; ++k) red[(ts * 8 + k) * kCpbBwdUnits + js] = v[k];
+    __syncthreads();
+    if (ts == 0) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (h0 + k < nH) {
-          const float gt = g[t * nH + h0 + k];
-          dw2j[k] = fmaf(gt, act, dw2j[k]);
-          dh = fmaf(gt, w2j[k], dh);
-        }
-      if (z > 0.f) {
-        dbj += dh;
-        for (int a = 0; a < kCpbMaxIn; ++a) dwj[a] = fmaf(dh, c[a], dwj[a]);
+      for (int k = 0; k < 8; ++k) {
+        float acc = 0.f;
+        for (int s2 = 0; s2 < kCpbBwdSlices; ++s2) acc += red[(s2 * 8 + k) * kCpbBwdUnits + js];
+        out[k] = acc;
       }
     }
+    __syncthreads();
+  };
+  for (int h0 = 0; h0 < nH; h0 += 8) {         // heads in groups of 8 register accumulators
+    __syncthreads();                           // previous group's g is no longer read
+    for (int i = tid; i < T * 8; i += blockDim.x) {
+      const int t = i >> 3, k = i & 7;
+      float v = 0.f;
+      if (h0 + k < nH) {
+        const float s16 = __ldg(tab16 + t * nH + h0 + k);
+        v = __ldg(dtab16 + t * nH + h0 + k) * s16 * (1.f - s16 * (1.f / 16.f));
+      }
+      g[i] = v;
+    }
+    __syncthreads();
+    float w2j[8], dw2j[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (h0 + k < nH) dw2[(h0 + k) * J + j] = dw2j[k];
+    for (int k = 0; k < 8; ++k) { w2j[k] = (live && h0 + k < nH) ? __ldg(w2 + (h0 + k) * J + j) : 0.f; dw2j[k] = 0.f; }
+    for (int t = ts; t < T; t += kCpbBwdSlices) {
+      const float c0 = sc[t * 3], c1 = sc[t * 3 + 1], c2 = sc[t * 3 + 2];
+      const float z = fmaf(wj[2], c2, fmaf(wj[1], c1, fmaf(wj[0], c0, bj)));
+      const float act = fmaxf(z, 0.f);
+      const float4 ga = *reinterpret_cast<const float4*>(g + t * 8), gb = *reinterpret_cast<const float4*>(g + t * 8 + 4);
+      const float gt[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+      float dh = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        dw2j[k] = fmaf(gt[k], act, dw2j[k]);
+        dh = fmaf(gt[k], w2j[k], dh);
+      }
+      if (z > 0.f) {
+        dbj += dh;
+        dwj[0] = fmaf(dh, c0, dwj[0]); dwj[1] = fmaf(dh, c1, dwj[1]); dwj[2] = fmaf(dh, c2, dwj[2]);
+      }
+    }
+    float tot[8];
+    reduce8(dw2j, tot);
+    if (ts == 0 && live) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (h0 + k < nH) dw2[(h0 + k) * J + j] = tot[k];
+    }
   }
-  db1[j] = dbj;
-  for (int a = 0; a < n_in; ++a) dw1[j * n_in + a] = dwj[a];
+  const float rest[8] = {dbj, dwj[0], dwj[1], dwj[2], 0.f, 0.f, 0.f, 0.f};
+  float tot[8];
+  reduce8(rest, tot);
+  if (ts == 0 && live) {
+    db1[j] = tot[0];
+    for (int a = 0; a < n_in; ++a) dw1[j * n_in + a] = tot[1 + a];
+  }
 }
 
 cudaError_t cpb_bias_fwd(const float* coords, const float* w1, const float* b1, const float* w2, const long long* index, int T,
@@ -131,8 +173,9 @@ cudaError_t cpb_bias_bwd(const float* coords, const float* w1, const float* b1, 
   cudaError_t e = cudaMemsetAsync(dtab16, 0, (size_t)T * nH * sizeof(float), st);
   if (e != cudaSuccess) return e;
   cpb_scatter_kernel<<<(NN + 255) / 256, 256, 0, st>>>(dbias, index, NN, nH, dtab16);
-  cpb_mlp_bwd_kernel<<<(J + 127) / 128, 128, (size_t)T * nH * sizeof(float), st>>>(coords, w1, b1, w2, tab16, dtab16, T, n_in, J, nH, dw1,
-                                                                                  db1, dw2);
+  const size_t smem = ((size_t)((T * kCpbMaxIn + 3) & ~3) + (size_t)T * 8 + (size_t)kCpbBwdSlices * 8 * kCpbBwdUnits) * sizeof(float);
+  cpb_mlp_bwd_kernel<<<(J + kCpbBwdUnits - 1) / kCpbBwdUnits, kCpbBwdUnits * kCpbBwdSlices, smem, st>>>(coords, w1, b1, w2, tab16, dtab16, T,
+                                                                                                    n_in, J, nH, dw1, db1, dw2);
   e = cudaGetLastError();
   if (e == cudaSuccess) *launches += 2;
   return e;
