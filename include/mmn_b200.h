@@ -95,7 +95,11 @@ const char* mmn_mha_path(const mmn_mha_desc* desc);
 uint64_t mmn_launch_count(void);
 
 /* bias (num_heads,N,N) fp32 or NULL; head_scale (num_heads) fp32, COSINE only;
- * mask (mask_windows,N,N) fp32, TENSOR only; out: token rows; lse (batch*nW*num_heads*N) fp32. */
+ * mask (mask_windows,N,N) fp32, TENSOR only; out: token rows; lse: FOUR slabs of batch*nW*num_heads*N fp32 --
+ * [0] log-sum-exp (batch*nW, num_heads, N) by window position; [1..3] one record per window and head,
+ * (batch*nW, num_heads, 3, N) = 1/max(||q||,eps) | 1/max(||k||,eps) | log2-domain lse in the kernel's tile row order,
+ * written by the tensor-core forward kernel for mmn_winattn_bwd, which must be given the same buffer
+ * (the generic kernels read and write slab 0 only). */
 int mmn_winattn_fwd(const mmn_winattn_desc* desc, const void* q, const void* k, const void* v,
                     const float* bias, const float* head_scale, const float* mask,
                     void* out, float* lse, int device, void* stream);
@@ -106,7 +110,7 @@ int mmn_winattn_fwd(const mmn_winattn_desc* desc, const void* q, const void* k, 
  * ACCUMULATED, may be NULL: column sums over all tokens of dq, dk, dv -- the bias gradients of the
  * projections that produced q, k, v (replaces the reductions autograd does for F.linear's bias,
  * swin_v2_module.py:147-148, swinfusion_module.py:121,221-222).  `workspace`: scratch of
- * TWICE the extent of lse (2*batch*nW*num_heads*N floats), contents undefined on return. */
+ * 2*batch*nW*num_heads*N floats (generic path only), contents undefined on return. */
 int mmn_winattn_bwd(const mmn_winattn_desc* desc, const void* q, const void* k, const void* v,
                     const float* bias, const float* head_scale, const float* mask,
                     const void* out, const float* lse, const void* dout,

@@ -60,7 +60,8 @@ struct BwdParams {
   const float* bias;
   const float* head_scale;
   const float* mask;
-  const float* lse;
+  const float* lse;     // written by the forward kernel: lse (B*nW, nH, 64), then the norms (B*nW, nH, 2, 64) in tile row order
+  long long slab;       // B*nW*nH*64
   float* dbias;         // (nH, 64, 64) accumulated, may be null
   float* dhead_scale;   // (nH) accumulated, may be null
   float* dcolsum;       // (3, nH*32) accumulated column sums of dq, dk, dv (= projection bias grads), may be null
@@ -81,9 +82,9 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
   uint8_t* sDS = sP + kPRegion;                           // dS'0 | Z | dS'1
   uint8_t* sOut = sDS + kPRegion;                         // dQ | dK | dV staging, 3 x kTile
   float* sTbl = reinterpret_cast<float*>(sOut + 3 * kTile);   // [64][kTblLd]
-  float* sA = sTbl + kN * kTblLd;                         // [3][128] logit multiplier per query row (natural units), ring over items
-  float* sRk = sA + 384;                                  // [3][128] 1/||k|| per key
-  float* sDelta = sRk + 384;                              // [4][128] partial deltas
+  float* sRec = sTbl + kN * kTblLd;                       // [kStagesB][2 slots][1/|q| | 1/|k| | lse log2][64 tile rows]: the forward kernel's
+                                                          //   per-window records, bulk-copied with the stage
+  float* sDelta = sRec + kStagesB * 2 * 3 * kN;           // [4][128] partial deltas
   float* sRed = sDelta + 512;                             // 16 floats: dhead_scale per softmax warp
   uint8_t* sPos = reinterpret_cast<uint8_t*>(sRed + 16);  // [8][64]
   uint8_t* sRid = sPos + 512;                             // [8][64] window position -> shift-mask region id
@@ -114,6 +115,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
     sPos[i] = (uint8_t)piece_position(S, i >> 6, i & 63);
     sRid[i] = (uint8_t)class_region_id(S, i >> 6, i & 63);
   }
+  for (int i = tid; i < kStagesB * 2 * 3 * kN; i += kBwdThreads) sRec[i] = 0.f;
   if (tid == 0) {
     sEnd[0] = 0x7fffffff;
     for (int s = 0; s < kStagesB; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kEpiThreads / 32); }
@@ -163,12 +165,15 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
             sItem[n & 7] = make_int4(cur.cls, g0.w, g1.w, nvalid);      // published by the arrive below
             sGeo[(n & 7) * 2] = make_int4(g0.b, g0.start[0], g0.start[1], g0.start[2]);
             sGeo[(n & 7) * 2 + 1] = make_int4(g1.b, g1.start[0], g1.start[1], g1.start[2]);
-            mbar_arrive_expect_tx(&full[stage], nvalid * 4 * kWinBytes);
+            mbar_arrive_expect_tx(&full[stage], nvalid * (4 * kWinBytes + 3 * kN * 4));
           }
           __syncwarp();
           uint8_t* base = sStage + stage * kStageBytesB;
           uint8_t* const dst[4] = {base, base + kOffDO, base + kOffK, base + kOffV};
           issue_item_boxes<true, 4>(S, g0, g1, nvalid, h * kD, maps, dst, slot_stride, &full[stage], lane);
+          if (lane < nvalid)                   // lane = slot: the window's record (norms and lse, already in tile row order)
+            bulk_load_1d(sRec + (stage * 2 + lane) * (3 * kN), P.lse + P.slab + ((long long)(lane ? g1.w : g0.w) * P.nH + h) * (3 * kN),
+                         3 * kN * 4, &full[stage]);
           trace_ev(P.trace, 2, n, 2);
         }
       }
@@ -370,8 +375,8 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
           xrow[0][c] = *reinterpret_cast<const uint4*>(qrow + ((c ^ rsw) << 4));
           xrow[1][c] = *reinterpret_cast<const uint4*>(krow_ + ((c ^ rsw) << 4));
         }
-        rinv2[0] = sA[(n % 3) * 128 + r] * inv_hscale;
-        rinv2[1] = sRk[(n % 3) * 128 + r];
+        rinv2[0] = sRec[(stage * 2 + slot) * (3 * kN) + i];
+        rinv2[1] = sRec[(stage * 2 + slot) * (3 * kN) + kN + i];
       }
       mbar_arrive_warp(&empty[stage]);
 
@@ -484,40 +489,20 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       }
     };
 
-    // Everything item n needs before its logits arrive -- its descriptor, the lse of this thread's row (a global
-    // load) and the row norms -- is prepared one item ahead, inside item n-1, so that the latencies hide under
-    // item n-1's arithmetic and the norms are published by item n-1's delta barrier (no barrier of their own).
-    int nx_cls = 0, nx_gw = 0, nx_ipos = 0;
-    bool nx_valid = false;
-    float nx_lse = 0.f;
-    auto prep = [&](int n) -> bool {
-      const int stage = n % kStagesB, phase = (n / kStagesB) & 1;
-      mbar_wait(&full[stage], phase);
-      TRB(n - 1, 10);
-      const int4 item = sItem[n & 7];                   // written by the producer before it armed full[stage]
-      // (an end marker, item.x < 0, runs through the same code as a harmless invalid item: no extra control flow here)
-      nx_cls = max(item.x, 0); nx_gw = slot ? item.z : item.y;
-      nx_valid = slot < item.w;
-      nx_ipos = sPos[nx_cls * 64 + i];
-      nx_lse = nx_valid ? __ldg(P.lse + ((size_t)nx_gw * P.nH + h) * kN + nx_ipos) : 0.f;
-      if (COS && qt < 2) {
-        const uint8_t* base = sStage + stage * kStageBytesB;
-        const float ss = row_sumsq(qt == 0 ? base + slot * 2 * kWinBytes + i * 64 : base + kOffK + r * 64, i);
-        const float rinv = rsqrtf(fmaxf(ss, 1e-24f));
-        if (qt == 0) sA[(n % 3) * 128 + r] = rinv * hscale; else sRk[(n % 3) * 128 + r] = rinv;
-      }
-      return item.x >= 0;
-    };
-    bool more = prep(0);
-    named_bar_sync(1, kSoftmaxThreadsB);
-
+    // Everything an item needs besides its logits -- descriptor, this row's lse, the q / k norms -- arrives in shared
+    // memory with the item's stage (descriptor ring + the forward kernel's per-window record), so the loop carries no
+    // per-item state in registers and issues no global load.
     int cls_loaded = -1;
-    for (int n = 0; more; ++n) {
-      const int b = n & 1;
+    for (int n = 0;; ++n) {
+      const int b = n & 1, stage = n % kStagesB;
       TRB(n, 0);
-      const int cls = nx_cls, gw = nx_gw, ipos = nx_ipos;
-      const bool valid = nx_valid;
-      const float lse2 = nx_lse * kLog2e;
+      mbar_wait(&full[stage], (n / kStagesB) & 1);
+      const int4 item = sItem[n & 7];                   // written by the producer before it armed full[stage]
+      if (item.x < 0) break;                            // end marker
+      const int cls = item.x;
+      const bool valid = slot < item.w;
+      const float* rec = sRec + (stage * 2 + slot) * (3 * kN);
+      const float lse2 = valid ? rec[2 * kN + i] : 0.f;
       if (cls != cls_loaded) {                          // rare: at most 8 times per CTA
         named_bar_sync(3, kSoftmaxThreadsB);            // everyone is done reading the old table
         if (gdb_head && cls_loaded >= 0) {
@@ -529,14 +514,18 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
         named_bar_sync(3, kSoftmaxThreadsB);
       }
       TRB(n, 2);
-      const float a_i = COS ? sA[(n % 3) * 128 + r] : hscale;
-      const float4* krow = reinterpret_cast<const float4*>(sRk + (n % 3) * 128 + slot * 64 + qt * KP);
+      const float a_i = COS ? rec[i] * hscale : hscale;
+      const float4* krow = reinterpret_cast<const float4*>(rec + kN + qt * KP);
 
       // ---- (b) additive terms of this thread's logits (table, mask, -lse), log2 domain
       float p[KP];
       {
         const float4* trow = reinterpret_cast<const float4*>(sTbl + i * kTblLd + qt * KP);
-        const float* mrow = (MASK == MMN_MASK_TENSOR) ? P.mask + ((size_t)(gw % P.mask_windows) * kN + ipos) * kN + qt * KP : nullptr;
+        const float* mrow = nullptr;
+        if (MASK == MMN_MASK_TENSOR) {
+          const int gw = slot ? item.z : item.y, ipos = sPos[cls * 64 + i];
+          mrow = P.mask + ((size_t)(gw % P.mask_windows) * kN + ipos) * kN + qt * KP;
+        }
 #pragma unroll
         for (int j4 = 0; j4 < KP / 4; ++j4) {
           float4 tt = trow[j4];
@@ -577,8 +566,6 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
           }
         }
       }
-      TRB(n, 9);
-      more = prep(n + 1);                               // published by the delta barrier below
       sDelta[qt * 128 + r] = delta;
       TRB(n, 5);
       // P (bf16) can go out before delta is known; the previous item's gradient MMAs must have finished reading P / dS'
@@ -646,7 +633,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
 }
 
 constexpr size_t kBwdSmemBytes = 1024 + kStagesB * kStageBytesB + 2 * kPRegion + 3 * kTile + kN * kTblLd * 4 +
-                                 (384 + 384 + 512 + 16) * 4 + 1024 + 24 * 16 + 16 + 24 * 8;
+                                 (kStagesB * 2 * 3 * kN + 512 + 16) * 4 + 1024 + 24 * 16 + 16 + 24 * 8;
 
 inline const char* bwd_why_not_impl(const mmn_winattn_desc* d) {
   const char* w = fwd_why_not_impl(d);
@@ -674,6 +661,7 @@ inline int winattn_bwd_launch(const mmn_winattn_desc* d, const void* q, const vo
   P.mask_windows = d->mask_windows > 0 ? d->mask_windows : 1;
   P.scale = d->scale;
   P.bias = bias; P.head_scale = head_scale; P.mask = mask; P.lse = lse;
+  P.slab = (long long)P.S.n_windows * d->num_heads * kN;
   P.dbias = bias ? dbias : nullptr;
   P.dhead_scale = d->score_kind == MMN_SCORE_COSINE ? dhead_scale : nullptr;
   P.dcolsum = dcolsum;

@@ -66,7 +66,9 @@ struct FwdParams {
   const float* bias;
   const float* head_scale;
   const float* mask;
-  float* lse;
+  float* lse;         // (B*nW, nH, 64) log-sum-exp by window position, then one record per window and head for the backward
+  long long slab;     //   kernel, (B*nW, nH, 3, 64) in the tile's (piece-major) row order: 1/max(||q||,eps) | 1/max(||k||,eps) |
+                      //   log2-domain lse (one 768-byte bulk copy per window there); slab = B*nW*nH*64
   int* work;          // dynamic schedule counters (tc_sched.cuh: ClassQueue), self-resetting
   TraceCfg trace;     // debug: per-phase clock64 stamps of one CTA (MMN_TC_TRACE=<file>), else buf == null
 };
@@ -305,12 +307,15 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
 
     // O epilogue of this group's item number ke: deferred behind the next item's softmax so that the PV MMA
     // runs under useful work.  o_full of that item has already been waited for.
-    auto epilogue = [&](int ke, float inv_l, float lse_val, long long lse_index, bool valid) {
+    auto epilogue = [&](int ke, float inv_l, float lse2_val, int gwh, int ipos_e, bool valid) {
       uint32_t oraw[32];
       tmem_ld_32x32b_x32(tmem + lane_base + 128 + (g * 2 + (ke & 1)) * 32, oraw);
       tmem_ld_wait();
       tcgen05_fence_before();
-      if (valid) P.lse[lse_index] = lse_val;
+      if (valid) {
+        P.lse[(long long)gwh * kN + ipos_e] = lse2_val * kLn2;
+        P.lse[P.slab + (long long)gwh * (3 * kN) + 2 * kN + i] = lse2_val;
+      }
       mbar_wait(&so_free[g], (ke & 1) ^ 1);              // the store warp has drained this group's staging tile
       const uint64_t inv2 = pk2(inv_l, inv_l);
 #pragma unroll
@@ -325,8 +330,8 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
 
     int cls_loaded = -1;
     bool have_prev = false, prev_valid = false;
-    float prev_inv = 0.f, prev_lse = 0.f;
-    long long prev_idx = 0;
+    float prev_inv = 0.f, prev_lse = 0.f;                 // prev_lse: log2 domain
+    int prev_gwh = 0, prev_ipos = 0;
     int kk = 0;
     for (int n = g;; n += 2, ++kk) {
       const int stage = n % kStagesF, phase = (n / kStagesF) & 1;
@@ -349,8 +354,14 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
       if (COS) {
         const float ssq = row_sumsq(base + slot * 2 * kWinBytes + i * 64, i);
         const float ssk = row_sumsq(base + kQRegion + r * 64, i);
-        a_i *= rsqrtf(fmaxf(ssq, 1e-24f));               // 1 / max(||q||, 1e-12) x logit scale x log2(e)
-        rkbuf[r] = rsqrtf(fmaxf(ssk, 1e-24f));
+        const float rq = rsqrtf(fmaxf(ssq, 1e-24f)), rkk = rsqrtf(fmaxf(ssk, 1e-24f));
+        a_i *= rq;                                       // 1 / max(||q||, 1e-12) x logit scale x log2(e)
+        rkbuf[r] = rkk;
+        if (valid) {                                     // kept for the backward kernel (it reads them with one bulk copy per window)
+          float* rec = P.lse + P.slab + ((long long)gw * P.nH + h) * (3 * kN) + i;    // [window][head][1/|q| | 1/|k| | lse log2][64 tile rows]
+          rec[0] = rq;
+          rec[kN] = rkk;
+        }
       }
       named_bar_sync(1 + g, kGroupThreads);             // rk (and a rebuilt table) visible to the group
       TR(n, 2);
@@ -440,18 +451,19 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
       mbar_arrive_warp(&p_full[g]);
       TR(n, 7);
 
-      if (have_prev) epilogue(kk - 1, prev_inv, prev_lse, prev_idx, prev_valid);
+      if (have_prev) epilogue(kk - 1, prev_inv, prev_lse, prev_gwh, prev_ipos, prev_valid);
       TR(n, 8);
       have_prev = true;
       prev_valid = valid;
       prev_inv = __frcp_rn(l);
-      prev_lse = (mx + __log2f(l)) * kLn2;
-      prev_idx = ((long long)gw * P.nH + h) * kN + ipos;
+      prev_lse = mx + __log2f(l);
+      prev_gwh = gw * P.nH + h;
+      prev_ipos = ipos;
     }
     if (have_prev) {
       mbar_wait(&o_full[g], (kk - 1) & 1);
       tcgen05_fence_after();
-      epilogue(kk - 1, prev_inv, prev_lse, prev_idx, prev_valid);
+      epilogue(kk - 1, prev_inv, prev_lse, prev_gwh, prev_ipos, prev_valid);
     }
     // farewell to the store warp: this group has produced kk tiles.  The store warp must have taken the last one
     // first -- two so_ready phases completing back to back would alias in its parity wait.
@@ -556,6 +568,7 @@ inline int winattn_fwd_launch(const mmn_winattn_desc* d, const void* q, const vo
   P.mask_windows = d->mask_windows > 0 ? d->mask_windows : 1;
   P.scale = d->scale;
   P.bias = bias; P.head_scale = head_scale; P.mask = mask; P.lse = lse;
+  P.slab = (long long)P.S.n_windows * d->num_heads * kN;
   P.work = work_slot(err, errlen);
   if (!P.work) return MMN_ERR_CUDA;
   const char* trace_path = getenv("MMN_TC_TRACE");

@@ -117,7 +117,10 @@ def winattn_fwd(a: Tensor, b: Optional[Tensor], bias: Optional[Tensor], head_sca
     for g, w in zip(grid, window):
         N *= w
         nW *= g // w
-    lse = torch.empty(a.shape[0] * nW, num_heads, N, dtype=torch.float32, device=a.device)
+    # four slabs.  [0]: log-sum-exp (B*nW, nH, N) by window position.  [1:4]: one record per window and head,
+    # (B*nW, nH, 3, N) = 1/max(||q||,eps) | 1/max(||k||,eps) | log2-domain lse in the kernel's tile row order, written
+    # by the tensor-core forward kernel for its backward kernel; the generic kernels use slab 0 only.
+    lse = torch.empty(4, a.shape[0] * nW, num_heads, N, dtype=torch.float32, device=a.device)
     if b is None:
         q, k, v = _ptr(a), _ptr(a, Cc), _ptr(a, 2 * Cc)
         d.q_row_stride = d.k_row_stride = d.v_row_stride = _row_stride(a)
@@ -143,7 +146,7 @@ def _(a, b, bias, head_scale, mask, grid, window, shift, num_heads, score_kind, 
     for g, w in zip(grid, window):
         N *= w
         nW *= g // w
-    return a.new_empty(*a.shape[:-1], Cc), a.new_empty(a.shape[0] * nW, num_heads, N, dtype=torch.float32)
+    return a.new_empty(*a.shape[:-1], Cc), a.new_empty(4, a.shape[0] * nW, num_heads, N, dtype=torch.float32)
 
 
 @torch.library.custom_op("mmn_b200::winattn_bwd", mutates_args=())
@@ -176,7 +179,7 @@ def winattn_bwd(dout: Tensor, a: Tensor, b: Optional[Tensor], bias: Optional[Ten
     d.do_row_stride = Cc
     dbias = torch.zeros_like(bias) if bias is not None else a.new_empty(0, dtype=torch.float32)
     dhs = torch.zeros_like(head_scale) if head_scale is not None else a.new_empty(0, dtype=torch.float32)
-    ws = lse.new_empty(2 * lse.numel())
+    ws = lse.new_empty(2 * lse[0].numel())
     dcs = torch.zeros(3, Cc, dtype=torch.float32, device=a.device) if want_colsum else a.new_empty(0, dtype=torch.float32)
     with _timed("winattn_bwd", a):
         _lib.check(lib.mmn_winattn_bwd(C.byref(d), q, k, v, _ptr(bias), _ptr(head_scale), _ptr(mask), _ptr(out), _ptr(lse),
