@@ -69,8 +69,6 @@ struct BwdParams {
   TraceCfg trace;       // debug: clock64 stamps of one CTA (MMN_TC_TRACE_BWD=<file>)
 };
 
-template <int R> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
-template <int R> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 
 template <bool COS, int MASK>
 __global__ void __launch_bounds__(kBwdThreads, 1)

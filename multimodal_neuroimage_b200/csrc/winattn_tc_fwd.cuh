@@ -33,17 +33,20 @@
 
 namespace mmn { namespace tc {
 
-constexpr int kStagesF = 4;
+constexpr int kStagesF = 5;
 constexpr int kWinBytes = 64 * 64;                 // one window's (64 tokens x 32 ch) bf16 tile
 constexpr int kTile = 2 * kWinBytes;               // a pair's tile
 constexpr int kQRegion = 3 * kWinBytes;            // Q0 | zero block | Q1
 constexpr int kStageBytesF = kQRegion + 2 * kTile; // + K0 K1 + V0 V1
-constexpr int kPRegion = 3 * 8192;                 // P0 (64 rows x 128 B) | zero block | P1
+constexpr int kPRegion = 3 * 8192;                 // (backward kernel) P0 (64 rows x 128 B) | zero block | P1
 constexpr int kGroupThreads = 128;
-constexpr int kProducerWarp = 8, kMmaWarp = 9, kStoreWarp = 10;
-constexpr int kFwdThreads = 352;
+constexpr int kGroupsF = 3;                        // softmax groups = items in flight
+constexpr int kProducerWarp = 4 * kGroupsF, kMmaWarp = kProducerWarp + 1, kStoreWarp = kProducerWarp + 2;
+constexpr int kFwdThreads = 32 * (kProducerWarp + 4);   // 4 warpgroups: 3 softmax groups + {producer, MMA, store, idle}
+constexpr int kRegSoftmaxF = 136, kRegAuxF = 104;  // setmaxnreg: 384 * 136 + 128 * 104 = 512 * 128
 constexpr int kTblLd = 68;                         // padded row of the shared table (conflict-free float4 rows)
-constexpr int kTmemColsF = 256;                    // S[g] at 64 g; O[g][b] at 128 + 32 (2 g + b)
+constexpr int kTmemColsF = 512;                    // group g: S at 160 g (64 columns), P at 160 g + 64 (64), O at 160 g + 128 (32)
+constexpr int kTmemGroup = 160;
 constexpr int kItemRing = 16;                      // item descriptors published by the TMA producer (see the ring-depth note there)
 constexpr int kChunkF = 8;                         // items a CTA claims per atomic
 constexpr float kLog2e = 1.4426950408889634f;
@@ -116,26 +119,26 @@ __device__ __forceinline__ float row_sumsq(const uint8_t* rowp, int row) {
 template <bool COS, int MASK>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
+  constexpr int G = kGroupsF;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024-B alignment
   uint8_t* sStage = smem;                                 // kStagesF x (Q0|Z|Q1 | K0 K1 | V0 V1)
-  uint8_t* sP = sStage + kStagesF * kStageBytesF;         // [2 groups] P0 | Z | P1
-  uint8_t* sO = sP + 2 * kPRegion;                        // [2 groups] output staging tile
-  float* sTbl = reinterpret_cast<float*>(sO + 2 * kTile); // [2 groups][64][kTblLd]
-  float* sRk = sTbl + 2 * kN * kTblLd;                    // [2 groups][2][128] per-key 1/||k||
-  uint8_t* sPos = reinterpret_cast<uint8_t*>(sRk + 512);  // [8 wrap classes][64]: tile row -> window position
+  uint8_t* sO = sStage + kStagesF * kStageBytesF;         // [G] output staging tile
+  float* sTbl = reinterpret_cast<float*>(sO + G * kTile); // [G][64][kTblLd]
+  float* sRk = sTbl + G * kN * kTblLd;                    // [G][2][128] per-key 1/||k|| (double-buffered over the group's items)
+  uint8_t* sPos = reinterpret_cast<uint8_t*>(sRk + G * 256);  // [8 wrap classes][64]: tile row -> window position
   uint8_t* sRid = sPos + 512;                             // [8 wrap classes][64]: window position -> shift-mask region id
   int4* sItem = reinterpret_cast<int4*>(sRid + 512);      // [kItemRing] {wrap class (-1: no more items), window of slot 0, of slot 1, valid slots}
-  int* sEnd = reinterpret_cast<int*>(sItem + kItemRing);  // [2] items group g has produced when it left its loop (else INT_MAX)
+  int* sEnd = reinterpret_cast<int*>(sItem + kItemRing);  // [G] items group g has produced when it left its loop (else INT_MAX)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sEnd + 4);
   uint64_t* full = bars;                                  // [kStagesF] TMA -> MMA, softmax
   uint64_t* empty = bars + kStagesF;                      // [kStagesF] MMA -> TMA
-  uint64_t* s_full = bars + 2 * kStagesF;                 // [2] S in TMEM
-  uint64_t* p_full = s_full + 2;                          // [2] P in smem (one arrival per warp)
-  uint64_t* o_full = s_full + 4;                          // [2] O in TMEM / P consumed
-  uint64_t* so_ready = s_full + 6;                        // [2] staging tile written (one arrival per warp)
-  uint64_t* so_free = s_full + 8;                         // [2] staging tile drained by the store warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 10);
+  uint64_t* s_full = bars + 2 * kStagesF;                 // [G] S in TMEM
+  uint64_t* p_full = s_full + G;                          // [G] P in TMEM (one arrival per warp)
+  uint64_t* o_full = s_full + 2 * G;                      // [G] O in TMEM
+  uint64_t* so_ready = s_full + 3 * G;                    // [G] staging tile written (one arrival per warp)
+  uint64_t* so_free = s_full + 4 * G;                     // [G] staging tile drained by the store warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 5 * G);
 
   const WinShape& S = P.S;
   const Sched& sc = P.sc;
@@ -144,16 +147,16 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
 
   // ---- one-time setup: zero the operand tiles (zero blocks stay zero for the whole kernel; the rest must
   // not hold NaN bit patterns, because cross terms multiply stale tiles by the zero blocks)
-  for (int i = tid; i < (kStagesF * kStageBytesF + 2 * kPRegion) / 16; i += kFwdThreads)
+  for (int i = tid; i < (kStagesF * kStageBytesF) / 16; i += kFwdThreads)
     reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < 512; i += kFwdThreads) {
     sPos[i] = (uint8_t)piece_position(S, i >> 6, i & 63);
     sRid[i] = (uint8_t)class_region_id(S, i >> 6, i & 63);
   }
   if (tid == 0) {
-    sEnd[0] = sEnd[1] = 0x7fffffff;
+    for (int g = 0; g < G; ++g) sEnd[g] = 0x7fffffff;
     for (int s = 0; s < kStagesF; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int g = 0; g < 2; ++g) {
+    for (int g = 0; g < G; ++g) {
       mbar_init(&s_full[g], 1); mbar_init(&p_full[g], kGroupThreads / 32); mbar_init(&o_full[g], 1);
       mbar_init(&so_ready[g], kGroupThreads / 32); mbar_init(&so_free[g], 1);
     }
@@ -170,170 +173,153 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
   trace_cta_time(P.trace, 0);
-#ifdef MMN_DEBUG_WAIT
-  if (tid == 0 && blockIdx.x == 0) printf("fwd barriers at smem 0x%x (full 4, empty 4, s_full 2, p_full 2, o_full 2, so_ready 2, so_free 2)\n", smem_u32(bars));
-#endif
 
-  if (warp == kProducerWarp) {
-    // ============================== TMA producer ==============================
-    // every lane runs the loop; lane l issues boxes l, l + 32 of the item (issue_item_boxes)
-    const CUtensorMap* const maps[3] = {P.q, P.k, P.v};
-    const int dst_base[3] = {0, kQRegion, kQRegion + kTile};
-    const int slot_stride[3] = {2 * kWinBytes, kWinBytes, kWinBytes};
-    BoxPlan<3> plan;
-    // Dynamic schedule (tc_sched.cuh: ClassQueue): chunks of kChunkF items of this head, home class first.
-    // Every other warp learns its items from the descriptor ring sItem (published by the full[] arrival).  Ring
-    // depth: entry n + 16 is written only after PV(n + 12) has completed, i.e. after its group wrote P(n + 12), which
-    // it does after the epilogue of item n + 8, which waited for the store of item n + 6 -- so entry n has been read
-    // by every consumer, the store warp included.
-    int n = 0;
-    ClassQueue wq;
-    wq.init(sc, sched_range_begin(sc, blockIdx.x / P.nH, P.per_head), P.work + h * 8, kChunkF, lane);
-    for (int c0, m; wq.next(sc, P.work + h * 8, kChunkF, lane, c0, m);) {
-      ItemCursor cur;
-      cur.seek(sc, c0);
-      for (int t = 0; t < m; ++t, ++n, cur.next_item(sc)) {
+  if (warp >= kProducerWarp) {
+    setmaxnreg_dec<kRegAuxF>();
+    if (warp == kProducerWarp) {
+      // ============================== TMA producer ==============================
+      // every lane runs the loop; lane l issues boxes l, l + 32 of the item (BoxPlan)
+      const CUtensorMap* const maps[3] = {P.q, P.k, P.v};
+      const int dst_base[3] = {0, kQRegion, kQRegion + kTile};
+      const int slot_stride[3] = {2 * kWinBytes, kWinBytes, kWinBytes};
+      BoxPlan<3> plan;
+      // Dynamic schedule (tc_sched.cuh: ClassQueue): chunks of kChunkF items of this head, home class first.
+      // Every other warp learns its items from the descriptor ring sItem (published by the full[] arrival).  Ring
+      // depth: entry n + 16 is written only once stage (n + 16) % kStagesF is free, i.e. after PV(n + 11) has completed,
+      // so its group has long finished item n + 8 and with it waited for the store of item n + 5 (so_free): every
+      // consumer of entry n, the store warp included, has read it.
+      int n = 0;
+      ClassQueue wq;
+      wq.init(sc, sched_range_begin(sc, blockIdx.x / P.nH, P.per_head), P.work + h * 8, kChunkF, lane);
+      for (int c0, m; wq.next(sc, P.work + h * 8, kChunkF, lane, c0, m);) {
+        ItemCursor cur;
+        cur.seek(sc, c0);
+        for (int t = 0; t < m; ++t, ++n, cur.next_item(sc)) {
+          const int stage = n % kStagesF, phase = (n / kStagesF) & 1;
+          if (cur.cls != plan.cls) plan.build(S, cur.cls, lane, maps, dst_base, slot_stride);
+          const int nvalid = cur.slot_valid(1) ? 2 : 1;
+          int w0, w1;
+          const WinStart ws0 = cursor_start(S, cur, 0, w0), ws1 = cursor_start(S, cur, 1, w1);
+          trace_evf(P.trace, 2, n, 0);
+          mbar_wait(&empty[stage], phase ^ 1);
+          trace_evf(P.trace, 2, n, 1);
+          if (lane == 0) {
+            sItem[n % kItemRing] = make_int4(cur.cls, w0, w1, nvalid);     // published by the arrive below
+            mbar_arrive_expect_tx(&full[stage], nvalid * 3 * kWinBytes);
+          }
+          __syncwarp();
+          plan.issue<true>(S, ws0, ws1, nvalid, h * kD, sStage + stage * kStageBytesF, &full[stage], lane);
+          trace_evf(P.trace, 2, n, 2);
+        }
+      }
+      // one end marker per softmax group (the MMA warp stops at the first)
+      for (int e = 0; e < G; ++e, ++n) {
         const int stage = n % kStagesF, phase = (n / kStagesF) & 1;
-        if (cur.cls != plan.cls) plan.build(S, cur.cls, lane, maps, dst_base, slot_stride);
-        const int nvalid = cur.slot_valid(1) ? 2 : 1;
-        int w0, w1;
-        const WinStart ws0 = cursor_start(S, cur, 0, w0), ws1 = cursor_start(S, cur, 1, w1);
-        trace_evf(P.trace, 2, n, 0);
         mbar_wait(&empty[stage], phase ^ 1);
-        trace_evf(P.trace, 2, n, 1);
         if (lane == 0) {
-          sItem[n % kItemRing] = make_int4(cur.cls, w0, w1, nvalid);     // published by the arrive below
-          mbar_arrive_expect_tx(&full[stage], nvalid * 3 * kWinBytes);
+          sItem[n % kItemRing] = make_int4(-1, 0, 0, 0);
+          mbar_arrive(&full[stage]);
         }
         __syncwarp();
-        plan.issue<true>(S, ws0, ws1, nvalid, h * kD, sStage + stage * kStageBytesF, &full[stage], lane);
-        trace_evf(P.trace, 2, n, 2);
       }
-    }
-    // two end markers (one per softmax group; the MMA warp stops at the first)
-    for (int e = 0; e < 2; ++e, ++n) {
-      const int stage = n % kStagesF, phase = (n / kStagesF) & 1;
-      mbar_wait(&empty[stage], phase ^ 1);
-      if (lane == 0) {
-        sItem[n % kItemRing] = make_int4(-1, 0, 0, 0);
-        mbar_arrive(&full[stage]);
-      }
-      __syncwarp();
-    }
-    if (lane == 0) ClassQueue::retire(P.work, P.nH);
-  } else if (warp == kMmaWarp) {
-    // ============================== MMA issuer ==============================
-    constexpr uint32_t idescS = umma_idesc_bf16(128, 64, 0, 0);    // [Q0;0],[0;Q1] (K-major) x K0,K1 (K-major)
-    constexpr uint32_t idescO = umma_idesc_bf16(128, 32, 0, 1);    // [P0;0],[0;P1] (K-major) x V (MN-major)
-    // descriptors: everything but the 14-bit start-address field is loop-invariant, and adding (bytes >> 4)
-    // to a descriptor moves its start address -- one add per operand instead of rebuilding it
-    const uint64_t dQK = umma_smem_desc(0, 0, 512, kSwz64);        // Q / K tiles, K-major
-    const uint64_t dP = umma_smem_desc(0, 0, 1024, kSwz128);       // P tile, K-major
-    const uint64_t dV = umma_smem_desc(0, 8192, 512, kSwz64);      // V tile, MN-major
-    const uint32_t stage0 = smem_u32(sStage) >> 4, p0 = smem_u32(sP) >> 4;
-    int total = 0x7fffffff;                                        // items of this CTA: known once the end marker shows up
-    auto issue_s = [&](int n) {
-      const int stage = n % kStagesF, phase = (n / kStagesF) & 1;
-      mbar_wait(&full[stage], phase);
-      if (sItem[n % kItemRing].x < 0) { total = n; return; }
-      tcgen05_fence_after();
-      if (elect_one()) {
-        const uint64_t aq = dQK + (stage0 + stage * (kStageBytesF >> 4)), bk = aq + (kQRegion >> 4);
-        const uint32_t tS = tmem + (n & 1) * 64;
+      if (lane == 0) ClassQueue::retire(P.work, P.nH);
+    } else if (warp == kMmaWarp) {
+      // ============================== MMA issuer ==============================
+      constexpr uint32_t idescS = umma_idesc_bf16(128, 64, 0, 0);    // [Q0;0],[0;Q1] (K-major) x K0,K1 (K-major)
+      constexpr uint32_t idescO = umma_idesc_bf16(128, 32, 0, 1);    // P (TMEM: [P0 0; 0 P1], K-major) x V (MN-major)
+      // descriptors: everything but the 14-bit start-address field is loop-invariant, and adding (bytes >> 4)
+      // to a descriptor moves its start address -- one add per operand instead of rebuilding it
+      const uint64_t dQK = umma_smem_desc(0, 0, 512, kSwz64);        // Q / K tiles, K-major
+      const uint64_t dV = umma_smem_desc(0, 8192, 512, kSwz64);      // V tile, MN-major
+      const uint32_t stage0 = smem_u32(sStage) >> 4;
+      int total = 0x7fffffff;                                        // items of this CTA: known once the end marker shows up
+      auto issue_s = [&](int n) {
+        const int stage = n % kStagesF, phase = (n / kStagesF) & 1;
+        mbar_wait(&full[stage], phase);
+        if (sItem[n % kItemRing].x < 0) { total = n; return; }
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint64_t aq = dQK + (stage0 + stage * (kStageBytesF >> 4)), bk = aq + (kQRegion >> 4);
+          const uint32_t tS = tmem + (n % G) * kTmemGroup;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)      // ks 0,1: window 0's channels; ks 2,3: window 1's
-          umma_bf16_ss(tS, aq + ((ks >> 1) * (kWinBytes >> 4) + (ks & 1) * 2), bk + ((ks >> 1) * (kWinBytes >> 4) + (ks & 1) * 2), idescS, ks);
-        umma_commit(&s_full[n & 1]);
-      }
-      __syncwarp();
-    };
-    issue_s(0);
-    if (total > 1) issue_s(1);
-    for (int n = 0; n < total; ++n) {
-      const int g = n & 1, kk = n >> 1, stage = n % kStagesF;
-      trace_evf(P.trace, 3, n, 0);
-      mbar_wait(&p_full[g], kk & 1);
-      trace_evf(P.trace, 3, n, 1);
-      tcgen05_fence_after();
-      if (elect_one()) {
-        const uint64_t ap = dP + (p0 + g * (kPRegion >> 4));
-        const uint64_t bv = dV + (stage0 + stage * (kStageBytesF >> 4) + ((kQRegion + kTile) >> 4));
-        const uint32_t tO = tmem + 128 + (g * 2 + (kk & 1)) * 32;
+          for (int ks = 0; ks < 4; ++ks)      // ks 0,1: window 0's channels; ks 2,3: window 1's
+            umma_bf16_ss(tS, aq + ((ks >> 1) * (kWinBytes >> 4) + (ks & 1) * 2), bk + ((ks >> 1) * (kWinBytes >> 4) + (ks & 1) * 2), idescS, ks);
+          umma_commit(&s_full[n % G]);
+        }
+        __syncwarp();
+      };
+      for (int n = 0; n < G && total == 0x7fffffff; ++n) issue_s(n);
+      for (int n = 0; n < total; ++n) {
+        const int g = n % G, kk = n / G, stage = n % kStagesF;
+        trace_evf(P.trace, 3, n, 0);
+        mbar_wait(&p_full[g], kk & 1);         // the group has read S(n) out and written P(n)
+        trace_evf(P.trace, 3, n, 1);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t tP = tmem + g * kTmemGroup + 64, tO = tmem + g * kTmemGroup + 128;
+          const uint64_t bv = dV + (stage0 + stage * (kStageBytesF >> 4) + ((kQRegion + kTile) >> 4));
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks)      // 16 keys per step; ks < 4: window 0's keys
-          umma_bf16_ss(tO, ap + ((ks >> 2) * (8192 >> 4) + (ks & 3) * 2), bv + ks * (1024 >> 4), idescO, ks);
-        umma_commit(&o_full[g]);
-        umma_commit(&empty[stage]);
+          for (int ks = 0; ks < 8; ++ks)      // 16 keys (8 TMEM columns of P) per step; ks < 4: window 0's keys
+            umma_bf16_ts(tO, tP + ks * 8, bv + ks * (1024 >> 4), idescO, ks);
+          umma_commit(&o_full[g]);
+          umma_commit(&empty[stage]);
+        }
+        __syncwarp();
+        if (total == 0x7fffffff) issue_s(n + G);   // this group's S buffer is free: it was read before P was written
+        trace_evf(P.trace, 3, n, 2);
       }
-      __syncwarp();
-      if (total == 0x7fffffff) issue_s(n + 2);
-      trace_evf(P.trace, 3, n, 2);
+    } else if (warp == kStoreWarp) {
+      // ============================== TMA store ==============================
+      const CUtensorMap* const maps[1] = {P.o};
+      const int dst_base[1] = {0};
+      const int slot_stride[1] = {kWinBytes};
+      BoxPlan<1> plan;
+      for (int n = 0;; ++n) {
+        const int g = n % G, kk = n / G;
+        trace_evf(P.trace, 4, n, 0);
+        mbar_wait(&so_ready[g], kk & 1);
+        if (kk >= *reinterpret_cast<volatile int*>(&sEnd[g])) break;   // the group left its loop: that arrival was its farewell
+        trace_evf(P.trace, 4, n, 1);
+        const int4 item = sItem[n % kItemRing];
+        if (item.x != plan.cls) plan.build(S, item.x, lane, maps, dst_base, slot_stride);
+        plan.issue<false>(S, window_start(S, item.y), window_start(S, item.z), item.w, h * kD, sO + g * kTile, nullptr, lane);
+        tma_store_commit();
+        tma_store_wait_read<0>();          // per thread: each lane waits for the smem reads of its own boxes
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&so_free[g]);
+        trace_evf(P.trace, 4, n, 2);
+      }
+      tma_store_wait_all<0>();
     }
-  } else if (warp == kStoreWarp) {
-    // ============================== TMA store ==============================
-    const CUtensorMap* const maps[1] = {P.o};
-    const int dst_base[1] = {0};
-    const int slot_stride[1] = {kWinBytes};
-    BoxPlan<1> plan;
-    for (int n = 0;; ++n) {
-      const int g = n & 1, kk = n >> 1;
-      trace_evf(P.trace, 4, n, 0);
-      mbar_wait(&so_ready[g], kk & 1);
-      if (kk >= *reinterpret_cast<volatile int*>(&sEnd[g])) break;   // the group left its loop: that arrival was its farewell
-      trace_evf(P.trace, 4, n, 1);
-      const int4 item = sItem[n % kItemRing];
-      if (item.x != plan.cls) plan.build(S, item.x, lane, maps, dst_base, slot_stride);
-      plan.issue<false>(S, window_start(S, item.y), window_start(S, item.z), item.w, h * kD, sO + g * kTile, nullptr, lane);
-      tma_store_commit();
-      tma_store_wait_read<0>();          // per thread: each lane waits for the smem reads of its own boxes
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&so_free[g]);
-      trace_evf(P.trace, 4, n, 2);
-    }
-    tma_store_wait_all<0>();
   } else {
     // ============================== softmax / epilogue: group g = warp / 4, one thread per query row ==============================
+    setmaxnreg_inc<kRegSoftmaxF>();
     const int g = warp >> 2;
     const int r = tid & 127;
     const int slot = r >> 6, i = r & 63;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem + lane_base + g * kTmemGroup, tP = tS + 64 + slot * 32, tO = tS + 128;
     const float hscale = COS ? __ldg(P.head_scale + h) * kLog2e : P.scale * kLog2e;
     float* tbl = sTbl + g * kN * kTblLd;
-    uint8_t* pbuf = sP + g * kPRegion + slot * 16384 + i * 128;       // this thread's P row
     uint8_t* obuf = sO + g * kTile + r * 64;                          // this thread's staging row
     const float* bias_h = P.bias ? P.bias + (size_t)h * kN * kN : nullptr;
-    const int trole = (warp & 3) == 0 ? g : -1;
+    const int trole = (warp & 3) == 0 && g < 2 ? g : -1;
 #define TR(item, ev) do { if (trole >= 0) trace_evf(P.trace, trole, item, ev); } while (0)
 
-    // O epilogue of this group's item number ke: deferred behind the next item's softmax so that the PV MMA
-    // runs under useful work.  o_full of that item has already been waited for.
-    auto epilogue = [&](int ke, float inv_l, float lse2_val, int gwh, int ipos_e, bool valid) {
-      uint32_t oraw[32];
-      tmem_ld_32x32b_x32(tmem + lane_base + 128 + (g * 2 + (ke & 1)) * 32, oraw);
-      tmem_ld_wait();
-      tcgen05_fence_before();
-      if (valid) {
-        P.lse[(long long)gwh * kN + ipos_e] = lse2_val * kLn2;
-        P.lse[P.slab + (long long)gwh * (3 * kN) + 2 * kN + i] = lse2_val;
-      }
-      mbar_wait(&so_free[g], (ke & 1) ^ 1);              // the store warp has drained this group's staging tile
-      const uint64_t inv2 = pk2(inv_l, inv_l);
+    // P lives in TMEM as the A operand of the second MMA: row = lane, two bf16 per column, K = the pair's 128 keys.
+    // A row of window 0 is [P0_i | 0], a row of window 1 [0 | P1_i]: the zero halves are written once, here.
+    {
+      uint32_t z[32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint4 v4 = make_uint4(pack_bf16x2(mul2(pk2u(oraw[c * 8 + 0], oraw[c * 8 + 1]), inv2)), pack_bf16x2(mul2(pk2u(oraw[c * 8 + 2], oraw[c * 8 + 3]), inv2)),
-                              pack_bf16x2(mul2(pk2u(oraw[c * 8 + 4], oraw[c * 8 + 5]), inv2)), pack_bf16x2(mul2(pk2u(oraw[c * 8 + 6], oraw[c * 8 + 7]), inv2)));
-        *reinterpret_cast<uint4*>(obuf + ((c ^ ((r >> 1) & 3)) << 4)) = v4;
-      }
-      fence_proxy_async_smem();
-      mbar_arrive_warp(&so_ready[g]);
-    };
+      for (int j = 0; j < 32; ++j) z[j] = 0u;
+      tmem_st_32x32b_x32(tS + 64, z);
+      tmem_st_32x32b_x32(tS + 96, z);
+      tmem_st_wait();
+    }
 
     int cls_loaded = -1;
-    bool have_prev = false, prev_valid = false;
-    float prev_inv = 0.f, prev_lse = 0.f;                 // prev_lse: log2 domain
-    int prev_gwh = 0, prev_ipos = 0;
     int kk = 0;
-    for (int n = g;; n += 2, ++kk) {
+    for (int n = g;; n += G, ++kk) {
       const int stage = n % kStagesF, phase = (n / kStagesF) & 1;
       TR(n, 0);
       mbar_wait(&full[stage], phase);
@@ -341,12 +327,13 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
       if (item.x < 0) break;
       const int cls = item.x, gw = slot ? item.z : item.y;
       const bool valid = slot < item.w;
-      if (cls != cls_loaded) {                          // rare: at most 8 times per CTA
+      if (cls != cls_loaded) {                          // rare: a CTA sees few classes (ClassQueue)
         named_bar_sync(1 + g, kGroupThreads);           // everyone is done reading the old table
         build_class_table(tbl, kTblLd, bias_h, sPos + cls * 64, sRid + cls * 64, MASK == MMN_MASK_SHIFT && cls != 0, r, kGroupThreads);
         cls_loaded = cls;
       }
       const int ipos = sPos[cls * 64 + i];              // window position of this thread's query row
+      const int gwh = gw * P.nH + h;
       const uint8_t* base = sStage + stage * kStageBytesF;
       float* rkbuf = sRk + (g * 2 + (kk & 1)) * 128;
       TR(n, 1);
@@ -358,7 +345,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
         a_i *= rq;                                       // 1 / max(||q||, 1e-12) x logit scale x log2(e)
         rkbuf[r] = rkk;
         if (valid) {                                     // kept for the backward kernel (it reads them with one bulk copy per window)
-          float* rec = P.lse + P.slab + ((long long)gw * P.nH + h) * (3 * kN) + i;    // [window][head][1/|q| | 1/|k| | lse log2][64 tile rows]
+          float* rec = P.lse + P.slab + (long long)gwh * (3 * kN) + i;    // [window][head][1/|q| | 1/|k| | lse log2][64 tile rows]
           rec[0] = rq;
           rec[kN] = rkk;
         }
@@ -373,10 +360,9 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
       uint64_t s2[32];                                   // this row's 64 logits as fp32 pairs
       {
         uint32_t raw0[32], raw1[32];
-        tmem_ld_32x32b_x32(tmem + lane_base + g * 64, raw0);
-        tmem_ld_32x32b_x32(tmem + lane_base + g * 64 + 32, raw1);
+        tmem_ld_32x32b_x32(tS, raw0);
+        tmem_ld_32x32b_x32(tS + 32, raw1);
         tmem_ld_wait();
-        tcgen05_fence_before();
 #pragma unroll
         for (int j = 0; j < 16; ++j) { s2[j] = pk2u(raw0[2 * j], raw0[2 * j + 1]); s2[16 + j] = pk2u(raw1[2 * j], raw1[2 * j + 1]); }
       }
@@ -418,7 +404,8 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
         }
         mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
       }
-      float s[64];
+      // ---- P = exp2(s - max) as packed bf16 pairs, straight into this row's half of the TMEM operand
+      uint32_t pp[32];
       float l;
       {
         const uint64_t nmx2 = pk2(-mx, -mx);
@@ -427,47 +414,51 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
         for (int j = 0; j < 32; ++j) {
           float a, b;
           upk2(add2(s2[j], nmx2), a, b);
-          s[2 * j] = fast_exp2(a); s[2 * j + 1] = fast_exp2(b);
-          l2[j & 3] = add2(l2[j & 3], pk2(s[2 * j], s[2 * j + 1]));
+          a = fast_exp2(a); b = fast_exp2(b);
+          l2[j & 3] = add2(l2[j & 3], pk2(a, b));
+          pp[j] = valid ? pack_bf16x2(a, b) : 0u;
         }
         float la, lb;
         upk2(add2(add2(l2[0], l2[1]), add2(l2[2], l2[3])), la, lb);
         l = la + lb;
       }
       TR(n, 5);
-
-      // ---- P (bf16) into the 128B-swizzled K-major tile.  The group's previous PV MMA must have finished
-      // reading it (it has had this whole softmax to do so).
-      if (have_prev) { mbar_wait(&o_full[g], (kk - 1) & 1); tcgen05_fence_after(); }
+      tmem_st_32x32b_x32(tP, pp);
+      tmem_st_wait();
+      tcgen05_fence_before();
+      mbar_arrive_warp(&p_full[g]);
       TR(n, 6);
+
+      // ---- while the second MMA runs: log-sum-exp out
+      const float lse2 = mx + __log2f(l), inv_l = __frcp_rn(l);
+      if (valid) {
+        P.lse[(long long)gwh * kN + ipos] = lse2 * kLn2;
+        P.lse[P.slab + (long long)gwh * (3 * kN) + 2 * kN + i] = lse2;
+      }
+
+      // ---- O / l -> bf16 -> staging tile -> store warp
+      mbar_wait(&o_full[g], kk & 1);
+      tcgen05_fence_after();
+      TR(n, 7);
+      uint32_t oraw[32];
+      tmem_ld_32x32b_x32(tO, oraw);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      mbar_wait(&so_free[g], (kk & 1) ^ 1);              // the store warp has drained this group's staging tile
+      const uint64_t inv2 = pk2(inv_l, inv_l);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint4 v4 = make_uint4(pack_bf16x2(s[c * 8 + 0], s[c * 8 + 1]), pack_bf16x2(s[c * 8 + 2], s[c * 8 + 3]),
-                              pack_bf16x2(s[c * 8 + 4], s[c * 8 + 5]), pack_bf16x2(s[c * 8 + 6], s[c * 8 + 7]));
-        if (!valid) v4 = make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(pbuf + ((c ^ (i & 7)) << 4)) = v4;
+      for (int c = 0; c < 4; ++c) {
+        uint4 v4 = make_uint4(pack_bf16x2(mul2(pk2u(oraw[c * 8 + 0], oraw[c * 8 + 1]), inv2)), pack_bf16x2(mul2(pk2u(oraw[c * 8 + 2], oraw[c * 8 + 3]), inv2)),
+                              pack_bf16x2(mul2(pk2u(oraw[c * 8 + 4], oraw[c * 8 + 5]), inv2)), pack_bf16x2(mul2(pk2u(oraw[c * 8 + 6], oraw[c * 8 + 7]), inv2)));
+        *reinterpret_cast<uint4*>(obuf + ((c ^ ((r >> 1) & 3)) << 4)) = v4;
       }
       fence_proxy_async_smem();
-      mbar_arrive_warp(&p_full[g]);
-      TR(n, 7);
-
-      if (have_prev) epilogue(kk - 1, prev_inv, prev_lse, prev_gwh, prev_ipos, prev_valid);
+      mbar_arrive_warp(&so_ready[g]);
       TR(n, 8);
-      have_prev = true;
-      prev_valid = valid;
-      prev_inv = __frcp_rn(l);
-      prev_lse = mx + __log2f(l);
-      prev_gwh = gw * P.nH + h;
-      prev_ipos = ipos;
-    }
-    if (have_prev) {
-      mbar_wait(&o_full[g], (kk - 1) & 1);
-      tcgen05_fence_after();
-      epilogue(kk - 1, prev_inv, prev_lse, prev_gwh, prev_ipos, prev_valid);
     }
     // farewell to the store warp: this group has produced kk tiles.  The store warp must have taken the last one
     // first -- two so_ready phases completing back to back would alias in its parity wait.
-    if (have_prev) mbar_wait(&so_free[g], (kk - 1) & 1);
+    if (kk > 0) mbar_wait(&so_free[g], (kk - 1) & 1);
     if (r == 0) sEnd[g] = kk;
     mbar_arrive_warp(&so_ready[g]);
 #undef TR
@@ -479,8 +470,8 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
   if (warp == kMmaWarp) tmem_dealloc<kTmemColsF>(tmem);
 }
 
-constexpr size_t kFwdSmemBytes = 1024 /*align slack*/ + kStagesF * kStageBytesF + 2 * kPRegion + 2 * kTile + 2 * kN * kTblLd * 4 +
-                                 512 * 4 + 1024 + kItemRing * 16 + 16 + 24 * 8;
+constexpr size_t kFwdSmemBytes = 1024 /*align slack*/ + kStagesF * kStageBytesF + kGroupsF * kTile + kGroupsF * kN * kTblLd * 4 +
+                                 kGroupsF * 256 * 4 + 1024 + kItemRing * 16 + 16 + (2 * kStagesF + 5 * kGroupsF + 1) * 8;
 
 // ------------------------------------------------------------------------------------------
 // Host side
