@@ -129,7 +129,8 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
   uint8_t* sPos = reinterpret_cast<uint8_t*>(sRk + G * 256);  // [8 wrap classes][64]: tile row -> window position
   uint8_t* sRid = sPos + 512;                             // [8 wrap classes][64]: window position -> shift-mask region id
   int4* sItem = reinterpret_cast<int4*>(sRid + 512);      // [kItemRing] {wrap class (-1: no more items), window of slot 0, of slot 1, valid slots}
-  int* sEnd = reinterpret_cast<int*>(sItem + kItemRing);  // [G] items group g has produced when it left its loop (else INT_MAX)
+  int4* sGeo = sItem + kItemRing;                         // [kItemRing][2] {sample, start coordinates} of the item's two windows (store warp)
+  int* sEnd = reinterpret_cast<int*>(sGeo + 2 * kItemRing);  // [G] items group g has produced when it left its loop (else INT_MAX)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sEnd + 4);
   uint64_t* full = bars;                                  // [kStagesF] TMA -> MMA, softmax
   uint64_t* empty = bars + kStagesF;                      // [kStagesF] MMA -> TMA
@@ -205,6 +206,8 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
           trace_evf(P.trace, 2, n, 1);
           if (lane == 0) {
             sItem[n % kItemRing] = make_int4(cur.cls, w0, w1, nvalid);     // published by the arrive below
+            sGeo[(n % kItemRing) * 2] = make_int4(ws0.b, ws0.s0, ws0.s1, ws0.s2);
+            sGeo[(n % kItemRing) * 2 + 1] = make_int4(ws1.b, ws1.s0, ws1.s1, ws1.s2);
             mbar_arrive_expect_tx(&full[stage], nvalid * 3 * kWinBytes);
           }
           __syncwarp();
@@ -232,41 +235,57 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
       const uint64_t dQK = umma_smem_desc(0, 0, 512, kSwz64);        // Q / K tiles, K-major
       const uint64_t dV = umma_smem_desc(0, 8192, 512, kSwz64);      // V tile, MN-major
       const uint32_t stage0 = smem_u32(sStage) >> 4;
+      // Two queues served in turn, neither blocking the other: S(ns) needs item ns's tiles (full[]) and its group's S
+      // buffer back (true once PV(ns - G) has been issued: the group wrote P after reading S); PV(np) needs P(np).
+      // A warp that waited for the tiles of S(n + G) right after PV(n) held up PV(n + 1) whenever the loads ran late.
       int total = 0x7fffffff;                                        // items of this CTA: known once the end marker shows up
-      auto issue_s = [&](int n) {
-        const int stage = n % kStagesF, phase = (n / kStagesF) & 1;
-        mbar_wait(&full[stage], phase);
-        if (sItem[n % kItemRing].x < 0) { total = n; return; }
-        tcgen05_fence_after();
-        if (elect_one()) {
-          const uint64_t aq = dQK + (stage0 + stage * (kStageBytesF >> 4)), bk = aq + (kQRegion >> 4);
-          const uint32_t tS = tmem + (n % G) * kTmemGroup;
+      int ns = 0, np = 0;
+      uint32_t idle = 0;
+      while (np < total) {
+        bool progressed = false;
+        if (total == 0x7fffffff && ns < np + G) {
+          const int stage = ns % kStagesF, phase = (ns / kStagesF) & 1;
+          if (mbar_test(&full[stage], phase)) {
+            progressed = true;
+            if (sItem[ns % kItemRing].x < 0) {
+              total = ns;
+            } else {
+              tcgen05_fence_after();
+              if (elect_one()) {
+                const uint64_t aq = dQK + (stage0 + stage * (kStageBytesF >> 4)), bk = aq + (kQRegion >> 4);
+                const uint32_t tS = tmem + (ns % G) * kTmemGroup;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)      // ks 0,1: window 0's channels; ks 2,3: window 1's
-            umma_bf16_ss(tS, aq + ((ks >> 1) * (kWinBytes >> 4) + (ks & 1) * 2), bk + ((ks >> 1) * (kWinBytes >> 4) + (ks & 1) * 2), idescS, ks);
-          umma_commit(&s_full[n % G]);
+                for (int ks = 0; ks < 4; ++ks)      // ks 0,1: window 0's channels; ks 2,3: window 1's
+                  umma_bf16_ss(tS, aq + ((ks >> 1) * (kWinBytes >> 4) + (ks & 1) * 2), bk + ((ks >> 1) * (kWinBytes >> 4) + (ks & 1) * 2), idescS, ks);
+                umma_commit(&s_full[ns % G]);
+              }
+              __syncwarp();
+              ++ns;
+            }
+          }
         }
-        __syncwarp();
-      };
-      for (int n = 0; n < G && total == 0x7fffffff; ++n) issue_s(n);
-      for (int n = 0; n < total; ++n) {
-        const int g = n % G, kk = n / G, stage = n % kStagesF;
-        trace_evf(P.trace, 3, n, 0);
-        mbar_wait(&p_full[g], kk & 1);         // the group has read S(n) out and written P(n)
-        trace_evf(P.trace, 3, n, 1);
-        tcgen05_fence_after();
-        if (elect_one()) {
-          const uint32_t tP = tmem + g * kTmemGroup + 64, tO = tmem + g * kTmemGroup + 128;
-          const uint64_t bv = dV + (stage0 + stage * (kStageBytesF >> 4) + ((kQRegion + kTile) >> 4));
+        if (np < ns) {
+          const int g = np % G, kk = np / G, stage = np % kStagesF;
+          if (mbar_test(&p_full[g], kk & 1)) {     // the group has read S(np) out and written P(np)
+            progressed = true;
+            trace_evf(P.trace, 3, np, 1);
+            tcgen05_fence_after();
+            if (elect_one()) {
+              const uint32_t tP = tmem + g * kTmemGroup + 64, tO = tmem + g * kTmemGroup + 128;
+              const uint64_t bv = dV + (stage0 + stage * (kStageBytesF >> 4) + ((kQRegion + kTile) >> 4));
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)      // 16 keys (8 TMEM columns of P) per step; ks < 4: window 0's keys
-            umma_bf16_ts(tO, tP + ks * 8, bv + ks * (1024 >> 4), idescO, ks);
-          umma_commit(&o_full[g]);
-          umma_commit(&empty[stage]);
+              for (int ks = 0; ks < 8; ++ks)      // 16 keys (8 TMEM columns of P) per step; ks < 4: window 0's keys
+                umma_bf16_ts(tO, tP + ks * 8, bv + ks * (1024 >> 4), idescO, ks);
+              umma_commit(&o_full[g]);
+              umma_commit(&empty[stage]);
+            }
+            __syncwarp();
+            trace_evf(P.trace, 3, np, 2);
+            ++np;
+          }
         }
-        __syncwarp();
-        if (total == 0x7fffffff) issue_s(n + G);   // this group's S buffer is free: it was read before P was written
-        trace_evf(P.trace, 3, n, 2);
+        if (progressed) idle = 0;
+        else if (++idle > (1u << 24)) __trap();    // a broken pipeline becomes a CUDA error, not a hang
       }
     } else if (warp == kStoreWarp) {
       // ============================== TMA store ==============================
@@ -274,21 +293,31 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
       const int dst_base[1] = {0};
       const int slot_stride[1] = {kWinBytes};
       BoxPlan<1> plan;
-      for (int n = 0;; ++n) {
+      // A tile goes back to its group one item late: the stores of item n are issued, then the warp waits only for the
+      // bulk group before (item n - 1) to have been read out of shared memory -- the read latency of one item's stores
+      // hides under the next item's issue.
+      int n = 0;
+      for (;; ++n) {
         const int g = n % G, kk = n / G;
         trace_evf(P.trace, 4, n, 0);
         mbar_wait(&so_ready[g], kk & 1);
         if (kk >= *reinterpret_cast<volatile int*>(&sEnd[g])) break;   // the group left its loop: that arrival was its farewell
         trace_evf(P.trace, 4, n, 1);
-        const int4 item = sItem[n % kItemRing];
+        const int4 item = sItem[n % kItemRing], a0 = sGeo[(n % kItemRing) * 2], a1 = sGeo[(n % kItemRing) * 2 + 1];
         if (item.x != plan.cls) plan.build(S, item.x, lane, maps, dst_base, slot_stride);
-        plan.issue<false>(S, window_start(S, item.y), window_start(S, item.z), item.w, h * kD, sO + g * kTile, nullptr, lane);
+        WinStart w0, w1;
+        w0.b = a0.x; w0.s0 = a0.y; w0.s1 = a0.z; w0.s2 = a0.w;
+        w1.b = a1.x; w1.s0 = a1.y; w1.s1 = a1.z; w1.s2 = a1.w;
+        plan.issue<false>(S, w0, w1, item.w, h * kD, sO + g * kTile, nullptr, lane);
         tma_store_commit();
-        tma_store_wait_read<0>();          // per thread: each lane waits for the smem reads of its own boxes
+        tma_store_wait_read<1>();          // per thread: its boxes of item n - 1 have been read
         __syncwarp();
-        if (lane == 0) mbar_arrive(&so_free[g]);
+        if (lane == 0 && n > 0) mbar_arrive(&so_free[(n - 1) % G]);
         trace_evf(P.trace, 4, n, 2);
       }
+      tma_store_wait_read<0>();
+      __syncwarp();
+      if (lane == 0 && n > 0) mbar_arrive(&so_free[(n - 1) % G]);
       tma_store_wait_all<0>();
     }
   } else {
@@ -471,7 +500,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
 }
 
 constexpr size_t kFwdSmemBytes = 1024 /*align slack*/ + kStagesF * kStageBytesF + kGroupsF * kTile + kGroupsF * kN * kTblLd * 4 +
-                                 kGroupsF * 256 * 4 + 1024 + kItemRing * 16 + 16 + (2 * kStagesF + 5 * kGroupsF + 1) * 8;
+                                 kGroupsF * 256 * 4 + 1024 + kItemRing * 48 + 16 + (2 * kStagesF + 5 * kGroupsF + 1) * 8;
 
 // ------------------------------------------------------------------------------------------
 // Host side
