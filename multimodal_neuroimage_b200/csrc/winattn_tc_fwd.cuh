@@ -41,8 +41,8 @@ constexpr int kStageBytesF = kQRegion + 2 * kTile; // + K0 K1 + V0 V1
 constexpr int kPRegion = 3 * 8192;                 // (backward kernel) P0 (64 rows x 128 B) | zero block | P1
 constexpr int kGroupThreads = 128;
 constexpr int kGroupsF = 3;                        // softmax groups = items in flight
-constexpr int kProducerWarp = 4 * kGroupsF, kMmaWarp = kProducerWarp + 1, kStoreWarp = kProducerWarp + 2;
-constexpr int kFwdThreads = 32 * (kProducerWarp + 4);   // 4 warpgroups: 3 softmax groups + {producer, MMA, store, idle}
+constexpr int kProducerWarp = 4 * kGroupsF, kMmaWarp = kProducerWarp + 1, kStoreWarp = kProducerWarp + 2, kProducerWarpKV = kProducerWarp + 3;
+constexpr int kFwdThreads = 32 * (kProducerWarp + 4);   // 4 warpgroups: 3 softmax groups + {Q producer, MMA, store, K/V producer}
 constexpr int kRegSoftmaxF = 136, kRegAuxF = 104;  // setmaxnreg: 384 * 136 + 128 * 104 = 512 * 128
 constexpr int kTblLd = 68;                         // padded row of the shared table (conflict-free float4 rows)
 constexpr int kTmemColsF = 512;                    // group g: S at 160 g (64 columns), P at 160 g + 64 (64), O at 160 g + 128 (32)
@@ -139,7 +139,8 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
   uint64_t* o_full = s_full + 2 * G;                      // [G] O in TMEM
   uint64_t* so_ready = s_full + 3 * G;                    // [G] staging tile written (one arrival per warp)
   uint64_t* so_free = s_full + 4 * G;                     // [G] staging tile drained by the store warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 5 * G);
+  uint64_t* desc_ready = s_full + 5 * G;                  // [kStagesF] item descriptor published (Q producer -> K/V producer)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(desc_ready + kStagesF);
 
   const WinShape& S = P.S;
   const Sched& sc = P.sc;
@@ -156,7 +157,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
   }
   if (tid == 0) {
     for (int g = 0; g < G; ++g) sEnd[g] = 0x7fffffff;
-    for (int s = 0; s < kStagesF; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kStagesF; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); mbar_init(&desc_ready[s], 1); }
     for (int g = 0; g < G; ++g) {
       mbar_init(&s_full[g], 1); mbar_init(&p_full[g], kGroupThreads / 32); mbar_init(&o_full[g], 1);
       mbar_init(&so_ready[g], kGroupThreads / 32); mbar_init(&so_free[g], 1);
@@ -164,7 +165,9 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
     fence_barrier_init();
   }
   if (warp == kProducerWarp && lane == 0)
-    for (int i = 0; i < 8; ++i) { tma_prefetch_desc(&P.q[i]); tma_prefetch_desc(&P.k[i]); tma_prefetch_desc(&P.v[i]); }
+    for (int i = 0; i < 8; ++i) tma_prefetch_desc(&P.q[i]);
+  if (warp == kProducerWarpKV && lane == 0)
+    for (int i = 0; i < 8; ++i) { tma_prefetch_desc(&P.k[i]); tma_prefetch_desc(&P.v[i]); }
   if (warp == kStoreWarp && lane == 0)
     for (int i = 0; i < 8; ++i) tma_prefetch_desc(&P.o[i]);
   if (warp == kMmaWarp) tmem_alloc<kTmemColsF>(tmem_slot);
@@ -178,12 +181,14 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
   if (warp >= kProducerWarp) {
     setmaxnreg_dec<kRegAuxF>();
     if (warp == kProducerWarp) {
-      // ============================== TMA producer ==============================
-      // every lane runs the loop; lane l issues boxes l, l + 32 of the item (BoxPlan)
-      const CUtensorMap* const maps[3] = {P.q, P.k, P.v};
-      const int dst_base[3] = {0, kQRegion, kQRegion + kTile};
-      const int slot_stride[3] = {2 * kWinBytes, kWinBytes, kWinBytes};
-      BoxPlan<3> plan;
+      // ============================== TMA producer (schedule, descriptors, Q tiles) ==============================
+      // every lane runs the loop; lane l issues boxes l, l + 32 of the item (BoxPlan).  The K and V tiles of the same items
+      // are issued by a second warp that follows the descriptor ring (one warp issuing all six boxes of an item, ~65
+      // cycles per box plus the cursor arithmetic, was what bounded the kernel).
+      const CUtensorMap* const maps[1] = {P.q};
+      const int dst_base[1] = {0};
+      const int slot_stride[1] = {2 * kWinBytes};
+      BoxPlan<1> plan;
       // Dynamic schedule (tc_sched.cuh: ClassQueue): chunks of kChunkF items of this head, home class first.
       // Every other warp learns its items from the descriptor ring sItem (published by the full[] arrival).  Ring
       // depth: entry n + 16 is written only once stage (n + 16) % kStagesF is free, i.e. after PV(n + 11) has completed,
@@ -205,10 +210,11 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
           mbar_wait(&empty[stage], phase ^ 1);
           trace_evf(P.trace, 2, n, 1);
           if (lane == 0) {
-            sItem[n % kItemRing] = make_int4(cur.cls, w0, w1, nvalid);     // published by the arrive below
+            sItem[n % kItemRing] = make_int4(cur.cls, w0, w1, nvalid);     // published by the arrivals below
             sGeo[(n % kItemRing) * 2] = make_int4(ws0.b, ws0.s0, ws0.s1, ws0.s2);
             sGeo[(n % kItemRing) * 2 + 1] = make_int4(ws1.b, ws1.s0, ws1.s1, ws1.s2);
-            mbar_arrive_expect_tx(&full[stage], nvalid * 3 * kWinBytes);
+            mbar_arrive(&desc_ready[stage]);
+            mbar_arrive_expect_tx(&full[stage], nvalid * kWinBytes);
           }
           __syncwarp();
           plan.issue<true>(S, ws0, ws1, nvalid, h * kD, sStage + stage * kStageBytesF, &full[stage], lane);
@@ -221,6 +227,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
         mbar_wait(&empty[stage], phase ^ 1);
         if (lane == 0) {
           sItem[n % kItemRing] = make_int4(-1, 0, 0, 0);
+          mbar_arrive(&desc_ready[stage]);
           mbar_arrive(&full[stage]);
         }
         __syncwarp();
@@ -319,6 +326,31 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
       __syncwarp();
       if (lane == 0 && n > 0) mbar_arrive(&so_free[(n - 1) % G]);
       tma_store_wait_all<0>();
+    } else {
+      // ============================== TMA producer (K and V tiles) ==============================
+      const CUtensorMap* const maps[2] = {P.k, P.v};
+      const int dst_base[2] = {kQRegion, kQRegion + kTile};
+      const int slot_stride[2] = {kWinBytes, kWinBytes};
+      BoxPlan<2> plan;
+      int ends = 0;
+      for (int n = 0; ends < G; ++n) {
+        const int stage = n % kStagesF, phase = (n / kStagesF) & 1;
+        mbar_wait(&desc_ready[stage], phase);             // the Q producer has waited for the stage and published the item
+        const int4 item = sItem[n % kItemRing], a0 = sGeo[(n % kItemRing) * 2], a1 = sGeo[(n % kItemRing) * 2 + 1];
+        if (item.x < 0) {                                 // end marker: complete the phase for its readers
+          if (lane == 0) mbar_arrive(&full[stage]);
+          __syncwarp();
+          ++ends;
+          continue;
+        }
+        if (item.x != plan.cls) plan.build(S, item.x, lane, maps, dst_base, slot_stride);
+        WinStart w0, w1;
+        w0.b = a0.x; w0.s0 = a0.y; w0.s1 = a0.z; w0.s2 = a0.w;
+        w1.b = a1.x; w1.s0 = a1.y; w1.s1 = a1.z; w1.s2 = a1.w;
+        if (lane == 0) mbar_arrive_expect_tx(&full[stage], item.w * 2 * kWinBytes);
+        __syncwarp();
+        plan.issue<true>(S, w0, w1, item.w, h * kD, sStage + stage * kStageBytesF, &full[stage], lane);
+      }
     }
   } else {
     // ============================== softmax / epilogue: group g = warp / 4, one thread per query row ==============================
@@ -500,7 +532,7 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
 }
 
 constexpr size_t kFwdSmemBytes = 1024 /*align slack*/ + kStagesF * kStageBytesF + kGroupsF * kTile + kGroupsF * kN * kTblLd * 4 +
-                                 kGroupsF * 256 * 4 + 1024 + kItemRing * 48 + 16 + (2 * kStagesF + 5 * kGroupsF + 1) * 8;
+                                 kGroupsF * 256 * 4 + 1024 + kItemRing * 48 + 16 + (3 * kStagesF + 5 * kGroupsF + 1) * 8;
 
 // ------------------------------------------------------------------------------------------
 // Host side
