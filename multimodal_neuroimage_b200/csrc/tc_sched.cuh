@@ -140,6 +140,9 @@ struct ItemCursor {
 constexpr int kWorkDone = 511, kWorkSlotInts = 512, kWorkSlots = 128;   // per slot: 63 heads x 8 classes, [511] = CTAs that ran dry
 struct ClassQueue {
   int cls, pend, tried;
+  // items per claim: the wrapped classes are small and their items cost up to 3x (2^k boxes per tile), so their chunks
+  // shrink with the number of wrapped axes -- a late chunk of eight 3-axis items was a 30 us tail
+  static __device__ __forceinline__ int chunk_of(int chunk, int c) { return max(1, chunk >> __popc(c)); }
   __device__ __forceinline__ void init(const Sched& sc, int home_item, int* work, int chunk, int lane) {
     cls = 0;
     while (cls < 7) {
@@ -150,7 +153,7 @@ struct ClassQueue {
     }
     tried = 0;
     pend = 0;
-    if (lane == 0) pend = atomicAdd(work + cls, chunk);
+    if (lane == 0) pend = atomicAdd(work + cls, chunk_of(chunk, cls));
   }
   // first item (index in the class-sorted list) and length of the next chunk; false when every class is exhausted
   __device__ __forceinline__ bool next(const Sched& sc, int* work, int chunk, int lane, int& item0, int& m) {
@@ -161,14 +164,14 @@ struct ClassQueue {
         int base = 0;
         for (int c = 0; c < cls; ++c) base += (sc.cnt[c] + 1) >> 1;
         item0 = base + c0;
-        m = min(chunk, np - c0);
-        if (lane == 0) pend = atomicAdd(work + cls, chunk);
+        m = min(chunk_of(chunk, cls), np - c0);
+        if (lane == 0) pend = atomicAdd(work + cls, chunk_of(chunk, cls));
         tried = 0;
         return true;
       }
       if (++tried >= 8) return false;
       cls = (cls + 1) & 7;
-      if (lane == 0) pend = atomicAdd(work + cls, chunk);
+      if (lane == 0) pend = atomicAdd(work + cls, chunk_of(chunk, cls));
     }
   }
   // called by lane 0 after the CTA ran dry: the last CTA re-arms the counters for the next launch that uses this slot
