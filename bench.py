@@ -460,10 +460,18 @@ def main():
     cand = {"winattn_fwd": CORE_FWD_BYTES_PER_WINDOW, "winattn_bwd": CORE_BWD_BYTES_PER_WINDOW}
     dom = max((k for k in cand if k in kern), key=lambda k: kern[k], default=None)
     roofline = None
+    traffic = None     # DRAM bytes per launch of the dominant kernel from the committed ncu capture (same batch only)
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
+            tj = json.load(f)
+        if dom is not None and tj.get("per_gpu_batch") == B:
+            traffic = tj.get(dom)
+    except (OSError, ValueError):
+        pass
     if dom is not None:
         gbs = per_launch_windows * cand[dom] / (kern[dom] * 1e-3) / 1e9
         roofline = {"kernel": dom, "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": gbs / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                    "frac": gbs / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk["source"],
                     "algorithmic_bytes_per_window": cand[dom], "ms_per_launch": kern[dom],
                     "kernels_ms": kern,
                     "all": {k: {"GB/s": per_launch_windows * cand[k] / (kern[k] * 1e-3) / 1e9,
