@@ -48,6 +48,7 @@ constexpr int kRegSoftmax = kRowSplit == 4 ? 80 : 168, kRegEpi = kRowSplit == 4 
 #define MMN_BWD_CHUNK 1
 #endif
 constexpr int kChunkB = MMN_BWD_CHUNK;  // items a CTA claims per atomic
+constexpr int kPDBytes = 7 * 8192;    // P0[2] | dS'0 | Z | dS'1 | P1[2]
 constexpr int kBwdTmemCols = 512;     // S[b] at 128 b, dP[b] at 128 b + 64; dV|dQ~|dK~ [b] at 256 + 96 b
 
 struct BwdParams {
@@ -76,9 +77,15 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sStage = smem;                                 // kStagesB x kStageBytesB
-  uint8_t* sP = sStage + kStagesB * kStageBytesB;         // P0 | Z | P1
-  uint8_t* sDS = sP + kPRegion;                           // dS'0 | Z | dS'1
-  uint8_t* sOut = sDS + kPRegion;                         // dQ | dK | dV staging, 3 x kTile
+  // P (double-buffered over items) and dS' around ONE shared zero block, 8 KB each:
+  //   P0[0] | P0[1] | dS'0 | Z | dS'1 | P1[0] | P1[1]
+  // dS' is read K-major (dQ~) and MN-major (dK~) and needs Z adjacent on both sides; P is only read MN-major (dV), where
+  // the second 64-row atom of the operand sits one leading-dimension offset away -- any distance -- so its zero half can be
+  // the same Z.  With P double-buffered the softmax warps write P(n + 1) while the gradient MMAs of item n still run
+  // (they were waiting ~1000 cycles per item for them); the second buffer costs 8 KB, not 24.
+  uint8_t* sPD = sStage + kStagesB * kStageBytesB;
+  uint8_t* sDS = sPD + 2 * 8192;                          // dS'0 | Z | dS'1
+  uint8_t* sOut = sPD + kPDBytes;                         // dQ | dK | dV staging, 3 x kTile
   float* sTbl = reinterpret_cast<float*>(sOut + 3 * kTile);   // [64][kTblLd]
   float* sRec = sTbl + kN * kTblLd;                       // [kStagesB][2 slots][1/|q| | 1/|k| | lse log2][64 tile rows]: the forward kernel's
                                                           //   per-window records, bulk-copied with the stage
@@ -107,7 +114,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
   const int h = blockIdx.x % P.nH;
 
   // ---- one-time setup
-  for (int i = tid; i < (kStagesB * kStageBytesB + 2 * kPRegion) / 16; i += kBwdThreads)
+  for (int i = tid; i < (kStagesB * kStageBytesB + kPDBytes) / 16; i += kBwdThreads)
     reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < 512; i += kBwdThreads) {
     sPos[i] = (uint8_t)piece_position(S, i >> 6, i & 63);
@@ -195,8 +202,8 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       const uint64_t dKm = umma_smem_desc(0, 0, 512, kSwz64);         // Q, K, V, dO tiles read K-major
       const uint64_t dMn = umma_smem_desc(0, 8192, 512, kSwz64);      // K, Q, dO tiles read MN-major
       const uint64_t dPk = umma_smem_desc(0, 0, 1024, kSwz128);       // dS' read K-major
-      const uint64_t dPm = umma_smem_desc(0, 8192, 1024, kSwz128);    // P, dS' read MN-major (transposed)
-      const uint32_t stage0 = smem_u32(sStage) >> 4, p0 = smem_u32(sP) >> 4, ds0 = smem_u32(sDS) >> 4;
+      const uint64_t dPm = umma_smem_desc(0, 8192, 1024, kSwz128);    // dS' read MN-major (transposed)
+      const uint32_t stage0 = smem_u32(sStage) >> 4, pd0 = smem_u32(sPD) >> 4, ds0 = smem_u32(sDS) >> 4;
       constexpr uint32_t W16 = kWinBytes >> 4;
       int total = 0x7fffffff;                                         // items of this CTA: known once the end marker shows up
       auto issue_sdp = [&](int n) {
@@ -229,13 +236,17 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
         tcgen05_fence_after();
         if (elect_one()) {
           const uint64_t sbm = dMn + (stage0 + stage * (kStageBytesB >> 4));
-          const uint64_t ap = dPm + p0, adk = dPk + ds0, adm = dPm + ds0;
+          const uint64_t adk = dPk + ds0, adm = dPm + ds0;
+          // P buffer b, read MN-major: window 0's steps start in P0[b] with the zero block one LBO above, window 1's start
+          // in the zero block with P1[b] one LBO above
+          const uint64_t ap0 = umma_smem_desc(0, 3 * 8192 - b * 8192, 1024, kSwz128) + (pd0 + b * (8192 >> 4));
+          const uint64_t ap1 = umma_smem_desc(0, 2 * 8192 + b * 8192, 1024, kSwz128) + (pd0 + ((3 * 8192) >> 4));
           const uint32_t tO = tmem + 256 + b * 96;
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {   // 16 queries (dV, dK~) or 16 keys (dQ~) per step; ks < 4: window 0
             const uint32_t wofs = (ks >> 2) * 2 * W16 + (ks & 3) * 64;     // 16 rows of window ks/4 inside a X0|Z|X1 region
             // dV[key][d] += P[query][key]^T dO[query][d]
-            umma_bf16_ss(tO, ap + ks * 128, sbm + ((kOffDO >> 4) + wofs), idescMM, ks);
+            umma_bf16_ss(tO, (ks < 4 ? ap0 : ap1) + (ks & 3) * 128, sbm + ((kOffDO >> 4) + wofs), idescMM, ks);
             // dQ~[query][d] += dS'[query][key] K[key][d]
             umma_bf16_ss(tO + 32, adk + ((ks >> 2) * 512 + (ks & 3) * 2), sbm + ((kOffK >> 4) + ks * 64), idescKM, ks);
             // dK~[key][d] += dS'[query][key]^T Q[query][d]
@@ -449,7 +460,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
     const float hscale = COS ? __ldg(P.head_scale + h) : P.scale;
     const float* bias_h = P.bias ? P.bias + (size_t)h * kN * kN : nullptr;
     float* const gdb_head = P.dbias ? P.dbias + (size_t)h * kN * kN : nullptr;
-    uint8_t* prow = sP + slot * 16384 + i * 128;
+    uint8_t* prow0 = sPD + slot * (5 * 8192) + i * 128;     // this thread's row of P0[0] / P1[0]; buffer 1 is 8 KB further
     uint8_t* drow = sDS + slot * 16384 + i * 128;
     float dbacc[KP];                                    // dbias[tile row i][KP*qt + j] of the current wrap class
 #pragma unroll
@@ -566,8 +577,9 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       }
       sDelta[qt * 128 + r] = delta;
       TRB(n, 5);
-      // P (bf16) can go out before delta is known; the previous item's gradient MMAs must have finished reading P / dS'
-      if (n > 0) mbar_wait(&out_full[b ^ 1], ((n - 1) >> 1) & 1);
+      // P (bf16) can go out before delta is known, into the buffer the gradient MMAs of item n - 2 have long left
+      if (n > 1) mbar_wait(&out_full[b], ((n - 2) >> 1) & 1);
+      uint8_t* prow = prow0 + b * 8192;
       TRB(n, 6);
 #pragma unroll
       for (int c = 0; c < KP / 8; ++c) {
@@ -595,6 +607,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
 #pragma unroll
         for (int j = 0; j < KP; ++j) dbacc[j] += p[j];
       }
+      if (n > 0) mbar_wait(&out_full[b ^ 1], ((n - 1) >> 1) & 1);   // the previous item's dQ~ / dK~ MMAs have read dS'
 #pragma unroll
       for (int c = 0; c < KP / 8; ++c) {
         float cj[8];
@@ -630,7 +643,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
   if (warp == kMmaWarpB) tmem_dealloc<kBwdTmemCols>(tmem);
 }
 
-constexpr size_t kBwdSmemBytes = 1024 + kStagesB * kStageBytesB + 2 * kPRegion + 3 * kTile + kN * kTblLd * 4 +
+constexpr size_t kBwdSmemBytes = 1024 + kStagesB * kStageBytesB + kPDBytes + 3 * kTile + kN * kTblLd * 4 +
                                  (kStagesB * 2 * 3 * kN + 512 + 16) * 4 + 1024 + 24 * 16 + 16 + 24 * 8;
 
 inline const char* bwd_why_not_impl(const mmn_winattn_desc* d) {
