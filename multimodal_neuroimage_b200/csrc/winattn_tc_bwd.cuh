@@ -212,6 +212,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
         if (sItem[n & 7].x < 0) { total = n; return; }
         mbar_wait(&sdp_empty[b], ((n >> 1) & 1) ^ 1);
         tcgen05_fence_after();
+        trace_ev(P.trace, 3, n - 2, 4);
         if (elect_one()) {
           const uint64_t sb = dKm + (stage0 + stage * (kStageBytesB >> 4));
           const uint32_t tS = tmem + b * 128, tDP = tS + 64;
@@ -224,6 +225,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
           umma_commit(&sdp_full[b]);
         }
         __syncwarp();
+        trace_ev(P.trace, 3, n - 2, 5);
       };
       issue_sdp(0);
       if (total > 1) issue_sdp(1);
