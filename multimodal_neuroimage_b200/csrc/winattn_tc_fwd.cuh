@@ -48,7 +48,7 @@ constexpr int kTblLd = 68;                         // padded row of the shared t
 constexpr int kTmemColsF = 512;                    // group g: S at 160 g (64 columns), P at 160 g + 64 (64), O at 160 g + 128 (32)
 constexpr int kTmemGroup = 160;
 constexpr int kItemRing = 16;                      // item descriptors published by the TMA producer (see the ring-depth note there)
-constexpr int kChunkF = 8;                         // items a CTA claims per atomic
+constexpr int kChunkF = 16;                        // most items a CTA claims per atomic
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -196,8 +196,10 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
       // consumer of entry n, the store warp included, has read it.
       int n = 0;
       ClassQueue wq;
-      wq.init(sc, sched_range_begin(sc, blockIdx.x / P.nH, P.per_head), P.work + h * 8, kChunkF, lane);
-      for (int c0, m; wq.next(sc, P.work + h * 8, kChunkF, lane, c0, m);) {
+      // claims of up to kChunkF items (each costs the producer a seek with integer divisions), an eighth of a CTA's share at most
+      const int chunk = max(1, min(kChunkF, sc.n_items / (P.per_head * 8)));
+      wq.init(sc, sched_range_begin(sc, blockIdx.x / P.nH, P.per_head), P.work + h * 8, chunk, lane);
+      for (int c0, m; wq.next(sc, P.work + h * 8, chunk, lane, c0, m);) {
         ItemCursor cur;
         cur.seek(sc, c0);
         for (int t = 0; t < m; ++t, ++n, cur.next_item(sc)) {
