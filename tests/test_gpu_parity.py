@@ -395,6 +395,55 @@ def test_full_size_backward_properties(mm):
     assert torch.equal(one[0], dqkv[1:2])
 
 
+def test_dynamic_schedule_streams_and_slot_reuse(mm):
+    """The tcgen05 kernels hand out work through self-resetting device counters, one slot per launch out of a pool of
+    128 (tc_sched.cuh: ClassQueue, winattn_tc_fwd.cuh: work_slot).  (a) Launches on two streams at the same time use
+    different slots: results equal the serial ones.  (b) More launches than slots: a slot is re-armed by the last
+    CTA of the launch that used it, so launch 300 is as good as launch 1.  (c) A captured CUDA graph replays correctly
+    (its slot is baked into the kernel parameters)."""
+    grid, window, shift, nH, d = (16, 16, 16), (4, 4, 4), (2, 2, 2), 3, 32
+    C, N = nH * d, 64
+    g = torch.Generator(device="cuda").manual_seed(1)
+    args = (list(grid), list(window), list(shift), nH, mm.lib.SCORE_COSINE, mm.lib.MASK_SHIFT, 1.0, 0.0, 0, 0, mm.lib.PATH_AUTO)
+    bias = torch.randn(nH, N, N, generator=g, device="cuda")
+    hs = torch.rand(nH, generator=g, device="cuda") * 10 + 1
+    xs = [torch.randn(B, *grid, 3 * C, generator=g, device="cuda", dtype=torch.bfloat16) for B in (3, 5)]
+    dys = [torch.randn(x.shape[0], *grid, C, generator=g, device="cuda", dtype=torch.bfloat16) for x in xs]
+    assert mm.ops.winattn_path_name(xs[0], None, grid, window, shift, nH, mm.lib.SCORE_COSINE, mm.lib.MASK_SHIFT) == "tcgen05"
+
+    def run(x, dy):
+        out, lse = torch.ops.mmn_b200.winattn_fwd(x, None, bias, hs, None, *args)
+        dx = torch.ops.mmn_b200.winattn_bwd(dy, x, None, bias, hs, None, out, lse, *args, True)[0]
+        return out, dx
+
+    want = [run(x, dy) for x, dy in zip(xs, dys)]
+    torch.cuda.synchronize()
+    # (a) two streams, interleaved
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    got = [None, None]
+    for _ in range(10):
+        for k in (0, 1):
+            with torch.cuda.stream(streams[k]):
+                got[k] = run(xs[k], dys[k])
+    torch.cuda.synchronize()
+    for k in (0, 1):
+        assert torch.equal(got[k][0], want[k][0]), "forward differs when two streams run it concurrently"
+        assert rel_err(got[k][1], want[k][1]) < 1e-2
+    # (b) slot pool wrap-around
+    for _ in range(300):
+        out, _ = torch.ops.mmn_b200.winattn_fwd(xs[0], None, bias, hs, None, *args)
+    assert torch.equal(out, want[0][0])
+    # (c) graph replay
+    static_x = xs[1].clone()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        g_out, g_dx = run(static_x, dys[1])
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(g_out, want[1][0]) and rel_err(g_dx, want[1][1]) < 1e-2
+
+
 @pytest.mark.parametrize("rows,n_out", [(128, 96), (1000, 288), (4096 + 37, 192), (70000, 288), (300, 96)])
 def test_linear_bwd_fused(mm, rows, n_out):
     """Fused projection backward (linbwd_tc.cu): dx, dw, db of y = x W^T + b against fp64 on the same bf16 operands;
