@@ -526,6 +526,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       }
       TRB(n, 2);
       const float a_i = COS ? rec[i] * hscale : hscale;
+      const float a_l2 = a_i * kLog2e;
       const float4* krow = reinterpret_cast<const float4*>(rec + kN + qt * KP);
 
       // ---- (b) additive terms of this thread's logits (table, mask, -lse), log2 domain
@@ -569,8 +570,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int j = j4 * 4 + e;
-            const float u = __uint_as_float(raw[j]) * (COS ? rk[e] * a_i : a_i);
-            const float pj = fast_exp2(fmaf(u, kLog2e, p[j]));
+            const float pj = fast_exp2(fmaf(__uint_as_float(raw[j]), COS ? rk[e] * a_l2 : a_l2, p[j]));   // log2 domain: a_l2 = a_i log2(e)
             const float dpj = __uint_as_float(dpr[j]);
             delta = fmaf(pj, dpj, delta);
             p[j] = pj;
