@@ -242,19 +242,11 @@ def main():
         after backward -- the module has ~47 K parameters, so bucketing/overlap has nothing to hide."""
         if world == 1:
             return
-        off = 0
-        for p in params:
-            n = p.numel()
-            flat[off:off + n].copy_(p.grad.reshape(-1) if p.grad is not None else torch.zeros(n, device=dev))
-            off += n
-        dist.all_reduce(flat)
-        flat.div_(world)
-        off = 0
-        for p in params:
-            n = p.numel()
-            if p.grad is not None:
-                p.grad.copy_(flat[off:off + n].view_as(p.grad))
-            off += n
+        # four launches, not one per parameter: gather (cat), all-reduce (average), scatter (foreach copy)
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
+        torch.cat([g.reshape(-1) for g in grads], out=flat)
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        torch._foreach_copy_([g.view(-1) for g in grads], list(flat.split([g.numel() for g in grads])))
 
     L = math.prod(GRID)
     x = torch.randn(B, L, C, device=dev, dtype=torch.bfloat16, requires_grad=True)
