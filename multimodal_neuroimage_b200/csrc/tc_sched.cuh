@@ -206,22 +206,6 @@ __device__ __forceinline__ ItemGeom item_geom(const WinShape& S, const Sched& sc
   return g;
 }
 
-// Geometry of window w (linear index b * nW + row-major window position) of wrap class `cls`: what a warp that only
-// has the producer's item descriptor needs to address the window's TMA boxes.
-__device__ __forceinline__ ItemGeom geom_from_window(const WinShape& S, int cls, int w) {
-  ItemGeom g;
-  g.w = w;
-  g.cls = cls;
-  g.b = w / S.nW;
-  int wl = w - g.b * S.nW;
-  g.idx[2] = wl % S.nwin[2]; wl /= S.nwin[2];
-  g.idx[1] = wl % S.nwin[1];
-  g.idx[0] = wl / S.nwin[1];
-#pragma unroll
-  for (int a = 0; a < 3; ++a) g.start[a] = g.idx[a] * S.win[a] + S.shift[a];
-  return g;
-}
-
 // Shift-mask region id of in-window position p for a window of wrap class `cls`
 // (swin_v2_module.py:247-258: along a wrapped axis the last window straddles regions 1 | 2 at
 // win - shift; every other window lies in region 0).
@@ -284,17 +268,6 @@ __device__ __forceinline__ WinStart cursor_start(const WinShape& S, const ItemCu
   r.s0 = i0 * S.win[0] + S.shift[0]; r.s1 = i1 * S.win[1] + S.shift[1]; r.s2 = i2 * S.win[2] + S.shift[2];
   return r;
 }
-// The same from a linear window index (warps that only have the producer's item descriptor).
-__device__ __forceinline__ WinStart window_start(const WinShape& S, int w) {
-  WinStart r;
-  r.b = w / S.nW;
-  int wl = w - r.b * S.nW;
-  const int i2 = wl % S.nwin[2]; wl /= S.nwin[2];
-  const int i1 = wl % S.nwin[1], i0 = wl / S.nwin[1];
-  r.s0 = i0 * S.win[0] + S.shift[0]; r.s1 = i1 * S.win[1] + S.shift[1]; r.s2 = i2 * S.win[2] + S.shift[2];
-  return r;
-}
-
 template <int T>
 struct BoxPlan {
   int cls = -1, nbox = 0;

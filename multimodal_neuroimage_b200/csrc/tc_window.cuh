@@ -1,7 +1,6 @@
 // tc_window.cuh -- window geometry shared by the tensor-core forward and backward kernels:
-// a div/mod-free cursor over windows, the decomposition of a (possibly wrapped) shifted
-// window into contiguous TMA boxes, the piece-major token permutation that goes with it,
-// and the shift-mask region ids.  All closed forms restate SURVEY.md 8a (a1-a4).
+// the decomposition of a (possibly wrapped) shifted window into contiguous TMA boxes and the
+// piece-major token permutation that goes with it.  All closed forms restate SURVEY.md 8a (a1-a4).
 #pragma once
 
 #include <cuda.h>
@@ -24,70 +23,18 @@ struct WinShape {                 // right-aligned geometry: unused leading axes
   int n_windows;                  // batch * nW
 };
 
-// Mixed-radix position (batch, i0, i1, i2) of a window; advancing by a fixed stride is a
-// handful of adds with carries instead of the six div/mod a decode costs.
-struct WinCursor {
-  int b, i0, i1, i2;
-  __device__ __forceinline__ void init(const WinShape& S, int w) {
-    b = w / S.nW;
-    int wl = w - b * S.nW;
-    i2 = wl % S.nwin[2];
-    int t = wl / S.nwin[2];
-    i1 = t % S.nwin[1];
-    i0 = t / S.nwin[1];
-  }
-  __device__ __forceinline__ void advance(const WinShape& S, const WinCursor& step) {
-    i2 += step.i2; int c = i2 >= S.nwin[2]; i2 -= c ? S.nwin[2] : 0;
-    i1 += step.i1 + c; c = i1 >= S.nwin[1]; i1 -= c ? S.nwin[1] : 0;
-    i0 += step.i0 + c; c = i0 >= S.nwin[0]; i0 -= c ? S.nwin[0] : 0;
-    b += step.b + c;
-  }
-};
-
 struct WinGeom {
   int b, start[3], idx[3];
   int cls;       // wrap class: bit x set if the window wraps around the volume edge along axis x
 };
-
-__device__ __forceinline__ WinGeom window_geom(const WinShape& S, const WinCursor& c) {
-  WinGeom g;
-  g.b = c.b;
-  g.idx[0] = c.i0; g.idx[1] = c.i1; g.idx[2] = c.i2;
-  g.cls = 0;
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    g.start[a] = g.idx[a] * S.win[a] + S.shift[a];
-    if (g.start[a] + S.win[a] > S.grid[a]) g.cls |= 1 << a;
-  }
-  return g;
-}
 
 // A window that wraps along k axes is 2^k contiguous pieces of the source volume.  Piece q is
 // one TMA box and lands at rows [q*psize, (q+1)*psize) of the window's 64-row tile, so the
 // tile holds the window's tokens in PIECE-MAJOR order.  Attention is equivariant to that
 // permutation as long as bias / mask / lse are addressed through it (piece_position) and the
 // outputs are stored through the same boxes.  Axis 2 is the least significant wrapped axis.
-// `maps` has one tensor map per wrap class (box = half extent along every wrapped axis).
-template <bool LOAD>
-__device__ __forceinline__ void issue_window_boxes(const WinShape& S, const CUtensorMap* maps, const WinGeom& g, int chan,
-                                                   uint8_t* tile, uint64_t* bar) {
-  const int npieces = 1 << __popc(g.cls);
-  const int psize_bytes = (kN >> __popc(g.cls)) * 64;
-  const CUtensorMap* m = &maps[g.cls];
-  for (int q = 0; q < npieces; ++q) {
-    int c[3], qq = q;
-#pragma unroll
-    for (int a = 2; a >= 0; --a) {
-      int bit = (g.cls >> a) & 1;
-      c[a] = g.start[a] + (bit ? (qq & 1) * (S.win[a] >> 1) : 0);
-      if (bit) qq >>= 1;
-      if (c[a] >= S.grid[a]) c[a] -= S.grid[a];
-    }
-    uint8_t* p = tile + q * psize_bytes;
-    if (LOAD) tma_load_5d(m, bar, p, chan, c[2], c[1], c[0], g.b);
-    else tma_store_5d(m, p, chan, c[2], c[1], c[0], g.b);
-  }
-}
+// The tensor maps come one per wrap class (box = half extent along every wrapped axis); the boxes of an item are issued by
+// tc_sched.cuh (BoxPlan / issue_item_boxes).
 
 // Window position (row-major over the window) of tile row `row` for wrap class `cls`.
 __device__ __forceinline__ int piece_position(const WinShape& S, int cls, int row) {
@@ -103,21 +50,6 @@ __device__ __forceinline__ int piece_position(const WinShape& S, int cls, int ro
   if (cls & 2) { a1 += (q & 1) * seg[1]; q >>= 1; }
   if (cls & 1) { a0 += (q & 1) * seg[0]; }
   return (a0 * S.win[1] + a1) * S.win[2] + a2;
-}
-
-// Region id of in-window position p in the shifted frame (swin_v2_module.py:247-258).
-__device__ __forceinline__ int region_id(const WinShape& S, const WinGeom& g, int p) {
-  int a2 = p % S.win[2]; int t = p / S.win[2];
-  int a1 = t % S.win[1]; int a0 = t / S.win[1];
-  int a[3] = {a0, a1, a2};
-  int rid = 0;
-#pragma unroll
-  for (int x = 0; x < 3; ++x) {
-    int v = g.idx[x] * S.win[x] + a[x];
-    int r = S.shift[x] == 0 ? 0 : (v < S.grid[x] - S.win[x] ? 0 : (v < S.grid[x] - S.shift[x] ? 1 : 2));
-    rid = rid * 3 + r;
-  }
-  return rid;
 }
 
 // ------------------------------------------------------------------------------------------

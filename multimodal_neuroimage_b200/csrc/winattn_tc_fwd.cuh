@@ -38,7 +38,6 @@ constexpr int kWinBytes = 64 * 64;                 // one window's (64 tokens x 
 constexpr int kTile = 2 * kWinBytes;               // a pair's tile
 constexpr int kQRegion = 3 * kWinBytes;            // Q0 | zero block | Q1
 constexpr int kStageBytesF = kQRegion + 2 * kTile; // + K0 K1 + V0 V1
-constexpr int kPRegion = 3 * 8192;                 // (backward kernel) P0 (64 rows x 128 B) | zero block | P1
 constexpr int kGroupThreads = 128;
 constexpr int kGroupsF = 3;                        // softmax groups = items in flight
 constexpr int kProducerWarp = 4 * kGroupsF, kMmaWarp = kProducerWarp + 1, kStoreWarp = kProducerWarp + 2, kProducerWarpKV = kProducerWarp + 3;
