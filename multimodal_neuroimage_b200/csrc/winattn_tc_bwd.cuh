@@ -14,13 +14,17 @@
 // rowsum(P o dP) is computed in-tile, so `out` is never read.
 //
 // 768 threads, one CTA per SM (the kernel is latency-bound: 4 softmax warps per scheduler hide what 2 cannot):
-//   warps 0-15   softmax: FOUR threads per query row (16 keys each); never wait for the gradient MMAs.
-//                dbias accumulates in registers in the item's tile order and is flushed through the
-//                class's permutation when the wrap class changes (at most 8 times per CTA).
-//   warps 16-19  epilogue: one thread per row, dQ~/dK~/dV out of TMEM -> normalisation Jacobian ->
-//                bf16 staging tiles; column sums of dq, dk (= q/k projection bias gradients) by a
-//                warp transpose-reduce.
-//   warp 20 TMA producer, warp 21 MMA issuer, warp 22 TMA store + column sums of dv, warp 23 idle.
+//   warps 0-15   softmax: FOUR threads per query row (16 keys each).  Descriptor, lse and the q / k norms of an
+//                item arrive in shared memory with its stage (producer ring + the forward kernel's per-window
+//                record), so the loop carries no per-item state and issues no global load.  dbias accumulates
+//                in registers in the item's tile order and leaves through the table buffer when the wrap
+//                class changes (a CTA sees few classes: ClassQueue).
+//   warps 16-19  epilogue: one thread per row; takes its q / k rows and norms out of the stage and hands the stage
+//                back, then dQ~/dK~/dV out of TMEM -> normalisation Jacobian -> bf16 staging tiles.
+//   warp 20 TMA producer (schedule, descriptor ring, tiles, records), warp 21 MMA issuer, warp 22 TMA store,
+//   warp 23 column sums of dq, dk, dv (= projection bias gradients) read from the staging tiles.
+// Shared memory: 3 stages (Q0|Z|Q1, K, V, dO0|Z|dO1), P double-buffered and dS' around one shared zero block,
+// three staging tiles, the class table, the records.
 // Register budget by warpgroup (setmaxnreg): softmax 80 (= launch), epilogue 104, the rest 56: 512*80 + 128*104 + 128*56 = 768*80.
 #pragma once
 

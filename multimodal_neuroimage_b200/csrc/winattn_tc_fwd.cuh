@@ -3,26 +3,29 @@
 //
 // Tuned shape: 64-token windows (4x4x4, 8x8, or 64 pre-windowed tokens), head_dim 32.
 // A work item is a PAIR of windows of one wrap class x one head (tc_sched.cuh): 128 query rows
-// = the 128 TMEM lanes.  A CTA serves one head and a contiguous range of items.  352 threads,
-// one CTA per SM, warp-specialised, TWO items in flight (ping-pong groups A/B):
+// = the 128 TMEM lanes.  A CTA serves one head and claims items at run time (ClassQueue).  512 threads,
+// one CTA per SM, warp-specialised, THREE items in flight (softmax groups 0-2 take items n % 3):
 //
-//   warps 0-3   softmax group A (even items), warps 4-7 group B (odd items): ONE thread per query
-//               row, all 64 keys of its window.  tcgen05.ld the logits, multiply by the cosine
-//               normalisation x logit scale (or q scale), add the per-class table (relative position
-//               bias + shift mask, pre-permuted to the tile's token order, log2 domain), exp2
-//               softmax in fp32, P (bf16) into the 128B-swizzled A tile of the second MMA; one
-//               item later, O / l -> bf16 -> 64B-swizzled staging tile.  No cross-thread exchange
-//               except the per-key norms (one named barrier per group and item).
-//   warp 8      TMA producer: q/k/v tiles of the pair, gathered straight out of the un-windowed,
-//               un-shifted (B,D,H,W,3C) tensor with 5-D tensor maps: the cyclic shift is a
-//               coordinate offset, a window that wraps around the volume edge is fetched as its
-//               2/4/8 contiguous pieces (tc_window.cuh).  4-stage ring.
-//   warp 9      MMA issuer: S = Q K^T as ONE M128 N64 K64 product per pair -- the two windows are
+//   warps 0-11  three softmax groups of four warps: ONE thread per query row, all 64 keys of its window.
+//               tcgen05.ld the logits, multiply by the cosine normalisation x logit scale (or q scale), add
+//               the per-class table (relative position bias + shift mask, pre-permuted to the tile's token
+//               order, log2 domain), exp2 softmax in fp32 on register pairs, P (bf16) straight back into TMEM
+//               (tcgen05.st) as the A operand of the second MMA; then O / l -> bf16 -> 64B-swizzled staging
+//               tile.  No cross-thread exchange except the per-key norms (one named barrier per group and item).
+//               Also writes lse and the per-window record (norms, log2 lse) the backward kernel reads back.
+//   warp 12     TMA producer: schedule (atomic claims), item descriptors (shared-memory ring) and the Q tiles,
+//               gathered straight out of the un-windowed, un-shifted (B,D,H,W,3C) tensor with 5-D tensor maps:
+//               the cyclic shift is a coordinate offset, a window that wraps around the volume edge is fetched
+//               as its 2/4/8 contiguous pieces (tc_window.cuh).  5-stage ring.
+//   warp 15     TMA producer for the K and V tiles of the same items (follows the descriptor ring).
+//   warp 13     MMA issuer: S = Q K^T as ONE M128 N64 K64 product per pair -- the two windows are
 //               stacked along M and their channels along K, the cross terms multiply a shared
 //               zero block ([Q0;0] x K0^T + [0;Q1] x K1^T), so the accumulator holds exactly the two
-//               64x64 diagonal blocks in 64 TMEM columns; O = P V (M128 N32 K128, same zero-block
-//               trick on P).  S double-buffered (one buffer per group), O 2 x 2.
-//   warp 10     TMA store: staging tile -> global through the same boxes (= window_reverse + roll back).
+//               64x64 diagonal blocks in 64 TMEM columns; O = P V (M128 N32 K128, A = [P0 0; 0 P1] from TMEM).
+//               Per group: S 64 + P 64 + O 32 TMEM columns.  Polls its two queues (S, PV) without blocking.
+//   warp 14     TMA store: staging tile -> global through the same boxes (= window_reverse + roll back); a tile
+//               goes back to its group one item late.
+// Registers by setmaxnreg: softmax 136, the four single warps 104.
 #pragma once
 
 #include <cstdio>
