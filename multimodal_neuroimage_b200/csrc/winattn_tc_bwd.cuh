@@ -682,7 +682,7 @@ inline int winattn_bwd_launch(const mmn_winattn_desc* d, const void* q, const vo
   P.dbias = bias ? dbias : nullptr;
   P.dhead_scale = d->score_kind == MMN_SCORE_COSINE ? dhead_scale : nullptr;
   P.dcolsum = dcolsum;
-  P.work = work_slot(err, errlen);
+  P.work = work_slot(st, err, errlen);
   if (!P.work) return MMN_ERR_CUDA;
   const char* trace_path = getenv("MMN_TC_TRACE_BWD");
   P.trace = trace_setup(trace_path, st);

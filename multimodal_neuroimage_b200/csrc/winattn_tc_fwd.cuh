@@ -585,27 +585,33 @@ inline TraceCfg trace_setup(const char* path, cudaStream_t st) {
   return t;
 }
 
-// Work counters of the dynamic schedule: kWorkSlots self-resetting slots per device, handed out round-robin so that
-// launches in flight on different streams do not share one (a slot is re-armed by the last CTA of the launch using it).
-// Allocated on first use (not capturable: run the op once before capturing it in a CUDA graph, as PyTorch requires anyway).
-inline int* work_slot(char* err, size_t errlen) {
+// Work counters of the dynamic schedule: two pools of kWorkSlots self-resetting slots per device, handed out round-robin
+// so that launches in flight on different streams do not share one (a slot is re-armed by the last CTA of the launch
+// using it).  Launches recorded into a CUDA graph keep their slot for every replay, so they draw from a pool of their own
+// that eager launches never touch.  Allocated on first use (not capturable: run the op once before capturing it in a
+// CUDA graph, as PyTorch requires anyway).
+inline int* work_slot(cudaStream_t st, char* err, size_t errlen) {
   static std::mutex mu;
   static int* base[64] = {};
-  static unsigned next[64] = {};
+  static unsigned next[64][2] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) dev = 0;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+  const int pool = cap == cudaStreamCaptureStatusActive ? 1 : 0;
   std::lock_guard<std::mutex> lock(mu);
   if (!base[dev]) {
     int* p = nullptr;
-    if (cudaMalloc(&p, kWorkSlots * kWorkSlotInts * sizeof(int)) != cudaSuccess || cudaMemset(p, 0, kWorkSlots * kWorkSlotInts * sizeof(int)) != cudaSuccess) {
-      snprintf(err, errlen, "work counters: cudaMalloc/cudaMemset failed (first call inside a stream capture?)");
+    const size_t bytes = 2 * (size_t)kWorkSlots * kWorkSlotInts * sizeof(int);
+    if (pool == 1 || cudaMalloc(&p, bytes) != cudaSuccess || cudaMemset(p, 0, bytes) != cudaSuccess) {
+      snprintf(err, errlen, "work counters: not allocated yet and the stream is capturing (run the op once before capturing it), or cudaMalloc failed");
       cudaGetLastError();
       return nullptr;
     }
     base[dev] = p;
   }
-  return base[dev] + (size_t)(next[dev]++ % kWorkSlots) * kWorkSlotInts;
+  return base[dev] + ((size_t)pool * kWorkSlots + next[dev][pool]++ % kWorkSlots) * kWorkSlotInts;
 }
 
 inline int winattn_fwd_launch(const mmn_winattn_desc* d, const void* q, const void* k, const void* v, const float* bias,
@@ -625,7 +631,7 @@ inline int winattn_fwd_launch(const mmn_winattn_desc* d, const void* q, const vo
   P.scale = d->scale;
   P.bias = bias; P.head_scale = head_scale; P.mask = mask; P.lse = lse;
   P.slab = (long long)P.S.n_windows * d->num_heads * kN;
-  P.work = work_slot(err, errlen);
+  P.work = work_slot(st, err, errlen);
   if (!P.work) return MMN_ERR_CUDA;
   const char* trace_path = getenv("MMN_TC_TRACE");
   P.trace = trace_setup(trace_path, st);
