@@ -41,7 +41,10 @@
 extern "C" {
 #endif
 
-#define MMN_ABI_VERSION 1
+#define MMN_ABI_VERSION 2
+/* scratch every window-attention launch needs: the tensor-core kernels keep the counters of their run-time work queue
+ * there (zeroed by the library on the launch's stream; one buffer per launch, never shared between launches in flight) */
+#define MMN_WINATTN_WORK_BYTES 2048
 
 enum { MMN_OK = 0, MMN_ERR_INVALID = -1, MMN_ERR_UNSUPPORTED = -2, MMN_ERR_CUDA = -3 };
 enum { MMN_DT_F32 = 0, MMN_DT_BF16 = 1 };
@@ -99,10 +102,11 @@ uint64_t mmn_launch_count(void);
  * [0] log-sum-exp (batch*nW, num_heads, N) by window position; [1..3] one record per window and head,
  * (batch*nW, num_heads, 3, N) = 1/max(||q||,eps) | 1/max(||k||,eps) | log2-domain lse in the kernel's tile row order,
  * written by the tensor-core forward kernel for mmn_winattn_bwd, which must be given the same buffer
- * (the generic kernels read and write slab 0 only). */
+ * (the generic kernels read and write slab 0 only).  `workspace`: MMN_WINATTN_WORK_BYTES of scratch owned by this
+ * launch until it has completed, contents undefined on return. */
 int mmn_winattn_fwd(const mmn_winattn_desc* desc, const void* q, const void* k, const void* v,
                     const float* bias, const float* head_scale, const float* mask,
-                    void* out, float* lse, int device, void* stream);
+                    void* out, float* lse, void* workspace, int device, void* stream);
 
 /* dbias (num_heads,N,N) fp32 and dhead_scale (num_heads) fp32 are ACCUMULATED into (the
  * caller zeroes them); either may be NULL to skip.  `out` is the forward output (may be NULL:
@@ -110,7 +114,8 @@ int mmn_winattn_fwd(const mmn_winattn_desc* desc, const void* q, const void* k, 
  * ACCUMULATED, may be NULL: column sums over all tokens of dq, dk, dv -- the bias gradients of the
  * projections that produced q, k, v (replaces the reductions autograd does for F.linear's bias,
  * swin_v2_module.py:147-148, swinfusion_module.py:121,221-222).  `workspace`: scratch of
- * 2*batch*nW*num_heads*N floats (generic path only), contents undefined on return. */
+ * max(2*batch*nW*num_heads*N floats, MMN_WINATTN_WORK_BYTES), owned by this launch until it has completed, contents
+ * undefined on return. */
 int mmn_winattn_bwd(const mmn_winattn_desc* desc, const void* q, const void* k, const void* v,
                     const float* bias, const float* head_scale, const float* mask,
                     const void* out, const float* lse, const void* dout,

@@ -36,6 +36,8 @@ DT_F32, DT_BF16 = 0, 1
 SCORE_SCALED, SCORE_COSINE = 0, 1
 MASK_NONE, MASK_SHIFT, MASK_TENSOR, MASK_FUTURE = 0, 1, 2, 3
 PATH_AUTO, PATH_GENERIC, PATH_TCGEN05 = 0, 1, 2
+ABI_VERSION = 2
+WINATTN_WORK_BYTES = 2048
 
 EXPORTS = ["mmn_abi_version", "mmn_last_error", "mmn_winattn_path", "mmn_mha_path", "mmn_launch_count",
            "mmn_winattn_fwd", "mmn_winattn_bwd", "mmn_mha_fwd", "mmn_mha_bwd", "mmn_mha_avg_weights", "mmn_colsum",
@@ -127,7 +129,7 @@ def load() -> C.CDLL:
         lib.mmn_mha_path.restype = C.c_char_p
         lib.mmn_mha_path.argtypes = [C.POINTER(MhaDesc)]
         lib.mmn_winattn_fwd.restype = C.c_int
-        lib.mmn_winattn_fwd.argtypes = [C.POINTER(WinAttnDesc), vp, vp, vp, fp, fp, fp, vp, fp, C.c_int, vp]
+        lib.mmn_winattn_fwd.argtypes = [C.POINTER(WinAttnDesc), vp, vp, vp, fp, fp, fp, vp, fp, vp, C.c_int, vp]
         lib.mmn_winattn_bwd.restype = C.c_int
         lib.mmn_winattn_bwd.argtypes = [C.POINTER(WinAttnDesc), vp, vp, vp, fp, fp, fp, vp, fp, vp, vp, vp, vp, fp, fp, fp, fp,
                                         C.c_int, vp]
@@ -151,7 +153,7 @@ def load() -> C.CDLL:
         lib.mmn_linear_bwd.restype = C.c_int
         lib.mmn_linear_bwd.argtypes = [vp, vp, vp, vp, fp, fp, vp, C.c_int, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
                                        C.c_int64, C.c_int, vp]
-        if lib.mmn_abi_version() != 1:
+        if lib.mmn_abi_version() != ABI_VERSION:
             raise RuntimeError("libmmn_b200.so ABI version mismatch")
         _lib = lib
         return lib

@@ -551,8 +551,7 @@ colsum_kernel(const T* __restrict__ x, long long rows, int cols, long long row_s
 #pragma unroll
   for (int e = 0; e < V; ++e) red[threadIdx.x * V + e] = ty < rpb ? acc[e] : 0.f;
   __syncthreads();
-  if (threadIdx.x < vcols * V) {
-    const int c = threadIdx.x;                        // column
+  for (int c = threadIdx.x; c < vcols * V; c += 256) {   // column (cols may exceed the block size: up to 2048)
     float s = 0.f;
     for (int y = 0; y < rpb; ++y) s += red[(y * vcols + c / V) * V + c % V];
     atomicAdd(out + c, s);

@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "generic_launch.h"
 
 namespace mmn {
@@ -70,8 +72,9 @@ __global__ void cpb_scatter_kernel(const float* __restrict__ dbias, const long l
 
 // Backward of the MLP.  A block owns 32 hidden units; its 16 warps split the T table entries (warp w takes
 // t = w, w + 16, ...), every thread recomputes its unit's activation and accumulates dW2[:, j], dW1[j, :], db1[j] for
-// its slice in registers; the 16 slices are then summed through shared memory in a fixed order (no atomics:
-// deterministic).  g[t][h] = d tab[t][h] is staged in shared memory eight heads at a time:
+// its slice in registers; the 16 slices are then summed through shared memory in a fixed order (this kernel uses no
+// atomics; the scatter of dbias into the table before it, cpb_scatter_kernel, does -- float atomicAdd, so the
+// last bits of the CPB gradients can differ from run to run).  g[t][h] = d tab[t][h] is staged in shared memory eight heads at a time:
 // d/dx 16 sigmoid(x) = tab16 (1 - tab16 / 16).  (One thread per hidden unit walking all T entries alone -- four blocks
 // on four SMs -- took 58 us at BASELINE cfg2, 4 % of the whole fused-module step.)
 constexpr int kCpbBwdUnits = 32, kCpbBwdSlices = 16;
@@ -158,6 +161,11 @@ cpb_mlp_bwd_kernel(const float* __restrict__ coords, const float* __restrict__ w
   }
 }
 
+// dynamic shared memory of cpb_mlp_bwd_kernel: coords [T][3] + g [T][8] + the slice-reduction buffer
+size_t cpb_bwd_smem_bytes(int T) {
+  return ((size_t)((T * kCpbMaxIn + 3) & ~3) + (size_t)T * 8 + (size_t)kCpbBwdSlices * 8 * kCpbBwdUnits) * sizeof(float);
+}
+
 cudaError_t cpb_bias_fwd(const float* coords, const float* w1, const float* b1, const float* w2, const long long* index, int T,
                          int n_in, int J, int nH, int NN, float* tab16, float* bias, cudaStream_t st, int* launches) {
   cpb_table_kernel<<<T, 128, 0, st>>>(coords, w1, b1, w2, n_in, J, nH, tab16);
@@ -173,7 +181,11 @@ cudaError_t cpb_bias_bwd(const float* coords, const float* w1, const float* b1, 
   cudaError_t e = cudaMemsetAsync(dtab16, 0, (size_t)T * nH * sizeof(float), st);
   if (e != cudaSuccess) return e;
   cpb_scatter_kernel<<<(NN + 255) / 256, 256, 0, st>>>(dbias, index, NN, nH, dtab16);
-  const size_t smem = ((size_t)((T * kCpbMaxIn + 3) & ~3) + (size_t)T * 8 + (size_t)kCpbBwdSlices * 8 * kCpbBwdUnits) * sizeof(float);
+  const size_t smem = cpb_bwd_smem_bytes(T);
+  if (smem > 48 * 1024) {      // 2-D windows of 16 (T = 961), 3-D windows of 6 / 7 (T = 1331 / 2197): opt in to large dynamic smem
+    static std::once_flag once;
+    std::call_once(once, [] { cudaFuncSetAttribute(cpb_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  }
   cpb_mlp_bwd_kernel<<<(J + kCpbBwdUnits - 1) / kCpbBwdUnits, kCpbBwdUnits * kCpbBwdSlices, smem, st>>>(coords, w1, b1, w2, tab16, dtab16, T,
                                                                                                     n_in, J, nH, dw1, db1, dw2);
   e = cudaGetLastError();

@@ -16,6 +16,7 @@ cudaError_t generic_avg_weights(const GenericProblem& P, int io_dtype, int batch
 cudaError_t colsum(int io_dtype, const void* x, long long rows, int cols, long long row_stride, float* out, cudaStream_t st,
                    int* launches);
 // continuous relative-position bias (cpb_bias.cu)
+size_t cpb_bwd_smem_bytes(int T);
 cudaError_t cpb_bias_fwd(const float* coords, const float* w1, const float* b1, const float* w2, const long long* index, int T,
                          int n_in, int J, int nH, int NN, float* tab16, float* bias, cudaStream_t st, int* launches);
 cudaError_t cpb_bias_bwd(const float* coords, const float* w1, const float* b1, const float* w2, const long long* index,

@@ -138,10 +138,11 @@ const char* mmn_mha_path(const mmn_mha_desc* d) {
 }
 
 int mmn_winattn_fwd(const mmn_winattn_desc* d, const void* q, const void* k, const void* v, const float* bias,
-                    const float* head_scale, const float* mask, void* out, float* lse, int device, void* stream) {
+                    const float* head_scale, const float* mask, void* out, float* lse, void* workspace, int device,
+                    void* stream) {
   int rc = validate_win(d);
   if (rc) return rc;
-  if (!q || !k || !v || !out || !lse) return fail(MMN_ERR_INVALID, "null tensor pointer");
+  if (!q || !k || !v || !out || !lse || !workspace) return fail(MMN_ERR_INVALID, "null tensor pointer");
   if (d->score_kind == MMN_SCORE_COSINE && !head_scale) return fail(MMN_ERR_INVALID, "cosine attention needs head_scale");
   if (d->mask_kind == MMN_MASK_TENSOR && !mask) return fail(MMN_ERR_INVALID, "MMN_MASK_TENSOR needs a mask");
   if (!have_device()) return fail(MMN_ERR_CUDA, "no CUDA device: libmmn_b200 has no CPU path");
@@ -152,7 +153,7 @@ int mmn_winattn_fwd(const mmn_winattn_desc* d, const void* q, const void* k, con
   bool tc_ok = why == nullptr;
   if (d->path == MMN_PATH_TCGEN05 && !tc_ok) return fail(MMN_ERR_UNSUPPORTED, "shape not supported by the tcgen05 path: %s", why);
   if (d->path != MMN_PATH_GENERIC && tc_ok) {
-    rc = mmn::tc::winattn_fwd(d, q, k, v, bias, head_scale, mask, out, lse, st, g_err, sizeof(g_err));
+    rc = mmn::tc::winattn_fwd(d, q, k, v, bias, head_scale, mask, out, lse, workspace, st, g_err, sizeof(g_err));
     if (rc == MMN_OK) g_launches.fetch_add(1, std::memory_order_relaxed);
     return rc;
   }
@@ -249,6 +250,7 @@ int mmn_colsum(const void* x, int io_dtype, int64_t rows, int32_t cols, int64_t 
 static int cpb_check(int T, int n_in, int J, int nH, int NN) {
   if (T < 1 || n_in < 1 || n_in > 3 || J < 1 || nH < 1 || nH > 64 || NN < 1) return fail(MMN_ERR_INVALID, "bad cpb_bias sizes");
   if ((long long)T * nH > 12288) return fail(MMN_ERR_UNSUPPORTED, "cpb_bias: T * num_heads = %lld > 12288", (long long)T * nH);
+  if (mmn::cpb_bwd_smem_bytes(T) > 227 * 1024) return fail(MMN_ERR_UNSUPPORTED, "cpb_bias: table of %d entries exceeds the backward kernel's shared memory", T);
   if (!have_device()) return fail(MMN_ERR_CUDA, "no CUDA device: libmmn_b200 has no CPU path");
   return MMN_OK;
 }

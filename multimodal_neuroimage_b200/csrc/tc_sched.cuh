@@ -137,7 +137,7 @@ struct ItemCursor {
 // per-class item costs are.  The next claim is always in flight while the current chunk is processed.
 // All lanes of the producer warp call next() together; lane 0 does the atomics.
 // ------------------------------------------------------------------------------------------
-constexpr int kWorkDone = 511, kWorkSlotInts = 512, kWorkSlots = 128;   // per slot: 63 heads x 8 classes, [511] = CTAs that ran dry
+constexpr int kWorkDone = 511, kWorkSlotInts = 512;   // counters of one launch: 63 heads x 8 classes (MMN_WINATTN_WORK_BYTES)
 struct ClassQueue {
   int cls, pend, tried;
   // items per claim: the wrapped classes are small and their items cost up to 3x (2^k boxes per tile), so their chunks
@@ -172,15 +172,6 @@ struct ClassQueue {
       if (++tried >= 8) return false;
       cls = (cls + 1) & 7;
       if (lane == 0) pend = atomicAdd(work + cls, chunk_of(chunk, cls));
-    }
-  }
-  // called by lane 0 after the CTA ran dry: the last CTA re-arms the counters for the next launch that uses this slot
-  static __device__ __forceinline__ void retire(int* slot, int num_heads) {
-    __threadfence();
-    if (atomicAdd(slot + kWorkDone, 1) == (int)gridDim.x - 1) {
-      for (int i = 0; i < num_heads * 8; ++i) slot[i] = 0;
-      slot[kWorkDone] = 0;
-      __threadfence();
     }
   }
 };

@@ -73,15 +73,16 @@ const char* fwd_why_not(const mmn_winattn_desc* d) { return fwd_why_not_impl(d);
 const char* bwd_why_not(const mmn_winattn_desc* d) { return bwd_why_not_impl(d); }
 
 int winattn_fwd(const mmn_winattn_desc* d, const void* q, const void* k, const void* v, const float* bias,
-                const float* head_scale, const float* mask, void* out, float* lse, cudaStream_t st, char* err, size_t errlen) {
-  return winattn_fwd_launch(d, q, k, v, bias, head_scale, mask, out, lse, st, err, errlen);
+                const float* head_scale, const float* mask, void* out, float* lse, void* workspace, cudaStream_t st, char* err,
+                size_t errlen) {
+  return winattn_fwd_launch(d, q, k, v, bias, head_scale, mask, out, lse, workspace, st, err, errlen);
 }
 
 int winattn_bwd(const mmn_winattn_desc* d, const void* q, const void* k, const void* v, const float* bias,
                 const float* head_scale, const float* mask, const void* /*out*/, const float* lse, const void* dout, void* dq,
-                void* dk, void* dv, float* dbias, float* dhead_scale, float* dcolsum, float* /*workspace*/, cudaStream_t st,
+                void* dk, void* dv, float* dbias, float* dhead_scale, float* dcolsum, float* workspace, cudaStream_t st,
                 char* err, size_t errlen, int* launches) {
-  int rc = winattn_bwd_launch(d, q, k, v, bias, head_scale, mask, lse, dout, dq, dk, dv, dbias, dhead_scale, dcolsum, st, err, errlen);
+  int rc = winattn_bwd_launch(d, q, k, v, bias, head_scale, mask, lse, dout, dq, dk, dv, dbias, dhead_scale, dcolsum, workspace, st, err, errlen);
   if (rc == MMN_OK) ++*launches;
   return rc;
 }

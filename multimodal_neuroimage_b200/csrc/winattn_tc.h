@@ -10,7 +10,8 @@ namespace mmn { namespace tc {
 const char* fwd_why_not(const mmn_winattn_desc* d);
 const char* bwd_why_not(const mmn_winattn_desc* d);
 int winattn_fwd(const mmn_winattn_desc* d, const void* q, const void* k, const void* v, const float* bias,
-                const float* head_scale, const float* mask, void* out, float* lse, cudaStream_t st, char* err, size_t errlen);
+                const float* head_scale, const float* mask, void* out, float* lse, void* workspace, cudaStream_t st, char* err,
+                size_t errlen);
 int winattn_bwd(const mmn_winattn_desc* d, const void* q, const void* k, const void* v, const float* bias,
                 const float* head_scale, const float* mask, const void* out, const float* lse, const void* dout, void* dq,
                 void* dk, void* dv, float* dbias, float* dhead_scale, float* dcolsum, float* workspace, cudaStream_t st,

@@ -70,7 +70,7 @@ struct BwdParams {
   float* dbias;         // (nH, 64, 64) accumulated, may be null
   float* dhead_scale;   // (nH) accumulated, may be null
   float* dcolsum;       // (3, nH*32) accumulated column sums of dq, dk, dv (= projection bias grads), may be null
-  int* work;            // dynamic schedule counters (winattn_tc_fwd.cuh: work_slot)
+  int* work;            // dynamic schedule counters (winattn_tc_fwd.cuh: arm_work_counters)
   TraceCfg trace;       // debug: clock64 stamps of one CTA (MMN_TC_TRACE_BWD=<file>)
 };
 
@@ -195,7 +195,6 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
         }
         __syncwarp();
       }
-      if (lane == 0) ClassQueue::retire(P.work, P.nH);
     } else if (warp == kMmaWarpB) {
       // ============================== MMA issuer ==============================
       constexpr uint32_t idescS = umma_idesc_bf16(128, 64, 0, 0);     // A K-major, B K-major
@@ -661,7 +660,7 @@ inline const char* bwd_why_not_impl(const mmn_winattn_desc* d) {
 
 inline int winattn_bwd_launch(const mmn_winattn_desc* d, const void* q, const void* k, const void* v, const float* bias,
                               const float* head_scale, const float* mask, const float* lse, const void* dout, void* dq, void* dk,
-                              void* dv, float* dbias, float* dhead_scale, float* dcolsum, cudaStream_t st, char* err, size_t errlen) {
+                              void* dv, float* dbias, float* dhead_scale, float* dcolsum, void* workspace, cudaStream_t st, char* err, size_t errlen) {
   BwdParams P;
   P.S = shape_from(d);
   P.sc = make_sched(P.S, d->batch, true);
@@ -682,7 +681,7 @@ inline int winattn_bwd_launch(const mmn_winattn_desc* d, const void* q, const vo
   P.dbias = bias ? dbias : nullptr;
   P.dhead_scale = d->score_kind == MMN_SCORE_COSINE ? dhead_scale : nullptr;
   P.dcolsum = dcolsum;
-  P.work = work_slot(st, err, errlen);
+  P.work = arm_work_counters(workspace, st, err, errlen);
   if (!P.work) return MMN_ERR_CUDA;
   const char* trace_path = getenv("MMN_TC_TRACE_BWD");
   P.trace = trace_setup(trace_path, st);

@@ -74,7 +74,7 @@ struct FwdParams {
   float* lse;         // (B*nW, nH, 64) log-sum-exp by window position, then one record per window and head for the backward
   long long slab;     //   kernel, (B*nW, nH, 3, 64) in the tile's (piece-major) row order: 1/max(||q||,eps) | 1/max(||k||,eps) |
                       //   log2-domain lse (one 768-byte bulk copy per window there); slab = B*nW*nH*64
-  int* work;          // dynamic schedule counters (tc_sched.cuh: ClassQueue), self-resetting
+  int* work;          // dynamic schedule counters (tc_sched.cuh: ClassQueue): this launch's own, zeroed before it
   TraceCfg trace;     // debug: per-phase clock64 stamps of one CTA (MMN_TC_TRACE=<file>), else buf == null
 };
 
@@ -236,7 +236,6 @@ winattn_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
         }
         __syncwarp();
       }
-      if (lane == 0) ClassQueue::retire(P.work, P.nH);
     } else if (warp == kMmaWarp) {
       // ============================== MMA issuer ==============================
       constexpr uint32_t idescS = umma_idesc_bf16(128, 64, 0, 0);    // [Q0;0],[0;Q1] (K-major) x K0,K1 (K-major)
@@ -585,38 +584,22 @@ inline TraceCfg trace_setup(const char* path, cudaStream_t st) {
   return t;
 }
 
-// Work counters of the dynamic schedule: two pools of kWorkSlots self-resetting slots per device, handed out round-robin
-// so that launches in flight on different streams do not share one (a slot is re-armed by the last CTA of the launch
-// using it).  Launches recorded into a CUDA graph keep their slot for every replay, so they draw from a pool of their own
-// that eager launches never touch.  Allocated on first use (not capturable: run the op once before capturing it in a
-// CUDA graph, as PyTorch requires anyway).
-inline int* work_slot(cudaStream_t st, char* err, size_t errlen) {
-  static std::mutex mu;
-  static int* base[64] = {};
-  static unsigned next[64][2] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64) dev = 0;
-  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
-  const int pool = cap == cudaStreamCaptureStatusActive ? 1 : 0;
-  std::lock_guard<std::mutex> lock(mu);
-  if (!base[dev]) {
-    int* p = nullptr;
-    const size_t bytes = 2 * (size_t)kWorkSlots * kWorkSlotInts * sizeof(int);
-    if (pool == 1 || cudaMalloc(&p, bytes) != cudaSuccess || cudaMemset(p, 0, bytes) != cudaSuccess) {
-      snprintf(err, errlen, "work counters: not allocated yet and the stream is capturing (run the op once before capturing it), or cudaMalloc failed");
-      cudaGetLastError();
-      return nullptr;
-    }
-    base[dev] = p;
+// Work counters of the dynamic schedule (tc_sched.cuh: ClassQueue): kWorkSlotInts ints that belong to ONE launch -- the
+// caller's `workspace` -- zeroed on the launch's stream right before the kernel (a memset node when captured).  Nothing
+// is shared between launches, so launches on different streams, captured graphs replayed side by side and any number
+// of launches in flight are independent by construction.
+inline int* arm_work_counters(void* workspace, cudaStream_t st, char* err, size_t errlen) {
+  if (!workspace || reinterpret_cast<uintptr_t>(workspace) % 4) { snprintf(err, errlen, "workspace missing or misaligned"); return nullptr; }
+  if (cudaMemsetAsync(workspace, 0, kWorkSlotInts * sizeof(int), st) != cudaSuccess) {
+    snprintf(err, errlen, "cudaMemsetAsync(work counters): %s", cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
   }
-  return base[dev] + ((size_t)pool * kWorkSlots + next[dev][pool]++ % kWorkSlots) * kWorkSlotInts;
+  return static_cast<int*>(workspace);
 }
 
 inline int winattn_fwd_launch(const mmn_winattn_desc* d, const void* q, const void* k, const void* v, const float* bias,
-                              const float* head_scale, const float* mask, void* out, float* lse, cudaStream_t st, char* err,
-                              size_t errlen) {
+                              const float* head_scale, const float* mask, void* out, float* lse, void* workspace, cudaStream_t st,
+                              char* err, size_t errlen) {
   FwdParams P;
   P.S = shape_from(d);
   P.sc = make_sched(P.S, d->batch, false);
@@ -631,7 +614,7 @@ inline int winattn_fwd_launch(const mmn_winattn_desc* d, const void* q, const vo
   P.scale = d->scale;
   P.bias = bias; P.head_scale = head_scale; P.mask = mask; P.lse = lse;
   P.slab = (long long)P.S.n_windows * d->num_heads * kN;
-  P.work = work_slot(st, err, errlen);
+  P.work = arm_work_counters(workspace, st, err, errlen);
   if (!P.work) return MMN_ERR_CUDA;
   const char* trace_path = getenv("MMN_TC_TRACE");
   P.trace = trace_setup(trace_path, st);

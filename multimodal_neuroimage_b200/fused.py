@@ -36,7 +36,8 @@ class WindowAttentionModuleFn(torch.autograd.Function):
         """x (B, L, C) [queries; also keys/values when y is None]; y (B, L, C) or None.
         self:  w_a (3C, C), b_a (3C) | None;  w_b, b_b = None.
         cross: w_a (C, C) for q from x;  w_b (2C, C), b_b for kv from y."""
-        cdt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+        odt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+        cdt = torch.bfloat16 if odt == torch.float16 else odt     # fp16 autocast (trainer.py:378) runs as bf16 (ops.kernel_io)
         B, L, C = x.shape
         with torch.autocast("cuda", enabled=False):
             cast = lambda t: None if t is None else t.to(cdt)
@@ -47,7 +48,7 @@ class WindowAttentionModuleFn(torch.autograd.Function):
             p, seed, off = dropout
             out, lse = torch.ops.mmn_b200.winattn_fwd(a, b, bias, head_scale, None, list(grid), list(window), list(shift),
                                                       num_heads, score_kind, mask_kind, scale, p, seed, off, path)
-            res = F.linear(out.view(B * L, C), wp, bp).view(B, L, C)
+            res = F.linear(out.view(B * L, C), wp, bp).view(B, L, C).to(odt)
         ctx.save_for_backward(xc, yc, a, b, out, lse, wa, wb, wp, bias, head_scale)
         ctx.cfg = (list(grid), list(window), list(shift), num_heads, score_kind, mask_kind, scale, p, seed, off, path)
         ctx.meta = (x.dtype, None if y is None else y.dtype, w_a.dtype, None if b_a is None else b_a.dtype,

@@ -117,9 +117,11 @@ class MultiheadAttention(nn.Module):
             mask = attn_mask.to(device=q.device, dtype=torch.float32).contiguous()
 
         p, seed, off = ops.next_dropout_stream(self.attn_dropout, self.training, q.device)
+        io = q.dtype                                   # float16 under the reference trainer's autocast: kernels run it as bf16
+        q, k, v = ops.kernel_io(q), ops.kernel_io(k), ops.kernel_io(v)
         attn, lse = torch.ops.mmn_b200.mha_fwd(q, k, v, mask, self.num_heads_mult, kind, diag, float(self.scaling),
                                                p, seed, off)
-        attn = self.out_proj(attn)
+        attn = self.out_proj(attn.to(io))
         need = self.need_weights if need_weights is None else need_weights
         weights = None
         if need:

@@ -15,10 +15,12 @@ from __future__ import annotations
 import math
 from typing import Optional, Sequence
 
+import numpy as np  # noqa: F401  (star-exported: the reference's model.py takes `np` from here, model.py:15)
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 import torch.utils.checkpoint as checkpoint
+from torch.nn.init import trunc_normal_  # noqa: F401  (the reference re-exports timm's; model.py:625,680,1085 call it)
 
 from .. import _lib, fused, geometry, ops
 
@@ -142,7 +144,24 @@ class WindowAttention(nn.Module):
 
     # -- pieces that stay in PyTorch: tiny, and they need autograd through learnable tables --
     def position_bias(self) -> torch.Tensor:
-        """(nH, N, N) fp32 = 16*sigmoid(cpb_mlp(table))[index] (swin_v2_module.py:158-162)."""
+        """(nH, N, N) fp32 = 16*sigmoid(cpb_mlp(table))[index] (swin_v2_module.py:158-162).  The reference re-runs the
+        MLP in every forward of every block; outside training (eval mode, or no gradient wanted) the table is a constant
+        of the weights and is cached -- keyed on the weights' in-place version counters, so an optimizer step,
+        `load_state_dict` or `.to()` invalidates it by construction."""
+        params = (self.cpb_mlp[0].weight, self.cpb_mlp[0].bias, self.cpb_mlp[2].weight)
+        cacheable = not (torch.is_grad_enabled() and any(p.requires_grad for p in params))
+        if cacheable:
+            key = tuple((p.data_ptr(), p._version) for p in params)
+            hit = getattr(self, "_bias_cache", None)
+            if hit is not None and hit[0] == key:
+                return hit[1]
+            with torch.no_grad():
+                b = self._position_bias()
+            self._bias_cache = (key, b)
+            return b
+        return self._position_bias()
+
+    def _position_bias(self) -> torch.Tensor:
         N = math.prod(self.window_size)
         with torch.autocast(device_type="cuda", enabled=False):
             coords = self.relative_coords_table.float().reshape(-1, self.relative_coords_table.shape[-1])
@@ -170,10 +189,10 @@ class WindowAttention(nn.Module):
 
     def _core(self, qkv, grid, window, shift, mask_kind, mask):
         p, seed, off = ops.next_dropout_stream(self.attn_drop.p, self.training, qkv.device)
-        out, _ = torch.ops.mmn_b200.winattn_fwd(qkv, None, self.position_bias(), self.head_scale(), mask,
+        out, _ = torch.ops.mmn_b200.winattn_fwd(ops.kernel_io(qkv), None, self.position_bias(), self.head_scale(), mask,
                                                 list(grid), list(window), list(shift), self.num_heads_swin,
                                                 _lib.SCORE_COSINE, mask_kind, 1.0, p, seed, off, self.kernel_path)
-        return out
+        return out.to(qkv.dtype)
 
     def forward(self, x, mask=None):
         """x: (num_windows*B, N, C) already partitioned; mask: (nW, N, N) additive or None."""

@@ -14,7 +14,9 @@ import math
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F  # noqa: F401  (star-exported like the reference's)
 import torch.utils.checkpoint as checkpoint
+from torch.nn.init import trunc_normal_  # noqa: F401  (model.py:1229,1374 call it through the star import)
 
 from .. import _lib, fused, geometry, ops
 from .swin_v2_module import DropPath, _GatherRows, to_2tuple, to_ntuple, window_partition, window_reverse
@@ -63,10 +65,10 @@ class _TableBiasAttention(nn.Module):
 
     def _core(self, a, b, grid, window, shift, mask_kind, mask):
         p, seed, off = ops.next_dropout_stream(self.attn_drop.p, self.training, a.device)
-        out, _ = torch.ops.mmn_b200.winattn_fwd(a, b, self.position_bias(), None, mask, list(grid), list(window),
-                                                list(shift), self.num_heads, _lib.SCORE_SCALED, mask_kind,
-                                                float(self.scale), p, seed, off, self.kernel_path)
-        return out
+        out, _ = torch.ops.mmn_b200.winattn_fwd(ops.kernel_io(a), ops.kernel_io(b), self.position_bias(), None, mask,
+                                                list(grid), list(window), list(shift), self.num_heads, _lib.SCORE_SCALED,
+                                                mask_kind, float(self.scale), p, seed, off, self.kernel_path)
+        return out.to(a.dtype)
 
     @staticmethod
     def _mask_args(mask, device):
@@ -468,3 +470,33 @@ class PatchUnEmbed(nn.Module):
 
     def flops(self):
         return 0
+
+
+class Upsample(nn.Sequential):
+    """Conv + PixelShuffle upsampler (swinfusion_module.py:1018-1040; `model.SwinFusion` builds it for
+    `upsampler='pixelshuffle'`, model.py:1348).  scale = 2^k: k x (Conv2d(f, 4f, 3) + PixelShuffle(2)); scale = 3: one
+    Conv2d(f, 9f, 3) + PixelShuffle(3)."""
+
+    def __init__(self, scale, num_feat):
+        layers = []
+        if scale >= 1 and scale & (scale - 1) == 0:
+            for _ in range(scale.bit_length() - 1):
+                layers += [nn.Conv2d(num_feat, 4 * num_feat, 3, 1, 1), nn.PixelShuffle(2)]
+        elif scale == 3:
+            layers += [nn.Conv2d(num_feat, 9 * num_feat, 3, 1, 1), nn.PixelShuffle(3)]
+        else:
+            raise ValueError(f'scale {scale} is not supported. Supported scales: 2^n and 3.')
+        super().__init__(*layers)
+
+
+class UpsampleOneStep(nn.Sequential):
+    """One Conv2d(f, scale^2 * out, 3) + PixelShuffle(scale) (swinfusion_module.py:1043-1061; model.py:1352)."""
+
+    def __init__(self, scale, num_feat, num_out_ch, input_resolution=None):
+        self.num_feat = num_feat
+        self.input_resolution = input_resolution
+        super().__init__(nn.Conv2d(num_feat, (scale ** 2) * num_out_ch, 3, 1, 1), nn.PixelShuffle(scale))
+
+    def flops(self):
+        H, W = self.input_resolution
+        return H * W * self.num_feat * 3 * 9

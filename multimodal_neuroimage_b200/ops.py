@@ -28,6 +28,13 @@ Tensor = torch.Tensor
 _DT = {torch.float32: _lib.DT_F32, torch.bfloat16: _lib.DT_BF16}
 
 
+def kernel_io(t: Optional[Tensor]) -> Optional[Tensor]:
+    """Activation dtype the kernels run in.  The kernels take float32 and bfloat16; float16 -- what the reference
+    trainer's `torch.cuda.amp.autocast()` produces (trainer.py:378, `--amp` default on, main.py:88) -- goes through them
+    as bfloat16 (same 16-bit traffic, fp32 softmax / accumulation inside; the caller casts the result back)."""
+    return t.to(torch.bfloat16) if t is not None and t.dtype == torch.float16 else t
+
+
 def _require_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -132,9 +139,10 @@ def winattn_fwd(a: Tensor, b: Optional[Tensor], bias: Optional[Tensor], head_sca
     for t in (bias, head_scale, mask):
         if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
             raise RuntimeError("bias / head_scale / mask must be contiguous float32")
+    work = torch.empty(_lib.WINATTN_WORK_BYTES, dtype=torch.uint8, device=a.device)   # this launch's work-queue counters
     with _timed("winattn_fwd", a):
         _lib.check(lib.mmn_winattn_fwd(C.byref(d), q, k, v, _ptr(bias), _ptr(head_scale), _ptr(mask), _ptr(out),
-                                       _ptr(lse), a.device.index, _stream(a)), "mmn_winattn_fwd")
+                                       _ptr(lse), _ptr(work), a.device.index, _stream(a)), "mmn_winattn_fwd")
     return out, lse
 
 
@@ -179,7 +187,7 @@ def winattn_bwd(dout: Tensor, a: Tensor, b: Optional[Tensor], bias: Optional[Ten
     d.do_row_stride = Cc
     dbias = torch.zeros_like(bias) if bias is not None else a.new_empty(0, dtype=torch.float32)
     dhs = torch.zeros_like(head_scale) if head_scale is not None else a.new_empty(0, dtype=torch.float32)
-    ws = lse.new_empty(2 * lse[0].numel())
+    ws = lse.new_empty(max(2 * lse[0].numel(), _lib.WINATTN_WORK_BYTES // 4))
     dcs = torch.zeros(3, Cc, dtype=torch.float32, device=a.device) if want_colsum else a.new_empty(0, dtype=torch.float32)
     with _timed("winattn_bwd", a):
         _lib.check(lib.mmn_winattn_bwd(C.byref(d), q, k, v, _ptr(bias), _ptr(head_scale), _ptr(mask), _ptr(out), _ptr(lse),
@@ -355,7 +363,8 @@ def cpb_bias_supported(coords: Tensor, w1: Tensor, w2: Tensor) -> bool:
     <= 64 heads, table x heads <= 12288)."""
     ok = coords.is_cuda and all(t.dtype == torch.float32 for t in (coords, w1, w2))
     T = coords.numel() // coords.shape[-1]
-    return bool(ok and coords.shape[-1] <= 3 and w2.shape[0] <= 64 and T * w2.shape[0] <= 12288)
+    # backward kernel's dynamic shared memory (csrc/cpb_bias.cu: cpb_bwd_smem_bytes): (11 T + 4096) floats <= 227 KB
+    return bool(ok and coords.shape[-1] <= 3 and w2.shape[0] <= 64 and T * w2.shape[0] <= 12288 and (11 * T + 4100) * 4 <= 227 * 1024)
 
 
 @torch.library.custom_op("mmn_b200::cpb_bias_fwd", mutates_args=())

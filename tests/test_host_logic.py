@@ -127,7 +127,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.mmn_abi_version() == 1
+    assert lib.mmn_abi_version() == _lib.ABI_VERSION
 
 
 def test_ctypes_structs_match_header(tmp_path):
@@ -170,7 +170,7 @@ def test_no_cpu_fallback():
     d.grid[0] = d.window[0] = 4
     buf = (ctypes.c_float * 64)()
     p = ctypes.cast(buf, ctypes.c_void_p)
-    rc = _lib.load().mmn_winattn_fwd(ctypes.byref(d), p, p, p, None, None, None, p, p, 0, None)
+    rc = _lib.load().mmn_winattn_fwd(ctypes.byref(d), p, p, p, None, None, None, p, p, p, 0, None)
     assert rc == -3 and b"no CPU path" in _lib.load().mmn_last_error()
 
 
@@ -181,11 +181,11 @@ def test_descriptor_validation():
     d.grid[0], d.grid[1], d.window[0], d.window[1] = 6, 6, 4, 3
     buf = (ctypes.c_float * 8)()
     p = ctypes.cast(buf, ctypes.c_void_p)
-    assert lib.mmn_winattn_fwd(ctypes.byref(d), p, p, p, None, None, None, p, p, 0, None) == -1
+    assert lib.mmn_winattn_fwd(ctypes.byref(d), p, p, p, None, None, None, p, p, p, 0, None) == -1
     assert b"does not divide" in lib.mmn_last_error()
     d.window[0] = 3
     d.shift[0] = 3
-    assert lib.mmn_winattn_fwd(ctypes.byref(d), p, p, p, None, None, None, p, p, 0, None) == -1
+    assert lib.mmn_winattn_fwd(ctypes.byref(d), p, p, p, None, None, None, p, p, p, 0, None) == -1
     assert lib.mmn_winattn_path(ctypes.byref(d)) == b"invalid"
 
 
