@@ -153,18 +153,30 @@ int mmn_cpb_bias_bwd(const float* coords, const float* w1, const float* b1, cons
                      const float* tab16, const float* dbias, int32_t T, int32_t n_in, int32_t J, int32_t num_heads, int32_t NN,
                      float* scratch, float* dw1, float* db1, float* dw2, int device, void* stream);
 
-/* Fused backward of a projection y = x W^T + b (F.linear: swin_v2_module.py:148,176, swinfusion_module.py:121,143,
- * 221-222,244) in one pass over dy and x:  dx = dy W (rows x in),  dw = dy^T x (out x in, fp32, OVERWRITTEN),
- * db = colsum(dy) (out, fp32, OVERWRITTEN; may be NULL).  w is (out, in) row-major contiguous; dy, x, dx have the
- * given leading dimensions (elements).  Tensor-core path only: bf16, in = 96, out in {96, 192, 288}
- * (mmn_linear_bwd_supported tells; other shapes are plain library GEMMs on the caller's side).
- * workspace: mmn_linear_bwd_workspace_bytes(out) bytes, contents undefined on return. */
+/* Projections on the tensor cores (csrc/gemm_tc.cu, csrc/linbwd_tc.cu).  They replace the F.linear calls of the path and
+ * their autograd backward: swin_v2_module.py:148,176 (qkv, proj) and :27-31 (Mlp: fc1 -> GELU -> fc2),
+ * swinfusion_module.py:121,143,221-222,244, crossmodal_transformer.py:158-160 (fc1 -> relu -> fc2).
+ * bf16 operands, fp32 accumulation, in_features and out_features multiples of 32 (mmn_linear_supported tells; other shapes
+ * -- the reference's own 12/24/48/84/168-wide layers -- are plain library GEMMs on the caller's side).
+ *   forward:  y (rows, out) = act(x (rows, in) w^T + bias);  w is (out, in) row-major contiguous, bias (out) fp32 or NULL;
+ *             y_pre (rows, out), optional, receives the value BEFORE the activation (what the backward needs for act');
+ *             x has leading dimension ld_x, y and y_pre ld_y (elements).
+ *   backward: dx (rows, in) = (dy w) o act'(act_aux)   -- act / act_aux describe the layer BELOW this one (the activation
+ *             whose output was this layer's input; act_aux is ITS pre-activation, (rows, in) with leading dimension ld_aux);
+ *             dw (out, in) fp32 = dy^T x, OVERWRITTEN; db (out) fp32 = column sums of dy, OVERWRITTEN.  dx or dw may be NULL
+ *             to skip that half (then db is skipped with dw == NULL only if db is NULL too).
+ *             workspace: mmn_linear_bwd_workspace_bytes(rows, in, out) bytes, contents undefined on return.
+ *             in = 96 and out in {96, 192, 288} with no activation run as ONE pass over dy and x (linbwd_tc.cu). */
+enum { MMN_ACT_NONE = 0, MMN_ACT_RELU = 1, MMN_ACT_GELU = 2 };
+int mmn_linear_supported(int io_dtype, int64_t rows, int32_t in_features, int32_t out_features, int64_t ld_x, int64_t ld_y);
+int mmn_linear_fwd(const void* x, const void* w, const float* bias, void* y, void* y_pre, int act, int io_dtype, int64_t rows,
+                   int32_t in_features, int32_t out_features, int64_t ld_x, int64_t ld_y, int device, void* stream);
 int mmn_linear_bwd_supported(int io_dtype, int64_t rows, int32_t in_features, int32_t out_features,
                              int64_t ld_dy, int64_t ld_x, int64_t ld_dx);
-size_t mmn_linear_bwd_workspace_bytes(int32_t out_features);
+size_t mmn_linear_bwd_workspace_bytes(int64_t rows, int32_t in_features, int32_t out_features);
 int mmn_linear_bwd(const void* dy, const void* x, const void* w, void* dx, float* dw, float* db, void* workspace,
-                   int io_dtype, int64_t rows, int32_t in_features, int32_t out_features,
-                   int64_t ld_dy, int64_t ld_x, int64_t ld_dx, int device, void* stream);
+                   const void* act_aux, int64_t ld_aux, int act, int io_dtype, int64_t rows, int32_t in_features,
+                   int32_t out_features, int64_t ld_dy, int64_t ld_x, int64_t ld_dx, int device, void* stream);
 
 #ifdef __cplusplus
 }

@@ -282,25 +282,77 @@ int mmn_cpb_bias_bwd(const float* coords, const float* w1, const float* b1, cons
   return finish(e, n, "cpb_bias_bwd");
 }
 
-int mmn_linear_bwd_supported(int io_dtype, int64_t rows, int32_t in_features, int32_t out_features, int64_t ld_dy, int64_t ld_x,
-                             int64_t ld_dx) {
-  return have_device() && mmn::tc::linbwd_why_not(io_dtype, rows, in_features, out_features, ld_dy, ld_x, ld_dx) == nullptr;
+int mmn_linear_supported(int io_dtype, int64_t rows, int32_t in_features, int32_t out_features, int64_t ld_x, int64_t ld_y) {
+  return have_device() && mmn::tc::linear_why_not(io_dtype, rows, in_features, out_features, ld_x, ld_y) == nullptr;
 }
 
-size_t mmn_linear_bwd_workspace_bytes(int32_t out_features) { return mmn::tc::linbwd_workspace_bytes(out_features); }
-
-int mmn_linear_bwd(const void* dy, const void* x, const void* w, void* dx, float* dw, float* db, void* workspace, int io_dtype,
-                   int64_t rows, int32_t in_features, int32_t out_features, int64_t ld_dy, int64_t ld_x, int64_t ld_dx, int device,
-                   void* stream) {
-  if (!dy || !x || !w || !dx || !dw || !workspace) return fail(MMN_ERR_INVALID, "null tensor pointer");
+int mmn_linear_fwd(const void* x, const void* w, const float* bias, void* y, void* y_pre, int act, int io_dtype, int64_t rows,
+                   int32_t in_features, int32_t out_features, int64_t ld_x, int64_t ld_y, int device, void* stream) {
+  if (!x || !w || !y) return fail(MMN_ERR_INVALID, "null tensor pointer");
+  if (act != MMN_ACT_NONE && act != MMN_ACT_RELU && act != MMN_ACT_GELU) return fail(MMN_ERR_INVALID, "bad activation %d", act);
+  if (y_pre && act == MMN_ACT_NONE) return fail(MMN_ERR_INVALID, "y_pre only makes sense with an activation");
   if (!have_device()) return fail(MMN_ERR_CUDA, "no CUDA device: libmmn_b200 has no CPU path");
-  const char* why = mmn::tc::linbwd_why_not(io_dtype, rows, in_features, out_features, ld_dy, ld_x, ld_dx);
-  if (why) return fail(MMN_ERR_UNSUPPORTED, "shape not supported by the fused projection backward: %s", why);
+  const char* why = mmn::tc::linear_why_not(io_dtype, rows, in_features, out_features, ld_x, ld_y);
+  if (why) return fail(MMN_ERR_UNSUPPORTED, "shape not supported by the tensor-core projection: %s", why);
   DeviceGuard g(device);
   if (!g.ok) return fail(MMN_ERR_CUDA, "cannot select device %d", device);
   int n = 0;
-  int rc = mmn::tc::linbwd(dy, x, w, dx, dw, db, (float*)workspace, rows, in_features, out_features, ld_dy, ld_x, ld_dx,
-                           (cudaStream_t)stream, g_err, sizeof(g_err), &n);
+  int rc = mmn::tc::linear_fwd(x, w, bias, y, y_pre, act, rows, in_features, out_features, ld_x, ld_y, (cudaStream_t)stream, g_err,
+                               sizeof(g_err), &n);
+  g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed);
+  return rc;
+}
+
+// in = 96, out in {96, 192, 288}: ONE pass over dy and x (linbwd_tc.cu); any other multiple of 32: dgrad + wgrad (gemm_tc.cu)
+static bool linbwd_fused_ok(int io_dtype, int64_t rows, int32_t in_features, int32_t out_features, int64_t ld_dy, int64_t ld_x,
+                            int64_t ld_dx) {
+  return mmn::tc::linbwd_why_not(io_dtype, rows, in_features, out_features, ld_dy, ld_x, ld_dx) == nullptr;
+}
+
+int mmn_linear_bwd_supported(int io_dtype, int64_t rows, int32_t in_features, int32_t out_features, int64_t ld_dy, int64_t ld_x,
+                             int64_t ld_dx) {
+  if (!have_device()) return 0;
+  if (linbwd_fused_ok(io_dtype, rows, in_features, out_features, ld_dy, ld_x, ld_dx)) return 1;
+  return mmn::tc::linear_why_not(io_dtype, rows, in_features, out_features, ld_x, ld_dy) == nullptr && ld_dx % 8 == 0;
+}
+
+size_t mmn_linear_bwd_workspace_bytes(int64_t rows, int32_t in_features, int32_t out_features) {
+  const size_t a = mmn::tc::linbwd_workspace_bytes(out_features);
+  const size_t b = mmn::tc::linear_wgrad_workspace_bytes(rows, in_features, out_features);
+  return a > b ? a : b;
+}
+
+int mmn_linear_bwd(const void* dy, const void* x, const void* w, void* dx, float* dw, float* db, void* workspace,
+                   const void* act_aux, int64_t ld_aux, int act, int io_dtype, int64_t rows, int32_t in_features,
+                   int32_t out_features, int64_t ld_dy, int64_t ld_x, int64_t ld_dx, int device, void* stream) {
+  if (!dy || !w || !workspace || (!dx && !dw)) return fail(MMN_ERR_INVALID, "null tensor pointer");
+  if (dw && !x) return fail(MMN_ERR_INVALID, "dw needs x");
+  if (act != MMN_ACT_NONE && act != MMN_ACT_RELU && act != MMN_ACT_GELU) return fail(MMN_ERR_INVALID, "bad activation %d", act);
+  if (act != MMN_ACT_NONE && (!act_aux || ld_aux % 8 || reinterpret_cast<uintptr_t>(act_aux) % 16))
+    return fail(MMN_ERR_INVALID, "activation gradient needs a 16-byte aligned pre-activation tensor");
+  if (!have_device()) return fail(MMN_ERR_CUDA, "no CUDA device: libmmn_b200 has no CPU path");
+  if (!mmn_linear_bwd_supported(io_dtype, rows, in_features, out_features, ld_dy, ld_x ? ld_x : in_features, ld_dx ? ld_dx : in_features))
+    return fail(MMN_ERR_UNSUPPORTED, "shape not supported by the tensor-core projection backward (bf16, widths multiples of 32)");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(MMN_ERR_CUDA, "cannot select device %d", device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int n = 0, rc;
+  if (dx && dw && act == MMN_ACT_NONE && linbwd_fused_ok(io_dtype, rows, in_features, out_features, ld_dy, ld_x, ld_dx)) {
+    rc = mmn::tc::linbwd(dy, x, w, dx, dw, db, (float*)workspace, rows, in_features, out_features, ld_dy, ld_x, ld_dx, st, g_err,
+                         sizeof(g_err), &n);
+  } else {
+    rc = mmn::tc::linear_bwd_general(dy, x, w, dx, dw, (float*)workspace, act_aux, ld_aux,
+                                     act == MMN_ACT_RELU ? 3 : act == MMN_ACT_GELU ? 4 : 0, rows, in_features, out_features, ld_dy,
+                                     ld_x, ld_dx, st, g_err, sizeof(g_err), &n);
+    if (rc == MMN_OK && db) {
+      // bias gradient: column sums of dy, 2048 columns per launch (colsum_kernel's block covers 256 x 8)
+      cudaError_t e = cudaMemsetAsync(db, 0, (size_t)out_features * sizeof(float), st);
+      for (int c0 = 0; e == cudaSuccess && c0 < out_features; c0 += 2048)
+        e = mmn::colsum(MMN_DT_BF16, static_cast<const uint16_t*>(dy) + c0, rows, out_features - c0 < 2048 ? out_features - c0 : 2048, ld_dy,
+                        db + c0, st, &n);
+      if (e != cudaSuccess) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); return finish(e, 0, "colsum_kernel"); }
+    }
+  }
   g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed);
   return rc;
 }

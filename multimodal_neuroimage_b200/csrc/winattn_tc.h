@@ -22,4 +22,12 @@ size_t linbwd_workspace_bytes(int out_features);
 int linbwd(const void* dy, const void* x, const void* w, void* dx, float* dw, float* db, float* workspace, long long rows,
            int in_features, int out_features, long long ld_dy, long long ld_x, long long ld_dx, cudaStream_t st, char* err,
            size_t errlen, int* launches);
+// tensor-core projections for any width that is a multiple of 32 (gemm_tc.cu)
+const char* linear_why_not(int io_dtype, long long rows, int in_features, int out_features, long long ld_x, long long ld_y);
+int linear_fwd(const void* x, const void* w, const float* bias, void* y, void* y_pre, int act, long long rows, int in_features,
+               int out_features, long long ld_x, long long ld_y, cudaStream_t st, char* err, size_t errlen, int* launches);
+size_t linear_wgrad_workspace_bytes(long long rows, int in_features, int out_features);
+int linear_bwd_general(const void* dy, const void* x, const void* w, void* dx, float* dw, float* workspace, const void* aux, long long ld_aux,
+                       int act_grad, long long rows, int in_features, int out_features, long long ld_dy, long long ld_x, long long ld_dx,
+                       cudaStream_t st, char* err, size_t errlen, int* launches);
 }}  // namespace mmn::tc

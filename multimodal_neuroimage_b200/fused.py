@@ -29,6 +29,15 @@ def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         return (a @ b).float()
 
 
+def _project(x2: torch.Tensor, w: torch.Tensor, b) -> torch.Tensor:
+    """x2 (rows, in) @ w^T + b.  bf16 with widths that are multiples of 32: the tensor-core projection kernel
+    (csrc/gemm_tc.cu), bias added in fp32 in its epilogue; anything else (fp32 parity path, the reference's 12/24/48-wide
+    stages): a plain library GEMM."""
+    if ops.linear_supported(x2, w):
+        return torch.ops.mmn_b200.linear_fwd(x2, w, None if b is None else b.float(), _lib.ACT_NONE, False)[0]
+    return F.linear(x2, w, None if b is None else b.to(x2.dtype))
+
+
 class WindowAttentionModuleFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, y, w_a, b_a, w_b, b_b, w_proj, b_proj, bias, head_scale, grid, window, shift, num_heads,
@@ -42,13 +51,13 @@ class WindowAttentionModuleFn(torch.autograd.Function):
         with torch.autocast("cuda", enabled=False):
             cast = lambda t: None if t is None else t.to(cdt)
             xc, yc = cast(x).reshape(B * L, C), (cast(y).reshape(B * L, C) if y is not None else None)
-            wa, ba, wb, bb, wp, bp = cast(w_a), cast(b_a), cast(w_b), cast(b_b), cast(w_proj), cast(b_proj)
-            a = F.linear(xc, wa, ba).view(B, *grid, -1)
-            b = F.linear(yc, wb, bb).view(B, *grid, -1) if y is not None else None
+            wa, wb, wp = cast(w_a), cast(w_b), cast(w_proj)          # biases stay in their own dtype: added in fp32
+            a = _project(xc, wa, b_a).view(B, *grid, -1)
+            b = _project(yc, wb, b_b).view(B, *grid, -1) if y is not None else None
             p, seed, off = dropout
             out, lse = torch.ops.mmn_b200.winattn_fwd(a, b, bias, head_scale, None, list(grid), list(window), list(shift),
                                                       num_heads, score_kind, mask_kind, scale, p, seed, off, path)
-            res = F.linear(out.view(B * L, C), wp, bp).view(B, L, C).to(odt)
+            res = _project(out.view(B * L, C), wp, b_proj).view(B, L, C).to(odt)
         ctx.save_for_backward(xc, yc, a, b, out, lse, wa, wb, wp, bias, head_scale)
         ctx.cfg = (list(grid), list(window), list(shift), num_heads, score_kind, mask_kind, scale, p, seed, off, path)
         ctx.meta = (x.dtype, None if y is None else y.dtype, w_a.dtype, None if b_a is None else b_a.dtype,
@@ -109,3 +118,59 @@ def window_attention_module(x: torch.Tensor, y: Optional[torch.Tensor], w_a, b_a
                             dropout=(0.0, 0, 0), path: int = 0) -> torch.Tensor:
     return WindowAttentionModuleFn.apply(x, y, w_a, b_a, w_b, b_b, w_proj, b_proj, bias, head_scale, tuple(grid), tuple(window),
                                          tuple(shift), num_heads, score_kind, mask_kind, float(scale), dropout, path)
+
+
+class MlpFn(torch.autograd.Function):
+    """fc1 -> activation -> fc2 (swin_v2_module.py:27-31, swinfusion_module.py:25-29, crossmodal_transformer.py:158-160) as
+    two tensor-core GEMMs with the bias + activation in the first one's epilogue, and a three-GEMM-pass backward:
+        dpre = (dy W2) o act'(pre)      dgrad of fc2 with the activation derivative as its epilogue
+        dW2  = dy^T h, db2              wgrad of fc2
+        dx, dW1, db1                    backward of fc1 (one fused pass for in = 96)
+    PyTorch runs this as 2 GEMMs + 1 elementwise kernel forward and 4 GEMMs + 3 elementwise/reduction kernels backward."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, act):
+        x2 = x.reshape(-1, x.shape[-1])
+        w1c, w2c = w1.to(torch.bfloat16), w2.to(torch.bfloat16)
+        h, pre = torch.ops.mmn_b200.linear_fwd(x2, w1c, None if b1 is None else b1.float(), act, True)
+        y, _ = torch.ops.mmn_b200.linear_fwd(h, w2c, None if b2 is None else b2.float(), _lib.ACT_NONE, False)
+        ctx.save_for_backward(x2, pre, h, w1c, w2c)
+        ctx.meta = (x.shape, w1.dtype, None if b1 is None else b1.dtype, w2.dtype, None if b2 is None else b2.dtype, act,
+                    x.requires_grad)
+        return y.view(*x.shape[:-1], w2.shape[0])
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        x2, pre, h, w1c, w2c = ctx.saved_tensors
+        shape, w1dt, b1dt, w2dt, b2dt, act, need_dx = ctx.meta
+        dy2 = dy.reshape(-1, dy.shape[-1]).to(torch.bfloat16)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dpre, dw2, db2 = torch.ops.mmn_b200.linear_bwd(dy2, h, w2c, pre, act, True, True)
+        dx, dw1, db1 = torch.ops.mmn_b200.linear_bwd(dpre, x2, w1c, None, 0, need_dx, True)
+        return (dx.view(shape) if need_dx else None, dw1.to(w1dt), db1.to(b1dt) if b1dt is not None else None, dw2.to(w2dt),
+                db2.to(b2dt) if b2dt is not None else None, None)
+
+
+def mlp(x: torch.Tensor, fc1: torch.nn.Linear, fc2: torch.nn.Linear, act: str, drop: float = 0.0, training: bool = False,
+        drop_out=None):
+    """The Mlp of a block.  Fused path: CUDA, bf16 activations (autocast), widths multiples of 32, no dropout in
+    between; otherwise the reference's own sequence of F.linear / activation / dropout.  `drop` follows the activation,
+    `drop_out` (default: the same p, as in the Swin Mlp) follows fc2."""
+    drop_out = drop if drop_out is None else drop_out
+    cdt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+    odt = cdt
+    if cdt == torch.float16:
+        cdt = torch.bfloat16
+    widths_ok = all(d % 32 == 0 for d in (fc1.in_features, fc1.out_features, fc2.out_features))
+    if x.is_cuda and cdt == torch.bfloat16 and widths_ok and x.numel() > 0 and not (training and (drop > 0.0 or drop_out > 0.0)):
+        with torch.autocast("cuda", enabled=False):
+            xc = x.to(torch.bfloat16)
+            if not xc.is_contiguous():
+                xc = xc.contiguous()
+            return MlpFn.apply(xc, fc1.weight, fc1.bias, fc2.weight, fc2.bias, ops._ACT[act]).to(odt)
+    h = fc1(x)
+    h = F.gelu(h) if act == "gelu" else F.relu(h)
+    h = F.dropout(h, drop, training)
+    return F.dropout(fc2(h), drop_out, training)

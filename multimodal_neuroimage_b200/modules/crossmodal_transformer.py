@@ -16,7 +16,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .. import geometry
+from .. import fused, geometry
 from .multihead_attention import MultiheadAttention, cached_future_mask
 from .position_embedding import SinusoidalPositionalEmbedding
 
@@ -100,9 +100,7 @@ class TransformerEncoderLayer(nn.Module):
 
         residual = x
         x = self.maybe_layer_norm(1, x, before=True)
-        x = F.relu(self.fc1(x))
-        x = F.dropout(x, p=self.relu_dropout, training=self.training)
-        x = self.fc2(x)
+        x = fused.mlp(x, self.fc1, self.fc2, "relu", self.relu_dropout, self.training, 0.0)     # fc1 -> relu -> dropout -> fc2 (:158-160)
         x = F.dropout(x, p=self.res_dropout, training=self.training)
         x = residual + x
         return self.maybe_layer_norm(1, x, after=True)

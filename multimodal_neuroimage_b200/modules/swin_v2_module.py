@@ -63,6 +63,9 @@ class Mlp(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def forward(self, x):
+        if isinstance(self.act, nn.GELU) and getattr(self.act, "approximate", "none") == "none":
+            # two tensor-core GEMMs, bias + GELU in the first one's epilogue (fused.MlpFn); plain F.linear off the fast path
+            return fused.mlp(x, self.fc1, self.fc2, "gelu", self.drop.p, self.training)
         return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
 
 

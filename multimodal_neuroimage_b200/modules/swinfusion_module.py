@@ -39,6 +39,8 @@ class Mlp_fusion(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def forward(self, x):
+        if isinstance(self.act, nn.GELU) and getattr(self.act, "approximate", "none") == "none":
+            return fused.mlp(x, self.fc1, self.fc2, "gelu", self.drop.p, self.training)      # swinfusion_module.py:25-29
         return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
 
 

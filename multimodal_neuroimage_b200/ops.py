@@ -417,38 +417,125 @@ def _cpb_backward(ctx, dbias, _dtab16):
 cpb_bias_fwd.register_autograd(_cpb_backward, setup_context=_cpb_setup)
 
 
+_ACT = {"none": _lib.ACT_NONE, "relu": _lib.ACT_RELU, "gelu": _lib.ACT_GELU}
+
+
+def _rows2d(t: Tensor) -> bool:
+    return t.dim() == 2 and t.stride(1) == 1 and t.is_cuda and t.dtype == torch.bfloat16
+
+
+def linear_supported(x: Tensor, w: Tensor) -> bool:
+    """True when the tensor-core projection kernels take these operands: bf16 CUDA, x (rows, in) with contiguous columns,
+    w (out, in) contiguous, in and out multiples of 32."""
+    if not (_rows2d(x) and w.is_cuda and w.dtype == torch.bfloat16 and w.dim() == 2 and w.is_contiguous()) or x.shape[0] < 1:
+        return False
+    return bool(_lib.load().mmn_linear_supported(_lib.DT_BF16, x.shape[0], x.shape[1], w.shape[0], x.stride(0), w.shape[0]))
+
+
+@torch.library.custom_op("mmn_b200::linear_fwd", mutates_args=())
+def linear_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], act: int, want_pre: bool) -> Tuple[Tensor, Tensor]:
+    """y = act(x w^T + bias) on the tensor cores; returns (y, pre) where pre is the value before the activation when
+    `want_pre` (what the backward needs for act'), else an empty tensor."""
+    _require_cuda(x, w, bias)
+    if not _rows2d(x) or w.dtype != torch.bfloat16 or not w.is_contiguous():
+        raise RuntimeError("linear_fwd expects bf16 x (rows, in) with contiguous columns and a contiguous bf16 weight")
+    if bias is not None and (bias.dtype != torch.float32 or not bias.is_contiguous()):
+        raise RuntimeError("linear_fwd takes its bias in float32")
+    rows, n_in, n_out = x.shape[0], x.shape[1], w.shape[0]
+    y = torch.empty(rows, n_out, dtype=x.dtype, device=x.device)
+    pre = torch.empty(rows, n_out, dtype=x.dtype, device=x.device) if want_pre else x.new_empty(0)
+    with _timed("linear_fwd", x):
+        _lib.check(_lib.load().mmn_linear_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(y), _ptr(pre) if want_pre else None, act,
+                                              _lib.DT_BF16, rows, n_in, n_out, x.stride(0), n_out, x.device.index, _stream(x)),
+                   "mmn_linear_fwd")
+    return y, pre
+
+
+@linear_fwd.register_fake
+def _(x, w, bias, act, want_pre):
+    return x.new_empty(x.shape[0], w.shape[0]), (x.new_empty(x.shape[0], w.shape[0]) if want_pre else x.new_empty(0))
+
+
 def linear_bwd_supported(dy: Tensor, x: Tensor, w: Tensor) -> bool:
-    """True when the fused tensor-core projection backward takes these operands (bf16, in = 96, out in {96,192,288})."""
-    if not (dy.is_cuda and dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16):
+    """True when the tensor-core projection backward takes these operands (bf16, in and out multiples of 32)."""
+    if not (_rows2d(dy) and _rows2d(x) and w.is_cuda and w.dtype == torch.bfloat16 and w.is_contiguous()) or dy.shape[0] < 1:
         return False
-    if dy.dim() != 2 or x.dim() != 2 or dy.stride(1) != 1 or x.stride(1) != 1 or not w.is_contiguous():
-        return False
-    return bool(_lib.load().mmn_linear_bwd_supported(_DT[dy.dtype], dy.shape[0], x.shape[1], dy.shape[1], dy.stride(0),
+    return bool(_lib.load().mmn_linear_bwd_supported(_lib.DT_BF16, dy.shape[0], x.shape[1], dy.shape[1], dy.stride(0),
                                                      x.stride(0), x.shape[1]))
 
 
 @torch.library.custom_op("mmn_b200::linear_bwd", mutates_args=())
-def linear_bwd(dy: Tensor, x: Tensor, w: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
-    """Backward of y = x w^T + b in one pass over dy and x: returns (dx bf16 (rows, in), dw fp32 (out, in),
-    db fp32 (out))."""
-    _require_cuda(dy, x, w)
+def linear_bwd(dy: Tensor, x: Tensor, w: Tensor, act_aux: Optional[Tensor] = None, act: int = 0, want_dx: bool = True,
+               want_dw: bool = True) -> Tuple[Tensor, Tensor, Tensor]:
+    """Backward of y = x w^T + b: returns (dx bf16 (rows, in), dw fp32 (out, in), db fp32 (out)).  With `act_aux` (the
+    pre-activation that produced x = act(act_aux)) dx is additionally multiplied by act'(act_aux) in the kernel's epilogue,
+    i.e. it is the gradient w.r.t. act_aux.  in = 96 runs as one fused pass over dy and x, other widths as dgrad + wgrad."""
+    _require_cuda(dy, x, w, act_aux)
     lib = _lib.load()
     rows, n_out, n_in = dy.shape[0], dy.shape[1], x.shape[1]
-    dx = torch.empty(rows, n_in, dtype=dy.dtype, device=dy.device)
-    dw = torch.empty(n_out, n_in, dtype=torch.float32, device=dy.device)
-    db = torch.empty(n_out, dtype=torch.float32, device=dy.device)
-    ws = torch.empty(lib.mmn_linear_bwd_workspace_bytes(n_out), dtype=torch.uint8, device=dy.device)
+    dx = torch.empty(rows, n_in, dtype=dy.dtype, device=dy.device) if want_dx else dy.new_empty(0)
+    dw = torch.empty(n_out, n_in, dtype=torch.float32, device=dy.device) if want_dw else dy.new_empty(0, dtype=torch.float32)
+    db = torch.empty(n_out, dtype=torch.float32, device=dy.device) if want_dw else dy.new_empty(0, dtype=torch.float32)
+    ws = torch.empty(lib.mmn_linear_bwd_workspace_bytes(rows, n_in, n_out), dtype=torch.uint8, device=dy.device)
+    if act_aux is not None and (not _rows2d(act_aux) or act_aux.shape != (rows, n_in)):
+        raise RuntimeError("act_aux must be a bf16 (rows, in) tensor with contiguous columns")
     with _timed("linear_bwd", dy):
-        _lib.check(lib.mmn_linear_bwd(_ptr(dy), _ptr(x), _ptr(w), _ptr(dx), _ptr(dw), _ptr(db), _ptr(ws), _DT[dy.dtype], rows,
-                                      n_in, n_out, dy.stride(0), x.stride(0), n_in, dy.device.index, _stream(dy)),
-                   "mmn_linear_bwd")
+        _lib.check(lib.mmn_linear_bwd(_ptr(dy), _ptr(x), _ptr(w), _ptr(dx) if want_dx else None, _ptr(dw) if want_dw else None,
+                                      _ptr(db) if want_dw else None, _ptr(ws), _ptr(act_aux),
+                                      act_aux.stride(0) if act_aux is not None else 0, act if act_aux is not None else 0,
+                                      _DT[dy.dtype], rows, n_in, n_out, dy.stride(0), x.stride(0), n_in, dy.device.index,
+                                      _stream(dy)), "mmn_linear_bwd")
     return dx, dw, db
 
 
 @linear_bwd.register_fake
-def _(dy, x, w):
-    return (dy.new_empty(dy.shape[0], x.shape[1]), dy.new_empty(dy.shape[1], x.shape[1], dtype=torch.float32),
-            dy.new_empty(dy.shape[1], dtype=torch.float32))
+def _(dy, x, w, act_aux=None, act=0, want_dx=True, want_dw=True):
+    f32 = dict(dtype=torch.float32)
+    return (dy.new_empty(dy.shape[0], x.shape[1]) if want_dx else dy.new_empty(0),
+            dy.new_empty(dy.shape[1], x.shape[1], **f32) if want_dw else dy.new_empty(0, **f32),
+            dy.new_empty(dy.shape[1], **f32) if want_dw else dy.new_empty(0, **f32))
+
+
+class LinearFn(torch.autograd.Function):
+    """y = act(x w^T + b) with the tensor-core forward and backward above; x (..., in) bf16, w / b master weights of any
+    float dtype (cast to bf16 / fp32 here, gradients returned in their dtypes)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        x2 = x.reshape(-1, x.shape[-1])
+        wc = w.to(torch.bfloat16)
+        y, pre = torch.ops.mmn_b200.linear_fwd(x2, wc, None if b is None else b.float(), act, act != _lib.ACT_NONE)
+        ctx.save_for_backward(x2, wc, pre)
+        ctx.meta = (x.shape, w.dtype, None if b is None else b.dtype, act, x.requires_grad)
+        return y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        x2, wc, pre = ctx.saved_tensors
+        shape, wdt, bdt, act, need_dx = ctx.meta
+        dy2 = dy.reshape(-1, dy.shape[-1]).to(torch.bfloat16)
+        if act != _lib.ACT_NONE:                       # through the activation: elementwise, then the plain projection backward
+            dy2 = _act_backward(dy2, pre, act)
+        dx, dw, db = torch.ops.mmn_b200.linear_bwd(dy2.contiguous(), x2, wc, None, 0, need_dx, True)
+        return (dx.view(shape) if need_dx else None, dw.to(wdt), db.to(bdt) if bdt is not None else None, None)
+
+
+def _act_backward(dy: Tensor, pre: Tensor, act: int) -> Tensor:
+    if act == _lib.ACT_RELU:
+        return dy * (pre > 0)
+    return torch.ops.aten.gelu_backward(dy, pre)
+
+
+def linear(x: Tensor, w: Tensor, b: Optional[Tensor] = None, act: str = "none") -> Tensor:
+    """Drop-in for F.linear (+ activation) on CUDA bf16 activations whose widths are multiples of 32; anything else falls
+    to F.linear (a plain library GEMM: the reference's own 12/24/48/84-wide layers)."""
+    x2 = x.reshape(-1, x.shape[-1]) if x.dim() != 2 else x
+    if x.is_cuda and x.dtype == torch.bfloat16 and x.numel() > 0 and w.shape[1] % 32 == 0 and w.shape[0] % 32 == 0 and \
+            x2.stride(-1) == 1 and x2.stride(0) % 8 == 0 and x2.data_ptr() % 16 == 0:
+        return LinearFn.apply(x, w, b, _ACT[act])
+    y = torch.nn.functional.linear(x, w.to(x.dtype), None if b is None else b.to(x.dtype))
+    return y if act == "none" else (torch.relu(y) if act == "relu" else torch.nn.functional.gelu(y))
 
 
 def next_dropout_stream(p: float, training: bool, device) -> Tuple[float, int, int]:
