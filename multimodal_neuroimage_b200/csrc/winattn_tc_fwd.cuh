@@ -549,6 +549,9 @@ inline const char* fwd_why_not_impl(const mmn_winattn_desc* d) {
   if (g.win[0] * g.win[1] * g.win[2] != kN) return "window does not hold 64 tokens";
   for (int a = 0; a < 3; ++a)
     if (g.shift[a] != 0 && (2 * g.shift[a] != g.win[a] || g.nwin[a] < 2)) return "shift is neither 0 nor window/2";
+  // a mask tensor is addressed by window position; tiles of wrapped windows hold their tokens piece-major, and the kernels
+  // read mask rows in tile order -- correct only while no window wraps (the modules pass tensors for pre-windowed calls only)
+  if (d->mask_kind == MMN_MASK_TENSOR && (g.shift[0] | g.shift[1] | g.shift[2])) return "mask tensor together with a cyclic shift";
   if (d->q_row_stride % 8 || d->k_row_stride % 8 || d->v_row_stride % 8 || d->o_row_stride % 8) return "row stride not 16-byte aligned";
   if (!encode_fn()) return "cuTensorMapEncodeTiled unavailable";
   return nullptr;

@@ -1,0 +1,159 @@
+"""Synthetic workloads for the volumetric BASELINE configurations (cfg3 / cfg4 / cfg5), built from the drop-in modules.
+
+The reference is 2-D only: its SwinFusion runs on 84x84 ROI matrices with C = 12.  BASELINE.json's
+configs 3-5 name 3-D volumes, so these are *our* 3-D instantiations of the reference's topologies: the same
+blocks in the same order, a strided Conv3d patch embedding in place of the 3x3 convolutions, and a pooled linear head in
+place of the image reconstruction + classifier.  They exist to measure the hot path inside a real training step
+(`bench.py --workload cfg3|cfg5`), not to replace `model.py`: through `install()` the reference's own 2-D models run on the
+same modules unchanged.
+
+  SwinFusion3D          cfg3 / cfg4: model.SwinFusion (model.py:1131-1555) in 3-D -- feature extraction Ex_A / Ex_B (RSTB),
+                        cross-modal fusion (CRSTB), reconstruction Re (RSTB) -- 96^3 volumes, patch 4, C = 96, 3 heads x 32,
+                        4x4x4 windows: every window-attention call runs the tcgen05 kernels.
+  SwinV2CrossModal3D    cfg5: two SwinV2 towers (model.SwinTransformerV2, model.py:970-1129, in 3-D; embed 192, depths
+                        2/2/6/2, heads 6/12/24/48, 128^3 volumes) joined by the cross-modal transformer
+                        (model.Transformer_Net_Cross_Attention's mixing, model.py:489-509) over the last stage's tokens.
+  synthetic_batch       the synthetic multimodal volumes + labels of a step.
+"""
+from __future__ import annotations
+
+import math
+from typing import Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from .modules import crossmodal_transformer as cm
+from .modules import swin_v2_module as v2
+from .modules import swinfusion_module as fu
+
+
+class SwinFusion3D(nn.Module):
+    def __init__(self, img_size: int = 96, patch_size: int = 4, embed_dim: int = 96, Ex_depths: Sequence[int] = (6, 6),
+                 Fusion_depths: Sequence[int] = (2, 2, 2), Re_depths: Sequence[int] = (6, 6), num_heads: int = 3,
+                 window_size: int = 4, mlp_ratio: float = 4.0, num_classes: int = 1, use_checkpoint: bool = False):
+        super().__init__()
+        C = embed_dim
+        self.grid = (img_size // patch_size,) * 3
+        self.patch_embed_A = v2.PatchEmbed3D(img_size, patch_size, 1, C, nn.LayerNorm)
+        self.patch_embed_B = v2.PatchEmbed3D(img_size, patch_size, 1, C, nn.LayerNorm)
+        kw = dict(dim=C, input_resolution=self.grid, num_heads=num_heads, window_size=window_size, mlp_ratio=mlp_ratio,
+                  use_checkpoint=use_checkpoint, img_size=self.grid, patch_size=1)
+        self.layers_Ex_A = nn.ModuleList([fu.RSTB(depth=d, **kw) for d in Ex_depths])
+        self.layers_Ex_B = nn.ModuleList([fu.RSTB(depth=d, **kw) for d in Ex_depths])
+        self.norm_Ex_A, self.norm_Ex_B = nn.LayerNorm(C), nn.LayerNorm(C)
+        self.layers_Fusion = nn.ModuleList([fu.CRSTB(depth=d, **kw) for d in Fusion_depths])
+        self.norm_Fusion_A, self.norm_Fusion_B = nn.LayerNorm(C), nn.LayerNorm(C)
+        self.fuse = nn.Linear(2 * C, C)                       # model.py:1457-1462: concatenate the streams, halve the channels
+        self.act = nn.LeakyReLU(0.2)
+        self.layers_Re = nn.ModuleList([fu.RSTB(depth=d, **kw) for d in Re_depths])
+        self.norm_Re = nn.LayerNorm(C)
+        self.head = nn.Linear(C, num_classes)
+        # the convolutions RSTB / CRSTB declare but never call (swinfusion_module.py:813,924) would sit in DDP buckets as
+        # parameters without gradients: drop them from the trainable set
+        for n, p in self.named_parameters():
+            if ".conv" in n:
+                p.requires_grad_(False)
+
+    def forward(self, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+        """A, B (batch, 1, D, H, W) -> logits (batch, num_classes)."""
+        x, y = self.patch_embed_A(A), self.patch_embed_B(B)
+        for layer in self.layers_Ex_A:
+            x = layer(x, self.grid)
+        for layer in self.layers_Ex_B:
+            y = layer(y, self.grid)
+        x, y = self.norm_Ex_A(x), self.norm_Ex_B(y)
+        for layer in self.layers_Fusion:
+            x, y = layer(x, y, self.grid)
+        x = self.act(self.fuse(torch.cat([self.norm_Fusion_A(x), self.norm_Fusion_B(y)], -1)))
+        for layer in self.layers_Re:
+            x = layer(x, self.grid)
+        return self.head(self.norm_Re(x).mean(1))
+
+    def attention_calls(self) -> int:
+        return sum(1 for m in self.modules() if isinstance(m, (fu.WindowAttention_fusion, fu.Cross_WindowAttention)))
+
+
+class PatchMerging3D(v2.PatchMerging):
+    """BasicLayer builds its downsample as `downsample(input_resolution, dim=, norm_layer=)`: the n-D PatchMerging does it."""
+
+
+class SwinV2Tower3D(nn.Module):
+    def __init__(self, img_size: int = 128, patch_size: int = 4, embed_dim: int = 192, depths: Sequence[int] = (2, 2, 6, 2),
+                 num_heads: Sequence[int] = (6, 12, 24, 48), window_size: int = 4, mlp_ratio: float = 4.0,
+                 use_checkpoint: bool = False):
+        super().__init__()
+        self.patch_embed = v2.PatchEmbed3D(img_size, patch_size, 1, embed_dim, nn.LayerNorm)
+        g = img_size // patch_size
+        self.layers = nn.ModuleList()
+        for i, (d, h) in enumerate(zip(depths, num_heads)):
+            last = i == len(depths) - 1
+            self.layers.append(v2.BasicLayer(dim=embed_dim * 2 ** i, input_resolution=(g // 2 ** i,) * 3, depth=d, num_heads_swin=h,
+                                             window_size=window_size, mlp_ratio=mlp_ratio,
+                                             downsample=None if last else v2.PatchMerging, use_checkpoint=use_checkpoint))
+        self.num_features = embed_dim * 2 ** (len(depths) - 1)
+        self.norm = nn.LayerNorm(self.num_features)
+        self.out_grid = (g // 2 ** (len(depths) - 1),) * 3
+
+    def forward(self, x):
+        x = self.patch_embed(x)
+        for layer in self.layers:
+            x = layer(x)
+        return self.norm(x)                                   # (B, tokens of the last stage, C_last)
+
+
+class SwinV2CrossModal3D(nn.Module):
+    def __init__(self, img_size: int = 128, embed_dim: int = 192, depths: Sequence[int] = (2, 2, 6, 2),
+                 num_heads: Sequence[int] = (6, 12, 24, 48), cross_layers: int = 2, cross_heads: int = 24, num_classes: int = 1,
+                 use_checkpoint: bool = False):
+        super().__init__()
+        self.tower_A = SwinV2Tower3D(img_size, 4, embed_dim, depths, num_heads, use_checkpoint=use_checkpoint)
+        self.tower_B = SwinV2Tower3D(img_size, 4, embed_dim, depths, num_heads, use_checkpoint=use_checkpoint)
+        E = self.tower_A.num_features
+        self.a_with_b = cm.TransformerEncoder(E, cross_heads, cross_layers)
+        self.b_with_a = cm.TransformerEncoder(E, cross_heads, cross_layers)
+        self.head = nn.Linear(2 * E, num_classes)
+
+    def forward(self, A, B):
+        x, y = self.tower_A(A).transpose(0, 1), self.tower_B(B).transpose(0, 1)      # (T, B, E) as the MulT encoder wants
+        xa, yb = self.a_with_b(x, y, y), self.b_with_a(y, x, x)
+        return self.head(torch.cat([xa.mean(0), yb.mean(0)], -1))
+
+
+def randomise_norms(model: nn.Module, seed: int = 0) -> None:
+    """SwinV2's res-post-norm init zeroes norm1/norm2 (every block is then the identity and attention gets no
+    gradient); synthetic runs give the norms non-trivial weights so the whole path carries signal."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if "norm" in n and n.endswith("weight"):
+                p.copy_(torch.empty(p.shape).uniform_(0.5, 1.5, generator=g).to(p.device))
+
+
+def synthetic_batch(batch: int, img_size: int, device, seed: int = 0, pinned: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Two modalities of (batch, 1, S, S, S) N(0,1) volumes (fp16 as the reference's datasets hand them over,
+    datasets.py:541-542) and Bernoulli(0.5) labels."""
+    g = torch.Generator().manual_seed(seed)
+    A = torch.randn(batch, 1, img_size, img_size, img_size, generator=g).half()
+    B = torch.randn(batch, 1, img_size, img_size, img_size, generator=g).half()
+    y = torch.bernoulli(torch.full((batch, 1), 0.5), generator=g)
+    if pinned:
+        return A.pin_memory(), B.pin_memory(), y.pin_memory()
+    return A.to(device), B.to(device), y.to(device)
+
+
+def count_params(model: nn.Module, trainable_only: bool = True) -> int:
+    return sum(p.numel() for p in model.parameters() if p.requires_grad or not trainable_only)
+
+
+def flops_per_sample(model: nn.Module) -> float:
+    """Algorithmic forward flops of the hot-path modules of one sample (attention modules by the SURVEY 8d formula
+    4 N^2 C + 8 N C^2 per window, Mlps 16 N C^2 per window at ratio 4); x3 for forward + backward."""
+    total = 0.0
+    for m in model.modules():
+        if isinstance(m, (v2.SwinTransformerBlock, fu.SwinTransformerBlock_fusion, fu.Cross_SwinTransformerBlock)):
+            L, C = math.prod(m.input_resolution), m.dim
+            N = m.window_size ** len(m.input_resolution)
+            per_win = 4 * N * N * C + 8 * N * C * C + 4 * N * C * C * m.mlp_ratio
+            total += (L / N) * per_win * (2 if isinstance(m, fu.Cross_SwinTransformerBlock) else 1)
+    return total

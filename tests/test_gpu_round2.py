@@ -65,23 +65,40 @@ def test_in_kernel_shift_mask_bit_exact_generic(mm, grid, window, shift, nH, d):
         assert torch.equal(x, y), f"{name}: in-kernel shift mask differs from the oracle mask tensor"
 
 
-@pytest.mark.parametrize("grid,window,shift", [((16, 16), (8, 8), (4, 4)), ((12, 12, 12), (4, 4, 4), (2, 2, 2)), ((8, 8, 4), (4, 4, 4), (2, 2, 0))],
+@pytest.mark.parametrize("grid,window,shift", [((24, 32), (8, 8), (4, 4)), ((12, 12, 12), (4, 4, 4), (2, 2, 2)), ((8, 8, 4), (4, 4, 4), (2, 2, 0))],
                          ids=["2d", "3d_all_classes", "3d_one_axis_unshifted"])
 def test_in_kernel_shift_mask_bit_exact_tcgen05(mm, grid, window, shift):
-    """Same on the tensor-core path: there the mask is folded per wrap class into the shared-memory table
-    (tc_sched.cuh: class_region_id).  With no bias both routes add exactly -100*log2(e) or 0 to the logit."""
+    """Same on the tensor-core path, where the mask is folded per wrap class into the shared-memory table (tc_sched.cuh:
+    class_region_id).  Reference = the same kernel on the PRE-ROLLED volume, shift 0, fed the oracle's mask tensor (no
+    window wraps there, so tile order = window order).  With no bias both routes add exactly -100*log2(e) or 0 to a logit:
+    windows that do not wrap must agree bit for bit; wrapped windows sum their keys in piece-major order, so they agree to
+    fp32-accumulation rounding of bf16 outputs only."""
     g = torch.Generator().manual_seed(5)
-    nH, d, B = 3, 32, 2
+    nH, d, B, n = 3, 32, 2, len(grid)
     C = nH * d
     qkv = torch.randn(B, *grid, 3 * C, generator=g).bfloat16().cuda()
     mask = R.shift_mask_nd(grid, window, shift, torch.float32).cuda().contiguous()
     assert mm.ops.winattn_path_name(qkv, None, grid, window, shift, nH, mm.lib.SCORE_SCALED, mm.lib.MASK_SHIFT) == "tcgen05"
-    outs = []
-    for kind, m in ((mm.lib.MASK_SHIFT, None), (mm.lib.MASK_TENSOR, mask)):
-        out, lse = torch.ops.mmn_b200.winattn_fwd(qkv, None, None, None, m, list(grid), list(window), list(shift), nH,
-                                                  mm.lib.SCORE_SCALED, kind, d ** -0.5, 0.0, 0, 0, mm.lib.PATH_TCGEN05)
-        outs.append((out, lse[0]))
-    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    zero = [0] * n
+    assert mm.ops.winattn_path_name(qkv, None, grid, window, zero, nH, mm.lib.SCORE_SCALED, mm.lib.MASK_TENSOR) == "tcgen05"
+    # a mask tensor plus a shift is not a tensor-core combination (tile order != window order for wrapped windows)
+    assert mm.ops.winattn_path_name(qkv, None, grid, window, shift, nH, mm.lib.SCORE_SCALED, mm.lib.MASK_TENSOR) == "generic"
+    dims = tuple(range(1, n + 1))
+    out_s, lse_s = torch.ops.mmn_b200.winattn_fwd(qkv, None, None, None, None, list(grid), list(window), list(shift), nH,
+                                                  mm.lib.SCORE_SCALED, mm.lib.MASK_SHIFT, d ** -0.5, 0.0, 0, 0, mm.lib.PATH_TCGEN05)
+    rolled = torch.roll(qkv, [-s for s in shift], dims).contiguous()
+    out_t, lse_t = torch.ops.mmn_b200.winattn_fwd(rolled, None, None, None, mask, list(grid), list(window), zero, nH,
+                                                  mm.lib.SCORE_SCALED, mm.lib.MASK_TENSOR, d ** -0.5, 0.0, 0, 0, mm.lib.PATH_TCGEN05)
+    out_sr = torch.roll(out_s, [-s for s in shift], dims)
+    inner = torch.ones(grid, dtype=torch.bool, device="cuda")       # tokens (rolled frame) of windows that do not wrap
+    for a in range(n):
+        if shift[a]:
+            idx = torch.arange(grid[a], device="cuda") // window[a] < grid[a] // window[a] - 1
+            inner &= idx.view([-1 if i == a else 1 for i in range(n)])
+    assert inner.any() and (~inner).any()
+    assert torch.equal(out_sr[:, inner], out_t[:, inner]), "unwrapped windows: in-kernel mask differs from the oracle mask tensor"
+    assert rel_err(out_sr, out_t) < 1e-2
+    assert torch.equal(lse_s[0].isfinite(), lse_t[0].isfinite())
 
 
 # ------------------------------------------------------------------------------------------
@@ -147,20 +164,20 @@ def test_fp16_autocast_gradscaler_like_the_reference_trainer(mm):
     w1 = R.swin_v2_block(xo, _sd64(blk), grid, 4, 2, nH)
     w2a, w2b = R.cross_block(xo, yo, _sd64(cross), grid, grid, 4, 2, nH)
     w3 = R.encoder_layer(so, _sd64(enc), 12, True)
-    gw = torch.autograd.grad(w1.sum() + w2a.sum() + w2b.sum() + w3.sum(), (xo, yo, so))
+    gw = torch.autograd.grad(w1.mean() + w2a.mean() + w2b.mean() + w3.mean(), (xo, yo, so))   # a mean, like the trainer's BCE
 
     blk, cross, enc = blk.cuda(), cross.cuda(), enc.cuda().eval()
     xc, yc, sc_ = (t.cuda().requires_grad_(True) for t in (x, y, s))
     params = [p for m in (blk, cross, enc) for p in m.parameters()]
     opt = torch.optim.SGD(params, lr=0.0)
-    scaler = torch.cuda.amp.GradScaler()
+    scaler = torch.amp.GradScaler('cuda')
     opt.zero_grad()
-    with torch.cuda.amp.autocast():                       # fp16, the reference's mode (main.py:88: --amp defaults to on)
+    with torch.amp.autocast('cuda'):                      # fp16 (torch.cuda.amp.autocast() of trainer.py:378), the reference's mode (main.py:88: --amp defaults to on)
         o1 = blk(xc)
         o2a, o2b = cross(xc, yc, grid)
         o3 = enc(sc_)
         assert o1.dtype == torch.float32 or o1.dtype == torch.float16
-        loss = o1.float().sum() + o2a.float().sum() + o2b.float().sum() + o3.float().sum()
+        loss = o1.float().mean() + o2a.float().mean() + o2b.float().mean() + o3.float().mean()
     scaler.scale(loss).backward()
     scaler.unscale_(opt)
     scaler.step(opt)
