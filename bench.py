@@ -15,8 +15,14 @@ roofline  the dominant kernel of the step, timed live with CUDA events on its st
 cpu_baseline / --impl reference  the CPU oracle port of the reference module (the reference
         is PyTorch/Python and is not on the GPU box) on a bounded sample, all host threads.
 
+gpu_eager_baseline  the same module as plain PyTorch ops (the oracle's restatement of the reference module) on THIS GPU
+        under bf16 autocast -- what a user of the reference gets today (the real comparator).
+train   BASELINE configs[2] ("cfg3") inside the same line: a full bf16 training step (forward, BCE loss, backward,
+        NCCL gradient all-reduce when N > 1, AdamW) of the 3-D SwinFusion workload, batch 8 per GPU, samples/s.
+
   python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--batch B]
   torchrun ... bench.py --gpus N ...        (one rank per GPU, NCCL; weak scaling)
+  python bench.py --workload cfg3|cfg5|cfg5-sweep|mha      (other BASELINE configs as the primary line)
 """
 from __future__ import annotations
 
@@ -153,8 +159,233 @@ def run_reference_arm(args, rank, world, emit):
             "config": workload_config(args.batch, world),
             "cpu_baseline": {"value": tflops, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": tflops, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "sample_per_step": "1 volume of 32^3 tokens = 512 windows"}
     emit(line)
+
+
+
+# ------------------------------------------------------------------------------------------
+# Eager-PyTorch-on-this-GPU comparator: the reference module's arithmetic as plain torch ops
+# ------------------------------------------------------------------------------------------
+def gpu_eager_baseline(dev, samples=4, steps=10, warmup=3):
+    from oracle import ref_nd as R
+    from multimodal_neuroimage_b200 import geometry
+    g = torch.Generator().manual_seed(0)
+    w3 = (WINDOW,) * 3
+    p = {"qkv.weight": torch.randn(3 * C, C, generator=g) * C ** -0.5, "q_bias": torch.randn(C, generator=g) * 0.1,
+         "v_bias": torch.randn(C, generator=g) * 0.1, "logit_scale": torch.log(10 * torch.ones(HEADS, 1, 1)),
+         "cpb_mlp.0.weight": torch.randn(512, 3, generator=g) * 0.5, "cpb_mlp.0.bias": torch.randn(512, generator=g) * 0.1,
+         "cpb_mlp.2.weight": torch.randn(HEADS, 512, generator=g) * 0.05,
+         "proj.weight": torch.randn(C, C, generator=g) * C ** -0.5, "proj.bias": torch.zeros(C),
+         "relative_coords_table": geometry.cpb_coords_table(w3), "relative_position_index": geometry.relative_position_index(w3)}
+    p = {k: v.to(dev) for k, v in p.items()}
+    for k in list(p):
+        if p[k].is_floating_point() and "relative" not in k:
+            p[k].requires_grad_(True)
+    mask = R.shift_mask_nd(GRID, w3, (SHIFT,) * 3).to(dev)
+    x = torch.randn(samples, math.prod(GRID), C, generator=g).to(dev).requires_grad_(True)
+    dy = torch.randn(samples, math.prod(GRID), C, generator=g).to(dev)
+
+    def step():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            xs = R.cyclic_shift_nd(x.view(samples, *GRID, C), (SHIFT,) * 3)
+            xw = R.window_partition_nd(xs, w3).view(-1, N, C)
+            aw = R.window_attention_cosine(xw, p, w3, HEADS, mask)
+            y = R.cyclic_shift_nd(R.window_reverse_nd(aw.view(-1, *w3, C), w3, GRID), (SHIFT,) * 3, inverse=True)
+        wrt = [x] + [t for t in p.values() if t.requires_grad]
+        torch.autograd.grad((y.reshape(samples, -1, C).float() * dy).sum(), wrt)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": samples * WINDOWS_PER_SAMPLE * FLOP_PER_WINDOW / (ms * 1e-3) / 1e12, "unit": UNIT, "ms_per_step": ms,
+            "sample": f"{samples} volumes ({samples * WINDOWS_PER_SAMPLE} windows) per step",
+            "kind": "PyTorch eager on this GPU, bf16 autocast: roll + window_partition + F.linear + normalize + bmm + softmax + "
+                    "bmm + F.linear + window_reverse + roll (the reference module's op sequence, swin_v2_module.py:138-178,277-297, "
+                    "restated n-D in oracle/ref_nd.py), autograd backward"}
+
+
+# ------------------------------------------------------------------------------------------
+# Training-step workloads: cfg3 (3-D SwinFusion) and cfg5 (SwinV2 cross-modal towers)
+# ------------------------------------------------------------------------------------------
+TRAIN_WORKLOADS = {
+    "cfg3": dict(img=96, batch=8, desc="cfg3: SwinFusion sMRI+fMRI fusion model, 3-D (96^3 volumes, patch 4 -> 24^3 tokens, C=96, 3 heads x 32, "
+                                       "4x4x4 windows; Ex 6+6 x2, Fusion 3 x (2+2+2), Re 6+6: 60 window-attention blocks), bf16 training step, "
+                                       "BCE loss, AdamW"),
+    "cfg5": dict(img=128, batch=1, desc="cfg5: two SwinV2-3D towers (embed 192, depths 2/2/6/2, heads 6/12/24/48, 128^3 volumes, patch 4) + "
+                                        "cross-modal transformer (E=1536, 2+2 layers), bf16 training step, BCE loss, AdamW"),
+}
+
+
+def run_train_workload(name, dev, rank, world, steps, warmup, batch=None, use_graph=True, ddp="flat", checkpoint=False):
+    """Returns a dict with device-timed and end-to-end samples/s of one training step (max over ranks)."""
+    import torch.distributed as dist
+    from multimodal_neuroimage_b200 import _lib
+    from multimodal_neuroimage_b200 import train_step as TS
+    from multimodal_neuroimage_b200 import workloads as W
+    cfg = TRAIN_WORKLOADS[name]
+    batch = batch or cfg["batch"]
+    torch.manual_seed(0)
+    model = W.SwinFusion3D(use_checkpoint=checkpoint) if name == "cfg3" else W.SwinV2CrossModal3D(use_checkpoint=checkpoint)
+    W.randomise_norms(model)
+    model = model.to(dev)
+    A, Bv, y = W.synthetic_batch(batch, cfg["img"], dev, seed=100 + rank, pinned=True)
+    loss_fn = torch.nn.functional.binary_cross_entropy_with_logits
+    mode = "eager"
+    try:
+        ts = TS.TrainStep(model, loss_fn, (A, Bv), y, world=world, use_graph=use_graph, ddp=ddp, warmup=max(2, warmup))
+        mode = "cuda-graph" if ts.g_fb is not None else "eager"
+    except Exception as exc:                               # capture not possible: eager step
+        print(f"bench: CUDA graph capture of the {name} step failed ({type(exc).__name__}: {exc}); eager", file=sys.stderr)
+        torch.cuda.synchronize(dev)
+        ts = TS.TrainStep(model, loss_fn, (A, Bv), y, world=world, use_graph=False, ddp=ddp)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, n):
+        barrier()
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), (_lib.launch_count() - l0) // n
+
+    losses = []
+    for _ in range(max(1, warmup)):
+        losses.append(float(ts().item()))
+    ms, launches = timed(lambda: ts(), steps)
+    ms_e2e, _ = timed(lambda: losses.append(float(ts((A, Bv), y).item())), max(3, steps // 2))
+    flops = W.flops_per_sample(model) * 3
+    out = {"workload": cfg["desc"], "per_gpu_batch": batch, "global_batch": batch * world, "ms_per_step": ms,
+           "samples_per_s": batch * world / (ms * 1e-3),
+           "e2e": {"samples_per_s": batch * world / (ms_e2e * 1e-3), "ms_per_step": ms_e2e,
+                   "h2d_bytes_per_step": int(A.numel() * 2 * 2 + y.numel() * 4), "d2h_bytes_per_step": 4,
+                   "note": "the batch (two fp16 volumes per sample + labels) copied from pinned host memory and the loss read back "
+                           "with .item() every step"},
+           "trainable_params": W.count_params(model), "grad_allreduce_bytes_per_step": ts.grad_bytes() if world > 1 else 0,
+           "mode": mode + (" forward+backward, one NCCL all-reduce of the flat fp32 gradient buffer, graphed fused AdamW"
+                           if ddp == "flat" else " torch DistributedDataParallel (bucketed overlap), fused AdamW"),
+           "hot_path_tflops": batch * world * flops / (ms * 1e-3) / 1e12, "hot_path_flop_per_sample": flops,
+           "kernel_launches_per_step_own_eager": launches if mode == "eager" else None,
+           "loss_first": losses[0], "loss_last": losses[-1]}
+    del ts, model
+    torch.cuda.empty_cache()
+    return out
+
+
+
+# ------------------------------------------------------------------------------------------
+# cfg5 roofline sweep: the fused window-attention module and the Mlp at the four stage widths of the scaled SwinV2-3D tower
+# ------------------------------------------------------------------------------------------
+def _time_fwd_bwd(fn_fwd, x, dy, steps, warmup):
+    def step():
+        x.grad = None
+        y = fn_fwd(x)
+        y.backward(dy)
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def run_cfg5_sweep(args, dev, rank, emit):
+    from multimodal_neuroimage_b200 import _lib
+    from multimodal_neuroimage_b200.modules import swin_v2_module as v2
+    pk = peaks()
+    stages = []
+    tokens_target = 262144                                   # 4096 windows per step at every stage
+    for C_, nH, g in ((96, 3, 32), (192, 6, 32), (384, 12, 16), (768, 24, 8), (1536, 48, 4)):
+        grid = (g, g, g)
+        L = g ** 3
+        Bs = max(1, tokens_target // L)
+        shift = (2, 2, 2) if g > 4 else (0, 0, 0)
+        attn = v2.WindowAttention(C_, (4, 4, 4), nH).to(dev)
+        mlp = v2.Mlp(C_, 4 * C_).to(dev)
+        x = torch.randn(Bs, L, C_, device=dev, dtype=torch.bfloat16, requires_grad=True)
+        dy = torch.randn(Bs, L, C_, device=dev, dtype=torch.bfloat16)
+        wins = Bs * L // 64
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            l0 = _lib.launch_count()
+            ms_a = _time_fwd_bwd(lambda t: attn.forward_grid(t, grid, shift), x, dy, args.steps, args.warmup)
+            n_launch = (_lib.launch_count() - l0) // (args.steps + args.warmup)
+            ms_m = _time_fwd_bwd(mlp, x, dy, args.steps, args.warmup)
+        f_attn = wins * 3 * (4 * 64 * 64 * C_ + 8 * 64 * C_ * C_)
+        f_mlp = wins * 3 * (16 * 64 * C_ * C_)
+        stages.append({"C": C_, "heads": nH, "grid": list(grid), "batch": Bs, "windows": wins,
+                       "attn_module_ms": ms_a, "attn_module_tflops": f_attn / ms_a / 1e9, "attn_frac_bf16_peak": f_attn / ms_a / 1e9 / pk["bf16_tflops"],
+                       "attn_ai_flop_per_byte": 2 * C_ + 64, "own_launches_per_step": n_launch,
+                       "mlp_ms": ms_m, "mlp_tflops": f_mlp / ms_m / 1e9, "mlp_frac_bf16_peak": f_mlp / ms_m / 1e9 / pk["bf16_tflops"]})
+        del attn, mlp, x, dy
+        torch.cuda.empty_cache()
+    if rank == 0:
+        best = max(st["attn_module_tflops"] for st in stages)
+        emit({"metric": "window_attn_fwd_bwd_stage_sweep", "value": best, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+              "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+              "config": {"workload": "cfg5 per-stage sweep: fused SwinV2-3D window-attention module (x -> qkv -> attention -> proj) and Mlp, "
+                                     "fwd+bwd, 4x4x4 windows, 4096 windows per step, eager launches", "parallelism": "dp1"},
+              "stages": stages, "peak_bf16_tflops": pk["bf16_tflops"], "peak_source": pk["source"]})
+
+
+# ------------------------------------------------------------------------------------------
+# Cross-modal multi-head attention (modules/multihead_attention.py:85-127): cfg1 sizes and a scaled shape
+# ------------------------------------------------------------------------------------------
+def run_mha(args, dev, rank, emit):
+    from multimodal_neuroimage_b200 import _lib
+    from multimodal_neuroimage_b200.modules import multihead_attention as mh
+    pk = peaks()
+    rows = []
+    for name, E, nH, T, S, Bm, dt in (("cfg1 cross (E=84, 12 heads, d=7)", 84, 12, 368, 368, 2, torch.float32),
+                                      ("cfg1 self (E=168, 12 heads, d=14)", 168, 12, 368, 368, 2, torch.float32),
+                                      ("scaled (E=768, 12 heads, d=64)", 768, 12, 2048, 2048, 32, torch.bfloat16)):
+        m = mh.MultiheadAttention(E, nH).to(dev)
+        m.need_weights = False
+        q = torch.randn(T, Bm, E, device=dev, requires_grad=True)
+        k = torch.randn(S, Bm, E, device=dev)
+        dy = torch.randn(T, Bm, E, device=dev)
+        mask = None
+        d = _lib.MhaDesc()
+        d.tgt_len, d.src_len, d.batch, d.num_heads, d.head_dim = T, S, Bm, nH, E // nH
+        d.io_dtype = _lib.DT_BF16 if dt == torch.bfloat16 else _lib.DT_F32
+        path = _lib.load().mmn_mha_path(d).decode()
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dt == torch.bfloat16):
+            ms = _time_fwd_bwd(lambda t: m(t, k, k, attn_mask=mask)[0], q, dy.to(dt) if dt == torch.bfloat16 else dy, args.steps, args.warmup)
+        flops = 3 * 4 * T * S * E * Bm
+        byts = 3 * 4 * E * (T + S) * Bm * (2 if dt == torch.bfloat16 else 4) // 2
+        rows.append({"shape": name, "T": T, "S": S, "batch": Bm, "dtype": str(dt).split(".")[-1], "ms_fwd_bwd_module": ms,
+                     "core_tflops": flops / ms / 1e9, "core_frac_bf16_peak": flops / ms / 1e9 / pk["bf16_tflops"],
+                     "core_algorithmic_GBs": byts / ms / 1e6, "path": path})
+        del m, q, k, dy
+        torch.cuda.empty_cache()
+    if rank == 0:
+        emit({"metric": "crossmodal_mha_fwd_bwd", "value": rows[-1]["core_tflops"], "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+              "warmup": args.warmup, "ms_per_step": rows[-1]["ms_fwd_bwd_module"], "higher_is_better": True, "scaling": "weak",
+              "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+              "config": {"workload": "cross-modal MultiheadAttention module fwd+bwd (in/out projections + attention core); value = "
+                                     "attention-core algorithmic flops 12 T S E per sample of the scaled shape over the module time",
+                         "parallelism": "dp1"},
+              "shapes": rows, "peak_bf16_tflops": pk["bf16_tflops"]})
 
 
 LAUNCH_MODE = ["eager"]
@@ -164,7 +395,9 @@ def workload_config(batch, world):
     return {"workload": "cfg2: SwinV2 3-D shifted-window attention module fwd+bwd, 4x4x4 windows shift 2, 3 heads x 32, "
                         "32^3 tokens x 96 ch per sample",
             "per_gpu_batch": batch, "global_batch": batch * world, "windows_per_step": batch * world * WINDOWS_PER_SAMPLE,
-            "flop_per_window": FLOP_PER_WINDOW, "l2_policy": "inputs larger than L2 (x, qkv, grads >> 126 MB)", "launch": LAUNCH_MODE[0],
+            "flop_per_window": FLOP_PER_WINDOW, "l2_policy": "inputs larger than L2 (x, qkv, grads >> 126 MB)",
+            "reference_arm_sample": "--impl reference times the CPU port on 1 volume (512 windows) per step; values are per-window "
+                                    "flop-normalised, so the arms compare directly",
             "parallelism": f"dp{world}"}
 
 
@@ -191,6 +424,17 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="volumes per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of one CUDA-graph replay per step")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg5", "cfg5-sweep", "mha"],
+                    help="primary line: cfg2 (default, BASELINE's kernel metric, with the cfg3 training step nested under 'train'), "
+                         "a training-step workload, the cfg5 per-stage roofline sweep, or cross-modal multi-head attention")
+    ap.add_argument("--no-train", action="store_true", help="cfg2 line without the nested cfg3 training step")
+    ap.add_argument("--no-eager-baseline", action="store_true")
+    ap.add_argument("--train-steps", type=int, default=10)
+    ap.add_argument("--train-batch", type=int, default=0, help="per-GPU batch of the training-step workload (0: its default)")
+    ap.add_argument("--ddp", default="flat", choices=["flat", "torch"],
+                    help="gradient exchange of the training step: one all-reduce of the flat gradient buffer after a graph-replayed "
+                         "backward (default) or torch DistributedDataParallel (eager, bucketed overlap)")
+    ap.add_argument("--checkpoint", action="store_true", help="activation checkpointing in the training-step workloads")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -213,6 +457,28 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
+
+    if args.workload in ("cfg3", "cfg5"):
+        with ClockSampler(local) as clk:
+            tr = run_train_workload(args.workload, dev, rank, world, args.steps, args.warmup, args.train_batch or None,
+                                    not args.no_graph, args.ddp, args.checkpoint)
+        if rank == 0:
+            emit({"metric": "train_samples_per_s", "value": tr["samples_per_s"], "unit": "samples/s", "n_gpus": world,
+                  "steps": args.steps, "warmup": args.warmup, "ms_per_step": tr["ms_per_step"], "higher_is_better": True,
+                  "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                  "config": {"workload": tr["workload"], "per_gpu_batch": tr["per_gpu_batch"], "global_batch": tr["global_batch"],
+                             "parallelism": f"dp{world}", "l2_policy": "activations of a step (GBs) exceed L2"},
+                  "e2e": {"value": tr["e2e"]["samples_per_s"], "unit": "samples/s", **{k: v for k, v in tr["e2e"].items() if k != "samples_per_s"}},
+                  "gpu_launches": tr["kernel_launches_per_step_own_eager"], "train": tr, "clocks": clk.summary()})
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    if args.workload == "cfg5-sweep":
+        run_cfg5_sweep(args, dev, rank, emit)
+        return
+    if args.workload == "mha":
+        run_mha(args, dev, rank, emit)
+        return
 
     B = args.batch
     torch.manual_seed(1234 + rank)
@@ -471,6 +737,25 @@ def main():
                             for k in kern if k in cand},
                     "module_tflops_frac_of_bf16_peak": value / world / pk["bf16_tflops"]}
 
+    # free the cfg2 buffers, then the nested cfg3 training step (every rank takes part: it has a collective when N > 1)
+    train = None
+    if not args.no_train:
+        try:
+            del x_slot, dy_slot
+            e2e_state.clear()
+            torch.cuda.empty_cache()
+            train = run_train_workload("cfg3", dev, rank, world, args.train_steps, 2, args.train_batch or None, not args.no_graph,
+                                       args.ddp, args.checkpoint)
+        except Exception as exc:
+            train = {"error": f"{type(exc).__name__}: {exc}"}
+            print(f"bench: nested cfg3 training step failed: {train['error']}", file=sys.stderr)
+    eager = None
+    if rank == 0 and not args.no_eager_baseline:
+        try:
+            eager = gpu_eager_baseline(dev)
+        except Exception as exc:
+            eager = {"error": f"{type(exc).__name__}: {exc}"}
+
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
@@ -486,7 +771,8 @@ def main():
                         "note": "x, dy from pinned host memory; y, dx back to pinned host memory; 8 chunks through 3 streams and "
                                 "3 device slots, one CUDA-graph replay per chunk: PCIe-bound (measured duplex floor of this box: "
                                 "8.7 ms for these bytes, tools/pcie_probe.py)"},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary(),
+                "gpu_launches": launches, "launch": LAUNCH_MODE[0], "roofline": roofline, "cpu_baseline": cpu,
+                "gpu_eager_baseline": eager, "train": train, "clocks": clk.summary(),
                 "paths": {"fwd": ops.winattn_path_name(torch.empty(1, *GRID, 3 * C, device=dev, dtype=torch.bfloat16), None, GRID,
                                                        (WINDOW,) * 3, (SHIFT,) * 3, HEADS, _lib.SCORE_COSINE, _lib.MASK_SHIFT)}}
         emit(line)
