@@ -178,6 +178,26 @@ int mmn_linear_bwd(const void* dy, const void* x, const void* w, void* dx, float
                    const void* act_aux, int64_t ld_aux, int act, int io_dtype, int64_t rows, int32_t in_features,
                    int32_t out_features, int64_t ld_dy, int64_t ld_x, int64_t ld_dx, int device, void* stream);
 
+/* LayerNorm fused with the residual add around it (csrc/layernorm.cu), one pass over the rows forward, one backward.
+ * Replaces the norm + add (+ autocast cast) sequences of swin_v2_module.py:299,302 (res-post-norm),
+ * swinfusion_module.py:345,377-378,491-492,535-539 (pre-norm) and crossmodal_transformer.py:143-165.  Per row of `cols`:
+ *   MMN_LN_PRE :  s = resid + delta;                       out_sum = s,  out_norm = LN(s) * gamma + beta
+ *   MMN_LN_POST:  s = resid + (LN(delta) * gamma + beta);  out_sum = s,  out_norm = s
+ * resid or (PRE only) delta may be NULL (= 0), out_sum or out_norm may be NULL (skipped); each tensor is MMN_DT_F32 or
+ * MMN_DT_BF16 on its own, rows contiguous; gamma / beta (cols) fp32, beta may be NULL; mean / rstd (rows) fp32 are written
+ * for the backward.  cols even and <= 1536.
+ * Backward: g_sum / g_norm = gradients w.r.t. out_sum / out_norm (either may be NULL), x = the normalised quantity (PRE: s,
+ * i.e. out_sum or the lone input; POST: delta).  d_resid / d_delta may be NULL.  dgamma / dbeta (cols) fp32 are ACCUMULATED
+ * into with atomics (the caller zeroes them); either may be NULL. */
+enum { MMN_LN_PRE = 0, MMN_LN_POST = 1 };
+int mmn_layernorm_supported(int32_t cols);
+int mmn_layernorm_fwd(const void* resid, int resid_dtype, const void* delta, int delta_dtype, const float* gamma, const float* beta,
+                      float eps, int mode, void* out_sum, int sum_dtype, void* out_norm, int norm_dtype, float* mean, float* rstd,
+                      int64_t rows, int32_t cols, int device, void* stream);
+int mmn_layernorm_bwd(const void* g_sum, int gs_dtype, const void* g_norm, int gn_dtype, const void* x, int x_dtype,
+                      const float* gamma, const float* mean, const float* rstd, int mode, void* d_resid, int dr_dtype,
+                      void* d_delta, int dd_dtype, float* dgamma, float* dbeta, int64_t rows, int32_t cols, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,6 +22,7 @@ SOURCES = {"mmn_abi.cu": ["generic_launch.h", "attn_generic.cuh", "winattn_tc.h"
            "winattn_tc.cu": ["winattn_tc.h", "winattn_tc_fwd.cuh", "winattn_tc_bwd.cuh", "tc_window.cuh", "tc_sched.cuh", "tc_common.cuh"],
            "linbwd_tc.cu": ["winattn_tc.h", "tc_window.cuh", "tc_common.cuh"],
            "gemm_tc.cu": ["winattn_tc.h", "tc_window.cuh", "tc_common.cuh"],
+           "layernorm.cu": ["generic_launch.h", "attn_generic.cuh"],
            "cpb_bias.cu": ["generic_launch.h", "attn_generic.cuh"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
@@ -38,13 +39,14 @@ SCORE_SCALED, SCORE_COSINE = 0, 1
 MASK_NONE, MASK_SHIFT, MASK_TENSOR, MASK_FUTURE = 0, 1, 2, 3
 PATH_AUTO, PATH_GENERIC, PATH_TCGEN05 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+LN_PRE, LN_POST = 0, 1
 ABI_VERSION = 2
 WINATTN_WORK_BYTES = 2048
 
 EXPORTS = ["mmn_abi_version", "mmn_last_error", "mmn_winattn_path", "mmn_mha_path", "mmn_launch_count",
            "mmn_winattn_fwd", "mmn_winattn_bwd", "mmn_mha_fwd", "mmn_mha_bwd", "mmn_mha_avg_weights", "mmn_colsum",
            "mmn_linear_supported", "mmn_linear_fwd", "mmn_linear_bwd", "mmn_linear_bwd_supported", "mmn_linear_bwd_workspace_bytes",
-           "mmn_cpb_bias_fwd", "mmn_cpb_bias_bwd"]
+           "mmn_cpb_bias_fwd", "mmn_cpb_bias_bwd", "mmn_layernorm_supported", "mmn_layernorm_fwd", "mmn_layernorm_bwd"]
 
 
 class WinAttnDesc(C.Structure):
@@ -161,6 +163,14 @@ def load() -> C.CDLL:
         lib.mmn_linear_fwd.restype = C.c_int
         lib.mmn_linear_fwd.argtypes = [vp, vp, fp, vp, vp, C.c_int, C.c_int, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
                                        C.c_int, vp]
+        lib.mmn_layernorm_supported.restype = C.c_int
+        lib.mmn_layernorm_supported.argtypes = [C.c_int32]
+        lib.mmn_layernorm_fwd.restype = C.c_int
+        lib.mmn_layernorm_fwd.argtypes = [vp, C.c_int, vp, C.c_int, fp, fp, C.c_float, C.c_int, vp, C.c_int, vp, C.c_int, fp, fp,
+                                          C.c_int64, C.c_int32, C.c_int, vp]
+        lib.mmn_layernorm_bwd.restype = C.c_int
+        lib.mmn_layernorm_bwd.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int, fp, fp, fp, C.c_int, vp, C.c_int, vp, C.c_int, fp, fp,
+                                          C.c_int64, C.c_int32, C.c_int, vp]
         if lib.mmn_abi_version() != ABI_VERSION:
             raise RuntimeError("libmmn_b200.so ABI version mismatch")
         _lib = lib

@@ -10,8 +10,9 @@
 // elements of the contiguous dimension (3-D tensor maps: element-in-panel, row, panel):
 //   K-major operand   (reduction dim contiguous: x and W in the forward, dy in dgrad)   stage = [KP panels][rows][64 B]
 //   MN-major operand  (output dim contiguous:    W in dgrad, dy^T and x in wgrad)        stage = [rows/32 panels][32 KP][64 B]
-// Warp roles: warps 0-7 epilogue (two per TMEM lane quarter, each half of the tile's columns), warp 8 TMA producer,
-// warp 9 MMA issuer.  Three pipelines: smem ring (TMA <-> MMA), two TMEM accumulators (MMA <-> epilogue), static
+// Warp roles: warps 0-15 epilogue (four per TMEM lane quarter, each a quarter of the tile's columns: the bias / GELU /
+// GELU' arithmetic of a 128 x BN tile is what bounds the small-K layers, so it gets the issue slots of 16 warps), warp 16
+// TMA producer, warp 17 MMA issuer.  Three pipelines: smem ring (TMA <-> MMA), two TMEM accumulators (MMA <-> epilogue), static
 // round-robin tile schedule with the n tiles of one row block adjacent (x is read from HBM once, W stays in L2).
 #include <cstdio>
 #include <mutex>
@@ -23,16 +24,13 @@ namespace mmn { namespace tc {
 
 enum { kEpiNone = 0, kEpiRelu = 1, kEpiGelu = 2, kEpiReluGrad = 3, kEpiGeluGrad = 4 };
 
-constexpr int kGEpiWarps = 8;
+constexpr int kGEpiWarps = 16;               // four per TMEM lane quarter, each a quarter of the tile's columns
 constexpr int kGThreads = 32 * (kGEpiWarps + 2);
 constexpr int kGProducerWarp = kGEpiWarps, kGMmaWarp = kGEpiWarps + 1;
 constexpr int kGTmemCols = 256;                // two accumulators of BN <= 128 columns
 
 struct GemmParams {
-  CUtensorMap a, b;
-  __nv_bfloat16* d;                            // bf16 output (M, N), row stride ld_d
-  __nv_bfloat16* d_pre;                        // optional second output: the value before the activation
-  long long ld_d;
+  CUtensorMap a, b, d, d_pre;
   int M, N;                                    // output rows / columns
   int tiles_n, n_tiles, k_blocks, splits, kb_per_split;
   int epi, has_pre;
@@ -51,11 +49,15 @@ template <int BN, int KP, int STAGES, bool A_MN, bool B_MN, bool F32OUT>
 __global__ void __launch_bounds__(kGThreads, 1)
 gemm_tc_kernel(const __grid_constant__ GemmParams P) {
   constexpr int kABytes = 8192 * KP, kBBytes = BN * 64 * KP;
+  constexpr int kPanelOut = 128 * 64;                       // one 32-column panel of the output tile
+  constexpr int kOutBytes = F32OUT ? 0 : (BN / 32) * kPanelOut;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = sA + STAGES * kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * kBBytes);
+  uint8_t* sOut = sB + STAGES * kBBytes;                    // two staging slots of [BN/32 panels][128 rows][64 B]: tiles alternate
+                                                            // between them; with a second output (pre-activation) a tile takes both
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + 2 * kOutBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* acc_full = bars + 2 * STAGES;                   // [2]
@@ -71,6 +73,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams P) {
     fence_barrier_init();
   }
   if (warp == kGProducerWarp && lane == 0) { tma_prefetch_desc(&P.a); tma_prefetch_desc(&P.b); }
+  if (!F32OUT && warp == 0 && lane == 0) { tma_prefetch_desc(&P.d); if (P.has_pre) tma_prefetch_desc(&P.d_pre); }
   if (warp == kGMmaWarp) tmem_alloc<kGTmemCols>(tmem_slot);
   tcgen05_fence_before();
   __syncthreads();
@@ -132,11 +135,11 @@ gemm_tc_kernel(const __grid_constant__ GemmParams P) {
     }
   } else {
     // ============================== epilogue: warp w -> TMEM lanes 32 (w % 4) .., column half w / 4 ==============================
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, cg = warp >> 2;               // TMEM lane quarter, column group
     const int r = q * 32 + lane;                          // row of the tile
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    constexpr int kChunks = BN / 32;                      // 32-column chunks; half 0 takes the first (kChunks + 1) / 2
-    const int c_begin = half == 0 ? 0 : (kChunks + 1) / 2, c_end = half == 0 ? (kChunks + 1) / 2 : kChunks;
+    constexpr int kChunks = BN / 32;                      // 32-column chunks: group cg takes chunks cg, cg + 4, ...
+    const int rsw = (r >> 1) & 3;
     int un = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++un) {
       const int tile = u / P.splits, sp = u - tile * P.splits;
@@ -145,13 +148,20 @@ gemm_tc_kernel(const __grid_constant__ GemmParams P) {
       const int as = un & 1;
       mbar_wait(&acc_full[as], (un >> 1) & 1);
       tcgen05_fence_after();
-      const bool row_ok = m0 + r < P.M;
-      for (int c = c_begin; c < c_end; ++c) {
+      uint8_t* slot_act = sOut + ((P.has_pre ? 0 : (un & 1)) * kOutBytes);
+      uint8_t* slot_pre = sOut + kOutBytes;
+      if (!F32OUT) {
+        if (tid == 0) {                                    // the store that last read this tile's slot(s) has drained them
+          if (P.has_pre) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+        }
+        named_bar_sync(1, 32 * kGEpiWarps);
+      }
+      for (int c = cg; c < kChunks; c += 4) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem + lane_base + as * BN + c * 32, v);
         tmem_ld_wait();
         if (F32OUT) {
-          if (row_ok) {
+          if (m0 + r < P.M) {
             float4* dst = reinterpret_cast<float4*>(P.out32 + ((size_t)sp * P.M + (m0 + r)) * P.N + n0 + c * 32);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -170,15 +180,13 @@ gemm_tc_kernel(const __grid_constant__ GemmParams P) {
               f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
             }
           }
-          // Each thread owns 32 consecutive columns of its row: four 16-byte stores = two full 32-byte sectors per
-          // row and chunk, straight to global (no staging tile, no proxy fence, no store-group wait between tiles).
-          const size_t o = (size_t)(m0 + r) * P.ld_d + n0 + c * 32;
-          if (P.has_pre && row_ok) {                       // pre-activation, kept for the backward's act'(pre)
-            uint4* dp = reinterpret_cast<uint4*>(P.d_pre + o);
+          const int ooff = c * kPanelOut + r * 64;
+          if (P.has_pre) {                                 // pre-activation, kept for the backward's act'(pre)
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              dp[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                 pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+              *reinterpret_cast<uint4*>(slot_pre + ooff + ((j ^ rsw) << 4)) =
+                  make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                             pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
           }
           if (P.epi == kEpiRelu) {
 #pragma unroll
@@ -188,7 +196,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams P) {
             for (int j = 0; j < 32; ++j) f[j] = gelu_f(f[j]);
           } else if (P.epi == kEpiReluGrad || P.epi == kEpiGeluGrad) {
             uint32_t x[16];
-            if (row_ok) {
+            if (m0 + r < P.M) {
               const uint4* ap = reinterpret_cast<const uint4*>(P.aux + (size_t)(m0 + r) * P.ld_aux + n0 + c * 32);
 #pragma unroll
               for (int j = 0; j < 4; ++j) { const uint4 t = __ldg(ap + j); x[4 * j] = t.x; x[4 * j + 1] = t.y; x[4 * j + 2] = t.z; x[4 * j + 3] = t.w; }
@@ -203,18 +211,26 @@ gemm_tc_kernel(const __grid_constant__ GemmParams P) {
               else { f[2 * j] *= gelu_grad_f(lo); f[2 * j + 1] *= gelu_grad_f(hi); }
             }
           }
-          if (row_ok) {
-            uint4* dp = reinterpret_cast<uint4*>(P.d + o);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              dp[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                 pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
-          }
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(slot_act + ooff + ((j ^ rsw) << 4)) =
+                make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                           pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
         }
       }
       tcgen05_fence_before();
       mbar_arrive_warp(&acc_empty[as]);
+      if (!F32OUT) {
+        fence_proxy_async_smem();
+        named_bar_sync(2, 32 * kGEpiWarps);
+        if (tid == 0) {
+          tma_store_3d(&P.d, slot_act, 0, m0, n0 >> 5);
+          if (P.has_pre) tma_store_3d(&P.d_pre, slot_pre, 0, m0, n0 >> 5);
+          tma_store_commit();
+        }
+      }
     }
+    if (!F32OUT && tid == 0) tma_store_wait_all<0>();
   }
 
   tcgen05_fence_before();
@@ -257,8 +273,9 @@ static int pick_kp(long long k) { const long long p = k / 32; return p % 2 == 0 
 template <int BN, int KP, bool A_MN, bool B_MN, bool F32OUT>
 struct GemmCfg {
   static constexpr int kStageBytes = 8192 * KP + BN * 64 * KP;
-  static constexpr int kStages = (200 * 1024) / kStageBytes >= 6 ? 6 : (200 * 1024) / kStageBytes;
-  static constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + (2 * kStages + 4) * 8 + 16;
+  static constexpr int kOut = F32OUT ? 0 : 2 * (BN / 32) * 128 * 64;
+  static constexpr int kStages = (200 * 1024 - kOut) / kStageBytes >= 6 ? 6 : (200 * 1024 - kOut) / kStageBytes;
+  static constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + kOut + (2 * kStages + 4) * 8 + 16;
   static int launch(const GemmParams& P, int grid, cudaStream_t st) {
     auto kern = gemm_tc_kernel<BN, KP, kStages, A_MN, B_MN, F32OUT>;
     static std::once_flag once;
@@ -304,13 +321,13 @@ int linear_fwd(const void* x, const void* w, const float* bias, void* y, void* y
   const int bn = pick_bn(out_features), kp = pick_kp(in_features);
   GemmParams P{};
   if (!panel_map(&P.a, x, rows, in_features, ld_x, 128, kp) || !panel_map(&P.b, w, out_features, in_features, in_features, bn, kp) ||
-      reinterpret_cast<uintptr_t>(y) % 16 || reinterpret_cast<uintptr_t>(y_pre) % 16) {
+      !panel_map(&P.d, y, rows, out_features, ld_y, 128, bn / 32) ||
+      (y_pre && !panel_map(&P.d_pre, y_pre, rows, out_features, ld_y, 128, bn / 32))) {
     snprintf(err, errlen, "cuTensorMapEncodeTiled failed (pointer alignment or strides)");
     return MMN_ERR_CUDA;
   }
   fill_schedule(P, rows, out_features, bn, (in_features / 32 + kp - 1) / kp, 1);
   P.epi = act; P.has_pre = y_pre ? 1 : 0; P.bias = bias;
-  P.d = static_cast<__nv_bfloat16*>(y); P.d_pre = static_cast<__nv_bfloat16*>(y_pre); P.ld_d = ld_y;
   int grid = num_sms_cached();
   if (grid > P.n_tiles) grid = P.n_tiles;
   const int rc = launch_gemm<false, false, false>(bn, kp, P, grid, st);
@@ -338,13 +355,12 @@ int linear_bwd_general(const void* dy, const void* x, const void* w, void* dx, f
     const int bn = pick_bn(in_features), kp = pick_kp(out_features);
     GemmParams P{};
     if (!panel_map(&P.a, dy, rows, out_features, ld_dy, 128, kp) || !panel_map(&P.b, w, out_features, in_features, in_features, 32 * kp, bn / 32) ||
-        reinterpret_cast<uintptr_t>(dx) % 16) {
+        !panel_map(&P.d, dx, rows, in_features, ld_dx, 128, bn / 32)) {
       snprintf(err, errlen, "cuTensorMapEncodeTiled failed (pointer alignment or strides)");
       return MMN_ERR_CUDA;
     }
     fill_schedule(P, rows, in_features, bn, (out_features / 32 + kp - 1) / kp, 1);
     P.epi = act_grad; P.aux = static_cast<const __nv_bfloat16*>(aux); P.ld_aux = ld_aux;
-    P.d = static_cast<__nv_bfloat16*>(dx); P.ld_d = ld_dx;
     int grid = num_sms_cached();
     if (grid > P.n_tiles) grid = P.n_tiles;
     const int rc = launch_gemm<false, true, false>(bn, kp, P, grid, st);

@@ -22,4 +22,12 @@ cudaError_t cpb_bias_fwd(const float* coords, const float* w1, const float* b1, 
 cudaError_t cpb_bias_bwd(const float* coords, const float* w1, const float* b1, const float* w2, const long long* index,
                          const float* tab16, const float* dbias, int T, int n_in, int J, int nH, int NN, float* dtab16, float* dw1,
                          float* db1, float* dw2, cudaStream_t st, int* launches);
+// LayerNorm fused with the residual add around it (layernorm.cu)
+bool layernorm_supported(int cols);
+cudaError_t layernorm_fwd(const void* resid, int resid_dt, const void* delta, int delta_dt, const float* gamma, const float* beta,
+                          float eps, int mode, void* out_sum, int sum_dt, void* out_norm, int norm_dt, float* mean, float* rstd,
+                          long long rows, int cols, cudaStream_t st, int* launches);
+cudaError_t layernorm_bwd(const void* g_sum, int gs_dt, const void* g_norm, int gn_dt, const void* x, int x_dt, const float* gamma,
+                          const float* mean, const float* rstd, int mode, void* d_resid, int dr_dt, void* d_delta, int dd_dt,
+                          float* dgamma, float* dbeta, long long rows, int cols, cudaStream_t st, int* launches);
 }  // namespace mmn

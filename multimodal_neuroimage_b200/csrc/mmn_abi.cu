@@ -357,4 +357,44 @@ int mmn_linear_bwd(const void* dy, const void* x, const void* w, void* dx, float
   return rc;
 }
 
+int mmn_layernorm_supported(int32_t cols) { return have_device() && mmn::layernorm_supported(cols); }
+
+static bool ln_dt_ok(int dt) { return dt == MMN_DT_F32 || dt == MMN_DT_BF16; }
+
+int mmn_layernorm_fwd(const void* resid, int resid_dtype, const void* delta, int delta_dtype, const float* gamma, const float* beta,
+                      float eps, int mode, void* out_sum, int sum_dtype, void* out_norm, int norm_dtype, float* mean, float* rstd,
+                      int64_t rows, int32_t cols, int device, void* stream) {
+  if ((!resid && !delta) || !gamma || !mean || !rstd || (!out_sum && !out_norm)) return fail(MMN_ERR_INVALID, "null tensor pointer");
+  if (mode != MMN_LN_PRE && mode != MMN_LN_POST) return fail(MMN_ERR_INVALID, "bad layernorm mode %d", mode);
+  if (mode == MMN_LN_POST && !delta) return fail(MMN_ERR_INVALID, "MMN_LN_POST normalises delta: it cannot be null");
+  if (!ln_dt_ok(resid_dtype) || !ln_dt_ok(delta_dtype) || !ln_dt_ok(sum_dtype) || !ln_dt_ok(norm_dtype)) return fail(MMN_ERR_INVALID, "bad dtype");
+  if (rows < 0) return fail(MMN_ERR_INVALID, "negative row count");
+  if (!mmn::layernorm_supported(cols)) return fail(MMN_ERR_UNSUPPORTED, "layernorm: cols = %d (even, <= 1536)", cols);
+  if (!have_device()) return fail(MMN_ERR_CUDA, "no CUDA device: libmmn_b200 has no CPU path");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(MMN_ERR_CUDA, "cannot select device %d", device);
+  if (rows == 0) return MMN_OK;
+  int n = 0;
+  cudaError_t e = mmn::layernorm_fwd(resid, resid_dtype, delta, delta_dtype, gamma, beta, eps, mode, out_sum, sum_dtype, out_norm, norm_dtype,
+                                     mean, rstd, rows, cols, (cudaStream_t)stream, &n);
+  return finish(e, n, "ln_fwd_kernel");
+}
+
+int mmn_layernorm_bwd(const void* g_sum, int gs_dtype, const void* g_norm, int gn_dtype, const void* x, int x_dtype, const float* gamma,
+                      const float* mean, const float* rstd, int mode, void* d_resid, int dr_dtype, void* d_delta, int dd_dtype,
+                      float* dgamma, float* dbeta, int64_t rows, int32_t cols, int device, void* stream) {
+  if ((!g_sum && !g_norm) || !x || !gamma || !mean || !rstd) return fail(MMN_ERR_INVALID, "null tensor pointer");
+  if (mode != MMN_LN_PRE && mode != MMN_LN_POST) return fail(MMN_ERR_INVALID, "bad layernorm mode %d", mode);
+  if (!ln_dt_ok(gs_dtype) || !ln_dt_ok(gn_dtype) || !ln_dt_ok(x_dtype) || !ln_dt_ok(dr_dtype) || !ln_dt_ok(dd_dtype)) return fail(MMN_ERR_INVALID, "bad dtype");
+  if (!mmn::layernorm_supported(cols)) return fail(MMN_ERR_UNSUPPORTED, "layernorm: cols = %d (even, <= 1536)", cols);
+  if (!have_device()) return fail(MMN_ERR_CUDA, "no CUDA device: libmmn_b200 has no CPU path");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(MMN_ERR_CUDA, "cannot select device %d", device);
+  if (rows <= 0) return MMN_OK;
+  int n = 0;
+  cudaError_t e = mmn::layernorm_bwd(g_sum, gs_dtype, g_norm, gn_dtype, x, x_dtype, gamma, mean, rstd, mode, d_resid, dr_dtype, d_delta,
+                                     dd_dtype, dgamma, dbeta, rows, cols, (cudaStream_t)stream, &n);
+  return finish(e, n, "ln_bwd_kernel");
+}
+
 }  // extern "C"

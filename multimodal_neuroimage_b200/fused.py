@@ -174,3 +174,48 @@ def mlp(x: torch.Tensor, fc1: torch.nn.Linear, fc2: torch.nn.Linear, act: str, d
     h = F.gelu(h) if act == "gelu" else F.relu(h)
     h = F.dropout(h, drop, training)
     return F.dropout(fc2(h), drop_out, training)
+
+
+# ------------------------------------------------------------------------------------------
+# LayerNorm + residual add (csrc/layernorm.cu) -- the glue between the attention and Mlp calls of a block
+# ------------------------------------------------------------------------------------------
+def _ln_ok(x: torch.Tensor, ln) -> bool:
+    return (isinstance(ln, torch.nn.LayerNorm) and ln.weight is not None and len(ln.normalized_shape) == 1
+            and ops.layernorm_supported(x, x.shape[-1]) and ln.normalized_shape[0] == x.shape[-1])
+
+
+def _act_dtype(x: torch.Tensor):
+    """dtype of activations handed to the next GEMM: the autocast dtype (fp16 runs as bf16, ops.kernel_io), else x's own."""
+    if torch.is_autocast_enabled("cuda"):
+        dt = torch.get_autocast_dtype("cuda")
+        return torch.bfloat16 if dt == torch.float16 else dt
+    return x.dtype
+
+
+def layer_norm(x: torch.Tensor, ln, out_dtype=None) -> torch.Tensor:
+    """ln(x), emitted directly in the dtype the consumer wants (bf16 under autocast: no separate cast kernel)."""
+    if not _ln_ok(x, ln):
+        return ln(x)
+    out_dtype = out_dtype or _act_dtype(x)
+    with torch.autocast("cuda", enabled=False):
+        return ops.AddLayerNormFn.apply(x, None, ln.weight, ln.bias, ln.eps, _lib.LN_PRE, out_dtype)[1]
+
+
+def add_layer_norm(resid: torch.Tensor, delta: torch.Tensor, ln, out_dtype=None):
+    """Pre-norm blocks: (s, ln(s)) with s = resid + delta, one pass (swinfusion_module.py:377-378,535-539)."""
+    if not _ln_ok(resid, ln) or delta.dtype not in (torch.float32, torch.bfloat16) or delta.shape != resid.shape:
+        s = resid + delta
+        return s, ln(s)
+    out_dtype = out_dtype or _act_dtype(resid)
+    with torch.autocast("cuda", enabled=False):
+        return ops.AddLayerNormFn.apply(resid, delta, ln.weight, ln.bias, ln.eps, _lib.LN_PRE, out_dtype)
+
+
+def post_norm_add(resid: torch.Tensor, delta: torch.Tensor, ln, copy_dtype=None):
+    """SwinV2 res-post-norm: s = resid + ln(delta) in one pass (swin_v2_module.py:299,302).  Returns (s, s cast to
+    `copy_dtype`) -- the copy is what the next GEMM reads; None skips it."""
+    if not _ln_ok(resid, ln) or delta.dtype not in (torch.float32, torch.bfloat16) or delta.shape != resid.shape:
+        s = resid + ln(delta)
+        return s, (s.to(copy_dtype) if copy_dtype is not None else None)
+    with torch.autocast("cuda", enabled=False):
+        return ops.AddLayerNormFn.apply(resid, delta, ln.weight, ln.bias, ln.eps, _lib.LN_POST, copy_dtype)

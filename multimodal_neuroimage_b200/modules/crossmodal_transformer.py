@@ -107,7 +107,8 @@ class TransformerEncoderLayer(nn.Module):
 
     def maybe_layer_norm(self, i, x, before=False, after=False):
         assert before ^ after
-        return self.layer_norms[i](x) if after ^ self.normalize_before else x
+        return fused.layer_norm(x, self.layer_norms[i], x.dtype if not torch.is_autocast_enabled("cuda") else None) \
+            if after ^ self.normalize_before else x
 
 
 def fill_with_neg_inf(t):

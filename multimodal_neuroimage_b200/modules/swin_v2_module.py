@@ -263,6 +263,12 @@ class SwinTransformerBlock(nn.Module):
         assert L == math.prod(self.input_resolution), "input feature has wrong size"
         n = len(self.input_resolution)
         a = self.attn.forward_grid(x, self.input_resolution, to_ntuple(self.shift_size, n))
+        if isinstance(self.drop_path, nn.Identity) or not self.training:
+            # x + norm(branch) in one pass each (csrc/layernorm.cu); the second output is x already cast for the Mlp's GEMM
+            cd = fused._act_dtype(x)
+            x, xc = fused.post_norm_add(x, a, self.norm1, cd if x.is_cuda and cd != x.dtype else None)
+            m = self.mlp(xc if xc is not None else x)
+            return fused.post_norm_add(x, m, self.norm2)[0]
         x = x + self.drop_path(self.norm1(a))
         return x + self.drop_path(self.norm2(self.mlp(x)))
 

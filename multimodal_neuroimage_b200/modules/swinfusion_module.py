@@ -194,9 +194,9 @@ class SwinTransformerBlock_fusion(_FusionBlockBase):
 
     def forward(self, x, x_size):
         n = len(x_size)
-        a = self.attn.forward_grid(self.norm1(x), tuple(x_size), to_ntuple(self.shift_size, n))
-        x = x + self.drop_path(a)
-        return x + self.drop_path(self.mlp(self.norm2(x)))
+        a = self.attn.forward_grid(fused.layer_norm(x, self.norm1), tuple(x_size), to_ntuple(self.shift_size, n))
+        x, h = fused.add_layer_norm(x, self.drop_path(a), self.norm2)          # x + a and norm2 of it in one pass
+        return x + self.drop_path(self.mlp(h))
 
     def flops(self):
         return self._flops(self.attn)
@@ -229,13 +229,13 @@ class Cross_SwinTransformerBlock(_FusionBlockBase):
     def forward(self, x, y, x_size):
         n = len(x_size)
         grid, shift = tuple(x_size), to_ntuple(self.shift_size, n)
-        xn, yn = self.norm1_A(x), self.norm1_B(y)
+        xn, yn = fused.layer_norm(x, self.norm1_A), fused.layer_norm(y, self.norm1_B)
         ax = self.attn_A.forward_grid(xn, yn, grid, shift)
         ay = self.attn_B.forward_grid(yn, xn, grid, shift)
-        x = x + self.drop_path_A(ax)
-        x = x + self.drop_path_A(self.mlp_A(self.norm2_A(x)))
-        y = y + self.drop_path_B(ay)
-        y = y + self.drop_path_B(self.mlp_B(self.norm2_B(y)))
+        x, hx = fused.add_layer_norm(x, self.drop_path_A(ax), self.norm2_A)
+        x = x + self.drop_path_A(self.mlp_A(hx))
+        y, hy = fused.add_layer_norm(y, self.drop_path_B(ay), self.norm2_B)
+        y = y + self.drop_path_B(self.mlp_B(hy))
         return x, y
 
     def flops(self):

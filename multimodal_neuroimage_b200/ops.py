@@ -538,6 +538,122 @@ def linear(x: Tensor, w: Tensor, b: Optional[Tensor] = None, act: str = "none") 
     return y if act == "none" else (torch.relu(y) if act == "relu" else torch.nn.functional.gelu(y))
 
 
+# ------------------------------------------------------------------------------------------
+# LayerNorm fused with the residual add (csrc/layernorm.cu)
+# ------------------------------------------------------------------------------------------
+_DTC = {torch.float32: _lib.DT_F32, torch.bfloat16: _lib.DT_BF16}
+_DTC_INV = {_lib.DT_F32: torch.float32, _lib.DT_BF16: torch.bfloat16}
+
+
+def layernorm_supported(x: Tensor, cols: int) -> bool:
+    return bool(x.is_cuda and x.dtype in _DTC and cols % 2 == 0 and 2 <= cols <= 1536 and x.numel() > 0)
+
+
+@torch.library.custom_op("mmn_b200::layernorm_fwd", mutates_args=())
+def layernorm_fwd(resid: Optional[Tensor], delta: Optional[Tensor], gamma: Tensor, beta: Optional[Tensor], eps: float, mode: int,
+                  want_sum: bool, norm_dt: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """mode 0 (pre-norm): s = resid + delta, out_norm = LN(s);  mode 1 (post-norm): s = resid + LN(delta), out_norm = s.
+    Returns (out_sum [dtype of resid, or delta's], out_norm [norm_dt: -1 none, else MMN_DT_*], mean, rstd); rows = all
+    leading dims.  Skipped outputs are empty tensors."""
+    _require_cuda(resid, delta, gamma, beta)
+    ref = resid if resid is not None else delta
+    cols = ref.shape[-1]
+    rows = ref.numel() // cols
+    for t in (resid, delta):
+        if t is not None and (not t.is_contiguous() or t.dtype not in _DTC or t.shape != ref.shape):
+            raise RuntimeError("layernorm_fwd expects contiguous float32/bfloat16 tensors of one shape")
+    if gamma.dtype != torch.float32 or (beta is not None and beta.dtype != torch.float32):
+        raise RuntimeError("layernorm_fwd takes gamma / beta in float32")
+    out_sum = torch.empty_like(ref) if want_sum else ref.new_empty(0)
+    out_norm = torch.empty(ref.shape, dtype=_DTC_INV[norm_dt], device=ref.device) if norm_dt >= 0 else ref.new_empty(0)
+    mean = torch.empty(rows, dtype=torch.float32, device=ref.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=ref.device)
+    dt = lambda t: _DTC[t.dtype] if t is not None else 0
+    with _timed("layernorm_fwd", ref):
+        _lib.check(_lib.load().mmn_layernorm_fwd(_ptr(resid), dt(resid), _ptr(delta), dt(delta), _ptr(gamma), _ptr(beta), eps, mode,
+                                                 _ptr(out_sum) if want_sum else None, _DTC[ref.dtype],
+                                                 _ptr(out_norm) if norm_dt >= 0 else None, max(norm_dt, 0), _ptr(mean), _ptr(rstd),
+                                                 rows, cols, ref.device.index, _stream(ref)), "mmn_layernorm_fwd")
+    return out_sum, out_norm, mean, rstd
+
+
+@layernorm_fwd.register_fake
+def _(resid, delta, gamma, beta, eps, mode, want_sum, norm_dt):
+    ref = resid if resid is not None else delta
+    rows = ref.numel() // ref.shape[-1]
+    return (torch.empty_like(ref) if want_sum else ref.new_empty(0),
+            ref.new_empty(ref.shape, dtype=_DTC_INV[norm_dt]) if norm_dt >= 0 else ref.new_empty(0),
+            ref.new_empty(rows, dtype=torch.float32), ref.new_empty(rows, dtype=torch.float32))
+
+
+@torch.library.custom_op("mmn_b200::layernorm_bwd", mutates_args=())
+def layernorm_bwd(g_sum: Optional[Tensor], g_norm: Optional[Tensor], x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor, mode: int,
+                  resid_dt: int, delta_dt: int, want_beta: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Returns (d_resid [resid_dt, -1: skipped], d_delta [delta_dt, -1: skipped], dgamma, dbeta)."""
+    _require_cuda(g_sum, g_norm, x, gamma, mean, rstd)
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    g_sum = g_sum.contiguous() if g_sum is not None else None
+    g_norm = g_norm.contiguous() if g_norm is not None else None
+    mk = lambda code: torch.empty(x.shape, dtype=_DTC_INV[code], device=x.device) if code >= 0 else x.new_empty(0)
+    d_resid, d_delta = mk(resid_dt), mk(delta_dt)
+    dgamma = torch.zeros(cols, dtype=torch.float32, device=x.device)
+    dbeta = torch.zeros(cols, dtype=torch.float32, device=x.device) if want_beta else x.new_empty(0, dtype=torch.float32)
+    dt = lambda t: _DTC[t.dtype] if t is not None else 0
+    with _timed("layernorm_bwd", x):
+        _lib.check(_lib.load().mmn_layernorm_bwd(_ptr(g_sum), dt(g_sum), _ptr(g_norm), dt(g_norm), _ptr(x), _DTC[x.dtype], _ptr(gamma),
+                                                 _ptr(mean), _ptr(rstd), mode, _ptr(d_resid) if resid_dt >= 0 else None, max(resid_dt, 0),
+                                                 _ptr(d_delta) if delta_dt >= 0 else None, max(delta_dt, 0), _ptr(dgamma),
+                                                 _ptr(dbeta) if want_beta else None, rows, cols, x.device.index, _stream(x)),
+                   "mmn_layernorm_bwd")
+    return d_resid, d_delta, dgamma, dbeta
+
+
+@layernorm_bwd.register_fake
+def _(g_sum, g_norm, x, gamma, mean, rstd, mode, resid_dt, delta_dt, want_beta):
+    mk = lambda code: x.new_empty(x.shape, dtype=_DTC_INV[code]) if code >= 0 else x.new_empty(0)
+    return (mk(resid_dt), mk(delta_dt), x.new_empty(x.shape[-1], dtype=torch.float32),
+            x.new_empty(x.shape[-1] if want_beta else 0, dtype=torch.float32))
+
+
+class AddLayerNormFn(torch.autograd.Function):
+    """(resid, delta, gamma, beta) -> (out_sum, out_norm) in one kernel each way; see layernorm_fwd for the two modes."""
+
+    @staticmethod
+    def forward(ctx, resid, delta, gamma, beta, eps, mode, norm_dtype):
+        ref = resid if resid is not None else delta
+        want_sum = resid is not None and delta is not None
+        g32 = gamma.float()
+        b32 = beta.float() if beta is not None else None
+        rc = resid.contiguous() if resid is not None else None
+        dc = delta.contiguous() if delta is not None else None
+        out_sum, out_norm, mean, rstd = torch.ops.mmn_b200.layernorm_fwd(rc, dc, g32, b32, eps, mode, want_sum,
+                                                                         _DTC[norm_dtype] if norm_dtype is not None else -1)
+        x = (out_sum if want_sum else (rc if rc is not None else dc)) if mode == _lib.LN_PRE else dc
+        ctx.save_for_backward(x, g32, mean, rstd)
+        ctx.meta = (mode, None if resid is None else resid.dtype, None if delta is None else delta.dtype, gamma.dtype,
+                    None if beta is None else beta.dtype, want_sum, norm_dtype is not None)
+        ctx.set_materialize_grads(False)
+        return (out_sum if want_sum else None), (out_norm if norm_dtype is not None else None)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_sum, g_norm):
+        x, g32, mean, rstd = ctx.saved_tensors
+        mode, rdt, ddt, gdt, bdt, had_sum, had_norm = ctx.meta
+        g_sum = g_sum if had_sum else None
+        g_norm = g_norm if had_norm else None
+        if g_sum is None and g_norm is None:
+            return (None,) * 7
+        need_r = rdt is not None and ctx.needs_input_grad[0]
+        need_d = ddt is not None and ctx.needs_input_grad[1]
+        d_resid, d_delta, dgamma, dbeta = torch.ops.mmn_b200.layernorm_bwd(
+            g_sum, g_norm, x, g32, mean, rstd, mode,
+            _DTC[rdt] if need_r else -1, _DTC[ddt] if need_d else -1, bdt is not None)
+        return (d_resid if need_r else None, d_delta if need_d else None, dgamma.to(gdt), dbeta.to(bdt) if bdt is not None else None,
+                None, None, None)
+
+
 def next_dropout_stream(p: float, training: bool, device) -> Tuple[float, int, int]:
     """(p, seed, offset) for one attention call: a fresh Philox offset drawn from torch's
     generator so `torch.manual_seed` controls it; p = 0 outside training."""

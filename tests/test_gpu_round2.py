@@ -408,3 +408,65 @@ def test_fused_mlp_matches_pytorch(mm, C, act):
     check(got, want, BF16_TOL, "mlp out")
     for a, b, n in zip(gg, gw, ("dx", "dw1", "db1", "dw2", "db2")):
         check(a, b, BF16_TOL, "mlp " + n)
+
+
+# ------------------------------------------------------------------------------------------
+# LayerNorm fused with the residual add (csrc/layernorm.cu) against torch.nn.functional.layer_norm in fp64
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cols", [12, 84, 96, 168, 192, 384, 768, 1536])
+@pytest.mark.parametrize("stream_dtype,act_dtype", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16)],
+                         ids=["f32_f32", "f32_bf16", "bf16_bf16"])
+def test_fused_layernorm(mm, cols, stream_dtype, act_dtype):
+    from multimodal_neuroimage_b200 import fused
+    F = torch.nn.functional
+    rows = (3, 211)
+    g = torch.Generator().manual_seed(cols)
+    ln = torch.nn.LayerNorm(cols)
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5, generator=g)
+        ln.bias.normal_(0, 0.3, generator=g)
+    resid = torch.randn(*rows, cols, generator=g).to(stream_dtype)
+    delta = (torch.randn(*rows, cols, generator=g) * 2 + 0.5).to(act_dtype)
+    c1, c2 = torch.randn(*rows, cols, generator=g), torch.randn(*rows, cols, generator=g)
+    tol = FP32_TOL * 2 if act_dtype == torch.float32 and stream_dtype == torch.float32 else BF16_TOL
+    W, Bv = ln.weight.detach().double(), ln.bias.detach().double()
+
+    def ref(mode):
+        r, d = resid.double().requires_grad_(True), delta.double().requires_grad_(True)
+        w, b = W.clone().requires_grad_(True), Bv.clone().requires_grad_(True)
+        if mode == "ln":
+            outs = (F.layer_norm(r, (cols,), w, b, ln.eps),)
+            loss = (outs[0] * c1.double()).sum()
+        elif mode == "pre":
+            s = r + d
+            outs = (s, F.layer_norm(s, (cols,), w, b, ln.eps))
+            loss = (outs[0] * c1.double()).sum() + (outs[1] * c2.double()).sum()
+        else:
+            s = r + F.layer_norm(d, (cols,), w, b, ln.eps)
+            outs = (s, s)
+            loss = (s * c1.double()).sum() + (s * c2.double()).sum()
+        return outs, torch.autograd.grad(loss, (r, d, w, b), allow_unused=True)
+
+    lnc = ln.cuda()
+    for mode in ("ln", "pre", "post"):
+        rc, dc = resid.cuda().requires_grad_(True), delta.cuda().requires_grad_(True)
+        lnc.zero_grad()
+        if mode == "ln":
+            outs = (fused.layer_norm(rc, lnc, act_dtype),)
+            loss = (outs[0].float() * c1.cuda()).sum()
+        elif mode == "pre":
+            outs = fused.add_layer_norm(rc, dc, lnc, act_dtype)
+            loss = (outs[0].float() * c1.cuda()).sum() + (outs[1].float() * c2.cuda()).sum()
+        else:
+            outs = fused.post_norm_add(rc, dc, lnc, act_dtype)
+            loss = (outs[0].float() * c1.cuda()).sum() + (outs[1].float() * c2.cuda()).sum()
+        loss.backward()
+        wo, wg = ref(mode)
+        for o, w_ in zip(outs, wo):
+            check(o, w_, tol, f"layernorm {mode} out")
+        assert outs[0].dtype == (act_dtype if mode == "ln" else stream_dtype)
+        check(rc.grad, wg[0], tol * 3, f"layernorm {mode} d resid")
+        if mode != "ln":
+            check(dc.grad, wg[1], tol * 3, f"layernorm {mode} d delta")
+        check(lnc.weight.grad, wg[2], tol * 3, f"layernorm {mode} d gamma")
+        check(lnc.bias.grad, wg[3], tol * 3, f"layernorm {mode} d beta")
