@@ -22,6 +22,7 @@ SOURCES = {"mmn_abi.cu": ["generic_launch.h", "attn_generic.cuh", "winattn_tc.h"
            "winattn_tc.cu": ["winattn_tc.h", "winattn_tc_fwd.cuh", "winattn_tc_bwd.cuh", "tc_window.cuh", "tc_sched.cuh", "tc_common.cuh"],
            "linbwd_tc.cu": ["winattn_tc.h", "tc_window.cuh", "tc_common.cuh"],
            "gemm_tc.cu": ["winattn_tc.h", "tc_window.cuh", "tc_common.cuh"],
+           "mha_tc.cu": ["winattn_tc.h", "tc_window.cuh", "tc_common.cuh"],
            "layernorm.cu": ["generic_launch.h", "attn_generic.cuh"],
            "cpb_bias.cu": ["generic_launch.h", "attn_generic.cuh"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -134,7 +134,8 @@ const char* mmn_winattn_path(const mmn_winattn_desc* d) {
 
 const char* mmn_mha_path(const mmn_mha_desc* d) {
   if (validate_mha(d) != MMN_OK) return "invalid";
-  return "generic";
+  if (d->path == MMN_PATH_GENERIC) return "generic";
+  return mmn::tc::mha_why_not(d, false) == nullptr ? "tcgen05" : "generic";
 }
 
 int mmn_winattn_fwd(const mmn_winattn_desc* d, const void* q, const void* k, const void* v, const float* bias,
@@ -201,6 +202,13 @@ int mmn_mha_fwd(const mmn_mha_desc* d, const void* q, const void* k, const void*
   DeviceGuard g(device);
   if (!g.ok) return fail(MMN_ERR_CUDA, "cannot select device %d", device);
   int n = 0;
+  const char* why = mmn::tc::mha_why_not(d, false);
+  if (d->path == MMN_PATH_TCGEN05 && why) return fail(MMN_ERR_UNSUPPORTED, "shape not supported by the tcgen05 MHA path: %s", why);
+  if (d->path != MMN_PATH_GENERIC && !why) {
+    rc = mmn::tc::mha_fwd(d, q, k, v, mask, out, lse, (cudaStream_t)stream, g_err, sizeof(g_err), &n);
+    g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed);
+    return rc;
+  }
   cudaError_t e = mmn::generic_fwd(problem_from(d, mask), d->io_dtype, q, k, v, out, lse, (cudaStream_t)stream, &n);
   return finish(e, n, "attn_fwd_generic");
 }
@@ -216,6 +224,13 @@ int mmn_mha_bwd(const mmn_mha_desc* d, const void* q, const void* k, const void*
   DeviceGuard g(device);
   if (!g.ok) return fail(MMN_ERR_CUDA, "cannot select device %d", device);
   int n = 0;
+  const char* why = mmn::tc::mha_why_not(d, true);
+  if (d->path == MMN_PATH_TCGEN05 && why) return fail(MMN_ERR_UNSUPPORTED, "shape not supported by the tcgen05 MHA backward path: %s", why);
+  if (d->path != MMN_PATH_GENERIC && !why) {
+    rc = mmn::tc::mha_bwd(d, q, k, v, mask, out, lse, dout, dq, dk, dv, workspace, (cudaStream_t)stream, g_err, sizeof(g_err), &n);
+    g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed);
+    return rc;
+  }
   cudaError_t e = mmn::generic_bwd(problem_from(d, mask), d->io_dtype, q, k, v, lse, dout, dq, dk, dv, nullptr, nullptr, workspace,
                                  nullptr, (cudaStream_t)stream, &n);
   return finish(e, n, "attn_bwd_generic");

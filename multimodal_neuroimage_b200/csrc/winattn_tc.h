@@ -30,4 +30,10 @@ size_t linear_wgrad_workspace_bytes(long long rows, int in_features, int out_fea
 int linear_bwd_general(const void* dy, const void* x, const void* w, void* dx, float* dw, float* workspace, const void* aux, long long ld_aux,
                        int act_grad, long long rows, int in_features, int out_features, long long ld_dy, long long ld_x, long long ld_dx,
                        cudaStream_t st, char* err, size_t errlen, int* launches);
+// cross-modal multi-head attention on the tensor cores (mha_tc.cu): bf16, head_dim 32 / 64, no attention dropout
+const char* mha_why_not(const mmn_mha_desc* d, bool backward);
+int mha_fwd(const mmn_mha_desc* d, const void* q, const void* k, const void* v, const float* mask, void* out, float* lse, cudaStream_t st,
+            char* err, size_t errlen, int* launches);
+int mha_bwd(const mmn_mha_desc* d, const void* q, const void* k, const void* v, const float* mask, const void* out, const float* lse,
+            const void* dout, void* dq, void* dk, void* dv, float* workspace, cudaStream_t st, char* err, size_t errlen, int* launches);
 }}  // namespace mmn::tc
