@@ -159,14 +159,15 @@ int mmn_cpb_bias_bwd(const float* coords, const float* w1, const float* b1, cons
  * bf16 operands, fp32 accumulation, in_features and out_features multiples of 32 (mmn_linear_supported tells; other shapes
  * -- the reference's own 12/24/48/84/168-wide layers -- are plain library GEMMs on the caller's side).
  *   forward:  y (rows, out) = act(x (rows, in) w^T + bias);  w is (out, in) row-major contiguous, bias (out) fp32 or NULL;
- *             y_pre (rows, out), optional, receives the value BEFORE the activation (what the backward needs for act');
+ *             y_pre (rows, out), optional, receives act'(x w^T + bias), the activation's DERIVATIVE at the pre-activation
+ *             (GELU: Phi(v) + v phi(v); ReLU: 0 / 1) -- what the backward multiplies with, computed where exp(-v^2/2) is at hand;
  *             x has leading dimension ld_x, y and y_pre ld_y (elements).
- *   backward: dx (rows, in) = (dy w) o act'(act_aux)   -- act / act_aux describe the layer BELOW this one (the activation
- *             whose output was this layer's input; act_aux is ITS pre-activation, (rows, in) with leading dimension ld_aux);
+ *   backward: dx (rows, in) = (dy w) o act_aux   -- act != NONE says the layer BELOW this one (whose output was this layer's
+ *             input) had an activation; act_aux is the y_pre ITS forward wrote, (rows, in) with leading dimension ld_aux;
  *             dw (out, in) fp32 = dy^T x, OVERWRITTEN; db (out) fp32 = column sums of dy, OVERWRITTEN.  dx or dw may be NULL
  *             to skip that half (then db is skipped with dw == NULL only if db is NULL too).
  *             workspace: mmn_linear_bwd_workspace_bytes(rows, in, out) bytes, contents undefined on return.
- *             in = 96 and out in {96, 192, 288} with no activation run as ONE pass over dy and x (linbwd_tc.cu). */
+ *             in = 96 and out in {96, 192, 288, 384} with no activation run as ONE pass over dy and x (linbwd_tc.cu). */
 enum { MMN_ACT_NONE = 0, MMN_ACT_RELU = 1, MMN_ACT_GELU = 2 };
 int mmn_linear_supported(int io_dtype, int64_t rows, int32_t in_features, int32_t out_features, int64_t ld_x, int64_t ld_y);
 int mmn_linear_fwd(const void* x, const void* w, const float* bias, void* y, void* y_pre, int act, int io_dtype, int64_t rows,

@@ -3,17 +3,22 @@
 //
 //   forward    y = act(x W^T + b)            F.linear of  swin_v2_module.py:148,176 (qkv, proj), :27-31 (Mlp fc1 -> GELU -> fc2),
 //                                            swinfusion_module.py:121,143,221-222,244, crossmodal_transformer.py:158-160 (relu)
-//   backward   dx = (dy W) o act'(pre)       the same layers' dgrad, with the activation derivative of the layer BELOW as epilogue
+//   backward   dx = (dy W) o act'(pre)       the same layers' dgrad; act'(pre) of the layer BELOW was written by ITS forward epilogue
 //              dW = dy^T x  (fp32)           wgrad, split over the token dimension, partials summed by a second kernel
 //
 // ONE persistent kernel, three operand layouts.  A 128 x BN output tile; operands arrive as 64B-swizzled panels of 32
 // elements of the contiguous dimension (3-D tensor maps: element-in-panel, row, panel):
 //   K-major operand   (reduction dim contiguous: x and W in the forward, dy in dgrad)   stage = [KP panels][rows][64 B]
 //   MN-major operand  (output dim contiguous:    W in dgrad, dy^T and x in wgrad)        stage = [rows/32 panels][32 KP][64 B]
-// Warp roles: warps 0-15 epilogue (four per TMEM lane quarter, each a quarter of the tile's columns: the bias / GELU /
-// GELU' arithmetic of a 128 x BN tile is what bounds the small-K layers, so it gets the issue slots of 16 warps), warp 16
-// TMA producer, warp 17 MMA issuer.  Three pipelines: smem ring (TMA <-> MMA), two TMEM accumulators (MMA <-> epilogue), static
-// round-robin tile schedule with the n tiles of one row block adjacent (x is read from HBM once, W stays in L2).
+// Warp roles: warps 0-15 epilogue, warp 16 TMA producer, warp 17 MMA issuer.  The epilogue warps form TWO groups of eight
+// (two per TMEM lane quarter, each half of the tile's columns); group g owns accumulator g, i.e. every other tile of the
+// CTA, with its own staging slots, named barriers and TMA-store leader.  At the small-K layers of the path (K = 96: one
+// k-block per tile) the epilogue IS the kernel -- TMEM load, bias / GELU arithmetic, swizzled smem stores, store issue --
+// and with one group all of it was a serial chain per tile whose waits nothing covered (fc1 + GELU: 50 us at cfg3 where
+// the same GEMM without GELU took 22: ALU time simply added to the memory time); two groups overlap one tile's arithmetic
+// with the other's loads and stores.  Three pipelines: smem ring (TMA <-> MMA), two TMEM accumulators (MMA <-> epilogue
+// groups), static round-robin tile schedule with the n tiles of one row block adjacent (x is read from HBM once, W stays
+// in L2).
 #include <cstdio>
 #include <mutex>
 
@@ -22,9 +27,9 @@
 
 namespace mmn { namespace tc {
 
-enum { kEpiNone = 0, kEpiRelu = 1, kEpiGelu = 2, kEpiReluGrad = 3, kEpiGeluGrad = 4 };
+enum { kEpiNone = 0, kEpiRelu = 1, kEpiGelu = 2, kEpiMulAux = 3 };
 
-constexpr int kGEpiWarps = 16;               // four per TMEM lane quarter, each a quarter of the tile's columns
+constexpr int kGEpiWarps = 16;               // two groups of eight: two per TMEM lane quarter, each half of the tile's columns
 constexpr int kGThreads = 32 * (kGEpiWarps + 2);
 constexpr int kGProducerWarp = kGEpiWarps, kGMmaWarp = kGEpiWarps + 1;
 constexpr int kGTmemCols = 256;                // two accumulators of BN <= 128 columns
@@ -35,29 +40,41 @@ struct GemmParams {
   int tiles_n, n_tiles, k_blocks, splits, kb_per_split;
   int epi, has_pre;
   const float* bias;                           // [N] fp32 or null
-  const __nv_bfloat16* aux;                    // *_GRAD: pre-activation of the layer below, (M, N) with row stride ld_aux
+  const __nv_bfloat16* aux;                    // kEpiMulAux: act'(pre) of the layer below, (M, N) with row stride ld_aux
   long long ld_aux;
   float* out32;                                // fp32 output: [splits][M][N]
 };
 
-__device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_grad_f(float v) {
-  return 0.5f * (1.f + erff(v * 0.70710678118654752f)) + v * 0.3989422804014327f * __expf(-0.5f * v * v);
+// Exact (erf) GELU and its derivative for the epilogues.  erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below the
+// bf16 rounding of the result): one MUFU.RCP, one MUFU.EX2 and seven FMAs; exp(-v^2 / 2) is shared between the CDF and the PDF.
+// libm's erff + expf cost ~50 instructions per element, which made the 128 x BN epilogue of the K = 96 layers -- not HBM -- the
+// bound of fc1 forward and fc2 dgrad (tools/bench_blocks.py: 84 / 104 us against a 29 us memory floor at cfg3).
+__device__ __forceinline__ void normal_cdf_pdf(float v, float& cdf, float& pdf) {
+  const float z = fabsf(v) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  const float e = fast_exp2(-1.4426950408889634f * z * z);                 // exp(-v^2 / 2)
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float erf_abs = fmaf(-p * t, e, 1.f);
+  cdf = fmaf(0.5f, copysignf(erf_abs, v), 0.5f);
+  pdf = 0.3989422804014327f * e;
 }
-
 template <int BN, int KP, int STAGES, bool A_MN, bool B_MN, bool F32OUT>
 __global__ void __launch_bounds__(kGThreads, 1)
 gemm_tc_kernel(const __grid_constant__ GemmParams P) {
   constexpr int kABytes = 8192 * KP, kBBytes = BN * 64 * KP;
   constexpr int kPanelOut = 128 * 64;                       // one 32-column panel of the output tile
   constexpr int kOutBytes = F32OUT ? 0 : (BN / 32) * kPanelOut;
+  constexpr int kSlots = BN <= 64 ? 4 : 2;                  // staging slots: one per epilogue group, two with a second output
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = sA + STAGES * kABytes;
-  uint8_t* sOut = sB + STAGES * kBBytes;                    // two staging slots of [BN/32 panels][128 rows][64 B]: tiles alternate
-                                                            // between them; with a second output (pre-activation) a tile takes both
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + 2 * kOutBytes);
+  uint8_t* sOut = sB + STAGES * kBBytes;                    // staging slots of [BN/32 panels][128 rows][64 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + kSlots * kOutBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* acc_full = bars + 2 * STAGES;                   // [2]
@@ -69,11 +86,11 @@ gemm_tc_kernel(const __grid_constant__ GemmParams P) {
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kGEpiWarps); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kGEpiWarps / 2); }
     fence_barrier_init();
   }
   if (warp == kGProducerWarp && lane == 0) { tma_prefetch_desc(&P.a); tma_prefetch_desc(&P.b); }
-  if (!F32OUT && warp == 0 && lane == 0) { tma_prefetch_desc(&P.d); if (P.has_pre) tma_prefetch_desc(&P.d_pre); }
+  if (!F32OUT && (warp == 0 || warp == 4) && lane == 0) { tma_prefetch_desc(&P.d); if (P.has_pre) tma_prefetch_desc(&P.d_pre); }
   if (warp == kGMmaWarp) tmem_alloc<kGTmemCols>(tmem_slot);
   tcgen05_fence_before();
   __syncthreads();
@@ -134,29 +151,29 @@ gemm_tc_kernel(const __grid_constant__ GemmParams P) {
       }
     }
   } else {
-    // ============================== epilogue: warp w -> TMEM lanes 32 (w % 4) .., column half w / 4 ==============================
-    const int q = warp & 3, cg = warp >> 2;               // TMEM lane quarter, column group
+    // ============================== epilogue: warp w -> TMEM lanes 32 (w % 4) .., group (w / 4) % 2, column half w / 8 ==============================
+    const int q = warp & 3, grp = (warp >> 2) & 1, cg = warp >> 3;
     const int r = q * 32 + lane;                          // row of the tile
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    constexpr int kChunks = BN / 32;                      // 32-column chunks: group cg takes chunks cg, cg + 4, ...
+    constexpr int kChunks = BN / 32;                      // 32-column chunks: column half cg takes chunks cg, cg + 2, ...
+    constexpr int kGroupThreads = 32 * kGEpiWarps / 2;
     const int rsw = (r >> 1) & 3;
-    int un = 0;
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++un) {
+    const bool leader = warp == 4 * grp && lane == 0;     // issues and retires this group's TMA stores
+    const uint32_t bar_a = 1 + 2 * grp, bar_b = 2 + 2 * grp;
+    uint8_t* slot_act = sOut + (P.has_pre ? 2 * grp : grp) * kOutBytes;
+    uint8_t* slot_pre = slot_act + kOutBytes;             // has_pre only (BN <= 64: four slots)
+    const int as = grp;
+    for (int un = grp, u = blockIdx.x + grp * gridDim.x; u < total_units; un += 2, u += 2 * gridDim.x) {
       const int tile = u / P.splits, sp = u - tile * P.splits;
       const int tm = tile / P.tiles_n, tn = tile - tm * P.tiles_n;
       const int m0 = tm * 128, n0 = tn * BN;
-      const int as = un & 1;
       mbar_wait(&acc_full[as], (un >> 1) & 1);
       tcgen05_fence_after();
-      uint8_t* slot_act = sOut + ((P.has_pre ? 0 : (un & 1)) * kOutBytes);
-      uint8_t* slot_pre = sOut + kOutBytes;
       if (!F32OUT) {
-        if (tid == 0) {                                    // the store that last read this tile's slot(s) has drained them
-          if (P.has_pre) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
-        }
-        named_bar_sync(1, 32 * kGEpiWarps);
+        if (leader) tma_store_wait_read<0>();              // the stores of this group's previous tile have drained its slot(s)
+        named_bar_sync(bar_a, kGroupThreads);
       }
-      for (int c = cg; c < kChunks; c += 4) {
+      for (int c = cg; c < kChunks; c += 2) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem + lane_base + as * BN + c * 32, v);
         tmem_ld_wait();
@@ -181,20 +198,30 @@ gemm_tc_kernel(const __grid_constant__ GemmParams P) {
             }
           }
           const int ooff = c * kPanelOut + r * 64;
-          if (P.has_pre) {                                 // pre-activation, kept for the backward's act'(pre)
+          if (P.epi == kEpiRelu || P.epi == kEpiGelu) {
+            // activation, and (has_pre) its derivative at the pre-activation: what the layer's backward multiplies with --
+            // computed here, where exp(-v^2 / 2) is already at hand, so that the dgrad epilogue is one multiply per element
+            float d[32];
+            if (P.epi == kEpiRelu) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(slot_pre + ooff + ((j ^ rsw) << 4)) =
-                  make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                             pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
-          }
-          if (P.epi == kEpiRelu) {
+              for (int j = 0; j < 32; ++j) { d[j] = f[j] > 0.f ? 1.f : 0.f; f[j] = fmaxf(f[j], 0.f); }
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-          } else if (P.epi == kEpiGelu) {
+              for (int j = 0; j < 32; ++j) {
+                float cdf, pdf;
+                normal_cdf_pdf(f[j], cdf, pdf);
+                d[j] = fmaf(f[j], pdf, cdf);
+                f[j] *= cdf;
+              }
+            }
+            if (P.has_pre) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_f(f[j]);
-          } else if (P.epi == kEpiReluGrad || P.epi == kEpiGeluGrad) {
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(slot_pre + ooff + ((j ^ rsw) << 4)) =
+                    make_uint4(pack_bf16x2(d[8 * j], d[8 * j + 1]), pack_bf16x2(d[8 * j + 2], d[8 * j + 3]),
+                               pack_bf16x2(d[8 * j + 4], d[8 * j + 5]), pack_bf16x2(d[8 * j + 6], d[8 * j + 7]));
+            }
+          } else if (P.epi == kEpiMulAux) {
             uint32_t x[16];
             if (m0 + r < P.M) {
               const uint4* ap = reinterpret_cast<const uint4*>(P.aux + (size_t)(m0 + r) * P.ld_aux + n0 + c * 32);
@@ -206,9 +233,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams P) {
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const float lo = __uint_as_float(x[j] << 16), hi = __uint_as_float(x[j] & 0xffff0000u);
-              if (P.epi == kEpiReluGrad) { f[2 * j] = lo > 0.f ? f[2 * j] : 0.f; f[2 * j + 1] = hi > 0.f ? f[2 * j + 1] : 0.f; }
-              else { f[2 * j] *= gelu_grad_f(lo); f[2 * j + 1] *= gelu_grad_f(hi); }
+              f[2 * j] *= __uint_as_float(x[j] << 16);
+              f[2 * j + 1] *= __uint_as_float(x[j] & 0xffff0000u);
             }
           }
 #pragma unroll
@@ -222,15 +248,15 @@ gemm_tc_kernel(const __grid_constant__ GemmParams P) {
       mbar_arrive_warp(&acc_empty[as]);
       if (!F32OUT) {
         fence_proxy_async_smem();
-        named_bar_sync(2, 32 * kGEpiWarps);
-        if (tid == 0) {
+        named_bar_sync(bar_b, kGroupThreads);
+        if (leader) {
           tma_store_3d(&P.d, slot_act, 0, m0, n0 >> 5);
           if (P.has_pre) tma_store_3d(&P.d_pre, slot_pre, 0, m0, n0 >> 5);
           tma_store_commit();
         }
       }
     }
-    if (!F32OUT && tid == 0) tma_store_wait_all<0>();
+    if (!F32OUT && leader) tma_store_wait_all<0>();
   }
 
   tcgen05_fence_before();
@@ -273,7 +299,7 @@ static int pick_kp(long long k) { const long long p = k / 32; return p % 2 == 0 
 template <int BN, int KP, bool A_MN, bool B_MN, bool F32OUT>
 struct GemmCfg {
   static constexpr int kStageBytes = 8192 * KP + BN * 64 * KP;
-  static constexpr int kOut = F32OUT ? 0 : 2 * (BN / 32) * 128 * 64;
+  static constexpr int kOut = F32OUT ? 0 : (BN <= 64 ? 4 : 2) * (BN / 32) * 128 * 64;
   static constexpr int kStages = (200 * 1024 - kOut) / kStageBytes >= 6 ? 6 : (200 * 1024 - kOut) / kStageBytes;
   static constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + kOut + (2 * kStages + 4) * 8 + 16;
   static int launch(const GemmParams& P, int grid, cudaStream_t st) {
@@ -318,7 +344,8 @@ static void fill_schedule(GemmParams& P, long long M, int N, int bn, long long k
 // y (rows, out) = act(x (rows, in) w^T (out, in) + bias); y_pre (optional) = the value before the activation
 int linear_fwd(const void* x, const void* w, const float* bias, void* y, void* y_pre, int act, long long rows, int in_features,
                int out_features, long long ld_x, long long ld_y, cudaStream_t st, char* err, size_t errlen, int* launches) {
-  const int bn = pick_bn(out_features), kp = pick_kp(in_features);
+  // a second output (act') takes two staging slots per epilogue group: tiles of at most 64 columns
+  const int bn = y_pre ? (out_features % 64 == 0 ? 64 : 32) : pick_bn(out_features), kp = pick_kp(in_features);
   GemmParams P{};
   if (!panel_map(&P.a, x, rows, in_features, ld_x, 128, kp) || !panel_map(&P.b, w, out_features, in_features, in_features, bn, kp) ||
       !panel_map(&P.d, y, rows, out_features, ld_y, 128, bn / 32) ||

@@ -201,6 +201,209 @@ ln_bwd_kernel(LnTensor gs, LnTensor gn, LnTensor x, const float* __restrict__ ga
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Vectorised kernels (cols % 4 == 0, cols <= 768): LPR lanes share a row, each lane owns V chunks of four consecutive
+// columns (16-byte fp32 / 8-byte bf16 accesses), a warp works on 32 / LPR rows at once.  At C = 96 that is 8 lanes x 3
+// chunks per row, four rows per warp: ~25 warp instructions per row where the one-row-per-warp kernels above need ~280
+// (they were issue-bound at a quarter of the HBM roofline; tools/bench_blocks.py).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld4(const LnTensor& t, long long idx) {
+  if (t.dt == MMN_DT_F32) return __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(t.p) + idx));
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(t.p) + idx));
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                     __uint_as_float(u.y & 0xffff0000u));
+}
+__device__ __forceinline__ void st4(const LnOut& t, long long idx, float4 v) {
+  if (t.dt == MMN_DT_F32) {
+    *reinterpret_cast<float4*>(static_cast<float*>(t.p) + idx) = v;
+  } else {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&a);
+    u.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(t.p) + idx) = u;
+  }
+}
+template <int LPR>
+__device__ __forceinline__ float row_sum(float v) {          // sum over the LPR lanes that share a row
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+template <int LPR, int V>
+__global__ void __launch_bounds__(kLnWarps * 32, V <= 3 ? 3 : 2)
+ln_fwd_v4_kernel(LnTensor resid, LnTensor delta, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int mode,
+                 LnOut out_sum, LnOut out_norm, float* __restrict__ mean, float* __restrict__ rstd, long long rows, int cols) {
+  constexpr int R = 32 / LPR;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lr = lane % LPR, sub = lane / LPR;
+  const float inv_n = 1.f / (float)cols;
+  const long long stride = (long long)gridDim.x * kLnWarps * R;
+  for (long long row0 = ((long long)blockIdx.x * kLnWarps + warp) * R; row0 < rows; row0 += stride) {
+    const long long row = row0 + sub;
+    const bool live = row < rows;
+    const long long base = row * cols;
+    float4 x[V], r[V];
+    float s1 = 0.f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int c = 4 * (lr + LPR * v);
+      x[v] = f4zero();
+      r[v] = f4zero();
+      if (live && c < cols) {
+        if (mode == 0) {
+          if (resid.p) x[v] = ld4(resid, base + c);
+          if (delta.p) { const float4 d = ld4(delta, base + c); x[v].x += d.x; x[v].y += d.y; x[v].z += d.z; x[v].w += d.w; }
+        } else {
+          x[v] = ld4(delta, base + c);
+          if (resid.p) r[v] = ld4(resid, base + c);
+        }
+        s1 += (x[v].x + x[v].y) + (x[v].z + x[v].w);
+      }
+    }
+    const float mu = row_sum<LPR>(s1) * inv_n;
+    float s2 = 0.f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int c = 4 * (lr + LPR * v);
+      if (c < cols) {
+        const float a0 = x[v].x - mu, a1 = x[v].y - mu, a2 = x[v].z - mu, a3 = x[v].w - mu;
+        s2 += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+      }
+    }
+    const float rs = rsqrtf(row_sum<LPR>(s2) * inv_n + eps);
+    if (live && lr == 0) { mean[row] = mu; rstd[row] = rs; }
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int c = 4 * (lr + LPR * v);
+      if (live && c < cols) {
+        // gamma / beta: 16-byte loads that hit L1 (keeping them in registers cost half the occupancy)
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 b = beta ? __ldg(reinterpret_cast<const float4*>(beta + c)) : f4zero();
+        const float4 n = make_float4((x[v].x - mu) * rs * g.x + b.x, (x[v].y - mu) * rs * g.y + b.y,
+                                     (x[v].z - mu) * rs * g.z + b.z, (x[v].w - mu) * rs * g.w + b.w);
+        if (mode == 0) {
+          if (out_sum.p) st4(out_sum, base + c, x[v]);
+          if (out_norm.p) st4(out_norm, base + c, n);
+        } else {
+          const float4 s = make_float4(r[v].x + n.x, r[v].y + n.y, r[v].z + n.z, r[v].w + n.w);
+          if (out_sum.p) st4(out_sum, base + c, s);
+          if (out_norm.p) st4(out_norm, base + c, s);
+        }
+      }
+    }
+  }
+}
+
+template <int LPR, int V>
+__global__ void __launch_bounds__(kLnWarps * 32, V <= 3 ? 3 : 1)
+ln_bwd_v4_kernel(LnTensor gs, LnTensor gn, LnTensor x, const float* __restrict__ gamma, const float* __restrict__ mean,
+                 const float* __restrict__ rstd, int mode, LnOut d_resid, LnOut d_delta, float* __restrict__ dgamma,
+                 float* __restrict__ dbeta, long long rows, int cols) {
+  constexpr int R = 32 / LPR;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lr = lane % LPR, sub = lane / LPR;
+  float4 ag[V], ab[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) { ag[v] = f4zero(); ab[v] = f4zero(); }
+  const float inv_n = 1.f / (float)cols;
+  const long long stride = (long long)gridDim.x * kLnWarps * R;
+  for (long long row0 = ((long long)blockIdx.x * kLnWarps + warp) * R; row0 < rows; row0 += stride) {
+    const long long row = row0 + sub;
+    const bool live = row < rows;
+    const long long base = row * cols;
+    const float mu = live ? __ldg(mean + row) : 0.f, rs = live ? __ldg(rstd + row) : 0.f;
+    // w = (gradient bypassing the LayerNorm) + rstd * u * gamma, u = gradient entering it: the row's output is
+    // w - rstd * (m1 + xhat * m2), so only w and xhat live across the row reductions
+    float4 w[V], xh[V];
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int c = 4 * (lr + LPR * v);
+      w[v] = xh[v] = f4zero();
+      if (live && c < cols) {
+        const float4 xv = ld4(x, base + c);
+        xh[v] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        const float4 a = gs.p ? ld4(gs, base + c) : f4zero();
+        const float4 n = gn.p ? ld4(gn, base + c) : f4zero();
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        float4 u;
+        if (mode == 0) { u = n; w[v] = a; }
+        else {
+          u = make_float4(a.x + n.x, a.y + n.y, a.z + n.z, a.w + n.w);
+          if (d_resid.p) st4(d_resid, base + c, u);
+        }
+        ag[v].x += u.x * xh[v].x; ag[v].y += u.y * xh[v].y; ag[v].z += u.z * xh[v].z; ag[v].w += u.w * xh[v].w;
+        ab[v].x += u.x; ab[v].y += u.y; ab[v].z += u.z; ab[v].w += u.w;
+        const float u0 = u.x * g.x, u1 = u.y * g.y, u2 = u.z * g.z, u3 = u.w * g.w;
+        m1 += (u0 + u1) + (u2 + u3);
+        m2 += (u0 * xh[v].x + u1 * xh[v].y) + (u2 * xh[v].z + u3 * xh[v].w);
+        w[v].x = fmaf(rs, u0, w[v].x); w[v].y = fmaf(rs, u1, w[v].y); w[v].z = fmaf(rs, u2, w[v].z); w[v].w = fmaf(rs, u3, w[v].w);
+      }
+    }
+    m1 = row_sum<LPR>(m1) * inv_n * rs;
+    m2 = row_sum<LPR>(m2) * inv_n * rs;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int c = 4 * (lr + LPR * v);
+      if (live && c < cols) {
+        const float4 t = make_float4(w[v].x - m1 - xh[v].x * m2, w[v].y - m1 - xh[v].y * m2, w[v].z - m1 - xh[v].z * m2,
+                                     w[v].w - m1 - xh[v].w * m2);
+        if (mode == 0) {
+          if (d_resid.p) st4(d_resid, base + c, t);
+          if (d_delta.p) st4(d_delta, base + c, t);
+        } else {
+          if (d_delta.p) st4(d_delta, base + c, t);
+        }
+      }
+    }
+  }
+  // column sums: rows of a warp (shuffles) -> warps (shared memory) -> one atomic per column and block
+  __shared__ float red[kLnWarps][4 * LPR * V];
+  for (int pass_id = 0; pass_id < 2; ++pass_id) {
+    float* dst = pass_id == 0 ? dgamma : dbeta;
+    if (!dst) continue;                                      // uniform
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      float4 a = pass_id == 0 ? ag[v] : ab[v];
+#pragma unroll
+      for (int o = LPR; o < 32; o <<= 1) {
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, o); a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+        a.z += __shfl_xor_sync(0xffffffffu, a.z, o); a.w += __shfl_xor_sync(0xffffffffu, a.w, o);
+      }
+      if (sub == 0) *reinterpret_cast<float4*>(&red[warp][4 * (lr + LPR * v)]) = a;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < cols; c += kLnWarps * 32) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < kLnWarps; ++w) s += red[w][c];
+      atomicAdd(dst + c, s);
+    }
+    __syncthreads();
+  }
+}
+
+struct V4Cfg { int lpr, v; };
+// lanes per row / chunks per lane for cols / 4 chunks; {0, 0} when the vectorised kernels do not apply
+V4Cfg v4_cfg(int cols) {
+  if (cols % 4 != 0 || cols > 768) return {0, 0};
+  const int ch = cols / 4;
+  const V4Cfg table[] = {{8, 1}, {8, 2}, {8, 3}, {16, 2}, {16, 3}, {32, 2}, {32, 3}, {32, 4}, {32, 6}};
+  for (const V4Cfg& c : table) if (ch <= c.lpr * c.v) return c;
+  return {0, 0};
+}
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int ln_grid_v4(long long rows, int lpr) {
+  const long long per_block = (long long)kLnWarps * (32 / lpr);
+  long long want = (rows + per_block - 1) / per_block;
+  const long long cap = 148ll * 8;
+  return (int)(want < cap ? want : cap);
+}
+
 int ln_grid(long long rows) {
   long long want = (rows + kLnWarps - 1) / kLnWarps;
   const long long cap = 148ll * 8;
@@ -238,6 +441,16 @@ cudaError_t layernorm_fwd(const void* resid, int resid_dt, const void* delta, in
   const int kk = ln_pairs(cols);
   LnTensor r{resid, resid_dt}, d{delta, delta_dt};
   LnOut os{out_sum, sum_dt}, on{out_norm, norm_dt};
+  const V4Cfg vc = v4_cfg(cols);
+  if (vc.lpr && aligned16(resid) && aligned16(delta) && aligned16(out_sum) && aligned16(out_norm) && aligned16(gamma) && aligned16(beta)) {
+#define MMN_LN_V4(L_, V_) if (vc.lpr == L_ && vc.v == V_) \
+    ln_fwd_v4_kernel<L_, V_><<<ln_grid_v4(rows, L_), kLnWarps * 32, 0, st>>>(r, d, gamma, beta, eps, mode, os, on, mean, rstd, rows, cols);
+    MMN_LN_V4(8, 1) MMN_LN_V4(8, 2) MMN_LN_V4(8, 3) MMN_LN_V4(16, 2) MMN_LN_V4(16, 3) MMN_LN_V4(32, 2) MMN_LN_V4(32, 3) MMN_LN_V4(32, 4) MMN_LN_V4(32, 6)
+#undef MMN_LN_V4
+    cudaError_t e4 = cudaGetLastError();
+    if (e4 == cudaSuccess) ++*launches;
+    return e4;
+  }
   MMN_LN_DISPATCH(kk, (ln_fwd_kernel<K><<<ln_grid(rows), kLnWarps * 32, 0, st>>>(r, d, gamma, beta, eps, mode, os, on, mean, rstd, rows, cols)));
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) ++*launches;
@@ -250,6 +463,16 @@ cudaError_t layernorm_bwd(const void* g_sum, int gs_dt, const void* g_norm, int 
   const int kk = ln_pairs(cols);
   LnTensor gs{g_sum, gs_dt}, gn{g_norm, gn_dt}, xx{x, x_dt};
   LnOut dr{d_resid, dr_dt}, dd{d_delta, dd_dt};
+  const V4Cfg vc = v4_cfg(cols);
+  if (vc.lpr && aligned16(g_sum) && aligned16(g_norm) && aligned16(x) && aligned16(d_resid) && aligned16(d_delta) && aligned16(gamma)) {
+#define MMN_LN_V4(L_, V_) if (vc.lpr == L_ && vc.v == V_) \
+    ln_bwd_v4_kernel<L_, V_><<<ln_grid_v4(rows, L_), kLnWarps * 32, 0, st>>>(gs, gn, xx, gamma, mean, rstd, mode, dr, dd, dgamma, dbeta, rows, cols);
+    MMN_LN_V4(8, 1) MMN_LN_V4(8, 2) MMN_LN_V4(8, 3) MMN_LN_V4(16, 2) MMN_LN_V4(16, 3) MMN_LN_V4(32, 2) MMN_LN_V4(32, 3) MMN_LN_V4(32, 4) MMN_LN_V4(32, 6)
+#undef MMN_LN_V4
+    cudaError_t e4 = cudaGetLastError();
+    if (e4 == cudaSuccess) ++*launches;
+    return e4;
+  }
   MMN_LN_DISPATCH(kk, (ln_bwd_kernel<K><<<ln_grid(rows), kLnWarps * 32, 0, st>>>(gs, gn, xx, gamma, mean, rstd, mode, dr, dd, dgamma, dbeta, rows, cols)));
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) ++*launches;

@@ -9,18 +9,18 @@
 // re-reading the (tokens x out) gradient from HBM; at BASELINE cfg2 those GEMMs are pure HBM streaming
 // (in = 96, out = 96 / 288), so reading dY once instead of two or three times is the whole game.
 //
-// Tuned shape: in = 96, out = 96 G (G = 1, 2, 3).  One persistent CTA per SM walks 128-token tiles:
+// Tuned shape: in = 96, out = 96 G (G = 1 .. 4: proj, kv, qkv, Mlp fc1).  One persistent CTA per SM walks 128-token tiles:
 //   warp 4   TMA producer: X tile (128 x 96) and the G chunks of the dY tile (128 x 96 each), as 64B-swizzled
 //            panels of 32 channels (3-D tensor maps: channel-in-panel, token, panel), into two rings.
 //   warp 5   MMA issuer, per chunk c:
-//              dX  (+)= dY_c (K-major A)    x  W_c (MN-major B)        M128 N96  K96   -> TMEM cols [384, 480)
-//              dW_c += dY_c^T (MN-major A)  x  [X | 1] (MN-major B)    M128 N128 K128  -> TMEM cols [128 c, 128 c + 128)
-//            The X tile carries a constant fourth panel whose first channel is 1, so column 96 of dW_c
-//            is colsum(dY_c) = db_c for free.  Rows 96..127 of dW_c (the A operand's fourth panel is whatever
-//            follows the tile in shared memory) are never read.
-//   warps 0-3  epilogue: dX accumulators -> bf16 -> staging panels -> TMA store; at the end the dW / db
+//              dX   (+)= dY_c (K-major A)       x  W_c (MN-major B)      M128 N96 K96   -> TMEM cols [384, 480)
+//              dW_c^T += [X | 1]^T (MN-major A) x  dY_c (MN-major B)     M128 N96 K128  -> TMEM cols [96 c, 96 c + 96)
+//            The X tile carries a constant fourth panel whose first channel is 1, so lane 96 of the dW^T
+//            accumulators is colsum(dY) = db for free (lanes 97..127 are zero).  Accumulating the TRANSPOSE keeps all of
+//            dW in 96 G <= 384 columns (dW_c as M = out-channel tiles of 128 x 128 took 128 G: G = 3 at most).
+//   warps 0-3  epilogue: dX accumulators -> bf16 -> staging panels -> TMA store; at the end the dW^T / db
 //            accumulators -> this CTA's slice of the workspace.  A second tiny kernel sums the per-CTA
-//            partials (deterministic, no atomics).
+//            partials (deterministic, no atomics) and transposes.
 #include <cstdio>
 #include <mutex>
 
@@ -34,38 +34,40 @@ constexpr int kLTile = 128;                    // tokens per tile
 constexpr int kPanel = kLTile * 64;            // 8 KB: 128 tokens x 32 channels bf16
 constexpr int kLTileBytes = 3 * kPanel;        // 24 KB
 constexpr int kXSlot = 4 * kPanel;             // X tile + the ones panel
-constexpr int kXStages = 2, kDyStages = 3;
+constexpr int kXStages = 2;
+constexpr int kMaxDyStages = 3;              // 3 dY stages for G <= 3, 2 for G = 4 (its four weight chunks take the room)
 constexpr int kWChunk = 3 * 96 * 64;           // one 96 x 96 weight chunk as 3 panels of [96 out][32 in]
 constexpr int kLThreads = 192;                 // 4 epilogue warps + producer + MMA
-constexpr int kLTmemCols = 512;                // dW_c at 128 c; dX at 384
+constexpr int kLTmemCols = 512;                // dW_c^T at 96 c; dX at 384
 
 struct LinBwdParams {
   CUtensorMap dy, x, w, dx;                    // 3-D maps (32, rows, panels), 64B swizzle
   int M, G, n_tiles;
-  float* ws;                                   // [gridDim.x][G * 96][97] partial dW | db
+  float* ws;                                   // [gridDim.x][97][G * 96] partial dW^T (rows 0..95 = in-channel) | db (row 96)
 };
 
 __global__ void __launch_bounds__(kLThreads, 1)
 linbwd_tc_kernel(const __grid_constant__ LinBwdParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int G = P.G;
+  const int kDyStages = G == 4 ? 2 : 3;
   uint8_t* sDY = smem;                                   // kDyStages x 24 KB
-  uint8_t* sX = sDY + kDyStages * kLTileBytes;           // kXStages x 32 KB (directly behind sDY: the 4th A panel of the last dY slot)
+  uint8_t* sX = sDY + kDyStages * kLTileBytes;           // kXStages x 32 KB (X tile + ones panel)
   uint8_t* sW = sX + kXStages * kXSlot;                  // G x 18 KB
-  uint8_t* sOut = sW + 3 * kWChunk;                      // 24 KB staging
+  uint8_t* sOut = sW + G * kWChunk;                      // 24 KB staging
   uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + kLTileBytes);
   uint64_t* x_full = bars;                               // [kXStages]
   uint64_t* x_empty = bars + kXStages;                   // [kXStages]
   uint64_t* dy_full = bars + 2 * kXStages;               // [kDyStages]
-  uint64_t* dy_empty = dy_full + kDyStages;              // [kDyStages]
-  uint64_t* w_full = dy_empty + kDyStages;
+  uint64_t* dy_empty = dy_full + kMaxDyStages;           // [kDyStages]
+  uint64_t* w_full = dy_empty + kMaxDyStages;
   uint64_t* dx_full = w_full + 1;
   uint64_t* dx_empty = w_full + 2;                       // 4 arrivals (one per epilogue warp)
   uint64_t* dw_full = w_full + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int G = P.G;
   // tiles of this CTA: blockIdx.x, + gridDim.x, ...
   const int my_tiles = P.n_tiles > (int)blockIdx.x ? (P.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
@@ -115,11 +117,10 @@ linbwd_tc_kernel(const __grid_constant__ LinBwdParams P) {
   } else if (warp == 5) {
     // ============================== MMA issuer ==============================
     constexpr uint32_t idescDX = umma_idesc_bf16(128, 96, 0, 1);     // A K-major (dY), B MN-major (W)
-    constexpr uint32_t idescDW = umma_idesc_bf16(128, 128, 1, 1);    // A MN-major (dY^T), B MN-major ([X | 1])
+    constexpr uint32_t idescDW = umma_idesc_bf16(128, 96, 1, 1);     // A MN-major ([X | 1]^T), B MN-major (dY)
     const uint64_t dAk = umma_smem_desc(0, 0, 512, kSwz64);          // dY tile, K-major
-    const uint64_t dAm = umma_smem_desc(0, kPanel, 512, kSwz64);     // dY tile, MN-major: channel panels 8 KB apart
+    const uint64_t dMn = umma_smem_desc(0, kPanel, 512, kSwz64);     // dY / X tile, MN-major: channel panels 8 KB apart
     const uint64_t dBw = umma_smem_desc(0, 96 * 64, 512, kSwz64);    // W chunk, MN-major: in-channel panels 6 KB apart
-    const uint64_t dBx = umma_smem_desc(0, kPanel, 512, kSwz64);     // X tile, MN-major
     const uint32_t dy0 = smem_u32(sDY) >> 4, x0 = smem_u32(sX) >> 4, w0 = smem_u32(sW) >> 4;
     mbar_wait(w_full, 0);
     int dn = 0;
@@ -139,7 +140,7 @@ linbwd_tc_kernel(const __grid_constant__ LinBwdParams P) {
                          dBw + (w0 + c * (kWChunk >> 4) + ks * 64), idescDX, (c | ks) != 0);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)                 // 16 tokens per step
-            umma_bf16_ss(tmem + c * 128, dAm + (a0 + ks * 64), dBx + (x0 + xs * (kXSlot >> 4) + ks * 64), idescDW, (n | ks) != 0);
+            umma_bf16_ss(tmem + c * 96, dMn + (x0 + xs * (kXSlot >> 4) + ks * 64), dMn + (a0 + ks * 64), idescDW, (n | ks) != 0);
           umma_commit(&dy_empty[ds]);
           if (c == G - 1) { umma_commit(dx_full); umma_commit(&x_empty[xs]); }
         }
@@ -183,28 +184,22 @@ linbwd_tc_kernel(const __grid_constant__ LinBwdParams P) {
       }
     }
     if (tid == 0) tma_store_wait_all<0>();
-    // ---- dW | db partials of this CTA: thread r = out-channel r of each chunk
+    // ---- dW^T | db partials of this CTA: thread r = in-channel r (r < 96) or the db row (r == 96)
     mbar_wait(dw_full, 0);
     tcgen05_fence_after();
-    float* wsb = P.ws + (size_t)blockIdx.x * G * 96 * 97;
-    for (int c = 0; c < G; ++c) {
+    const int ncol = G * 96;
+    float* wsb = P.ws + (size_t)blockIdx.x * 97 * ncol;
+    for (int p = 0; p < 3 * G; ++p) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem + lane_base + p * 32, v);
+      tmem_ld_wait();
+      if (r < 97) {
+        float4* dst = reinterpret_cast<float4*>(wsb + (size_t)r * ncol + p * 32);
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem + lane_base + c * 128 + p * 32, v);
-        tmem_ld_wait();
-        if (r < 96 && my_tiles > 0) {
-          float* dst = wsb + (size_t)(c * 96 + r) * 97 + p * 32;
-          if (p < 3) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) dst[e] = __uint_as_float(v[e]);
-          } else {
-            dst[0] = __uint_as_float(v[0]);               // column 96: colsum(dY) of this out-channel
-          }
-        } else if (r < 96) {
-          float* dst = wsb + (size_t)(c * 96 + r) * 97 + p * 32;
-          for (int e = 0; e < (p < 3 ? 32 : 1); ++e) dst[e] = 0.f;
-        }
+        for (int e = 0; e < 8; ++e)
+          dst[e] = my_tiles > 0 ? make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
+                                              __uint_as_float(v[4 * e + 3]))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
   }
@@ -214,14 +209,14 @@ linbwd_tc_kernel(const __grid_constant__ LinBwdParams P) {
   if (warp == 5) tmem_dealloc<kLTmemCols>(tmem);
 }
 
-// out[e] = sum over CTAs of ws[cta][e]; element e = (out-channel, 0..96): columns 0..95 -> dW, column 96 -> db.
+// out[e] = sum over CTAs of ws[cta][e]; element e = (row i in 0..96, out-channel o): rows 0..95 -> dW[o][i], row 96 -> db[o].
 // Block = 32 elements x 8 slices of the CTA range (a 148-long serial chain of dependent loads per thread took 10 us).
 __global__ void __launch_bounds__(256)
-linbwd_reduce_kernel(const float* __restrict__ ws, int n_cta, int rows, float* __restrict__ dw, float* __restrict__ db) {
+linbwd_reduce_kernel(const float* __restrict__ ws, int n_cta, int ncol, float* __restrict__ dw, float* __restrict__ db) {
   __shared__ float part[8][33];
   const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int e = blockIdx.x * 32 + lane;
-  const int n = rows * 97;
+  const int n = 97 * ncol;
   float s = 0.f;
   if (e < n)
     for (int c = sl; c < n_cta; c += 8) s += ws[(size_t)c * n + e];
@@ -230,13 +225,13 @@ linbwd_reduce_kernel(const float* __restrict__ ws, int n_cta, int rows, float* _
   if (sl == 0 && e < n) {
 #pragma unroll
     for (int k = 1; k < 8; ++k) s += part[k][lane];
-    const int o = e / 97, i = e - o * 97;
+    const int i = e / ncol, o = e - i * ncol;
     if (i < 96) dw[o * 96 + i] = s;
     else if (db) db[o] = s;
   }
 }
 
-constexpr size_t kLSmemBytes = 1024 + kDyStages * kLTileBytes + kXStages * kXSlot + 3 * kWChunk + kLTileBytes + 32 * 8;
+static size_t linbwd_smem_bytes(int G) { return 1024 + (size_t)(G == 4 ? 2 : 3) * kLTileBytes + kXStages * kXSlot + (size_t)G * kWChunk + kLTileBytes + 32 * 8; }
 
 static bool make_panel_map(CUtensorMap* out, const void* ptr, long long rows, int cols, long long ld, int box_rows, int box_panels) {
   EncodeTiledFn enc = encode_fn();
@@ -252,7 +247,7 @@ static bool make_panel_map(CUtensorMap* out, const void* ptr, long long rows, in
 const char* linbwd_why_not(int io_dtype, long long rows, int in_features, int out_features, long long ld_dy, long long ld_x, long long ld_dx) {
   if (io_dtype != MMN_DT_BF16) return "io dtype is not bf16";
   if (in_features != kLC) return "in_features != 96";
-  if (out_features != 96 && out_features != 192 && out_features != 288) return "out_features is not 96, 192 or 288";
+  if (out_features != 96 && out_features != 192 && out_features != 288 && out_features != 384) return "out_features is not 96, 192, 288 or 384";
   if (rows < 1) return "no rows";
   if (ld_dy % 8 || ld_x % 8 || ld_dx % 8) return "leading dimension not 16-byte aligned";
   if (!encode_fn()) return "cuTensorMapEncodeTiled unavailable";
@@ -275,15 +270,16 @@ int linbwd(const void* dy, const void* x, const void* w, void* dx, float* dw, fl
     return MMN_ERR_CUDA;
   }
   static std::once_flag once;
-  std::call_once(once, [] { cudaFuncSetAttribute(linbwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLSmemBytes); });
+  std::call_once(once, [] { cudaFuncSetAttribute(linbwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)(linbwd_smem_bytes(3) > linbwd_smem_bytes(4) ? linbwd_smem_bytes(3) : linbwd_smem_bytes(4))); });
   int grid = num_sms_cached();
   if (grid > P.n_tiles) grid = P.n_tiles;
-  linbwd_tc_kernel<<<grid, kLThreads, kLSmemBytes, st>>>(P);
+  linbwd_tc_kernel<<<grid, kLThreads, linbwd_smem_bytes(P.G), st>>>(P);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { snprintf(err, errlen, "linbwd_tc_kernel: %s", cudaGetErrorString(e)); return MMN_ERR_CUDA; }
   ++*launches;
   const int n = out_features * 97;
-  linbwd_reduce_kernel<<<(n + 31) / 32, 256, 0, st>>>(workspace, grid, out_features, dw, db);
+  linbwd_reduce_kernel<<<(n + 31) / 32, 256, 0, st>>>(workspace, grid, out_features, dw, db);   // ncol = out_features
   e = cudaGetLastError();
   if (e != cudaSuccess) { snprintf(err, errlen, "linbwd_reduce_kernel: %s", cudaGetErrorString(e)); return MMN_ERR_CUDA; }
   ++*launches;

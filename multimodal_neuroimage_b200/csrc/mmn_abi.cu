@@ -318,7 +318,7 @@ int mmn_linear_fwd(const void* x, const void* w, const float* bias, void* y, voi
   return rc;
 }
 
-// in = 96, out in {96, 192, 288}: ONE pass over dy and x (linbwd_tc.cu); any other multiple of 32: dgrad + wgrad (gemm_tc.cu)
+// in = 96, out in {96, 192, 288, 384}: ONE pass over dy and x (linbwd_tc.cu); any other multiple of 32: dgrad + wgrad (gemm_tc.cu)
 static bool linbwd_fused_ok(int io_dtype, int64_t rows, int32_t in_features, int32_t out_features, int64_t ld_dy, int64_t ld_x,
                             int64_t ld_dx) {
   return mmn::tc::linbwd_why_not(io_dtype, rows, in_features, out_features, ld_dy, ld_x, ld_dx) == nullptr;
@@ -344,7 +344,7 @@ int mmn_linear_bwd(const void* dy, const void* x, const void* w, void* dx, float
   if (dw && !x) return fail(MMN_ERR_INVALID, "dw needs x");
   if (act != MMN_ACT_NONE && act != MMN_ACT_RELU && act != MMN_ACT_GELU) return fail(MMN_ERR_INVALID, "bad activation %d", act);
   if (act != MMN_ACT_NONE && (!act_aux || ld_aux % 8 || reinterpret_cast<uintptr_t>(act_aux) % 16))
-    return fail(MMN_ERR_INVALID, "activation gradient needs a 16-byte aligned pre-activation tensor");
+    return fail(MMN_ERR_INVALID, "activation gradient needs a 16-byte aligned act'(pre) tensor");
   if (!have_device()) return fail(MMN_ERR_CUDA, "no CUDA device: libmmn_b200 has no CPU path");
   if (!mmn_linear_bwd_supported(io_dtype, rows, in_features, out_features, ld_dy, ld_x ? ld_x : in_features, ld_dx ? ld_dx : in_features))
     return fail(MMN_ERR_UNSUPPORTED, "shape not supported by the tensor-core projection backward (bf16, widths multiples of 32)");
@@ -357,7 +357,7 @@ int mmn_linear_bwd(const void* dy, const void* x, const void* w, void* dx, float
                          sizeof(g_err), &n);
   } else {
     rc = mmn::tc::linear_bwd_general(dy, x, w, dx, dw, (float*)workspace, act_aux, ld_aux,
-                                     act == MMN_ACT_RELU ? 3 : act == MMN_ACT_GELU ? 4 : 0, rows, in_features, out_features, ld_dy,
+                                     act != MMN_ACT_NONE ? 3 : 0, rows, in_features, out_features, ld_dy,
                                      ld_x, ld_dx, st, g_err, sizeof(g_err), &n);
     if (rc == MMN_OK && db) {
       // bias gradient: column sums of dy, 2048 columns per launch (colsum_kernel's block covers 256 x 8)

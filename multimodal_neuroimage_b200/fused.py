@@ -123,7 +123,7 @@ def window_attention_module(x: torch.Tensor, y: Optional[torch.Tensor], w_a, b_a
 class MlpFn(torch.autograd.Function):
     """fc1 -> activation -> fc2 (swin_v2_module.py:27-31, swinfusion_module.py:25-29, crossmodal_transformer.py:158-160) as
     two tensor-core GEMMs with the bias + activation in the first one's epilogue, and a three-GEMM-pass backward:
-        dpre = (dy W2) o act'(pre)      dgrad of fc2 with the activation derivative as its epilogue
+        dpre = (dy W2) o act'(pre)      dgrad of fc2; act'(pre) was written by fc1's forward epilogue next to act(pre)
         dW2  = dy^T h, db2              wgrad of fc2
         dx, dW1, db1                    backward of fc1 (one fused pass for in = 96)
     PyTorch runs this as 2 GEMMs + 1 elementwise kernel forward and 4 GEMMs + 3 elementwise/reduction kernels backward."""
@@ -132,9 +132,9 @@ class MlpFn(torch.autograd.Function):
     def forward(ctx, x, w1, b1, w2, b2, act):
         x2 = x.reshape(-1, x.shape[-1])
         w1c, w2c = w1.to(torch.bfloat16), w2.to(torch.bfloat16)
-        h, pre = torch.ops.mmn_b200.linear_fwd(x2, w1c, None if b1 is None else b1.float(), act, True)
+        h, dact = torch.ops.mmn_b200.linear_fwd(x2, w1c, None if b1 is None else b1.float(), act, True)   # act(pre), act'(pre)
         y, _ = torch.ops.mmn_b200.linear_fwd(h, w2c, None if b2 is None else b2.float(), _lib.ACT_NONE, False)
-        ctx.save_for_backward(x2, pre, h, w1c, w2c)
+        ctx.save_for_backward(x2, dact, h, w1c, w2c)
         ctx.meta = (x.shape, w1.dtype, None if b1 is None else b1.dtype, w2.dtype, None if b2 is None else b2.dtype, act,
                     x.requires_grad)
         return y.view(*x.shape[:-1], w2.shape[0])
@@ -142,12 +142,12 @@ class MlpFn(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
-        x2, pre, h, w1c, w2c = ctx.saved_tensors
+        x2, dact, h, w1c, w2c = ctx.saved_tensors
         shape, w1dt, b1dt, w2dt, b2dt, act, need_dx = ctx.meta
         dy2 = dy.reshape(-1, dy.shape[-1]).to(torch.bfloat16)
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
-        dpre, dw2, db2 = torch.ops.mmn_b200.linear_bwd(dy2, h, w2c, pre, act, True, True)
+        dpre, dw2, db2 = torch.ops.mmn_b200.linear_bwd(dy2, h, w2c, dact, act, True, True)
         dx, dw1, db1 = torch.ops.mmn_b200.linear_bwd(dpre, x2, w1c, None, 0, need_dx, True)
         return (dx.view(shape) if need_dx else None, dw1.to(w1dt), db1.to(b1dt) if b1dt is not None else None, dw2.to(w2dt),
                 db2.to(b2dt) if b2dt is not None else None, None)

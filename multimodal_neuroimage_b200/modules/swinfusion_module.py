@@ -192,11 +192,23 @@ class SwinTransformerBlock_fusion(_FusionBlockBase):
         self.mlp = Mlp_fusion(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
         self._register_mask()
 
-    def forward(self, x, x_size):
+    def forward_deferred(self, x, delta, x_size):
+        """The block on the stream `x + delta` (delta None: just x), returning (x', delta') with the block's output
+        = x' + delta'.  The residual add that closes a block is left to the LayerNorm kernel that opens the next one
+        (BasicLayer_fusion chains blocks this way), so a block is two add+LayerNorm passes and no separate add -- forward
+        and backward (each intermediate stream feeds exactly one kernel: autograd has nothing to accumulate)."""
         n = len(x_size)
-        a = self.attn.forward_grid(fused.layer_norm(x, self.norm1), tuple(x_size), to_ntuple(self.shift_size, n))
+        if delta is None:
+            h = fused.layer_norm(x, self.norm1)
+        else:
+            x, h = fused.add_layer_norm(x, delta, self.norm1)
+        a = self.attn.forward_grid(h, tuple(x_size), to_ntuple(self.shift_size, n))
         x, h = fused.add_layer_norm(x, self.drop_path(a), self.norm2)          # x + a and norm2 of it in one pass
-        return x + self.drop_path(self.mlp(h))
+        return x, self.drop_path(self.mlp(h))
+
+    def forward(self, x, x_size):
+        x, d = self.forward_deferred(x, None, x_size)
+        return x + d
 
     def flops(self):
         return self._flops(self.attn)
@@ -226,17 +238,27 @@ class Cross_SwinTransformerBlock(_FusionBlockBase):
         self.mlp_B = Mlp_fusion(in_features=dim, hidden_features=hidden, act_layer=act_layer, drop=drop)
         self._register_mask()
 
-    def forward(self, x, y, x_size):
+    def forward_deferred(self, x, dx, y, dy, x_size):
+        """As SwinTransformerBlock_fusion.forward_deferred, for the two streams x + dx and y + dy."""
         n = len(x_size)
         grid, shift = tuple(x_size), to_ntuple(self.shift_size, n)
-        xn, yn = fused.layer_norm(x, self.norm1_A), fused.layer_norm(y, self.norm1_B)
+        if dx is None:
+            xn = fused.layer_norm(x, self.norm1_A)
+        else:
+            x, xn = fused.add_layer_norm(x, dx, self.norm1_A)
+        if dy is None:
+            yn = fused.layer_norm(y, self.norm1_B)
+        else:
+            y, yn = fused.add_layer_norm(y, dy, self.norm1_B)
         ax = self.attn_A.forward_grid(xn, yn, grid, shift)
         ay = self.attn_B.forward_grid(yn, xn, grid, shift)
         x, hx = fused.add_layer_norm(x, self.drop_path_A(ax), self.norm2_A)
-        x = x + self.drop_path_A(self.mlp_A(hx))
         y, hy = fused.add_layer_norm(y, self.drop_path_B(ay), self.norm2_B)
-        y = y + self.drop_path_B(self.mlp_B(hy))
-        return x, y
+        return x, self.drop_path_A(self.mlp_A(hx)), y, self.drop_path_B(self.mlp_B(hy))
+
+    def forward(self, x, y, x_size):
+        x, dx, y, dy = self.forward_deferred(x, None, y, None, x_size)
+        return x + dx, y + dy
 
     def flops(self):
         return self._flops(self.attn_A)
@@ -298,8 +320,15 @@ class BasicLayer_fusion(nn.Module):
         self.downsample = downsample(input_resolution, dim=dim, norm_layer=norm_layer) if downsample is not None else None
 
     def forward(self, x, x_size):
-        for blk in self.blocks:
-            x = checkpoint.checkpoint(blk, x, x_size, use_reentrant=False) if self.use_checkpoint else blk(x, x_size)
+        if self.use_checkpoint:
+            for blk in self.blocks:
+                x = checkpoint.checkpoint(blk, x, x_size, use_reentrant=False)
+        else:
+            delta = None                      # the stream is x + delta: each block's closing add rides on the next LayerNorm
+            for blk in self.blocks:
+                x, delta = blk.forward_deferred(x, delta, x_size)
+            if delta is not None:
+                x = x + delta
         if self.downsample is not None:
             x = self.downsample(x)
         return x
@@ -333,11 +362,15 @@ class Cross_BasicLayer(nn.Module):
         self.downsample = downsample(input_resolution, dim=dim, norm_layer=norm_layer) if downsample is not None else None
 
     def forward(self, x, y, x_size):
-        for blk in self.blocks:
-            if self.use_checkpoint:
+        if self.use_checkpoint:
+            for blk in self.blocks:
                 x, y = checkpoint.checkpoint(blk, x, y, x_size, use_reentrant=False)
-            else:
-                x, y = blk(x, y, x_size)
+        else:
+            dx = dy = None
+            for blk in self.blocks:
+                x, dx, y, dy = blk.forward_deferred(x, dx, y, dy, x_size)
+            if dx is not None:
+                x, y = x + dx, y + dy
         if self.downsample is not None:
             x = self.downsample(x)
             y = self.downsample(y)

@@ -434,8 +434,8 @@ def linear_supported(x: Tensor, w: Tensor) -> bool:
 
 @torch.library.custom_op("mmn_b200::linear_fwd", mutates_args=())
 def linear_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], act: int, want_pre: bool) -> Tuple[Tensor, Tensor]:
-    """y = act(x w^T + bias) on the tensor cores; returns (y, pre) where pre is the value before the activation when
-    `want_pre` (what the backward needs for act'), else an empty tensor."""
+    """y = act(x w^T + bias) on the tensor cores; returns (y, dact) where dact = act'(x w^T + bias), the activation's derivative
+    at the pre-activation (what the backward multiplies with) when `want_pre`, else an empty tensor."""
     _require_cuda(x, w, bias)
     if not _rows2d(x) or w.dtype != torch.bfloat16 or not w.is_contiguous():
         raise RuntimeError("linear_fwd expects bf16 x (rows, in) with contiguous columns and a contiguous bf16 weight")
@@ -468,8 +468,9 @@ def linear_bwd_supported(dy: Tensor, x: Tensor, w: Tensor) -> bool:
 def linear_bwd(dy: Tensor, x: Tensor, w: Tensor, act_aux: Optional[Tensor] = None, act: int = 0, want_dx: bool = True,
                want_dw: bool = True) -> Tuple[Tensor, Tensor, Tensor]:
     """Backward of y = x w^T + b: returns (dx bf16 (rows, in), dw fp32 (out, in), db fp32 (out)).  With `act_aux` (the
-    pre-activation that produced x = act(act_aux)) dx is additionally multiplied by act'(act_aux) in the kernel's epilogue,
-    i.e. it is the gradient w.r.t. act_aux.  in = 96 runs as one fused pass over dy and x, other widths as dgrad + wgrad."""
+    act'(pre) that linear_fwd wrote for the layer whose activation produced x) dx is additionally multiplied by it in the
+    kernel's epilogue, i.e. it is the gradient w.r.t. that pre-activation.  in = 96 runs as one fused pass over dy and x,
+    other widths as dgrad + wgrad."""
     _require_cuda(dy, x, w, act_aux)
     lib = _lib.load()
     rows, n_out, n_in = dy.shape[0], dy.shape[1], x.shape[1]
@@ -515,16 +516,10 @@ class LinearFn(torch.autograd.Function):
         x2, wc, pre = ctx.saved_tensors
         shape, wdt, bdt, act, need_dx = ctx.meta
         dy2 = dy.reshape(-1, dy.shape[-1]).to(torch.bfloat16)
-        if act != _lib.ACT_NONE:                       # through the activation: elementwise, then the plain projection backward
-            dy2 = _act_backward(dy2, pre, act)
+        if act != _lib.ACT_NONE:                       # through the activation: dy o act'(pre), then the plain projection backward
+            dy2 = dy2 * pre
         dx, dw, db = torch.ops.mmn_b200.linear_bwd(dy2.contiguous(), x2, wc, None, 0, need_dx, True)
         return (dx.view(shape) if need_dx else None, dw.to(wdt), db.to(bdt) if bdt is not None else None, None)
-
-
-def _act_backward(dy: Tensor, pre: Tensor, act: int) -> Tensor:
-    if act == _lib.ACT_RELU:
-        return dy * (pre > 0)
-    return torch.ops.aten.gelu_backward(dy, pre)
 
 
 def linear(x: Tensor, w: Tensor, b: Optional[Tensor] = None, act: str = "none") -> Tensor:

@@ -357,8 +357,11 @@ def test_linear_fwd_tensor_core(mm, rows, n_in, n_out, act):
     want_pre = x.double() @ w.double().t() + (0 if b is None else b.double())
     want = {"none": lambda t: t, "gelu": torch.nn.functional.gelu, "relu": torch.relu}[act](want_pre)
     check(y, want, 1e-2, f"linear_fwd {act}")
-    if act != "none":
-        check(pre, want_pre, 1e-2, "linear_fwd pre-activation")
+    if act != "none":                                      # second output: act'(pre), what the backward multiplies with
+        p64 = want_pre.clone().requires_grad_(True)
+        want_d, = torch.autograd.grad(({"gelu": torch.nn.functional.gelu, "relu": torch.relu}[act](p64)).sum(), p64)
+        away = want_pre.abs() > 0.05                       # relu' jumps at 0: compare where bf16 rounding cannot flip the sign
+        check(pre.double().cpu() * away, want_d * away, 1e-2, "linear_fwd act'(pre)")
     # strided input rows (a channel slice of a wider tensor)
     wide = torch.randn(rows, n_in + 64, generator=g).bfloat16().cuda()
     y2, _ = torch.ops.mmn_b200.linear_fwd(wide[:, :n_in], w.cuda(), None, 0, False)
@@ -378,11 +381,9 @@ def test_linear_bwd_tensor_core(mm, rows, n_in, n_out):
     check(dx, dyd @ wd, BF16_TOL, "linear_bwd dx")
     check(dw, dyd.t() @ xd, 2e-3, "linear_bwd dw")
     check(db, dyd.sum(0), 2e-3, "linear_bwd db")
-    for act, fn in (("gelu", torch.nn.functional.gelu), ("relu", torch.relu)):
-        p64 = pre.double().requires_grad_(True)
-        gp, = torch.autograd.grad(fn(p64), p64, dyd @ wd)
+    for act in ("gelu", "relu"):                           # act_aux = act'(pre) as linear_fwd writes it
         dx2, dw2, _ = torch.ops.mmn_b200.linear_bwd(dy.cuda(), x.cuda(), w.cuda(), pre.cuda(), mm.ops._ACT[act], True, True)
-        check(dx2, gp, BF16_TOL, f"linear_bwd dx through {act}'")
+        check(dx2, (dyd @ wd) * pre.double(), BF16_TOL, f"linear_bwd dx through {act}'")
         check(dw2, dyd.t() @ xd, 2e-3, "linear_bwd dw (general path)")
     only_dx = torch.ops.mmn_b200.linear_bwd(dy.cuda(), x.cuda(), w.cuda(), None, 0, True, False)
     assert only_dx[1].numel() == 0 and rel_err(only_dx[0], dyd @ wd) < BF16_TOL
