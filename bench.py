@@ -233,6 +233,8 @@ def run_train_workload(name, dev, rank, world, steps, warmup, batch=None, use_gr
     cfg = TRAIN_WORKLOADS[name]
     batch = batch or cfg["batch"]
     torch.manual_seed(0)
+    from multimodal_neuroimage_b200 import fused
+    fused.PARALLEL_BRANCHES = ddp == "flat" and not os.environ.get("MMN_SERIAL_BRANCHES")     # the modalities' independent stages on two streams
     model = W.SwinFusion3D(use_checkpoint=checkpoint) if name == "cfg3" else W.SwinV2CrossModal3D(use_checkpoint=checkpoint)
     W.randomise_norms(model)
     model = model.to(dev)

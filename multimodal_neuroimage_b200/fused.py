@@ -219,3 +219,34 @@ def post_norm_add(resid: torch.Tensor, delta: torch.Tensor, ln, copy_dtype=None)
         return s, (s.to(copy_dtype) if copy_dtype is not None else None)
     with torch.autocast("cuda", enabled=False):
         return ops.AddLayerNormFn.apply(resid, delta, ln.weight, ln.bias, ln.eps, _lib.LN_POST, copy_dtype)
+
+
+# ------------------------------------------------------------------------------------------
+# Independent branches on two streams
+# ------------------------------------------------------------------------------------------
+PARALLEL_BRANCHES = False      # opt-in (bench / TrainStep switch it on): same arithmetic, two CUDA streams
+_side_streams = {}
+
+
+def parallel(fn_a, fn_b, ref: torch.Tensor):
+    """(fn_a(), fn_b()) for two branches that do not depend on each other -- the two modalities' intra-modal groups
+    (swinfusion_module.py:916-917; model.py's Ex_A / Ex_B stages).  With PARALLEL_BRANCHES on CUDA, fn_b is issued on a
+    side stream forked from and joined back to the current one, so its kernels fill the SMs that fn_a's persistent
+    kernels leave idle in their ramp-up and tail (at cfg3 a launch is 20-60 us of work: ~40 % of it is ramp and tail,
+    tools/bench_blocks.py).  Autograd replays each branch's backward on the stream its forward ran on, and a CUDA-graph
+    capture records the fork / join as parallel branches of the graph."""
+    if not (PARALLEL_BRANCHES and ref.is_cuda):
+        return fn_a(), fn_b()
+    cur = torch.cuda.current_stream(ref.device)
+    side = _side_streams.get(ref.device.index)
+    if side is None:
+        side = _side_streams[ref.device.index] = torch.cuda.Stream(ref.device)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        b = fn_b()
+    a = fn_a()
+    cur.wait_stream(side)
+    for t in (b if isinstance(b, (tuple, list)) else (b,)):
+        if isinstance(t, torch.Tensor):
+            t.record_stream(cur)           # allocated from the side stream's pool, consumed on the current stream
+    return a, b

@@ -385,7 +385,7 @@ class PatchEmbed(nn.Module):
         assert H == self.img_size_h and W == self.img_size_w, \
             f"Input image size ({H}*{W}) doesn't match model ({self.img_size_h}*{self.img_size_w})."
         x = self.proj(x).flatten(2).transpose(1, 2)
-        return self.norm(x) if self.norm is not None else x
+        return fused.layer_norm(x, self.norm, out_dtype=torch.float32) if self.norm is not None else x
 
     def flops(self):
         Ho, Wo = self.patches_resolution
@@ -410,4 +410,4 @@ class PatchEmbed3D(nn.Module):
     def forward(self, x):
         assert tuple(x.shape[2:]) == self.img_size, f"Input volume {tuple(x.shape[2:])} doesn't match {self.img_size}"
         x = self.proj(x).flatten(2).transpose(1, 2)
-        return self.norm(x) if self.norm is not None else x
+        return fused.layer_norm(x, self.norm, out_dtype=torch.float32) if self.norm is not None else x

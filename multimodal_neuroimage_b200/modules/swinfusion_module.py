@@ -450,8 +450,8 @@ class CRSTB(nn.Module):
                                           norm_layer=None)
 
     def forward(self, x, y, x_size):
-        x = self.residual_group_A(x, x_size) + x
-        y = self.residual_group_B(y, x_size) + y
+        # the two intra-modal groups are independent: fused.parallel may run them on two streams
+        x, y = fused.parallel(lambda: self.residual_group_A(x, x_size) + x, lambda: self.residual_group_B(y, x_size) + y, x)
         x1, y1 = x, y
         x, y = self.residual_group(x1, y1, x_size)
         return x + x1, y + y1

@@ -23,6 +23,7 @@ from typing import Sequence, Tuple
 import torch
 import torch.nn as nn
 
+from . import fused
 from .modules import crossmodal_transformer as cm
 from .modules import swin_v2_module as v2
 from .modules import swinfusion_module as fu
@@ -57,18 +58,22 @@ class SwinFusion3D(nn.Module):
 
     def forward(self, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
         """A, B (batch, 1, D, H, W) -> logits (batch, num_classes)."""
-        x, y = self.patch_embed_A(A), self.patch_embed_B(B)
-        for layer in self.layers_Ex_A:
-            x = layer(x, self.grid)
-        for layer in self.layers_Ex_B:
-            y = layer(y, self.grid)
-        x, y = self.norm_Ex_A(x), self.norm_Ex_B(y)
+        f32 = torch.float32
+
+        def extract(vol, embed, layers, norm):              # one modality's feature extraction: independent of the other's
+            t = embed(vol)
+            for layer in layers:
+                t = layer(t, self.grid)
+            return fused.layer_norm(t, norm, out_dtype=f32)
+
+        x, y = fused.parallel(lambda: extract(A, self.patch_embed_A, self.layers_Ex_A, self.norm_Ex_A),
+                              lambda: extract(B, self.patch_embed_B, self.layers_Ex_B, self.norm_Ex_B), A)
         for layer in self.layers_Fusion:
             x, y = layer(x, y, self.grid)
-        x = self.act(self.fuse(torch.cat([self.norm_Fusion_A(x), self.norm_Fusion_B(y)], -1)))
+        x = self.act(self.fuse(torch.cat([fused.layer_norm(x, self.norm_Fusion_A), fused.layer_norm(y, self.norm_Fusion_B)], -1)))
         for layer in self.layers_Re:
             x = layer(x, self.grid)
-        return self.head(self.norm_Re(x).mean(1))
+        return self.head(fused.layer_norm(x, self.norm_Re, out_dtype=f32).mean(1))
 
     def attention_calls(self) -> int:
         return sum(1 for m in self.modules() if isinstance(m, (fu.WindowAttention_fusion, fu.Cross_WindowAttention)))
@@ -99,7 +104,7 @@ class SwinV2Tower3D(nn.Module):
         x = self.patch_embed(x)
         for layer in self.layers:
             x = layer(x)
-        return self.norm(x)                                   # (B, tokens of the last stage, C_last)
+        return fused.layer_norm(x, self.norm, out_dtype=torch.float32)      # (B, tokens of the last stage, C_last)
 
 
 class SwinV2CrossModal3D(nn.Module):
@@ -115,7 +120,8 @@ class SwinV2CrossModal3D(nn.Module):
         self.head = nn.Linear(2 * E, num_classes)
 
     def forward(self, A, B):
-        x, y = self.tower_A(A).transpose(0, 1), self.tower_B(B).transpose(0, 1)      # (T, B, E) as the MulT encoder wants
+        x, y = fused.parallel(lambda: self.tower_A(A), lambda: self.tower_B(B), A)      # independent towers
+        x, y = x.transpose(0, 1), y.transpose(0, 1)                                  # (T, B, E) as the MulT encoder wants
         xa, yb = self.a_with_b(x, y, y), self.b_with_a(y, x, x)
         return self.head(torch.cat([xa.mean(0), yb.mean(0)], -1))
 

@@ -298,7 +298,7 @@ def test_swinv2_block_3d(mm, dtype):
     if dtype == torch.bfloat16:
         # logit scales of trained SwinV2 models (init ln 10).  Near the clamp (g = 100) a 16-bit q / k operand moves a logit by
         # ~0.1 whatever computes it (tools/debug_fp16.py), so a whole-block bf16 comparison there measures the operand
-        # rounding, not the kernels; the clamp range is covered in fp32 here and by the core tests.
+        # rounding, not the kernels; the clamp range is covered by the fp32 variant of this test.
         with torch.no_grad():
             blk.attn.logit_scale.copy_(torch.tensor([1.0, 10.0, 20.0]).log().view(3, 1, 1))
     x = torch.randn(B, math.prod(grid), C, generator=torch.Generator().manual_seed(5))

@@ -158,7 +158,7 @@ def test_fp16_autocast_gradscaler_like_the_reference_trainer(mm):
     for i, m in enumerate((blk, cross, enc)):
         _randomise(m, 20 + i)
     with torch.no_grad():
-        # SwinV2's own initial logit scale (swin_v2_module.py:89).  The clamp range up to 100 is covered by the core tests;
+        # SwinV2's own initial logit scale (swin_v2_module.py:89).  The clamp range up to 100 is covered in fp32 (test_swinv2_block_3d);
         # at g = 100 a 16-bit q/k operand moves a logit by ~0.1 whatever the kernel (tools/debug_fp16.py: same error under
         # bf16 autocast), which says nothing about the fp16 / GradScaler plumbing this test is about.
         blk.attn.logit_scale.fill_(math.log(10.0))
@@ -563,3 +563,45 @@ def test_mha_tensor_core_matches_generic_at_scale(mm):
         res[name] = (out.float(), lse, gx.float())
     for i, n in enumerate(("out", "lse", "dqkv")):
         assert rel_err(res["tc"][i], res["gen"][i]) < BF16_TOL, n
+
+
+def test_parallel_branches_match_serial(mm):
+    """fused.parallel: the two modalities' independent groups on two streams (eager and under CUDA-graph capture) give the
+    serial result -- outputs and every gradient."""
+    from multimodal_neuroimage_b200 import fused
+    grid, C, nH, B = (8, 8, 8), 96, 3, 2
+    blk = mm.fu.CRSTB(dim=C, input_resolution=grid, depth=2, num_heads=nH, window_size=4, img_size=grid, patch_size=1).cuda()
+    _randomise(blk, 3)
+    params = list(blk.parameters())                       # the convolutions CRSTB declares but never calls get no gradient
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(B, math.prod(grid), C, device="cuda", generator=g).requires_grad_(True)
+    y = torch.randn(B, math.prod(grid), C, device="cuda", generator=g).requires_grad_(True)
+
+    def run():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ox, oy = blk(x, y, grid)
+        gr = torch.autograd.grad((ox.float() ** 2).mean() + oy.float().mean(), [x, y] + params, allow_unused=True)
+        return [ox.detach().clone(), oy.detach().clone()] + [t.detach().clone() for t in gr if t is not None]
+
+    try:
+        fused.PARALLEL_BRANCHES = False
+        serial = run()
+        fused.PARALLEL_BRANCHES = True
+        par = run()
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            run()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            captured = run()
+        for t in captured:
+            t.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+    finally:
+        fused.PARALLEL_BRANCHES = False
+    for a, b, c in zip(serial, par, captured):
+        assert rel_err(b, a) < 1e-5 and rel_err(c, a) < 1e-5       # LayerNorm's dgamma / dbeta sums use atomics: order varies
