@@ -35,7 +35,7 @@ constexpr int kGProducerWarp = kGEpiWarps, kGMmaWarp = kGEpiWarps + 1;
 constexpr int kGTmemCols = 256;                // two accumulators of BN <= 128 columns
 
 struct GemmParams {
-  CUtensorMap a, b, d, d_pre;
+  CUtensorMap a, b, d, d_pre, aux_map;         // aux_map: kEpiMulAux, boxes = output tiles (L2 prefetch only)
   int M, N;                                    // output rows / columns
   int tiles_n, n_tiles, k_blocks, splits, kb_per_split;
   int epi, has_pre;
@@ -89,7 +89,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams P) {
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kGEpiWarps / 2); }
     fence_barrier_init();
   }
-  if (warp == kGProducerWarp && lane == 0) { tma_prefetch_desc(&P.a); tma_prefetch_desc(&P.b); }
+  if (warp == kGProducerWarp && lane == 0) { tma_prefetch_desc(&P.a); tma_prefetch_desc(&P.b); if (!F32OUT && P.epi == kEpiMulAux) tma_prefetch_desc(&P.aux_map); }
   if (!F32OUT && (warp == 0 || warp == 4) && lane == 0) { tma_prefetch_desc(&P.d); if (P.has_pre) tma_prefetch_desc(&P.d_pre); }
   if (warp == kGMmaWarp) tmem_alloc<kGTmemCols>(tmem_slot);
   tcgen05_fence_before();
@@ -106,6 +106,9 @@ gemm_tc_kernel(const __grid_constant__ GemmParams P) {
         const int tm = tile / P.tiles_n, tn = tile - tm * P.tiles_n;
         const int m0 = tm * 128, n0 = tn * BN;
         const int kb0 = sp * P.kb_per_split, kb1 = min(kb0 + P.kb_per_split, P.k_blocks);
+        // the epilogue multiplies this tile by aux with plain loads: pull that box into L2 now, a pipeline depth ahead
+        // (the loads were ~1 us of exposed HBM latency per tile: long-scoreboard stalls 13.6 per issue in the fc2 dgrad)
+        if (!F32OUT && P.epi == kEpiMulAux) tma_prefetch_3d(&P.aux_map, 0, m0, n0 >> 5);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
@@ -264,17 +267,27 @@ gemm_tc_kernel(const __grid_constant__ GemmParams P) {
   if (warp == kGMmaWarp) tmem_dealloc<kGTmemCols>(tmem);
 }
 
-// out[e] = sum over splits of part[s][e]
+// out[e] = sum over splits of part[s][e].  Block = 128 elements (one float4 per lane) x 8 slices of the split range.
 __global__ void __launch_bounds__(256)
 gemm_reduce_kernel(const float* __restrict__ part, int splits, long long n, float* __restrict__ out) {
-  const long long e = ((long long)blockIdx.x * 256 + threadIdx.x) * 4;
-  if (e >= n) return;
+  __shared__ float4 red[8][32];
+  const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const long long e = ((long long)blockIdx.x * 32 + lane) * 4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int s = 0; s < splits; ++s) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(part + (size_t)s * n + e));
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  if (e < n) {
+#pragma unroll 4
+    for (int s = sl; s < splits; s += 8) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(part + (size_t)s * n + e));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
   }
-  *reinterpret_cast<float4*>(out + e) = acc;
+  red[sl][lane] = acc;
+  __syncthreads();
+  if (sl == 0 && e < n) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { const float4 v = red[k][lane]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+    *reinterpret_cast<float4*>(out + e) = acc;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -366,7 +379,7 @@ int linear_fwd(const void* x, const void* w, const float* bias, void* y, void* y
 size_t linear_wgrad_workspace_bytes(long long rows, int in_features, int out_features) {
   const int bn = pick_bn(in_features);
   const long long tiles = ((out_features + 127) / 128) * (long long)(in_features / bn);
-  long long splits = (2ll * num_sms_cached() + tiles - 1) / tiles;
+  long long splits = num_sms_cached() / tiles;             // one unit per SM (one round, no ragged second one)
   const long long kb = (rows + 63) / 64;
   if (splits > kb) splits = kb;
   if (splits < 1) splits = 1;
@@ -382,7 +395,8 @@ int linear_bwd_general(const void* dy, const void* x, const void* w, void* dx, f
     const int bn = pick_bn(in_features), kp = pick_kp(out_features);
     GemmParams P{};
     if (!panel_map(&P.a, dy, rows, out_features, ld_dy, 128, kp) || !panel_map(&P.b, w, out_features, in_features, in_features, 32 * kp, bn / 32) ||
-        !panel_map(&P.d, dx, rows, in_features, ld_dx, 128, bn / 32)) {
+        !panel_map(&P.d, dx, rows, in_features, ld_dx, 128, bn / 32) ||
+        (act_grad && !panel_map(&P.aux_map, aux, rows, in_features, ld_aux, 128, bn / 32))) {
       snprintf(err, errlen, "cuTensorMapEncodeTiled failed (pointer alignment or strides)");
       return MMN_ERR_CUDA;
     }
@@ -403,7 +417,7 @@ int linear_bwd_general(const void* dy, const void* x, const void* w, void* dx, f
       return MMN_ERR_CUDA;
     }
     const long long tiles = ((out_features + 127) / 128) * (long long)(in_features / bn);
-    const int want = (int)((2ll * num_sms_cached() + tiles - 1) / tiles);
+    const int want = (int)(num_sms_cached() / tiles);        // one unit per SM: one round of the persistent grid
     fill_schedule(P, out_features, in_features, bn, (rows + 32 * kp - 1) / (32 * kp), want);
     P.out32 = P.splits > 1 ? workspace : dw;
     int grid = num_sms_cached();
@@ -413,7 +427,7 @@ int linear_bwd_general(const void* dy, const void* x, const void* w, void* dx, f
     ++*launches;
     if (P.splits > 1) {
       const long long n = (long long)out_features * in_features;
-      gemm_reduce_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(workspace, P.splits, n, dw);
+      gemm_reduce_kernel<<<(unsigned)((n / 4 + 31) / 32), 256, 0, st>>>(workspace, P.splits, n, dw);
       if (cudaGetLastError() != cudaSuccess) { snprintf(err, errlen, "gemm_reduce_kernel launch failed"); return MMN_ERR_CUDA; }
       ++*launches;
     }

@@ -232,75 +232,90 @@ __device__ __forceinline__ float row_sum(float v) {          // sum over the LPR
 }
 __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
-template <int LPR, int V>
-__global__ void __launch_bounds__(kLnWarps * 32, V <= 3 ? 3 : 2)
-ln_fwd_v4_kernel(LnTensor resid, LnTensor delta, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int mode,
+// MODE (pre- / post-norm) is a template parameter: the pre-norm forward keeps no residual copy and fits 64 registers (four
+// blocks per SM).  U row groups per iteration with all their loads issued up front (U = 2 at two blocks per SM measured
+// no better than U = 1 at three or four: tools/bench_blocks.py, r2o vs r2k), so the launches use U = 1.
+template <int LPR, int V, int MODE, int U>
+__global__ void __launch_bounds__(kLnWarps * 32)
+ln_fwd_v4_kernel(LnTensor resid, LnTensor delta, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                  LnOut out_sum, LnOut out_norm, float* __restrict__ mean, float* __restrict__ rstd, long long rows, int cols) {
   constexpr int R = 32 / LPR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lr = lane % LPR, sub = lane / LPR;
   const float inv_n = 1.f / (float)cols;
-  const long long stride = (long long)gridDim.x * kLnWarps * R;
-  for (long long row0 = ((long long)blockIdx.x * kLnWarps + warp) * R; row0 < rows; row0 += stride) {
-    const long long row = row0 + sub;
-    const bool live = row < rows;
-    const long long base = row * cols;
-    float4 x[V], r[V];
-    float s1 = 0.f;
+  const long long stride = (long long)gridDim.x * kLnWarps * R * U;
+  for (long long row0 = ((long long)blockIdx.x * kLnWarps + warp) * R * U; row0 < rows; row0 += stride) {
+    float4 x[U][V], r[MODE == 0 ? 1 : U][MODE == 0 ? 1 : V];
+    float s1[U];
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const int c = 4 * (lr + LPR * v);
-      x[v] = f4zero();
-      r[v] = f4zero();
-      if (live && c < cols) {
-        if (mode == 0) {
-          if (resid.p) x[v] = ld4(resid, base + c);
-          if (delta.p) { const float4 d = ld4(delta, base + c); x[v].x += d.x; x[v].y += d.y; x[v].z += d.z; x[v].w += d.w; }
-        } else {
-          x[v] = ld4(delta, base + c);
-          if (resid.p) r[v] = ld4(resid, base + c);
+    for (int u = 0; u < U; ++u) {
+      const long long row = row0 + u * R + sub;
+      const bool live = row < rows;
+      const long long base = row * cols;
+      s1[u] = 0.f;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int c = 4 * (lr + LPR * v);
+        x[u][v] = f4zero();
+        if (MODE != 0) r[u][v] = f4zero();
+        if (live && c < cols) {
+          if (MODE == 0) {
+            if (resid.p) x[u][v] = ld4(resid, base + c);
+            if (delta.p) { const float4 d = ld4(delta, base + c); x[u][v].x += d.x; x[u][v].y += d.y; x[u][v].z += d.z; x[u][v].w += d.w; }
+          } else {
+            x[u][v] = ld4(delta, base + c);
+            if (resid.p) r[u][v] = ld4(resid, base + c);
+          }
+          s1[u] += (x[u][v].x + x[u][v].y) + (x[u][v].z + x[u][v].w);
         }
-        s1 += (x[v].x + x[v].y) + (x[v].z + x[v].w);
       }
     }
-    const float mu = row_sum<LPR>(s1) * inv_n;
-    float s2 = 0.f;
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const int c = 4 * (lr + LPR * v);
-      if (c < cols) {
-        const float a0 = x[v].x - mu, a1 = x[v].y - mu, a2 = x[v].z - mu, a3 = x[v].w - mu;
-        s2 += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    for (int u = 0; u < U; ++u) {
+      const long long row = row0 + u * R + sub;
+      const bool live = row < rows;
+      const long long base = row * cols;
+      const float mu = row_sum<LPR>(s1[u]) * inv_n;
+      float s2 = 0.f;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int c = 4 * (lr + LPR * v);
+        if (c < cols) {
+          const float a0 = x[u][v].x - mu, a1 = x[u][v].y - mu, a2 = x[u][v].z - mu, a3 = x[u][v].w - mu;
+          s2 += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+        }
       }
-    }
-    const float rs = rsqrtf(row_sum<LPR>(s2) * inv_n + eps);
-    if (live && lr == 0) { mean[row] = mu; rstd[row] = rs; }
+      const float rs = rsqrtf(row_sum<LPR>(s2) * inv_n + eps);
+      if (live && lr == 0) { mean[row] = mu; rstd[row] = rs; }
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const int c = 4 * (lr + LPR * v);
-      if (live && c < cols) {
-        // gamma / beta: 16-byte loads that hit L1 (keeping them in registers cost half the occupancy)
-        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
-        const float4 b = beta ? __ldg(reinterpret_cast<const float4*>(beta + c)) : f4zero();
-        const float4 n = make_float4((x[v].x - mu) * rs * g.x + b.x, (x[v].y - mu) * rs * g.y + b.y,
-                                     (x[v].z - mu) * rs * g.z + b.z, (x[v].w - mu) * rs * g.w + b.w);
-        if (mode == 0) {
-          if (out_sum.p) st4(out_sum, base + c, x[v]);
-          if (out_norm.p) st4(out_norm, base + c, n);
-        } else {
-          const float4 s = make_float4(r[v].x + n.x, r[v].y + n.y, r[v].z + n.z, r[v].w + n.w);
-          if (out_sum.p) st4(out_sum, base + c, s);
-          if (out_norm.p) st4(out_norm, base + c, s);
+      for (int v = 0; v < V; ++v) {
+        const int c = 4 * (lr + LPR * v);
+        if (live && c < cols) {
+          // gamma / beta: 16-byte loads that hit L1 (keeping them in registers cost half the occupancy)
+          const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+          const float4 b = beta ? __ldg(reinterpret_cast<const float4*>(beta + c)) : f4zero();
+          const float4 xv = x[u][v];
+          const float4 n = make_float4((xv.x - mu) * rs * g.x + b.x, (xv.y - mu) * rs * g.y + b.y,
+                                       (xv.z - mu) * rs * g.z + b.z, (xv.w - mu) * rs * g.w + b.w);
+          if (MODE == 0) {
+            if (out_sum.p) st4(out_sum, base + c, xv);
+            if (out_norm.p) st4(out_norm, base + c, n);
+          } else {
+            const float4 rv = r[u][v];
+            const float4 s = make_float4(rv.x + n.x, rv.y + n.y, rv.z + n.z, rv.w + n.w);
+            if (out_sum.p) st4(out_sum, base + c, s);
+            if (out_norm.p) st4(out_norm, base + c, s);
+          }
         }
       }
     }
   }
 }
 
-template <int LPR, int V>
+template <int LPR, int V, int MODE, int U>
 __global__ void __launch_bounds__(kLnWarps * 32, V <= 3 ? 3 : 1)
 ln_bwd_v4_kernel(LnTensor gs, LnTensor gn, LnTensor x, const float* __restrict__ gamma, const float* __restrict__ mean,
-                 const float* __restrict__ rstd, int mode, LnOut d_resid, LnOut d_delta, float* __restrict__ dgamma,
+                 const float* __restrict__ rstd, LnOut d_resid, LnOut d_delta, float* __restrict__ dgamma,
                  float* __restrict__ dbeta, long long rows, int cols) {
   constexpr int R = 32 / LPR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -309,53 +324,74 @@ ln_bwd_v4_kernel(LnTensor gs, LnTensor gn, LnTensor x, const float* __restrict__
 #pragma unroll
   for (int v = 0; v < V; ++v) { ag[v] = f4zero(); ab[v] = f4zero(); }
   const float inv_n = 1.f / (float)cols;
-  const long long stride = (long long)gridDim.x * kLnWarps * R;
-  for (long long row0 = ((long long)blockIdx.x * kLnWarps + warp) * R; row0 < rows; row0 += stride) {
-    const long long row = row0 + sub;
-    const bool live = row < rows;
-    const long long base = row * cols;
-    const float mu = live ? __ldg(mean + row) : 0.f, rs = live ? __ldg(rstd + row) : 0.f;
-    // w = (gradient bypassing the LayerNorm) + rstd * u * gamma, u = gradient entering it: the row's output is
-    // w - rstd * (m1 + xhat * m2), so only w and xhat live across the row reductions
-    float4 w[V], xh[V];
-    float m1 = 0.f, m2 = 0.f;
+  const long long stride = (long long)gridDim.x * kLnWarps * R * U;
+  for (long long row0 = ((long long)blockIdx.x * kLnWarps + warp) * R * U; row0 < rows; row0 += stride) {
+    // raw loads of all U row groups first
+    float4 xv[U][V], a[U][V], n[U][V];
+    float mu[U], rs[U];
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const int c = 4 * (lr + LPR * v);
-      w[v] = xh[v] = f4zero();
-      if (live && c < cols) {
-        const float4 xv = ld4(x, base + c);
-        xh[v] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        const float4 a = gs.p ? ld4(gs, base + c) : f4zero();
-        const float4 n = gn.p ? ld4(gn, base + c) : f4zero();
-        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
-        float4 u;
-        if (mode == 0) { u = n; w[v] = a; }
-        else {
-          u = make_float4(a.x + n.x, a.y + n.y, a.z + n.z, a.w + n.w);
-          if (d_resid.p) st4(d_resid, base + c, u);
+    for (int u = 0; u < U; ++u) {
+      const long long row = row0 + u * R + sub;
+      const bool live = row < rows;
+      const long long base = row * cols;
+      mu[u] = live ? __ldg(mean + row) : 0.f;
+      rs[u] = live ? __ldg(rstd + row) : 0.f;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int c = 4 * (lr + LPR * v);
+        xv[u][v] = a[u][v] = n[u][v] = f4zero();
+        if (live && c < cols) {
+          xv[u][v] = ld4(x, base + c);
+          if (gs.p) a[u][v] = ld4(gs, base + c);
+          if (gn.p) n[u][v] = ld4(gn, base + c);
         }
-        ag[v].x += u.x * xh[v].x; ag[v].y += u.y * xh[v].y; ag[v].z += u.z * xh[v].z; ag[v].w += u.w * xh[v].w;
-        ab[v].x += u.x; ab[v].y += u.y; ab[v].z += u.z; ab[v].w += u.w;
-        const float u0 = u.x * g.x, u1 = u.y * g.y, u2 = u.z * g.z, u3 = u.w * g.w;
-        m1 += (u0 + u1) + (u2 + u3);
-        m2 += (u0 * xh[v].x + u1 * xh[v].y) + (u2 * xh[v].z + u3 * xh[v].w);
-        w[v].x = fmaf(rs, u0, w[v].x); w[v].y = fmaf(rs, u1, w[v].y); w[v].z = fmaf(rs, u2, w[v].z); w[v].w = fmaf(rs, u3, w[v].w);
       }
     }
-    m1 = row_sum<LPR>(m1) * inv_n * rs;
-    m2 = row_sum<LPR>(m2) * inv_n * rs;
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const int c = 4 * (lr + LPR * v);
-      if (live && c < cols) {
-        const float4 t = make_float4(w[v].x - m1 - xh[v].x * m2, w[v].y - m1 - xh[v].y * m2, w[v].z - m1 - xh[v].z * m2,
-                                     w[v].w - m1 - xh[v].w * m2);
-        if (mode == 0) {
-          if (d_resid.p) st4(d_resid, base + c, t);
-          if (d_delta.p) st4(d_delta, base + c, t);
-        } else {
-          if (d_delta.p) st4(d_delta, base + c, t);
+    for (int u = 0; u < U; ++u) {
+      const long long row = row0 + u * R + sub;
+      const bool live = row < rows;
+      const long long base = row * cols;
+      // w = (gradient bypassing the LayerNorm) + rstd * u * gamma, u = gradient entering it: the row's output is
+      // w - rstd * (m1 + xhat * m2), so only w and xhat live across the row reductions
+      float4 w[V], xh[V];
+      float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int c = 4 * (lr + LPR * v);
+        w[v] = xh[v] = f4zero();
+        if (live && c < cols) {
+          const float4 t = xv[u][v];
+          xh[v] = make_float4((t.x - mu[u]) * rs[u], (t.y - mu[u]) * rs[u], (t.z - mu[u]) * rs[u], (t.w - mu[u]) * rs[u]);
+          const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+          float4 uu;
+          if (MODE == 0) { uu = n[u][v]; w[v] = a[u][v]; }
+          else {
+            uu = make_float4(a[u][v].x + n[u][v].x, a[u][v].y + n[u][v].y, a[u][v].z + n[u][v].z, a[u][v].w + n[u][v].w);
+            if (d_resid.p) st4(d_resid, base + c, uu);
+          }
+          ag[v].x += uu.x * xh[v].x; ag[v].y += uu.y * xh[v].y; ag[v].z += uu.z * xh[v].z; ag[v].w += uu.w * xh[v].w;
+          ab[v].x += uu.x; ab[v].y += uu.y; ab[v].z += uu.z; ab[v].w += uu.w;
+          const float u0 = uu.x * g.x, u1 = uu.y * g.y, u2 = uu.z * g.z, u3 = uu.w * g.w;
+          m1 += (u0 + u1) + (u2 + u3);
+          m2 += (u0 * xh[v].x + u1 * xh[v].y) + (u2 * xh[v].z + u3 * xh[v].w);
+          w[v].x = fmaf(rs[u], u0, w[v].x); w[v].y = fmaf(rs[u], u1, w[v].y); w[v].z = fmaf(rs[u], u2, w[v].z); w[v].w = fmaf(rs[u], u3, w[v].w);
+        }
+      }
+      m1 = row_sum<LPR>(m1) * inv_n * rs[u];
+      m2 = row_sum<LPR>(m2) * inv_n * rs[u];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int c = 4 * (lr + LPR * v);
+        if (live && c < cols) {
+          const float4 t = make_float4(w[v].x - m1 - xh[v].x * m2, w[v].y - m1 - xh[v].y * m2, w[v].z - m1 - xh[v].z * m2,
+                                       w[v].w - m1 - xh[v].w * m2);
+          if (MODE == 0) {
+            if (d_resid.p) st4(d_resid, base + c, t);
+            if (d_delta.p) st4(d_delta, base + c, t);
+          } else {
+            if (d_delta.p) st4(d_delta, base + c, t);
+          }
         }
       }
     }
@@ -367,13 +403,13 @@ ln_bwd_v4_kernel(LnTensor gs, LnTensor gn, LnTensor x, const float* __restrict__
     if (!dst) continue;                                      // uniform
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      float4 a = pass_id == 0 ? ag[v] : ab[v];
+      float4 acc = pass_id == 0 ? ag[v] : ab[v];
 #pragma unroll
       for (int o = LPR; o < 32; o <<= 1) {
-        a.x += __shfl_xor_sync(0xffffffffu, a.x, o); a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
-        a.z += __shfl_xor_sync(0xffffffffu, a.z, o); a.w += __shfl_xor_sync(0xffffffffu, a.w, o);
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
       }
-      if (sub == 0) *reinterpret_cast<float4*>(&red[warp][4 * (lr + LPR * v)]) = a;
+      if (sub == 0) *reinterpret_cast<float4*>(&red[warp][4 * (lr + LPR * v)]) = acc;
     }
     __syncthreads();
     for (int c = threadIdx.x; c < cols; c += kLnWarps * 32) {
@@ -397,10 +433,11 @@ V4Cfg v4_cfg(int cols) {
 }
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-int ln_grid_v4(long long rows, int lpr) {
-  const long long per_block = (long long)kLnWarps * (32 / lpr);
+// up to blocks_per_sm x 148 blocks (grid-stride loops inside)
+int ln_grid_v4(long long rows, int lpr, int unroll, int blocks_per_sm) {
+  const long long per_block = (long long)kLnWarps * (32 / lpr) * unroll;
   long long want = (rows + per_block - 1) / per_block;
-  const long long cap = 148ll * 8;
+  const long long cap = 148ll * blocks_per_sm;
   return (int)(want < cap ? want : cap);
 }
 
@@ -443,8 +480,11 @@ cudaError_t layernorm_fwd(const void* resid, int resid_dt, const void* delta, in
   LnOut os{out_sum, sum_dt}, on{out_norm, norm_dt};
   const V4Cfg vc = v4_cfg(cols);
   if (vc.lpr && aligned16(resid) && aligned16(delta) && aligned16(out_sum) && aligned16(out_norm) && aligned16(gamma) && aligned16(beta)) {
-#define MMN_LN_V4(L_, V_) if (vc.lpr == L_ && vc.v == V_) \
-    ln_fwd_v4_kernel<L_, V_><<<ln_grid_v4(rows, L_), kLnWarps * 32, 0, st>>>(r, d, gamma, beta, eps, mode, os, on, mean, rstd, rows, cols);
+#define MMN_LN_V4(L_, V_) if (vc.lpr == L_ && vc.v == V_) {                                                                       \
+      constexpr int U0 = 1, U1 = 1, BPS = 8;                                                         \
+      if (mode == 0) ln_fwd_v4_kernel<L_, V_, 0, U0><<<ln_grid_v4(rows, L_, U0, BPS), kLnWarps * 32, 0, st>>>(r, d, gamma, beta, eps, os, on, mean, rstd, rows, cols); \
+      else ln_fwd_v4_kernel<L_, V_, 1, U1><<<ln_grid_v4(rows, L_, U1, BPS), kLnWarps * 32, 0, st>>>(r, d, gamma, beta, eps, os, on, mean, rstd, rows, cols);           \
+    }
     MMN_LN_V4(8, 1) MMN_LN_V4(8, 2) MMN_LN_V4(8, 3) MMN_LN_V4(16, 2) MMN_LN_V4(16, 3) MMN_LN_V4(32, 2) MMN_LN_V4(32, 3) MMN_LN_V4(32, 4) MMN_LN_V4(32, 6)
 #undef MMN_LN_V4
     cudaError_t e4 = cudaGetLastError();
@@ -465,8 +505,11 @@ cudaError_t layernorm_bwd(const void* g_sum, int gs_dt, const void* g_norm, int 
   LnOut dr{d_resid, dr_dt}, dd{d_delta, dd_dt};
   const V4Cfg vc = v4_cfg(cols);
   if (vc.lpr && aligned16(g_sum) && aligned16(g_norm) && aligned16(x) && aligned16(d_resid) && aligned16(d_delta) && aligned16(gamma)) {
-#define MMN_LN_V4(L_, V_) if (vc.lpr == L_ && vc.v == V_) \
-    ln_bwd_v4_kernel<L_, V_><<<ln_grid_v4(rows, L_), kLnWarps * 32, 0, st>>>(gs, gn, xx, gamma, mean, rstd, mode, dr, dd, dgamma, dbeta, rows, cols);
+#define MMN_LN_V4(L_, V_) if (vc.lpr == L_ && vc.v == V_) {                                                                       \
+      constexpr int U = 1, BPS = 8;                                                                  \
+      if (mode == 0) ln_bwd_v4_kernel<L_, V_, 0, U><<<ln_grid_v4(rows, L_, U, BPS), kLnWarps * 32, 0, st>>>(gs, gn, xx, gamma, mean, rstd, dr, dd, dgamma, dbeta, rows, cols); \
+      else ln_bwd_v4_kernel<L_, V_, 1, U><<<ln_grid_v4(rows, L_, U, BPS), kLnWarps * 32, 0, st>>>(gs, gn, xx, gamma, mean, rstd, dr, dd, dgamma, dbeta, rows, cols);           \
+    }
     MMN_LN_V4(8, 1) MMN_LN_V4(8, 2) MMN_LN_V4(8, 3) MMN_LN_V4(16, 2) MMN_LN_V4(16, 3) MMN_LN_V4(32, 2) MMN_LN_V4(32, 3) MMN_LN_V4(32, 4) MMN_LN_V4(32, 6)
 #undef MMN_LN_V4
     cudaError_t e4 = cudaGetLastError();

@@ -228,13 +228,16 @@ PARALLEL_BRANCHES = False      # opt-in (bench / TrainStep switch it on): same a
 _side_streams = {}
 
 
-def parallel(fn_a, fn_b, ref: torch.Tensor):
+def parallel(fn_a, fn_b, ref: torch.Tensor, inputs_b=()):
     """(fn_a(), fn_b()) for two branches that do not depend on each other -- the two modalities' intra-modal groups
     (swinfusion_module.py:916-917; model.py's Ex_A / Ex_B stages).  With PARALLEL_BRANCHES on CUDA, fn_b is issued on a
     side stream forked from and joined back to the current one, so its kernels fill the SMs that fn_a's persistent
     kernels leave idle in their ramp-up and tail (at cfg3 a launch is 20-60 us of work: ~40 % of it is ramp and tail,
     tools/bench_blocks.py).  Autograd replays each branch's backward on the stream its forward ran on, and a CUDA-graph
-    capture records the fork / join as parallel branches of the graph."""
+    capture records the fork / join as parallel branches of the graph.  `inputs_b`: the tensors fn_b reads that were
+    produced on the current stream -- the caching allocator is told that the side stream uses them too (and, below, that
+    the current stream uses fn_b's results), so neither pool hands their memory out again while the other stream may still
+    be reading it."""
     if not (PARALLEL_BRANCHES and ref.is_cuda):
         return fn_a(), fn_b()
     cur = torch.cuda.current_stream(ref.device)
@@ -242,6 +245,9 @@ def parallel(fn_a, fn_b, ref: torch.Tensor):
     if side is None:
         side = _side_streams[ref.device.index] = torch.cuda.Stream(ref.device)
     side.wait_stream(cur)
+    for t in inputs_b:
+        if isinstance(t, torch.Tensor):
+            t.record_stream(side)
     with torch.cuda.stream(side):
         b = fn_b()
     a = fn_a()

@@ -242,19 +242,22 @@ class Cross_SwinTransformerBlock(_FusionBlockBase):
         """As SwinTransformerBlock_fusion.forward_deferred, for the two streams x + dx and y + dy."""
         n = len(x_size)
         grid, shift = tuple(x_size), to_ntuple(self.shift_size, n)
-        if dx is None:
-            xn = fused.layer_norm(x, self.norm1_A)
-        else:
-            x, xn = fused.add_layer_norm(x, dx, self.norm1_A)
-        if dy is None:
-            yn = fused.layer_norm(y, self.norm1_B)
-        else:
-            y, yn = fused.add_layer_norm(y, dy, self.norm1_B)
-        ax = self.attn_A.forward_grid(xn, yn, grid, shift)
-        ay = self.attn_B.forward_grid(yn, xn, grid, shift)
-        x, hx = fused.add_layer_norm(x, self.drop_path_A(ax), self.norm2_A)
-        y, hy = fused.add_layer_norm(y, self.drop_path_B(ay), self.norm2_B)
-        return x, self.drop_path_A(self.mlp_A(hx)), y, self.drop_path_B(self.mlp_B(hy))
+
+        def open_stream(t, dt, ln):                       # the stream's pending add + norm1
+            return (t, fused.layer_norm(t, ln)) if dt is None else fused.add_layer_norm(t, dt, ln)
+
+        def side(t, tn, on, attn, drop_path, norm2, mlp):  # one modality: attends to the other's normalised stream
+            a = attn.forward_grid(tn, on, grid, shift)
+            t, h = fused.add_layer_norm(t, drop_path(a), norm2)
+            return t, drop_path(mlp(h))
+
+        # the two modalities only meet in the attention calls (each reads both normalised streams): everything else of the
+        # two sides is independent, so fused.parallel may run them on two streams
+        (x, xn), (y, yn) = fused.parallel(lambda: open_stream(x, dx, self.norm1_A), lambda: open_stream(y, dy, self.norm1_B), x, (y, dy))
+        (x, dxo), (y, dyo) = fused.parallel(lambda: side(x, xn, yn, self.attn_A, self.drop_path_A, self.norm2_A, self.mlp_A),
+                                            lambda: side(y, yn, xn, self.attn_B, self.drop_path_B, self.norm2_B, self.mlp_B),
+                                            x, (y, yn, xn))
+        return x, dxo, y, dyo
 
     def forward(self, x, y, x_size):
         x, dx, y, dy = self.forward_deferred(x, None, y, None, x_size)
@@ -451,7 +454,7 @@ class CRSTB(nn.Module):
 
     def forward(self, x, y, x_size):
         # the two intra-modal groups are independent: fused.parallel may run them on two streams
-        x, y = fused.parallel(lambda: self.residual_group_A(x, x_size) + x, lambda: self.residual_group_B(y, x_size) + y, x)
+        x, y = fused.parallel(lambda: self.residual_group_A(x, x_size) + x, lambda: self.residual_group_B(y, x_size) + y, x, (y,))
         x1, y1 = x, y
         x, y = self.residual_group(x1, y1, x_size)
         return x + x1, y + y1
