@@ -409,5 +409,23 @@ class PatchEmbed3D(nn.Module):
 
     def forward(self, x):
         assert tuple(x.shape[2:]) == self.img_size, f"Input volume {tuple(x.shape[2:])} doesn't match {self.img_size}"
-        x = self.proj(x).flatten(2).transpose(1, 2)
+        x = self._embed(x)
         return fused.layer_norm(x, self.norm, out_dtype=torch.float32) if self.norm is not None else x
+
+    def _embed(self, x):
+        """The strided convolution as what it is -- a projection of non-overlapping patches: one gather of the patches
+        into rows (cast to the compute dtype on the way), then the tensor-core projection kernel with the conv weight
+        viewed as (E, C p^3).  cuDNN runs the same convolution as layout conversions + an implicit GEMM, four times the
+        GPU time at the cfg3 / cfg5 sizes (tools/profile_step.py)."""
+        B, C = x.shape[:2]
+        p, g = self.patch_size, self.patches_resolution
+        K = C * p[0] * p[1] * p[2]
+        dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+        dt = torch.bfloat16 if dt == torch.float16 else dt
+        if not (x.is_cuda and dt == torch.bfloat16 and K % 32 == 0 and self.embed_dim % 32 == 0):
+            return self.proj(x).flatten(2).transpose(1, 2)
+        rows = torch.empty(B, g[0], g[1], g[2], C, p[0], p[1], p[2], device=x.device, dtype=dt)
+        rows.copy_(x.view(B, C, g[0], p[0], g[1], p[1], g[2], p[2]).permute(0, 2, 4, 6, 1, 3, 5, 7))
+        with torch.autocast("cuda", enabled=False):
+            y = ops.linear(rows.view(-1, K), self.proj.weight.view(self.embed_dim, K), self.proj.bias)
+        return y.view(B, self.num_patches, self.embed_dim)

@@ -181,6 +181,8 @@ class SwinV2CrossModal3D(nn.Module):
         self.a_with_b = cm.TransformerEncoder(E, cross_heads, cross_layers)
         self.b_with_a = cm.TransformerEncoder(E, cross_heads, cross_layers)
         self.head = nn.Linear(2 * E, num_classes)
+        nn.init.normal_(self.head.weight, std=1e-3)           # logits start near 0 (loss ~ ln 2), whatever the features' scale
+        nn.init.zeros_(self.head.bias)
 
     def forward(self, A, B):
         x, y = fused.parallel(lambda: self.tower_A(A), lambda: self.tower_B(B), A, (B,))      # independent towers

@@ -627,3 +627,21 @@ def test_cfg4_workload_steps(mm):
     losses = [float(ts().item()) for _ in range(6)]
     assert all(math.isfinite(v) for v in losses) and losses[-1] < losses[0]
     assert torch.isfinite(ts.flat).all() and (ts.flat != 0).float().mean() > 0.5      # every parameter's gradient arrived in the flat buffer
+
+
+def test_patch_embed_3d_projection_matches_conv(mm):
+    """PatchEmbed3D as gather + tensor-core projection against the Conv3d it replaces (outputs and parameter gradients)."""
+    pe = mm.v2.PatchEmbed3D(32, 4, 1, 96, torch.nn.LayerNorm).cuda()
+    x = torch.randn(2, 1, 32, 32, 32, device="cuda").half()
+    cot = torch.randn(2, 512, 96, device="cuda")
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        got = pe(x)
+    gg = torch.autograd.grad((got * cot).sum(), [pe.proj.weight, pe.proj.bias, pe.norm.weight])
+    w, b = pe.proj.weight.detach().double().requires_grad_(True), pe.proj.bias.detach().double().requires_grad_(True)
+    nw = pe.norm.weight.detach().double().requires_grad_(True)
+    ref = torch.nn.functional.conv3d(x.double(), w, b, stride=4).flatten(2).transpose(1, 2)
+    ref = torch.nn.functional.layer_norm(ref, (96,), nw, pe.norm.bias.detach().double(), pe.norm.eps)
+    gw = torch.autograd.grad((ref * cot.double()).sum(), [w, b, nw])
+    check(got, ref, BF16_TOL, "patch embed")
+    for a, b_, n in zip(gg, gw, ("dW", "db", "dgamma")):
+        check(a, b_, BF16_TOL, "patch embed " + n)
