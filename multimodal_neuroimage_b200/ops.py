@@ -263,8 +263,9 @@ def mha_fwd(q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor], num_heads: 
     d.o_stride_t, d.o_stride_b = _tb_strides(out)
     if mask is not None and (mask.dtype != torch.float32 or not mask.is_contiguous()):
         raise RuntimeError("attn_mask must be contiguous float32")
-    _lib.check(lib.mmn_mha_fwd(C.byref(d), _ptr(q), _ptr(k), _ptr(v), _ptr(mask), _ptr(out), _ptr(lse), q.device.index,
-                               _stream(q)), "mmn_mha_fwd")
+    with _timed("mha_fwd", q):
+        _lib.check(lib.mmn_mha_fwd(C.byref(d), _ptr(q), _ptr(k), _ptr(v), _ptr(mask), _ptr(out), _ptr(lse), q.device.index,
+                                   _stream(q)), "mmn_mha_fwd")
     return out, lse
 
 
@@ -293,9 +294,10 @@ def mha_bwd(dout: Tensor, q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor
     d.dq_stride_t, d.dq_stride_b = _tb_strides(dq)
     d.dk_stride_t, d.dk_stride_b = _tb_strides(dk)
     d.dv_stride_t, d.dv_stride_b = _tb_strides(dv)
-    _lib.check(lib.mmn_mha_bwd(C.byref(d), _ptr(q), _ptr(k), _ptr(v), _ptr(mask), _ptr(out), _ptr(lse), _ptr(dout),
-                               _ptr(dq), _ptr(dk), _ptr(dv), _ptr(lse.new_empty(2 * lse.numel())), q.device.index, _stream(q)),
-               "mmn_mha_bwd")
+    ws = lse.new_empty(2 * lse.numel())
+    with _timed("mha_bwd", q):
+        _lib.check(lib.mmn_mha_bwd(C.byref(d), _ptr(q), _ptr(k), _ptr(v), _ptr(mask), _ptr(out), _ptr(lse), _ptr(dout),
+                                   _ptr(dq), _ptr(dk), _ptr(dv), _ptr(ws), q.device.index, _stream(q)), "mmn_mha_bwd")
     return dq, dk, dv
 
 
