@@ -176,27 +176,6 @@ struct ClassQueue {
   }
 };
 
-struct ItemGeom : WinGeom {
-  int w;             // linear window index (b * nW + row-major window position): addresses lse
-};
-
-// Geometry of window `slot` (0 / 1) of the cursor's item.
-__device__ __forceinline__ ItemGeom item_geom(const WinShape& S, const Sched& sc, const ItemCursor& c, int slot) {
-  ItemCursor t = c;
-  if (slot) t.step_window();
-  ItemGeom g;
-  g.b = t.b;
-  g.cls = t.cls;
-  const int j[3] = {t.j0, t.j1, t.j2};
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    g.idx[a] = (t.cls >> a) & 1 ? S.nwin[a] - 1 : j[a];
-    g.start[a] = g.idx[a] * S.win[a] + S.shift[a];
-  }
-  g.w = t.b * S.nW + (g.idx[0] * S.nwin[1] + g.idx[1]) * S.nwin[2] + g.idx[2];
-  return g;
-}
-
 // Shift-mask region id of in-window position p for a window of wrap class `cls`
 // (swin_v2_module.py:247-258: along a wrapped axis the last window straddles regions 1 | 2 at
 // win - shift; every other window lies in region 0).
@@ -297,8 +276,9 @@ struct BoxPlan {
   }
 
   template <bool LOAD>
+  // map_ofs: tensor maps further on in the same array (dq[8] | dk[8] | dv[8]: the backward's store warp)
   __device__ __forceinline__ void issue(const WinShape& S, const WinStart& w0, const WinStart& w1, int nvalid, int chan, uint8_t* stage,
-                                        uint64_t* bar, int lane) const {
+                                        uint64_t* bar, int lane, int map_ofs = 0) const {
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       if (lane + 32 * r < nbox && slot[r] < nvalid) {
@@ -307,49 +287,11 @@ struct BoxPlan {
         if (c0 >= S.grid[0]) c0 -= S.grid[0];
         if (c1 >= S.grid[1]) c1 -= S.grid[1];
         if (c2 >= S.grid[2]) c2 -= S.grid[2];
-        if (LOAD) tma_load_5d(map[r], bar, stage + dst[r], chan, c2, c1, c0, w.b);
-        else tma_store_5d(map[r], stage + dst[r], chan, c2, c1, c0, w.b);
+        if (LOAD) tma_load_5d(map[r] + map_ofs, bar, stage + dst[r], chan, c2, c1, c0, w.b);
+        else tma_store_5d(map[r] + map_ofs, stage + dst[r], chan, c2, c1, c0, w.b);
       }
     }
   }
 };
-
-// All TMA boxes of one item, one box per lane and round: box x = (slot, tensor t, piece) in piece-fastest order.
-// The coordinate arithmetic runs in parallel over the lanes; only the few instructions that feed the TMA unit
-// are serialised.  Tensor t's tile of slot s starts at dst[t] + s * slot_stride[t]; pieces land back to back
-// (piece-major token order, tc_window.cuh).  Both windows of an item have the same wrap class.
-template <bool LOAD, int T>
-__device__ __forceinline__ void issue_item_boxes(const WinShape& S, const ItemGeom& g0, const ItemGeom& g1, int nvalid, int chan,
-                                                 const CUtensorMap* const (&maps)[T], uint8_t* const (&dst)[T],
-                                                 const int (&slot_stride)[T], uint64_t* bar, int lane) {
-  const int cls = g0.cls;
-  const int lp = __popc(cls);
-  const int psize_bytes = (kN >> lp) * 64;
-  const int nbox = (nvalid * T) << lp;
-  for (int x = lane; x < nbox; x += 32) {
-    const int piece = x & ((1 << lp) - 1);
-    const int rest = x >> lp;
-    const int slot = rest / T, t = rest - slot * T;
-    const ItemGeom& g = slot ? g1 : g0;
-    int c[3], qq = piece;
-#pragma unroll
-    for (int a = 2; a >= 0; --a) {
-      const int bit = (cls >> a) & 1;
-      c[a] = g.start[a] + (bit ? (qq & 1) * (S.win[a] >> 1) : 0);
-      if (bit) qq >>= 1;
-      if (c[a] >= S.grid[a]) c[a] -= S.grid[a];
-    }
-    const CUtensorMap* m = maps[0];
-    uint8_t* p = dst[0];
-    int ss = slot_stride[0];
-#pragma unroll
-    for (int u = 1; u < T; ++u)
-      if (t == u) { m = maps[u]; p = dst[u]; ss = slot_stride[u]; }
-    m += cls;
-    p += slot * ss + piece * psize_bytes;
-    if (LOAD) tma_load_5d(m, bar, p, chan, c[2], c[1], c[0], g.b);
-    else tma_store_5d(m, p, chan, c[2], c[1], c[0], g.b);
-  }
-}
 
 }}  // namespace mmn::tc

@@ -23,6 +23,7 @@
 //                back, then dQ~/dK~/dV out of TMEM -> normalisation Jacobian -> bf16 staging tiles.
 //   warp 20 TMA producer (schedule, descriptor ring, tiles, records), warp 21 MMA issuer, warp 22 TMA store,
 //   warp 23 column sums of dq, dk, dv (= projection bias gradients) read from the staging tiles.
+//   (A 25th warp -- a second producer as in the forward -- does not launch: 800 threads x 80 registers are refused.)
 // Shared memory: 3 stages (Q0|Z|Q1, K, V, dO0|Z|dO1), P double-buffered and dS' around one shared zero block,
 // three staging tiles, the class table, the records.
 // Register budget by warpgroup (setmaxnreg): softmax 80 (= launch), epilogue 104, the rest 56: 512*80 + 128*104 + 128*56 = 768*80.
@@ -42,6 +43,7 @@ constexpr int kKeysPerThread = MMN_BWD_KEYS_PER_THREAD;     // 16: four threads 
 constexpr int kRowSplit = kN / kKeysPerThread;
 constexpr int kSoftmaxThreadsB = 128 * kRowSplit, kEpiThreads = 128;
 constexpr int kEpiWarp0 = kSoftmaxThreadsB / 32, kProducerWarpB = kEpiWarp0 + 4, kMmaWarpB = kEpiWarp0 + 5, kStoreWarpB = kEpiWarp0 + 6;
+constexpr int kColsumWarpB = kEpiWarp0 + 7;
 constexpr int kBwdThreads = kSoftmaxThreadsB + 256;
 // register budget by warpgroup (setmaxnreg only moves registers inside the CTA's launch allocation):
 //   4 threads/row: launch 80 -> softmax 80, epilogue 104, the rest 56     (512*80 + 128*104 + 128*56 = 768*80)
@@ -151,12 +153,17 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
   if (warp >= kProducerWarpB) {
     setmaxnreg_dec<kRegAux>();
     if (warp == kProducerWarpB) {
-      // ============================== TMA producer ==============================
-      // every lane runs the loop; lane l issues boxes l, l + 32 of the item (issue_item_boxes)
+      // ============================== TMA producer (schedule, descriptor ring, tiles, records) ==============================
+      // every lane runs the loop; lane l issues boxes l, l + 32 of the item (BoxPlan: which map, piece offset and
+      // shared-memory offset a lane's boxes have depends only on the wrap class)
       const CUtensorMap* const maps[4] = {P.q, P.dout, P.k, P.v};
+      const int dst_base[4] = {0, kOffDO, kOffK, kOffV};
       const int slot_stride[4] = {2 * kWinBytes, 2 * kWinBytes, kWinBytes, kWinBytes};
+      BoxPlan<4> plan;
       // Dynamic schedule (see the forward kernel's producer): chunks of kChunkB items of this head's class-sorted list
       // through an atomic counter; every other warp follows the descriptor rings sItem / sGeo.  One end marker.
+      // (An L2 prefetch of item n + 1's boxes issued right after item n's loads made the kernel 33 % SLOWER, 0.46 -> 0.61 ms:
+      // the extra boxes queue in the SM's TMA unit in front of the next loads and the gradient stores.)
       int n = 0;
       ClassQueue wq;
       wq.init(sc, sched_range_begin(sc, blockIdx.x / P.nH, P.per_head), P.work + h * 8, kChunkB, lane);
@@ -165,23 +172,23 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
         cur.seek(sc, c0);
         for (int t = 0; t < m; ++t, ++n, cur.next_item(sc)) {
           const int stage = n % kStagesB, phase = (n / kStagesB) & 1;
+          if (cur.cls != plan.cls) plan.build(S, cur.cls, lane, maps, dst_base, slot_stride);
           const int nvalid = cur.slot_valid(1) ? 2 : 1;
-          const ItemGeom g0 = item_geom(S, sc, cur, 0), g1 = item_geom(S, sc, cur, 1);
+          int w0, w1;
+          const WinStart ws0 = cursor_start(S, cur, 0, w0), ws1 = cursor_start(S, cur, 1, w1);
           trace_ev(P.trace, 2, n, 0);
           mbar_wait(&empty[stage], phase ^ 1);
           trace_ev(P.trace, 2, n, 1);
           if (lane == 0) {
-            sItem[n & 7] = make_int4(cur.cls, g0.w, g1.w, nvalid);      // published by the arrive below
-            sGeo[(n & 7) * 2] = make_int4(g0.b, g0.start[0], g0.start[1], g0.start[2]);
-            sGeo[(n & 7) * 2 + 1] = make_int4(g1.b, g1.start[0], g1.start[1], g1.start[2]);
+            sItem[n & 7] = make_int4(cur.cls, w0, w1, nvalid);          // published by the arrival below
+            sGeo[(n & 7) * 2] = make_int4(ws0.b, ws0.s0, ws0.s1, ws0.s2);
+            sGeo[(n & 7) * 2 + 1] = make_int4(ws1.b, ws1.s0, ws1.s1, ws1.s2);
             mbar_arrive_expect_tx(&full[stage], nvalid * (4 * kWinBytes + 3 * kN * 4));
           }
           __syncwarp();
-          uint8_t* base = sStage + stage * kStageBytesB;
-          uint8_t* const dst[4] = {base, base + kOffDO, base + kOffK, base + kOffV};
-          issue_item_boxes<true, 4>(S, g0, g1, nvalid, h * kD, maps, dst, slot_stride, &full[stage], lane);
+          plan.issue<true>(S, ws0, ws1, nvalid, h * kD, sStage + stage * kStageBytesB, &full[stage], lane);
           if (lane < nvalid)                   // lane = slot: the window's record (norms and lse, already in tile row order)
-            bulk_load_1d(sRec + (stage * 2 + lane) * (3 * kN), P.lse + P.slab + ((long long)(lane ? g1.w : g0.w) * P.nH + h) * (3 * kN),
+            bulk_load_1d(sRec + (stage * 2 + lane) * (3 * kN), P.lse + P.slab + ((long long)(lane ? w1 : w0) * P.nH + h) * (3 * kN),
                          3 * kN * 4, &full[stage]);
           trace_ev(P.trace, 2, n, 2);
         }
@@ -277,28 +284,29 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
       // The three staging tiles (dq, dk, dv) are handed over one by one, so the epilogue warps fill the next
       // tile while this one drains.  Each lane issues its share of a tile's boxes; a tile is returned to the
       // epilogue once the bulk group two behind has finished reading shared memory.
+      const CUtensorMap* const maps[1] = {P.dq};        // dq[8] | dk[8] | dv[8] are contiguous in BwdParams: tensor t's maps are 8 t further
+      const int dst_base[1] = {0};
+      const int slot_stride[1] = {kWinBytes};
+      BoxPlan<1> plan;
       int grp = 0;
       bool done = false;
       for (int n = 0; !done; ++n) {
-        ItemGeom g0, g1;
+        WinStart w0, w1;
         int nvalid = 0;
 #pragma unroll
         for (int t = 0; t < 3; ++t, ++grp) {
-          const CUtensorMap* const maps[1] = {t == 0 ? P.dq : (t == 1 ? P.dk : P.dv)};
-          const int slot_stride[1] = {kWinBytes};
-          uint8_t* const dst[1] = {sOut + t * kTile};
           if (t == 0) trace_ev(P.trace, 4, n, 0);
           mbar_wait(&so_ready[t], n & 1);
           if (t == 0) {
             if (n >= *reinterpret_cast<volatile int*>(sEnd)) { done = true; break; }   // that arrival was the epilogue warps' farewell
             const int4 it = sItem[n & 7], a0 = sGeo[(n & 7) * 2], a1 = sGeo[(n & 7) * 2 + 1];
             nvalid = it.w;
-            g0.cls = g1.cls = it.x;
-            g0.b = a0.x; g0.start[0] = a0.y; g0.start[1] = a0.z; g0.start[2] = a0.w;
-            g1.b = a1.x; g1.start[0] = a1.y; g1.start[1] = a1.z; g1.start[2] = a1.w;
+            if (it.x != plan.cls) plan.build(S, it.x, lane, maps, dst_base, slot_stride);
+            w0.b = a0.x; w0.s0 = a0.y; w0.s1 = a0.z; w0.s2 = a0.w;
+            w1.b = a1.x; w1.s0 = a1.y; w1.s1 = a1.z; w1.s2 = a1.w;
             trace_ev(P.trace, 4, n, 1);
           }
-          issue_item_boxes<false, 1>(S, g0, g1, nvalid, h * kD, maps, dst, slot_stride, nullptr, lane);
+          plan.issue<false>(S, w0, w1, nvalid, h * kD, sOut + t * kTile, nullptr, lane, 8 * t);
           tma_store_commit();
           tma_store_wait_read<2>();        // per thread: the group two behind (tile (t + 1) % 3) has been read out
           __syncwarp();
@@ -307,7 +315,7 @@ winattn_bwd_tc_kernel(const __grid_constant__ BwdParams P) {
         trace_ev(P.trace, 4, n, 2);
       }
       tma_store_wait_all<0>();
-    } else if (P.dcolsum) {
+    } else if (warp == kColsumWarpB && P.dcolsum) {
       // ============================== column sums of dq, dk, dv (= q / k / v projection bias gradients) ==============================
       // One warp sums the bf16 staging tiles while the TMA store drains them: lane (r0, c) owns the 16-byte channel group
       // c of rows r0, r0 + 8, ...; 24 running fp32 sums per lane for the whole kernel, reduced across lanes once at the
