@@ -27,8 +27,13 @@ namespace mmn { namespace tc {
 
 constexpr float kMLog2e = 1.4426950408889634f;
 constexpr float kMLn2 = 0.6931471805599453f;
-constexpr int kMThreads = 192;                 // 4 softmax warps + TMA producer + MMA issuer
-constexpr int kMStages = 2;
+// 12 warps: 8 compute warps (two warpgroups), then a warpgroup holding the TMA producer (warp 8) and the MMA issuer (warp 9).
+// Launched at 168 registers per thread; the compute warpgroups take 216 (a thread holds a whole row of logits), the third 72.
+constexpr int kMThreads = 384;
+constexpr int kMRegCompute = 216, kMRegAux = 72;   // 256 x 216 + 128 x 72 = 384 x 168: the launch allocation is the pool
+constexpr int kMStagesF = 4;                   // forward: K / V ring
+constexpr int kMStagesB = 3;                   // backward: streamed-tile ring
+constexpr float kMRescaleTau = 8.f;            // forward: the running maximum is only raised when it grows by more than 2^tau
 
 struct MhaParams {
   CUtensorMap q, k, v, dout;                   // 4-D maps (32, rows, E / 32, batch); box (32, 128, D / 32, 1)
@@ -71,179 +76,259 @@ __device__ __forceinline__ bool tile_needs_mask(const MhaParams& P, int t0, int 
   return false;
 }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {       // sm_100: one FMNMX3
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
 // ------------------------------------------------------------------------------------------
 // Forward
 // ------------------------------------------------------------------------------------------
+// CTA = (256 queries = two 128-row tiles, head, batch), one CTA per SM.  Compute warpgroup g owns query tile g: its own
+// S / P / O columns in TMEM (S 128 | P 64 | O D, at column 256 g) and its own barriers, so the two tiles are two independent
+// streams over the SAME K / V tiles (loaded once for both: half the L2 -> SM traffic of one tile per CTA), and while one
+// stream's threads are in their exp2 phase (MUFU-bound: 128 exp2 per row and key tile) the other's MMAs and bookkeeping run.
+// Per key tile a thread (= one query row) loads its 128 logits into registers in ONE pass and hands the S buffer back at
+// once -- Q K^T of the next key tile is issued while this one's exponentials are computed.  O accumulates in TMEM over all
+// key tiles (the MMA's accumulate flag); it is rescaled only when a row's maximum grows by more than 2^tau since the last
+// rescale (P then stays <= 2^tau, exact in fp32 / fine in bf16), which after the first key tiles practically never happens.
 template <int D>
-__global__ void __launch_bounds__(kMThreads, 2)
+__global__ void __launch_bounds__(kMThreads, 1)
 mha_fwd_tc_kernel(const __grid_constant__ MhaParams P) {
   constexpr int kTileB = D * 256;                       // 128 rows x D bf16
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kTileB;                            // [kMStages]
-  uint8_t* sV = sK + kMStages * kTileB;                 // [kMStages]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kMStages * kTileB);
+  uint8_t* sQ = smem;                                   // [2]
+  uint8_t* sK = sQ + 2 * kTileB;                        // [kMStagesF]
+  uint8_t* sV = sK + kMStagesF * kTileB;                // [kMStagesF]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kMStagesF * kTileB);
   uint64_t* q_full = bars;
-  uint64_t* full = bars + 1;                            // [kMStages]
-  uint64_t* empty = full + kMStages;                    // [kMStages]
-  uint64_t* s_full = empty + kMStages;
-  uint64_t* p_ready = s_full + 1;                       // 4 arrivals
-  uint64_t* pv_full = s_full + 2;
-  uint64_t* pv_empty = s_full + 3;                      // 4 arrivals
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 4);
+  uint64_t* full = bars + 1;                            // [kMStagesF]
+  uint64_t* empty = full + kMStagesF;                   // [kMStagesF]
+  uint64_t* s_full = empty + kMStagesF;                 // [2] S(j) of stream g is in TMEM
+  uint64_t* s_free = s_full + 2;                        // [2] ... and in the rows' registers (4 warp arrivals)
+  uint64_t* p_ready = s_full + 4;                       // [2] P(j) is in TMEM, O has been rescaled if it had to be (4 warp arrivals)
+  uint64_t* pv_done = s_full + 6;                       // [2] P V(j) has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int t0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-  const int n_tiles = visible_key_tiles(P, t0);
+  const int t0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+  int n_g[2];
+#pragma unroll
+  for (int g = 0; g < 2; ++g) n_g[g] = t0 + g * 128 < P.T ? visible_key_tiles(P, t0 + g * 128) : 0;
+  const int n_max = max(n_g[0], n_g[1]);
+  const bool two = t0 + 128 < P.T;
 
   if (tid == 0) {
     mbar_init(q_full, 1);
-    for (int s = 0; s < kMStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(s_full, 1); mbar_init(p_ready, 4); mbar_init(pv_full, 1); mbar_init(pv_empty, 4);
+    for (int s = 0; s < kMStagesF; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int g = 0; g < 2; ++g) { mbar_init(&s_full[g], 1); mbar_init(&s_free[g], 4); mbar_init(&p_ready[g], 4); mbar_init(&pv_done[g], 1); }
     fence_barrier_init();
   }
-  if (warp == 4 && lane == 0) { tma_prefetch_desc(&P.q); tma_prefetch_desc(&P.k); tma_prefetch_desc(&P.v); }
-  if (warp == 5) tmem_alloc<256>(tmem_slot);
+  if (warp == 8 && lane == 0) { tma_prefetch_desc(&P.q); tma_prefetch_desc(&P.k); tma_prefetch_desc(&P.v); }
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tP = tmem + 128, tPV = tmem + 192;
 
-  if (warp == 4) {
-    if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, kTileB);
-      tma_load_4d(&P.q, q_full, sQ, 0, t0, h * (D / 32), b);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j % kMStages;
-        mbar_wait(&empty[s], ((j / kMStages) & 1) ^ 1);
-        mbar_arrive_expect_tx(&full[s], 2 * kTileB);
-        tma_load_4d(&P.k, &full[s], sK + s * kTileB, 0, j * 128, h * (D / 32), b);
-        tma_load_4d(&P.v, &full[s], sV + s * kTileB, 0, j * 128, h * (D / 32), b);
-      }
-    }
-  } else if (warp == 5) {
-    constexpr uint32_t idescS = umma_idesc_bf16(128, 128, 0, 0);
-    constexpr uint32_t idescPV = umma_idesc_bf16(128, D, 0, 1);
-    const uint64_t dK = umma_smem_desc(0, 0, 512, kSwz64);            // K-major tiles (Q, K)
-    const uint64_t dVm = umma_smem_desc(0, 8192, 512, kSwz64);        // V read MN-major: channel panels 8 KB apart
-    const uint32_t q0 = smem_u32(sQ) >> 4, k0 = smem_u32(sK) >> 4, v0 = smem_u32(sV) >> 4;
-    auto issue_S = [&](int j) {
-      const int s = j % kMStages;
-      mbar_wait(&full[s], (j / kMStages) & 1);
-      tcgen05_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int ks = 0; ks < D / 16; ++ks) {
-          const uint32_t o = (ks >> 1) * (8192 >> 4) + (ks & 1) * 2;
-          umma_bf16_ss(tS, dK + (q0 + o), dK + (k0 + s * (kTileB >> 4) + o), idescS, ks > 0 ? 1u : 0u);
+  if (warp >= 8) {
+    setmaxnreg_dec<kMRegAux>();
+    if (warp == 8) {
+      if (elect_one() && n_max > 0) {
+        mbar_arrive_expect_tx(q_full, (two ? 2 : 1) * kTileB);
+        tma_load_4d(&P.q, q_full, sQ, 0, t0, h * (D / 32), b);
+        if (two) tma_load_4d(&P.q, q_full, sQ + kTileB, 0, t0 + 128, h * (D / 32), b);
+        for (int j = 0; j < n_max; ++j) {
+          const int s = j % kMStagesF;
+          mbar_wait(&empty[s], ((j / kMStagesF) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full[s], 2 * kTileB);
+          tma_load_4d(&P.k, &full[s], sK + s * kTileB, 0, j * 128, h * (D / 32), b);
+          tma_load_4d(&P.v, &full[s], sV + s * kTileB, 0, j * 128, h * (D / 32), b);
         }
-        umma_commit(s_full);
       }
-      __syncwarp();
-    };
-    if (n_tiles > 0) {
-      mbar_wait(q_full, 0);
-      issue_S(0);
-    }
-    for (int j = 0; j < n_tiles; ++j) {
-      const int s = j % kMStages;
-      mbar_wait(p_ready, j & 1);                    // P(j) is in TMEM, S(j) has been read out
-      mbar_wait(pv_empty, (j & 1) ^ 1);             // the rows have folded PV(j - 1) into their outputs
-      tcgen05_fence_after();
-      if (elect_one()) {
+    } else if (warp == 9) {
+      constexpr uint32_t idescS = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idescPV = umma_idesc_bf16(128, D, 0, 1);
+      const uint64_t dK = umma_smem_desc(0, 0, 512, kSwz64);            // K-major tiles (Q, K)
+      const uint64_t dVm = umma_smem_desc(0, 8192, 512, kSwz64);        // V read MN-major: channel panels 8 KB apart
+      const uint32_t q0 = smem_u32(sQ) >> 4, k0 = smem_u32(sK) >> 4, v0 = smem_u32(sV) >> 4;
+      auto issue_S = [&](int g, int j) {
+        const int s = j % kMStagesF;
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks)              // 16 keys = 8 TMEM columns of P per step
-          umma_bf16_ts(tPV, tP + ks * 8, dVm + (v0 + s * (kTileB >> 4) + ks * 64), idescPV, ks > 0 ? 1u : 0u);
-        umma_commit(pv_full);
-        umma_commit(&empty[s]);
+          for (int ks = 0; ks < D / 16; ++ks) {
+            const uint32_t o = (ks >> 1) * (8192 >> 4) + (ks & 1) * 2;
+            umma_bf16_ss(tmem + g * 256, dK + (q0 + g * (kTileB >> 4) + o), dK + (k0 + s * (kTileB >> 4) + o), idescS, ks > 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full[g]);
+        }
+        __syncwarp();
+      };
+      if (n_max > 0) {
+        mbar_wait(q_full, 0);
+        mbar_wait(&full[0], 0);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+          if (n_g[g] > 0) issue_S(g, 0);
       }
-      __syncwarp();
-      if (j + 1 < n_tiles) issue_S(j + 1);
+      for (int j = 0; j < n_max; ++j) {
+        const int s = j % kMStagesF;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (j < n_g[g]) {
+            mbar_wait(&p_ready[g], j & 1);            // P(j) is in TMEM, S(j) was read out long ago
+            tcgen05_fence_after();
+            if (elect_one()) {
+              const uint32_t tP = tmem + g * 256 + 128, tO = tmem + g * 256 + 192;
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)          // 16 keys = 8 TMEM columns of P per step
+                umma_bf16_ts(tO, tP + ks * 8, dVm + (v0 + s * (kTileB >> 4) + ks * 64), idescPV, (j > 0 || ks > 0) ? 1u : 0u);
+              umma_commit(&pv_done[g]);
+            }
+            __syncwarp();
+          }
+          if (g == 1) {                               // every MMA that reads stage s has been issued
+            if (elect_one()) umma_commit(&empty[s]);
+            __syncwarp();
+          }
+          if (j + 1 < n_g[g]) {
+            mbar_wait(&full[(j + 1) % kMStagesF], ((j + 1) / kMStagesF) & 1);
+            mbar_wait(&s_free[g], j & 1);             // the rows hold S(j) in registers
+            tcgen05_fence_after();
+            issue_S(g, j + 1);
+          }
+        }
+      }
     }
   } else {
-    // ============================== softmax: thread = query row ==============================
-    const int r = tid;                              // 0..127
-    const int t = t0 + r;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    // ============================== softmax: warpgroup = query tile, thread = query row ==============================
+    setmaxnreg_inc<kMRegCompute>();
+    const int g = warp >> 2, r = tid & 127;
+    const int tg0 = t0 + g * 128, t = tg0 + r;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem + g * 256 + lane_base, tP = tS + 128, tO = tS + 192;
+    const int n_tiles = n_g[g];
     const float sc = P.scale * kMLog2e;
-    float m = -INFINITY, l = 0.f;
-    float O[D];
-#pragma unroll
-    for (int e = 0; e < D; ++e) O[e] = 0.f;
+    float m_use = -INFINITY, l = 0.f;
     for (int j = 0; j < n_tiles; ++j) {
       const int s0 = j * 128;
-      const bool masked = tile_needs_mask(P, t0, s0);
-      mbar_wait(s_full, j & 1);
+      const bool masked = tile_needs_mask(P, tg0, s0);
+      mbar_wait(&s_full[g], j & 1);
       tcgen05_fence_after();
-      // pass 1: row maximum
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tS + lane_base + c * 32, v);
+      uint32_t v[128];
+      {
+        uint32_t (*v32)[32] = reinterpret_cast<uint32_t (*)[32]>(v);
+        tmem_ld_32x32b_x32(tS, v32[0]); tmem_ld_32x32b_x32(tS + 32, v32[1]);
+        tmem_ld_32x32b_x32(tS + 64, v32[2]); tmem_ld_32x32b_x32(tS + 96, v32[3]);
         tmem_ld_wait();
-        if (masked) {
+      }
+      tcgen05_fence_before();
+      mbar_arrive_warp(&s_free[g]);
+      float a_mul = sc;                               // logit (log2 domain) = v * a_mul
+      if (masked) {                                   // rare tiles: fold scale and mask into v
 #pragma unroll
-          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, fmaf(__uint_as_float(v[e]), sc, mask_term(P, t, s0 + c * 32 + e)));
-        } else {
+        for (int e = 0; e < 128; ++e) v[e] = __float_as_uint(fmaf(__uint_as_float(v[e]), sc, mask_term(P, t, s0 + e)));
+        a_mul = 1.f;
+      }
+      // row maximum: a tree of three-input maxima (the scale is positive, so it commutes with the maximum)
+      float mx;
+      {
+        float m3[43];
 #pragma unroll
-          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(v[e]) * sc);
+        for (int e = 0; e < 42; ++e) m3[e] = fmax3(__uint_as_float(v[3 * e]), __uint_as_float(v[3 * e + 1]), __uint_as_float(v[3 * e + 2]));
+        m3[42] = fmaxf(__uint_as_float(v[126]), __uint_as_float(v[127]));
+#pragma unroll
+        for (int e = 0; e < 14; ++e) m3[e] = fmax3(m3[3 * e], m3[3 * e + 1], m3[3 * e + 2]);
+        m3[14] = m3[42];
+#pragma unroll
+        for (int e = 0; e < 5; ++e) m3[e] = fmax3(m3[3 * e], m3[3 * e + 1], m3[3 * e + 2]);
+        mx = fmaxf(fmax3(m3[0], m3[1], m3[2]), fmaxf(m3[3], m3[4]));
+      }
+      const float m_new = fmaxf(m_use, mx * a_mul);
+      bool pv_waited = false;
+      if (__any_sync(0xffffffffu, m_new > m_use + kMRescaleTau)) {
+        // raise the maximum of every row of this warp (rows that would not have had to are rescaled for free)
+        const float alpha = m_new == -INFINITY ? 1.f : fast_exp2(m_use - m_new);     // m_use = -inf: 0
+        l *= alpha;
+        m_use = m_new;
+        if (j > 0) {                                  // O holds P V of tiles < j: wait for the last of them, rescale in place
+          mbar_wait(&pv_done[g], (j - 1) & 1);
+          tcgen05_fence_after();
+          pv_waited = true;
+#pragma unroll
+          for (int c = 0; c < D / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld_32x32b_x16(tO + c * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+            tmem_st_32x32b_x16(tO + c * 16, o);
+          }
         }
       }
-      const float m_new = fmaxf(m, mx);
-      const float m_use = m_new == -INFINITY ? 0.f : m_new;
-      const float alpha = fast_exp2(m - m_use);      // m = -inf: 0
-      // pass 2: P = exp2(s - m) -> bf16 pairs -> TMEM (A operand of P V), row sum
-      float rs = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32], pk[16];
-        tmem_ld_32x32b_x32(tS + lane_base + c * 32, v);
-        tmem_ld_wait();
+      const float m_eff = m_use == -INFINITY ? 0.f : m_use;
+      // P = exp2(v * a_mul - m) -> bf16 pairs, row sum
+      const uint64_t a2 = pk2(a_mul, a_mul), nm2 = pk2(-m_eff, -m_eff);
+      uint64_t rs2[2] = {0ull, 0ull};
+      uint32_t pk[64];
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          float a = fmaf(__uint_as_float(v[e]), sc, -m_use), bb = fmaf(__uint_as_float(v[e + 1]), sc, -m_use);
-          if (masked) { a += mask_term(P, t, s0 + c * 32 + e); bb += mask_term(P, t, s0 + c * 32 + e + 1); }
-          a = fast_exp2(a); bb = fast_exp2(bb);
-          rs += a + bb;
-          pk[e >> 1] = pack_bf16x2(a, bb);
-        }
-        tmem_st_32x32b_x16(tP + lane_base + c * 16, pk);
+      for (int e = 0; e < 64; ++e) {
+        float x0, x1;
+        upk2(fma2(pk2u(v[2 * e], v[2 * e + 1]), a2, nm2), x0, x1);
+        x0 = fast_exp2(x0); x1 = fast_exp2(x1);
+        rs2[e & 1] = add2(rs2[e & 1], pk2(x0, x1));
+        pk[e] = pack_bf16x2(x0, x1);
+      }
+      if (j > 0 && !pv_waited) {                      // P V(j - 1) has read the P buffer
+        mbar_wait(&pv_done[g], (j - 1) & 1);
+        tcgen05_fence_after();
+      }
+      {
+        uint32_t (*p16)[16] = reinterpret_cast<uint32_t (*)[16]>(pk);
+        tmem_st_32x32b_x16(tP, p16[0]); tmem_st_32x32b_x16(tP + 16, p16[1]);
+        tmem_st_32x32b_x16(tP + 32, p16[2]); tmem_st_32x32b_x16(tP + 48, p16[3]);
       }
       tmem_st_wait();
       tcgen05_fence_before();
-      mbar_arrive_warp(p_ready);
-      l = l * alpha + rs;
-      m = m_new;
-      // fold this tile's P V into the row's output
-      mbar_wait(pv_full, j & 1);
+      mbar_arrive_warp(&p_ready[g]);
+      float r0, r1, r2, r3;
+      upk2(rs2[0], r0, r1); upk2(rs2[1], r2, r3);
+      l += (r0 + r1) + (r2 + r3);
+    }
+    // ---- epilogue: O / l -> bf16 rows, lse
+    if (n_tiles > 0) {
+      mbar_wait(&pv_done[g], (n_tiles - 1) & 1);
       tcgen05_fence_after();
+    }
+    const float inv = l > 0.f ? __frcp_rn(l) : 0.f;
+    uint4* dst = reinterpret_cast<uint4*>(P.out + (long long)t * P.o_st + (long long)b * P.o_sb + h * D);
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tPV + lane_base + c * 32, v);
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t o[32];
+      if (n_tiles > 0) {
+        tmem_ld_32x32b_x32(tO + c * 32, o);
         tmem_ld_wait();
+      } else {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) O[c * 32 + e] = fmaf(O[c * 32 + e], alpha, __uint_as_float(v[e]));
+        for (int e = 0; e < 32; ++e) o[e] = 0u;
       }
-      tcgen05_fence_before();
-      mbar_arrive_warp(pv_empty);
-    }
-    if (t < P.T) {
-      const float inv = l > 0.f ? __frcp_rn(l) : 0.f;
-      uint4* dst = reinterpret_cast<uint4*>(P.out + (long long)t * P.o_st + (long long)b * P.o_sb + h * D);
+      if (t < P.T) {
 #pragma unroll
-      for (int e = 0; e < D / 8; ++e)
-        dst[e] = make_uint4(pack_bf16x2(O[8 * e] * inv, O[8 * e + 1] * inv), pack_bf16x2(O[8 * e + 2] * inv, O[8 * e + 3] * inv),
-                            pack_bf16x2(O[8 * e + 4] * inv, O[8 * e + 5] * inv), pack_bf16x2(O[8 * e + 6] * inv, O[8 * e + 7] * inv));
-      P.lse[((long long)b * P.nH + h) * P.T + t] = l > 0.f ? (m + __log2f(l)) * kMLn2 : -INFINITY;
+        for (int e = 0; e < 4; ++e)
+          dst[c * 4 + e] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * e]) * inv, __uint_as_float(o[8 * e + 1]) * inv),
+                                      pack_bf16x2(__uint_as_float(o[8 * e + 2]) * inv, __uint_as_float(o[8 * e + 3]) * inv),
+                                      pack_bf16x2(__uint_as_float(o[8 * e + 4]) * inv, __uint_as_float(o[8 * e + 5]) * inv),
+                                      pack_bf16x2(__uint_as_float(o[8 * e + 6]) * inv, __uint_as_float(o[8 * e + 7]) * inv));
+      }
     }
+    if (t < P.T) P.lse[((long long)b * P.nH + h) * P.T + t] = l > 0.f ? (m_use + __log2f(l)) * kMLn2 : -INFINITY;
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<256>(tmem);
+  if (warp == 9) tmem_dealloc<512>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -272,6 +357,11 @@ __global__ void mha_delta_kernel(const __nv_bfloat16* __restrict__ o, long long 
 }
 
 // MODE 0: dK, dV (CTA = key tile, query tiles stream).  MODE 1: dQ (CTA = query tile, key tiles stream).
+// Eight compute warps: warps w and w + 4 share the TMEM lane quadrant (rows 32 (w % 4) ..) and take the key columns
+// 0..63 / 64..127 of the block -- lse and delta are per-row inputs, so the two halves of a row never talk.  A thread loads
+// its 64 logits and 64 dP values into registers in one go and hands the S / dP buffer back: the MMA warp issues S and dP
+// of the next block at once (they run under this block's exponentials), then this block's gradient MMAs when P / dS are in
+// shared memory.
 template <int D, int MODE>
 __global__ void __launch_bounds__(kMThreads, 1)
 mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
@@ -281,19 +371,20 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sR0 = smem;                                  // resident: K (mode 0) / Q (mode 1)
   uint8_t* sR1 = sR0 + kTileB;                          // resident: V (mode 0) / dO (mode 1)
-  uint8_t* sS0 = sR1 + kTileB;                          // [kMStages] streamed: Q (mode 0) / K (mode 1)
-  uint8_t* sS1 = sS0 + kMStages * kTileB;               // [kMStages] streamed: dO (mode 0) / V (mode 1)
-  uint8_t* sdS = sS1 + kMStages * kTileB;
+  uint8_t* sS0 = sR1 + kTileB;                          // [kMStagesB] streamed: Q (mode 0) / K (mode 1)
+  uint8_t* sS1 = sS0 + kMStagesB * kTileB;              // [kMStagesB] streamed: dO (mode 0) / V (mode 1)
+  uint8_t* sdS = sS1 + kMStagesB * kTileB;
   uint8_t* sP = sdS + kPB;                              // mode 0 only
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (MODE == 0 ? kPB : 0));
   uint64_t* r_full = bars;
-  uint64_t* full = bars + 1;                            // [kMStages]
-  uint64_t* empty = full + kMStages;                    // [kMStages]
-  uint64_t* s_full = empty + kMStages;                  // S and dP in TMEM
-  uint64_t* ps_ready = s_full + 1;                      // P / dS tiles in shared memory (4 arrivals)
-  uint64_t* ps_free = s_full + 2;                       // the gradient MMAs have read them
-  uint64_t* acc_done = s_full + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 4);
+  uint64_t* full = bars + 1;                            // [kMStagesB]
+  uint64_t* empty = full + kMStagesB;                   // [kMStagesB]
+  uint64_t* s_full = empty + kMStagesB;                 // S and dP in TMEM
+  uint64_t* sdp_free = s_full + 1;                      // ... and in the threads' registers (8 warp arrivals)
+  uint64_t* ps_ready = s_full + 2;                      // P / dS tiles in shared memory (8 warp arrivals)
+  uint64_t* ps_free = s_full + 3;                       // the gradient MMAs have read them
+  uint64_t* acc_done = s_full + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 5);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int o0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;     // first key (mode 0) / query (mode 1) of this CTA
@@ -304,145 +395,165 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
 
   if (tid == 0) {
     mbar_init(r_full, 1);
-    for (int s = 0; s < kMStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(s_full, 1); mbar_init(ps_ready, 4); mbar_init(ps_free, 1); mbar_init(acc_done, 1);
+    for (int s = 0; s < kMStagesB; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(s_full, 1); mbar_init(sdp_free, 8); mbar_init(ps_ready, 8); mbar_init(ps_free, 1); mbar_init(acc_done, 1);
     fence_barrier_init();
   }
-  if (warp == 4 && lane == 0) { tma_prefetch_desc(&P.q); tma_prefetch_desc(&P.k); tma_prefetch_desc(&P.v); tma_prefetch_desc(&P.dout); }
-  if (warp == 5) tmem_alloc<512>(tmem_slot);
+  if (warp == 8 && lane == 0) { tma_prefetch_desc(&P.q); tma_prefetch_desc(&P.k); tma_prefetch_desc(&P.v); tma_prefetch_desc(&P.dout); }
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tS = tmem, tdP = tmem + 128, tA0 = tmem + 256, tA1 = tmem + 256 + D;
 
-  if (warp == 4) {
-    if (elect_one() && n_tiles > 0) {
-      mbar_arrive_expect_tx(r_full, 2 * kTileB);
-      tma_load_4d(MODE == 0 ? &P.k : &P.q, r_full, sR0, 0, o0, h * (D / 32), b);
-      tma_load_4d(MODE == 0 ? &P.v : &P.dout, r_full, sR1, 0, o0, h * (D / 32), b);
-      for (int n = 0; n < n_tiles; ++n) {
-        const int s = n % kMStages, row0 = (n_begin + n) * 128;
-        mbar_wait(&empty[s], ((n / kMStages) & 1) ^ 1);
-        mbar_arrive_expect_tx(&full[s], 2 * kTileB);
-        tma_load_4d(MODE == 0 ? &P.q : &P.k, &full[s], sS0 + s * kTileB, 0, row0, h * (D / 32), b);
-        tma_load_4d(MODE == 0 ? &P.dout : &P.v, &full[s], sS1 + s * kTileB, 0, row0, h * (D / 32), b);
+  if (warp >= 8) {
+    setmaxnreg_dec<kMRegAux>();
+    if (warp == 8) {
+      if (elect_one() && n_tiles > 0) {
+        mbar_arrive_expect_tx(r_full, 2 * kTileB);
+        tma_load_4d(MODE == 0 ? &P.k : &P.q, r_full, sR0, 0, o0, h * (D / 32), b);
+        tma_load_4d(MODE == 0 ? &P.v : &P.dout, r_full, sR1, 0, o0, h * (D / 32), b);
+        for (int n = 0; n < n_tiles; ++n) {
+          const int s = n % kMStagesB, row0 = (n_begin + n) * 128;
+          mbar_wait(&empty[s], ((n / kMStagesB) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full[s], 2 * kTileB);
+          tma_load_4d(MODE == 0 ? &P.q : &P.k, &full[s], sS0 + s * kTileB, 0, row0, h * (D / 32), b);
+          tma_load_4d(MODE == 0 ? &P.dout : &P.v, &full[s], sS1 + s * kTileB, 0, row0, h * (D / 32), b);
+        }
       }
-    }
-  } else if (warp == 5) {
-    constexpr uint32_t idescS = umma_idesc_bf16(128, 128, 0, 0);
-    constexpr uint32_t idescG0 = umma_idesc_bf16(128, D, 1, 1);       // mode 0: A = P / dS transposed, B = dO / Q transposed
-    constexpr uint32_t idescG1 = umma_idesc_bf16(128, D, 0, 1);       // mode 1: A = dS, B = K transposed
-    const uint64_t dKm = umma_smem_desc(0, 0, 512, kSwz64);           // K-major
-    const uint64_t dMn = umma_smem_desc(0, 8192, 512, kSwz64);        // MN-major, 32-wide panels 8 KB (128 rows) apart
-    const uint32_t r0 = smem_u32(sR0) >> 4, r1 = smem_u32(sR1) >> 4, s0b = smem_u32(sS0) >> 4, s1b = smem_u32(sS1) >> 4;
-    const uint32_t ds0 = smem_u32(sdS) >> 4, p0 = smem_u32(sP) >> 4;
-    auto issue_grad = [&](int n) {                                     // gradient MMAs of streamed tile n
-      const int s = n % kMStages;
-      mbar_wait(ps_ready, n & 1);
-      tcgen05_fence_after();
-      if (elect_one()) {
-        const uint32_t acc = n > 0 ? 1u : 0u;
+    } else if (warp == 9) {
+      constexpr uint32_t idescS = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idescG0 = umma_idesc_bf16(128, D, 1, 1);       // mode 0: A = P / dS transposed, B = dO / Q transposed
+      constexpr uint32_t idescG1 = umma_idesc_bf16(128, D, 0, 1);       // mode 1: A = dS, B = K transposed
+      const uint64_t dKm = umma_smem_desc(0, 0, 512, kSwz64);           // K-major
+      const uint64_t dMn = umma_smem_desc(0, 8192, 512, kSwz64);        // MN-major, 32-wide panels 8 KB (128 rows) apart
+      const uint32_t r0 = smem_u32(sR0) >> 4, r1 = smem_u32(sR1) >> 4, s0b = smem_u32(sS0) >> 4, s1b = smem_u32(sS1) >> 4;
+      const uint32_t ds0 = smem_u32(sdS) >> 4, p0 = smem_u32(sP) >> 4;
+      auto issue_grad = [&](int n) {                                     // gradient MMAs of streamed tile n
+        const int s = n % kMStagesB;
+        mbar_wait(ps_ready, n & 1);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t acc = n > 0 ? 1u : 0u;
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          if (MODE == 0) {   // 16 query rows per step
-            umma_bf16_ss(tA0, dMn + (p0 + ks * 64), dMn + (s1b + s * (kTileB >> 4) + ks * 64), idescG0, acc | (ks > 0));    // dV += P^T dO
-            umma_bf16_ss(tA1, dMn + (ds0 + ks * 64), dMn + (s0b + s * (kTileB >> 4) + ks * 64), idescG0, acc | (ks > 0));   // dK += dS^T Q
-          } else {           // 16 keys per step
-            umma_bf16_ss(tA0, dKm + (ds0 + (ks >> 1) * (8192 >> 4) + (ks & 1) * 2), dMn + (s0b + s * (kTileB >> 4) + ks * 64), idescG1,
-                         acc | (ks > 0));                                                                                   // dQ += dS K
+          for (int ks = 0; ks < 8; ++ks) {
+            if (MODE == 0) {   // 16 query rows per step
+              umma_bf16_ss(tA0, dMn + (p0 + ks * 64), dMn + (s1b + s * (kTileB >> 4) + ks * 64), idescG0, acc | (ks > 0));    // dV += P^T dO
+              umma_bf16_ss(tA1, dMn + (ds0 + ks * 64), dMn + (s0b + s * (kTileB >> 4) + ks * 64), idescG0, acc | (ks > 0));   // dK += dS^T Q
+            } else {           // 16 keys per step
+              umma_bf16_ss(tA0, dKm + (ds0 + (ks >> 1) * (8192 >> 4) + (ks & 1) * 2), dMn + (s0b + s * (kTileB >> 4) + ks * 64), idescG1,
+                           acc | (ks > 0));                                                                                   // dQ += dS K
+            }
           }
+          umma_commit(ps_free);
+          umma_commit(&empty[s]);
         }
-        umma_commit(ps_free);
-        umma_commit(&empty[s]);
-      }
-      __syncwarp();
-    };
-    if (n_tiles > 0) mbar_wait(r_full, 0);
-    for (int n = 0; n < n_tiles; ++n) {
-      const int s = n % kMStages;
-      mbar_wait(&full[s], (n / kMStages) & 1);
-      if (n > 0) issue_grad(n - 1);                                    // also: the rows have read S(n - 1), dP(n - 1)
-      tcgen05_fence_after();
-      if (elect_one()) {
-        const uint32_t qa = MODE == 0 ? s0b + s * (kTileB >> 4) : r0, kb = MODE == 0 ? r0 : s0b + s * (kTileB >> 4);
-        const uint32_t da = MODE == 0 ? s1b + s * (kTileB >> 4) : r1, vb = MODE == 0 ? r1 : s1b + s * (kTileB >> 4);
+        __syncwarp();
+      };
+      if (n_tiles > 0) mbar_wait(r_full, 0);
+      for (int n = 0; n < n_tiles; ++n) {
+        const int s = n % kMStagesB;
+        mbar_wait(&full[s], (n / kMStagesB) & 1);
+        if (n > 0) mbar_wait(sdp_free, (n - 1) & 1);                     // S(n - 1), dP(n - 1) are in registers
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t qa = MODE == 0 ? s0b + s * (kTileB >> 4) : r0, kb = MODE == 0 ? r0 : s0b + s * (kTileB >> 4);
+          const uint32_t da = MODE == 0 ? s1b + s * (kTileB >> 4) : r1, vb = MODE == 0 ? r1 : s1b + s * (kTileB >> 4);
 #pragma unroll
-        for (int ks = 0; ks < D / 16; ++ks) {
-          const uint32_t o = (ks >> 1) * (8192 >> 4) + (ks & 1) * 2;
-          umma_bf16_ss(tS, dKm + (qa + o), dKm + (kb + o), idescS, ks > 0 ? 1u : 0u);       // S = Q K^T
-        }
+          for (int ks = 0; ks < D / 16; ++ks) {
+            const uint32_t o = (ks >> 1) * (8192 >> 4) + (ks & 1) * 2;
+            umma_bf16_ss(tS, dKm + (qa + o), dKm + (kb + o), idescS, ks > 0 ? 1u : 0u);       // S = Q K^T
+          }
 #pragma unroll
-        for (int ks = 0; ks < D / 16; ++ks) {
-          const uint32_t o = (ks >> 1) * (8192 >> 4) + (ks & 1) * 2;
-          umma_bf16_ss(tdP, dKm + (da + o), dKm + (vb + o), idescS, ks > 0 ? 1u : 0u);      // dP = dO V^T
+          for (int ks = 0; ks < D / 16; ++ks) {
+            const uint32_t o = (ks >> 1) * (8192 >> 4) + (ks & 1) * 2;
+            umma_bf16_ss(tdP, dKm + (da + o), dKm + (vb + o), idescS, ks > 0 ? 1u : 0u);      // dP = dO V^T
+          }
+          umma_commit(s_full);
         }
-        umma_commit(s_full);
+        __syncwarp();
+        if (n > 0) issue_grad(n - 1);
       }
-      __syncwarp();
-    }
-    if (n_tiles > 0) {
-      issue_grad(n_tiles - 1);
-      if (elect_one()) umma_commit(acc_done);
-      __syncwarp();
+      if (n_tiles > 0) {
+        issue_grad(n_tiles - 1);
+        if (elect_one()) umma_commit(acc_done);
+        __syncwarp();
+      }
     }
   } else {
-    // ============================== P / dS: thread = query row of the current block ==============================
-    const int r = tid;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    // ============================== P / dS: thread = (query row, half of the block's keys) ==============================
+    setmaxnreg_inc<kMRegCompute>();
+    const int r = tid & 127, hh = warp >> 2;            // row of the block; key columns 64 hh .. 64 hh + 63
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const float sc = P.scale * kMLog2e;
     const long long item = (long long)b * P.nH + h;
     const int rsw = (r >> 1) & 3;
     float lse2 = INFINITY, dl = 0.f;
     if (MODE == 1 && o0 + r < P.T) { lse2 = __ldg(P.lse + item * P.T + o0 + r) * kMLog2e; dl = __ldg(P.delta + item * P.T + o0 + r); }
+    if (MODE == 1 && lse2 == -INFINITY) lse2 = INFINITY;                // a fully masked row has P = 0
     for (int n = 0; n < n_tiles; ++n) {
       const int t0 = MODE == 0 ? (n_begin + n) * 128 : o0, s0 = MODE == 0 ? o0 : (n_begin + n) * 128;
       const int t = t0 + r;
       if (MODE == 0) {
         lse2 = INFINITY; dl = 0.f;
         if (t < P.T) { lse2 = __ldg(P.lse + item * P.T + t) * kMLog2e; dl = __ldg(P.delta + item * P.T + t); }
+        if (lse2 == -INFINITY) lse2 = INFINITY;
       }
-      if (lse2 == -INFINITY) lse2 = INFINITY;       // a fully masked row has P = 0
       const bool masked = tile_needs_mask(P, t0, s0);
       mbar_wait(s_full, n & 1);
       tcgen05_fence_after();
-      if (n > 0) mbar_wait(ps_free, (n - 1) & 1);   // the gradient MMAs of the previous block have read the P / dS tiles
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t vs[32], vd[32];
-        tmem_ld_32x32b_x32(tS + lane_base + c * 32, vs);
-        tmem_ld_32x32b_x32(tdP + lane_base + c * 32, vd);
+      uint32_t vs[64], vd[64];
+      {
+        uint32_t (*a32)[32] = reinterpret_cast<uint32_t (*)[32]>(vs);
+        uint32_t (*d32)[32] = reinterpret_cast<uint32_t (*)[32]>(vd);
+        tmem_ld_32x32b_x32(tS + lane_base + hh * 64, a32[0]); tmem_ld_32x32b_x32(tS + lane_base + hh * 64 + 32, a32[1]);
+        tmem_ld_32x32b_x32(tdP + lane_base + hh * 64, d32[0]); tmem_ld_32x32b_x32(tdP + lane_base + hh * 64 + 32, d32[1]);
         tmem_ld_wait();
-        uint32_t pp[16], dd[16];
+      }
+      tcgen05_fence_before();
+      mbar_arrive_warp(sdp_free);
+      // P = exp2(s sc - lse), dS = P (dP - delta) scale  ->  bf16 pairs
+      float a_mul = sc;                               // logit (log2 domain) = vs * a_mul
+      if (masked) {                                   // rare blocks: fold scale and mask into vs (kept out of the main loop:
+#pragma unroll                                        //  a branch per element defeated the instruction prefetch)
+        for (int e = 0; e < 64; ++e) vs[e] = __float_as_uint(fmaf(__uint_as_float(vs[e]), sc, mask_term(P, t, s0 + hh * 64 + e)));
+        a_mul = 1.f;
+      }
+      const float nds = -dl * P.scale;
+      const uint64_t a2 = pk2(a_mul, a_mul), nl2 = pk2(-lse2, -lse2), sc2 = pk2(P.scale, P.scale), nds2 = pk2(nds, nds);
+      uint32_t pp[32], dd[32];
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          float a = fmaf(__uint_as_float(vs[e]), sc, -lse2), bb = fmaf(__uint_as_float(vs[e + 1]), sc, -lse2);
-          if (masked) { a += mask_term(P, t, s0 + c * 32 + e); bb += mask_term(P, t, s0 + c * 32 + e + 1); }
-          a = fast_exp2(a); bb = fast_exp2(bb);
-          pp[e >> 1] = pack_bf16x2(a, bb);
-          dd[e >> 1] = pack_bf16x2(a * (__uint_as_float(vd[e]) - dl) * P.scale, bb * (__uint_as_float(vd[e + 1]) - dl) * P.scale);
-        }
-        uint8_t* prow = sdS + c * 8192 + r * 64;
+      for (int e = 0; e < 32; ++e) {
+        float x0, x1;
+        upk2(fma2(pk2u(vs[2 * e], vs[2 * e + 1]), a2, nl2), x0, x1);
+        x0 = fast_exp2(x0); x1 = fast_exp2(x1);
+        pp[e] = pack_bf16x2(x0, x1);
+        dd[e] = pack_bf16x2(mul2(pk2(x0, x1), fma2(pk2u(vd[2 * e], vd[2 * e + 1]), sc2, nds2)));
+      }
+      if (n > 0) mbar_wait(ps_free, (n - 1) & 1);     // the gradient MMAs of the previous block have read the P / dS tiles
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {                   // this thread's two 32-key panels
+        uint8_t* prow = sdS + (hh * 2 + c) * 8192 + r * 64;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
-          *reinterpret_cast<uint4*>(prow + ((q4 ^ rsw) << 4)) = make_uint4(dd[4 * q4], dd[4 * q4 + 1], dd[4 * q4 + 2], dd[4 * q4 + 3]);
+          *reinterpret_cast<uint4*>(prow + ((q4 ^ rsw) << 4)) = make_uint4(dd[16 * c + 4 * q4], dd[16 * c + 4 * q4 + 1], dd[16 * c + 4 * q4 + 2], dd[16 * c + 4 * q4 + 3]);
           if (MODE == 0)
-            *reinterpret_cast<uint4*>(prow + (sP - sdS) + ((q4 ^ rsw) << 4)) = make_uint4(pp[4 * q4], pp[4 * q4 + 1], pp[4 * q4 + 2], pp[4 * q4 + 3]);
+            *reinterpret_cast<uint4*>(prow + (sP - sdS) + ((q4 ^ rsw) << 4)) = make_uint4(pp[16 * c + 4 * q4], pp[16 * c + 4 * q4 + 1], pp[16 * c + 4 * q4 + 2], pp[16 * c + 4 * q4 + 3]);
         }
       }
       fence_proxy_async_smem();
-      tcgen05_fence_before();
       mbar_arrive_warp(ps_ready);
     }
-    // ---- epilogue: the accumulators -> bf16 rows
+    // ---- epilogue: the accumulators -> bf16 rows (warpgroup 0: dV / dQ, warpgroup 1: dK)
     const int row = o0 + r;
     const int limit = MODE == 0 ? P.S : P.T;
     if (n_tiles > 0) {
       mbar_wait(acc_done, 0);
       tcgen05_fence_after();
     }
-#pragma unroll
-    for (int which = 0; which < (MODE == 0 ? 2 : 1); ++which) {
+    if (hh < (MODE == 0 ? 2 : 1)) {
+      const int which = hh;
       __nv_bfloat16* base = MODE == 0 ? (which == 0 ? P.dv : P.dk) : P.dq;
       const long long st = MODE == 0 ? (which == 0 ? P.dv_st : P.dk_st) : P.dq_st, sb = MODE == 0 ? (which == 0 ? P.dv_sb : P.dk_sb) : P.dq_sb;
 #pragma unroll
@@ -469,7 +580,7 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<512>(tmem);
+  if (warp == 9) tmem_dealloc<512>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -512,10 +623,10 @@ static void fill_common(MhaParams& P, const mmn_mha_desc* d, const float* mask) 
 
 template <int D>
 static int mha_fwd_launch(const MhaParams& P, cudaStream_t st) {
-  constexpr size_t smem = 1024 + (size_t)(1 + 2 * kMStages) * D * 256 + 16 * 8 + 16;
+  constexpr size_t smem = 1024 + (size_t)(2 + 2 * kMStagesF) * D * 256 + 24 * 8 + 16;
   static std::once_flag once;
   std::call_once(once, [] { cudaFuncSetAttribute(mha_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
-  dim3 grid((P.T + 127) / 128, P.nH, P.B);
+  dim3 grid((P.T + 255) / 256, P.nH, P.B);
   mha_fwd_tc_kernel<D><<<grid, kMThreads, smem, st>>>(P);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
@@ -540,7 +651,7 @@ int mha_fwd(const mmn_mha_desc* d, const void* q, const void* k, const void* v, 
 
 template <int D, int MODE>
 static int mha_bwd_launch(const MhaParams& P, cudaStream_t st) {
-  constexpr size_t smem = 1024 + (size_t)(2 + 2 * kMStages) * D * 256 + (MODE == 0 ? 2 : 1) * 32768 + 16 * 8 + 16;
+  constexpr size_t smem = 1024 + (size_t)(2 + 2 * kMStagesB) * D * 256 + (MODE == 0 ? 2 : 1) * 32768 + 16 * 8 + 16;
   static std::once_flag once;
   std::call_once(once, [] { cudaFuncSetAttribute(mha_bwd_tc_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
   dim3 grid(((MODE == 0 ? P.S : P.T) + 127) / 128, P.nH, P.B);
