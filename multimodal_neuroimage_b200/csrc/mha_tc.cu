@@ -490,15 +490,25 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
     const long long item = (long long)b * P.nH + h;
     const int rsw = (r >> 1) & 3;
     float lse2 = INFINITY, dl = 0.f;
-    if (MODE == 1 && o0 + r < P.T) { lse2 = __ldg(P.lse + item * P.T + o0 + r) * kMLog2e; dl = __ldg(P.delta + item * P.T + o0 + r); }
-    if (MODE == 1 && lse2 == -INFINITY) lse2 = INFINITY;                // a fully masked row has P = 0
+    // per-row inputs: this CTA's rows (mode 1) or the streamed tile's (mode 0: loaded one block ahead -- consumed right
+    // after the load, the L2 latency was ~10 % of the compute warps' time)
+    auto load_row = [&](int t, float& lse_out, float& dl_out) {
+      lse_out = INFINITY; dl_out = 0.f;
+      if (t < P.T) { lse_out = __ldg(P.lse + item * P.T + t); dl_out = __ldg(P.delta + item * P.T + t); }
+    };
+    float lse_nx = INFINITY, dl_nx = 0.f;
+    if (n_tiles > 0) load_row(MODE == 0 ? n_begin * 128 + r : o0 + r, lse_nx, dl_nx);
+    if (MODE == 1) {
+      lse2 = lse_nx == -INFINITY ? INFINITY : lse_nx * kMLog2e;           // a fully masked row has P = 0
+      dl = dl_nx;
+    }
     for (int n = 0; n < n_tiles; ++n) {
       const int t0 = MODE == 0 ? (n_begin + n) * 128 : o0, s0 = MODE == 0 ? o0 : (n_begin + n) * 128;
       const int t = t0 + r;
       if (MODE == 0) {
-        lse2 = INFINITY; dl = 0.f;
-        if (t < P.T) { lse2 = __ldg(P.lse + item * P.T + t) * kMLog2e; dl = __ldg(P.delta + item * P.T + t); }
-        if (lse2 == -INFINITY) lse2 = INFINITY;
+        lse2 = lse_nx == -INFINITY ? INFINITY : lse_nx * kMLog2e;
+        dl = dl_nx;
+        if (n + 1 < n_tiles) load_row(t + 128, lse_nx, dl_nx);
       }
       const bool masked = tile_needs_mask(P, t0, s0);
       mbar_wait(s_full, n & 1);
@@ -507,8 +517,8 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
       {
         uint32_t (*a32)[32] = reinterpret_cast<uint32_t (*)[32]>(vs);
         uint32_t (*d32)[32] = reinterpret_cast<uint32_t (*)[32]>(vd);
-        tmem_ld_32x32b_x32(tS + lane_base + hh * 64, a32[0]); tmem_ld_32x32b_x32(tS + lane_base + hh * 64 + 32, a32[1]);
-        tmem_ld_32x32b_x32(tdP + lane_base + hh * 64, d32[0]); tmem_ld_32x32b_x32(tdP + lane_base + hh * 64 + 32, d32[1]);
+        tmem_ld_32x32b_x32(tS + lane_base + hh * 64, a32[0]); tmem_ld_32x32b_x32(tdP + lane_base + hh * 64, d32[0]);
+        tmem_ld_32x32b_x32(tS + lane_base + hh * 64 + 32, a32[1]); tmem_ld_32x32b_x32(tdP + lane_base + hh * 64 + 32, d32[1]);
         tmem_ld_wait();
       }
       tcgen05_fence_before();
@@ -522,24 +532,24 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
       }
       const float nds = -dl * P.scale;
       const uint64_t a2 = pk2(a_mul, a_mul), nl2 = pk2(-lse2, -lse2), sc2 = pk2(P.scale, P.scale), nds2 = pk2(nds, nds);
-      uint32_t pp[32], dd[32];
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        float x0, x1;
-        upk2(fma2(pk2u(vs[2 * e], vs[2 * e + 1]), a2, nl2), x0, x1);
-        x0 = fast_exp2(x0); x1 = fast_exp2(x1);
-        pp[e] = pack_bf16x2(x0, x1);
-        dd[e] = pack_bf16x2(mul2(pk2(x0, x1), fma2(pk2u(vd[2 * e], vd[2 * e + 1]), sc2, nds2)));
-      }
-      if (n > 0) mbar_wait(ps_free, (n - 1) & 1);     // the gradient MMAs of the previous block have read the P / dS tiles
+      for (int c = 0; c < 2; ++c) {                   // this thread's two 32-key panels: the stores of the first run under
+        uint32_t pp[16], dd[16];                      //  the exponentials of the second
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {                   // this thread's two 32-key panels
+        for (int e = 0; e < 16; ++e) {
+          float x0, x1;
+          upk2(fma2(pk2u(vs[32 * c + 2 * e], vs[32 * c + 2 * e + 1]), a2, nl2), x0, x1);
+          x0 = fast_exp2(x0); x1 = fast_exp2(x1);
+          pp[e] = pack_bf16x2(x0, x1);
+          dd[e] = pack_bf16x2(mul2(pk2(x0, x1), fma2(pk2u(vd[32 * c + 2 * e], vd[32 * c + 2 * e + 1]), sc2, nds2)));
+        }
+        if (c == 0 && n > 0) mbar_wait(ps_free, (n - 1) & 1);   // the gradient MMAs of the previous block have read the P / dS tiles
         uint8_t* prow = sdS + (hh * 2 + c) * 8192 + r * 64;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
-          *reinterpret_cast<uint4*>(prow + ((q4 ^ rsw) << 4)) = make_uint4(dd[16 * c + 4 * q4], dd[16 * c + 4 * q4 + 1], dd[16 * c + 4 * q4 + 2], dd[16 * c + 4 * q4 + 3]);
+          *reinterpret_cast<uint4*>(prow + ((q4 ^ rsw) << 4)) = make_uint4(dd[4 * q4], dd[4 * q4 + 1], dd[4 * q4 + 2], dd[4 * q4 + 3]);
           if (MODE == 0)
-            *reinterpret_cast<uint4*>(prow + (sP - sdS) + ((q4 ^ rsw) << 4)) = make_uint4(pp[16 * c + 4 * q4], pp[16 * c + 4 * q4 + 1], pp[16 * c + 4 * q4 + 2], pp[16 * c + 4 * q4 + 3]);
+            *reinterpret_cast<uint4*>(prow + (sP - sdS) + ((q4 ^ rsw) << 4)) = make_uint4(pp[4 * q4], pp[4 * q4 + 1], pp[4 * q4 + 2], pp[4 * q4 + 3]);
         }
       }
       fence_proxy_async_smem();
