@@ -82,6 +82,44 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {       // sm_
   return d;
 }
 
+// exp2 of an fp32 pair WITHOUT the special-function unit: round-to-nearest split x = i + f through the 1.5 * 2^23 magic
+// add, a cubic for 2^f on [-0.5, 0.5] (relative error <= 7.5e-5, fifty times below the bf16 rounding the probabilities get
+// as MMA operands), and i added into the exponent field.  MUFU (16 lanes per clock and SM) is what bounds these kernels:
+// 128 x 128 exponentials per block are 1024 cycles of it.  MMN_MHA_POLY_FWD / _BWD of every 8 pairs take this route on the FMA pipe
+// (packed fp32x2 arithmetic) instead, so both pipes work on the exponentials at once.
+#ifndef MMN_MHA_POLY_FWD
+#define MMN_MHA_POLY_FWD 3
+#endif
+#ifndef MMN_MHA_POLY_BWD
+#define MMN_MHA_POLY_BWD 0
+#endif
+__device__ __forceinline__ void exp2_poly_pair(uint64_t x2, float& e0, float& e1) {
+  float x0, x1;
+  upk2(x2, x0, x1);
+  const uint64_t xc = pk2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));          // also catches -inf (masked logits)
+  const uint64_t t2 = add2(xc, pk2(12582912.f, 12582912.f));              // low mantissa bits = round(x)
+  const uint64_t r2 = add2(t2, pk2(-12582912.f, -12582912.f));
+  const uint64_t f2 = fma2(r2, pk2(-1.f, -1.f), xc);
+  uint64_t p2 = fma2(f2, pk2(0.0551716685f, 0.0551716685f), pk2(0.2426111251f, 0.2426111251f));
+  p2 = fma2(p2, f2, pk2(0.6932609677f, 0.6932609677f));
+  p2 = fma2(p2, f2, pk2(0.9999280572f, 0.9999280572f));
+  float p0, p1, t0, t1;
+  upk2(p2, p0, p1);
+  upk2(t2, t0, t1);
+  e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+  e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+}
+// exp2 of the pair x2; `e` is the pair's (compile-time) index: which unit computes it
+template <int POLY_OF8>
+__device__ __forceinline__ void exp2_pair(uint64_t x2, int e, float& e0, float& e1) {
+  if ((e & 7) < POLY_OF8) {
+    exp2_poly_pair(x2, e0, e1);
+  } else {
+    upk2(x2, e0, e1);
+    e0 = fast_exp2(e0); e1 = fast_exp2(e1);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Forward
 // ------------------------------------------------------------------------------------------
@@ -174,12 +212,27 @@ mha_fwd_tc_kernel(const __grid_constant__ MhaParams P) {
         for (int g = 0; g < 2; ++g)
           if (n_g[g] > 0) issue_S(g, 0);
       }
-      for (int j = 0; j < n_max; ++j) {
-        const int s = j % kMStagesF;
+      // Four queues served in turn, none blocking another: S_g(j + 1) goes out as soon as stream g's rows hold S_g(j) in
+      // registers (s_free) and K(j + 1) has landed -- it then runs under the exponentials of tile j -- and P V_g(j) as
+      // soon as P_g(j) is in TMEM.  (Waiting for P_g(j) before issuing S_g(j + 1) left the rows without logits for ~30 %
+      // of their time.)  A K / V stage is released once both streams' P V of its tile have been issued.
+      int ns[2] = {1, 1}, np[2] = {0, 0}, released = 0;
+      uint32_t idle = 0;
+      while (np[0] < n_g[0] || np[1] < n_g[1]) {
+        bool progressed = false;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-          if (j < n_g[g]) {
-            mbar_wait(&p_ready[g], j & 1);            // P(j) is in TMEM, S(j) was read out long ago
+          if (ns[g] < n_g[g]) {
+            const int j = ns[g];                       // S_g(j): needs K(j) and the S buffer back from tile j - 1
+            if (mbar_test(&full[j % kMStagesF], (j / kMStagesF) & 1) && mbar_test(&s_free[g], (j - 1) & 1)) {
+              tcgen05_fence_after();
+              issue_S(g, j);
+              ++ns[g];
+              progressed = true;
+            }
+          }
+          if (np[g] < n_g[g] && np[g] < ns[g] && mbar_test(&p_ready[g], np[g] & 1)) {
+            const int j = np[g], s = j % kMStagesF;
             tcgen05_fence_after();
             if (elect_one()) {
               const uint32_t tP = tmem + g * 256 + 128, tO = tmem + g * 256 + 192;
@@ -189,18 +242,18 @@ mha_fwd_tc_kernel(const __grid_constant__ MhaParams P) {
               umma_commit(&pv_done[g]);
             }
             __syncwarp();
-          }
-          if (g == 1) {                               // every MMA that reads stage s has been issued
-            if (elect_one()) umma_commit(&empty[s]);
-            __syncwarp();
-          }
-          if (j + 1 < n_g[g]) {
-            mbar_wait(&full[(j + 1) % kMStagesF], ((j + 1) / kMStagesF) & 1);
-            mbar_wait(&s_free[g], j & 1);             // the rows hold S(j) in registers
-            tcgen05_fence_after();
-            issue_S(g, j + 1);
+            ++np[g];
+            progressed = true;
           }
         }
+        // tile `released` is done with once every stream that sees it has had its P V issued (S of that tile went out before)
+        while (released < n_max && (np[0] > released || released >= n_g[0]) && (np[1] > released || released >= n_g[1])) {
+          if (elect_one()) umma_commit(&empty[released % kMStagesF]);
+          __syncwarp();
+          ++released;
+        }
+        if (progressed) idle = 0;
+        else if (++idle > (1u << 26)) __trap();       // a broken pipeline becomes a CUDA error, not a hang
       }
     }
   } else {
@@ -277,8 +330,7 @@ mha_fwd_tc_kernel(const __grid_constant__ MhaParams P) {
 #pragma unroll
       for (int e = 0; e < 64; ++e) {
         float x0, x1;
-        upk2(fma2(pk2u(v[2 * e], v[2 * e + 1]), a2, nm2), x0, x1);
-        x0 = fast_exp2(x0); x1 = fast_exp2(x1);
+        exp2_pair<MMN_MHA_POLY_FWD>(fma2(pk2u(v[2 * e], v[2 * e + 1]), a2, nm2), e, x0, x1);
         rs2[e & 1] = add2(rs2[e & 1], pk2(x0, x1));
         pk[e] = pack_bf16x2(x0, x1);
       }
@@ -538,8 +590,7 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           float x0, x1;
-          upk2(fma2(pk2u(vs[32 * c + 2 * e], vs[32 * c + 2 * e + 1]), a2, nl2), x0, x1);
-          x0 = fast_exp2(x0); x1 = fast_exp2(x1);
+          exp2_pair<MMN_MHA_POLY_BWD>(fma2(pk2u(vs[32 * c + 2 * e], vs[32 * c + 2 * e + 1]), a2, nl2), e, x0, x1);
           pp[e] = pack_bf16x2(x0, x1);
           dd[e] = pack_bf16x2(mul2(pk2(x0, x1), fma2(pk2u(vd[32 * c + 2 * e], vd[32 * c + 2 * e + 1]), sc2, nds2)));
         }
