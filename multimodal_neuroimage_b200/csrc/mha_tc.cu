@@ -32,7 +32,8 @@ constexpr float kMLn2 = 0.6931471805599453f;
 constexpr int kMThreads = 384;
 constexpr int kMRegCompute = 216, kMRegAux = 72;   // 256 x 216 + 128 x 72 = 384 x 168: the launch allocation is the pool
 constexpr int kMStagesF = 4;                   // forward: K / V ring
-constexpr int kMStagesB = 3;                   // backward: streamed-tile ring
+constexpr int kMStagesB = 4;                   // backward: streamed-tile ring
+constexpr int kMComputeWarpsB = 16, kMThreadsB = (kMComputeWarpsB + 2) * 32;   // backward: + TMA producer + MMA issuer
 constexpr float kMRescaleTau = 8.f;            // forward: the running maximum is only raised when it grows by more than 2^tau
 
 struct MhaParams {
@@ -409,31 +410,39 @@ __global__ void mha_delta_kernel(const __nv_bfloat16* __restrict__ o, long long 
 }
 
 // MODE 0: dK, dV (CTA = key tile, query tiles stream).  MODE 1: dQ (CTA = query tile, key tiles stream).
-// Eight compute warps: warps w and w + 4 share the TMEM lane quadrant (rows 32 (w % 4) ..) and take the key columns
-// 0..63 / 64..127 of the block -- lse and delta are per-row inputs, so the two halves of a row never talk.  A thread loads
-// its 64 logits and 64 dP values into registers in one go and hands the S / dP buffer back: the MMA warp issues S and dP
-// of the next block at once (they run under this block's exponentials), then this block's gradient MMAs when P / dS are in
-// shared memory.
+//
+// Per 128 x 128 block both kernels recompute the logits and dP with the CTA's RESIDENT rows along M (TMEM lanes) and the
+// STREAMED rows along N (TMEM columns):
+//   mode 0   S^T = K Q^T, dP^T = V dO^T   (lane = key, column = query);   dV += P^T dO,  dK += dS^T Q
+//   mode 1   S   = Q K^T, dP   = dO V^T   (lane = query, column = key);   dQ += dS K
+// so that P / dS, written by the thread that owns the lane, are already the A operand (M x K, K along the columns) of the
+// gradient MMAs and go back into TENSOR MEMORY as bf16 pairs (tcgen05.st), never through shared memory.  (With P and dS as
+// shared-memory tiles the kernels were bound by shared-memory bandwidth: an M128 N64 K16 MMA with both operands in shared
+// memory reads 6 KB per 32 tensor cycles, 192 B/clk of the SM's 128, on top of 64 KB of P / dS stores per block.)
+// Sixteen compute warps: warps w, w + 4, w + 8, w + 12 share the TMEM lane quadrant 32 (w % 4) and take one 32-column
+// panel of the block each.  A thread loads its 32 logits and 32 dP values into registers in one go and hands the S / dP
+// buffer back: the MMA warp issues S and dP of the next block at once (they run under this block's exponentials), then
+// this block's gradient MMAs when P / dS are in TMEM.  lse and delta belong to the query: the thread's own row in mode 1;
+// in mode 0 the streamed tile's 128 values, staged in shared memory (double-buffered, loaded one block ahead).
+// TMEM columns: S 0 | dP 128 | accumulators 256 (dV or dQ), 256 + D (dK) | P 384 | dS 448.   576 threads x 96 registers.
 template <int D, int MODE>
-__global__ void __launch_bounds__(kMThreads, 1)
+__global__ void __launch_bounds__(kMThreadsB, 1)
 mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
   constexpr int kTileB = D * 256;
-  constexpr int kPB = 128 * 128 * 2;                    // P / dS tile: [4 panels of 32 keys][128 query rows][64 B]
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sR0 = smem;                                  // resident: K (mode 0) / Q (mode 1)
   uint8_t* sR1 = sR0 + kTileB;                          // resident: V (mode 0) / dO (mode 1)
   uint8_t* sS0 = sR1 + kTileB;                          // [kMStagesB] streamed: Q (mode 0) / K (mode 1)
   uint8_t* sS1 = sS0 + kMStagesB * kTileB;              // [kMStagesB] streamed: dO (mode 0) / V (mode 1)
-  uint8_t* sdS = sS1 + kMStagesB * kTileB;
-  uint8_t* sP = sdS + kPB;                              // mode 0 only
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (MODE == 0 ? kPB : 0));
+  float4* sRow = reinterpret_cast<float4*>(sS1 + kMStagesB * kTileB);   // mode 0: [2][64] {-lse2(q), -lse2(q + 1), -delta scale (q), (q + 1)}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRow + 128);
   uint64_t* r_full = bars;
   uint64_t* full = bars + 1;                            // [kMStagesB]
   uint64_t* empty = full + kMStagesB;                   // [kMStagesB]
   uint64_t* s_full = empty + kMStagesB;                 // S and dP in TMEM
-  uint64_t* sdp_free = s_full + 1;                      // ... and in the threads' registers (8 warp arrivals)
-  uint64_t* ps_ready = s_full + 2;                      // P / dS tiles in shared memory (8 warp arrivals)
+  uint64_t* sdp_free = s_full + 1;                      // ... and in the threads' registers (one arrival per compute warp)
+  uint64_t* ps_ready = s_full + 2;                      // P / dS in TMEM (one arrival per compute warp)
   uint64_t* ps_free = s_full + 3;                       // the gradient MMAs have read them
   uint64_t* acc_done = s_full + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 5);
@@ -448,20 +457,19 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
   if (tid == 0) {
     mbar_init(r_full, 1);
     for (int s = 0; s < kMStagesB; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(s_full, 1); mbar_init(sdp_free, 8); mbar_init(ps_ready, 8); mbar_init(ps_free, 1); mbar_init(acc_done, 1);
+    mbar_init(s_full, 1); mbar_init(sdp_free, kMComputeWarpsB); mbar_init(ps_ready, kMComputeWarpsB); mbar_init(ps_free, 1); mbar_init(acc_done, 1);
     fence_barrier_init();
   }
-  if (warp == 8 && lane == 0) { tma_prefetch_desc(&P.q); tma_prefetch_desc(&P.k); tma_prefetch_desc(&P.v); tma_prefetch_desc(&P.dout); }
-  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  if (warp == kMComputeWarpsB && lane == 0) { tma_prefetch_desc(&P.q); tma_prefetch_desc(&P.k); tma_prefetch_desc(&P.v); tma_prefetch_desc(&P.dout); }
+  if (warp == kMComputeWarpsB + 1) tmem_alloc<512>(tmem_slot);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tdP = tmem + 128, tA0 = tmem + 256, tA1 = tmem + 256 + D;
+  const uint32_t tS = tmem, tdP = tmem + 128, tA0 = tmem + 256, tA1 = tmem + 256 + D, tP = tmem + 384, tdS = tmem + 448;
 
-  if (warp >= 8) {
-    setmaxnreg_dec<kMRegAux>();
-    if (warp == 8) {
+  if (warp >= kMComputeWarpsB) {
+    if (warp == kMComputeWarpsB) {
       if (elect_one() && n_tiles > 0) {
         mbar_arrive_expect_tx(r_full, 2 * kTileB);
         tma_load_4d(MODE == 0 ? &P.k : &P.q, r_full, sR0, 0, o0, h * (D / 32), b);
@@ -474,14 +482,12 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
           tma_load_4d(MODE == 0 ? &P.dout : &P.v, &full[s], sS1 + s * kTileB, 0, row0, h * (D / 32), b);
         }
       }
-    } else if (warp == 9) {
-      constexpr uint32_t idescS = umma_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idescG0 = umma_idesc_bf16(128, D, 1, 1);       // mode 0: A = P / dS transposed, B = dO / Q transposed
-      constexpr uint32_t idescG1 = umma_idesc_bf16(128, D, 0, 1);       // mode 1: A = dS, B = K transposed
+    } else {
+      constexpr uint32_t idescS = umma_idesc_bf16(128, 128, 0, 0);      // A = resident tile, B = streamed tile, both K-major
+      constexpr uint32_t idescG = umma_idesc_bf16(128, D, 0, 1);        // A = P / dS (TMEM), B = streamed tile read MN-major
       const uint64_t dKm = umma_smem_desc(0, 0, 512, kSwz64);           // K-major
       const uint64_t dMn = umma_smem_desc(0, 8192, 512, kSwz64);        // MN-major, 32-wide panels 8 KB (128 rows) apart
       const uint32_t r0 = smem_u32(sR0) >> 4, r1 = smem_u32(sR1) >> 4, s0b = smem_u32(sS0) >> 4, s1b = smem_u32(sS1) >> 4;
-      const uint32_t ds0 = smem_u32(sdS) >> 4, p0 = smem_u32(sP) >> 4;
       auto issue_grad = [&](int n) {                                     // gradient MMAs of streamed tile n
         const int s = n % kMStagesB;
         mbar_wait(ps_ready, n & 1);
@@ -489,13 +495,12 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
         if (elect_one()) {
           const uint32_t acc = n > 0 ? 1u : 0u;
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            if (MODE == 0) {   // 16 query rows per step
-              umma_bf16_ss(tA0, dMn + (p0 + ks * 64), dMn + (s1b + s * (kTileB >> 4) + ks * 64), idescG0, acc | (ks > 0));    // dV += P^T dO
-              umma_bf16_ss(tA1, dMn + (ds0 + ks * 64), dMn + (s0b + s * (kTileB >> 4) + ks * 64), idescG0, acc | (ks > 0));   // dK += dS^T Q
-            } else {           // 16 keys per step
-              umma_bf16_ss(tA0, dKm + (ds0 + (ks >> 1) * (8192 >> 4) + (ks & 1) * 2), dMn + (s0b + s * (kTileB >> 4) + ks * 64), idescG1,
-                           acc | (ks > 0));                                                                                   // dQ += dS K
+          for (int ks = 0; ks < 8; ++ks) {                               // 16 streamed rows = 8 TMEM columns of P / dS per step
+            if (MODE == 0) {
+              umma_bf16_ts(tA0, tP + ks * 8, dMn + (s1b + s * (kTileB >> 4) + ks * 64), idescG, acc | (ks > 0));    // dV += P^T dO
+              umma_bf16_ts(tA1, tdS + ks * 8, dMn + (s0b + s * (kTileB >> 4) + ks * 64), idescG, acc | (ks > 0));   // dK += dS^T Q
+            } else {
+              umma_bf16_ts(tA0, tdS + ks * 8, dMn + (s0b + s * (kTileB >> 4) + ks * 64), idescG, acc | (ks > 0));   // dQ += dS K
             }
           }
           umma_commit(ps_free);
@@ -510,17 +515,15 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
         if (n > 0) mbar_wait(sdp_free, (n - 1) & 1);                     // S(n - 1), dP(n - 1) are in registers
         tcgen05_fence_after();
         if (elect_one()) {
-          const uint32_t qa = MODE == 0 ? s0b + s * (kTileB >> 4) : r0, kb = MODE == 0 ? r0 : s0b + s * (kTileB >> 4);
-          const uint32_t da = MODE == 0 ? s1b + s * (kTileB >> 4) : r1, vb = MODE == 0 ? r1 : s1b + s * (kTileB >> 4);
 #pragma unroll
           for (int ks = 0; ks < D / 16; ++ks) {
             const uint32_t o = (ks >> 1) * (8192 >> 4) + (ks & 1) * 2;
-            umma_bf16_ss(tS, dKm + (qa + o), dKm + (kb + o), idescS, ks > 0 ? 1u : 0u);       // S = Q K^T
+            umma_bf16_ss(tS, dKm + (r0 + o), dKm + (s0b + s * (kTileB >> 4) + o), idescS, ks > 0 ? 1u : 0u);      // S(^T) = R0 S0^T
           }
 #pragma unroll
           for (int ks = 0; ks < D / 16; ++ks) {
             const uint32_t o = (ks >> 1) * (8192 >> 4) + (ks & 1) * 2;
-            umma_bf16_ss(tdP, dKm + (da + o), dKm + (vb + o), idescS, ks > 0 ? 1u : 0u);      // dP = dO V^T
+            umma_bf16_ss(tdP, dKm + (r1 + o), dKm + (s1b + s * (kTileB >> 4) + o), idescS, ks > 0 ? 1u : 0u);     // dP(^T) = R1 S1^T
           }
           umma_commit(s_full);
         }
@@ -534,80 +537,81 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
       }
     }
   } else {
-    // ============================== P / dS: thread = (query row, half of the block's keys) ==============================
-    setmaxnreg_inc<kMRegCompute>();
-    const int r = tid & 127, hh = warp >> 2;            // row of the block; key columns 64 hh .. 64 hh + 63
+    // ============================== P / dS: thread = (resident row, one 32-column panel of the block) ==============================
+    const int r = tid & 127, hh = warp >> 2;            // lane = resident row; streamed columns 32 hh .. 32 hh + 31
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const float sc = P.scale * kMLog2e;
     const long long item = (long long)b * P.nH + h;
-    const int rsw = (r >> 1) & 3;
-    float lse2 = INFINITY, dl = 0.f;
-    // per-row inputs: this CTA's rows (mode 1) or the streamed tile's (mode 0: loaded one block ahead -- consumed right
-    // after the load, the L2 latency was ~10 % of the compute warps' time)
+    // per-query inputs, loaded one block ahead (threads 0..127 in mode 0: the streamed tile's rows; every thread in mode 1:
+    // its own row, once)
     auto load_row = [&](int t, float& lse_out, float& dl_out) {
       lse_out = INFINITY; dl_out = 0.f;
       if (t < P.T) { lse_out = __ldg(P.lse + item * P.T + t); dl_out = __ldg(P.delta + item * P.T + t); }
     };
     float lse_nx = INFINITY, dl_nx = 0.f;
-    if (n_tiles > 0) load_row(MODE == 0 ? n_begin * 128 + r : o0 + r, lse_nx, dl_nx);
-    if (MODE == 1) {
-      lse2 = lse_nx == -INFINITY ? INFINITY : lse_nx * kMLog2e;           // a fully masked row has P = 0
-      dl = dl_nx;
-    }
+    if (n_tiles > 0 && (MODE == 1 || tid < 128)) load_row(MODE == 0 ? n_begin * 128 + tid : o0 + r, lse_nx, dl_nx);
+    // a fully masked row (lse = -inf) has P = 0: exp2(s - inf)
+    const float nl_own = lse_nx == -INFINITY ? -INFINITY : -lse_nx * kMLog2e, nds_own = -dl_nx * P.scale;   // mode 1
     for (int n = 0; n < n_tiles; ++n) {
       const int t0 = MODE == 0 ? (n_begin + n) * 128 : o0, s0 = MODE == 0 ? o0 : (n_begin + n) * 128;
-      const int t = t0 + r;
+      const float4* row = sRow + (n & 1) * 64 + hh * 16;
       if (MODE == 0) {
-        lse2 = lse_nx == -INFINITY ? INFINITY : lse_nx * kMLog2e;
-        dl = dl_nx;
-        if (n + 1 < n_tiles) load_row(t + 128, lse_nx, dl_nx);
+        if (tid < 128) {
+          float* dst = reinterpret_cast<float*>(sRow + (n & 1) * 64 + (tid >> 1)) + (tid & 1);
+          dst[0] = lse_nx == -INFINITY ? -INFINITY : -lse_nx * kMLog2e;
+          dst[2] = -dl_nx * P.scale;
+          if (n + 1 < n_tiles) load_row(t0 + 128 + tid, lse_nx, dl_nx);
+        }
+        named_bar_sync(1, kMComputeWarpsB * 32);        // also: everybody has finished reading the buffer of block n - 1
       }
       const bool masked = tile_needs_mask(P, t0, s0);
       mbar_wait(s_full, n & 1);
       tcgen05_fence_after();
-      uint32_t vs[64], vd[64];
-      {
-        uint32_t (*a32)[32] = reinterpret_cast<uint32_t (*)[32]>(vs);
-        uint32_t (*d32)[32] = reinterpret_cast<uint32_t (*)[32]>(vd);
-        tmem_ld_32x32b_x32(tS + lane_base + hh * 64, a32[0]); tmem_ld_32x32b_x32(tdP + lane_base + hh * 64, d32[0]);
-        tmem_ld_32x32b_x32(tS + lane_base + hh * 64 + 32, a32[1]); tmem_ld_32x32b_x32(tdP + lane_base + hh * 64 + 32, d32[1]);
-        tmem_ld_wait();
-      }
+      uint32_t vs[32], vd[32];
+      tmem_ld_32x32b_x32(tS + lane_base + hh * 32, vs);
+      tmem_ld_32x32b_x32(tdP + lane_base + hh * 32, vd);
+      tmem_ld_wait();
       tcgen05_fence_before();
       mbar_arrive_warp(sdp_free);
       // P = exp2(s sc - lse), dS = P (dP - delta) scale  ->  bf16 pairs
       float a_mul = sc;                               // logit (log2 domain) = vs * a_mul
       if (masked) {                                   // rare blocks: fold scale and mask into vs (kept out of the main loop:
 #pragma unroll                                        //  a branch per element defeated the instruction prefetch)
-        for (int e = 0; e < 64; ++e) vs[e] = __float_as_uint(fmaf(__uint_as_float(vs[e]), sc, mask_term(P, t, s0 + hh * 64 + e)));
+        for (int e = 0; e < 32; ++e) {
+          const int col = hh * 32 + e;
+          const float mt = MODE == 0 ? mask_term(P, t0 + col, s0 + r) : mask_term(P, t0 + r, s0 + col);
+          vs[e] = __float_as_uint(fmaf(__uint_as_float(vs[e]), sc, mt));
+        }
         a_mul = 1.f;
       }
-      const float nds = -dl * P.scale;
-      const uint64_t a2 = pk2(a_mul, a_mul), nl2 = pk2(-lse2, -lse2), sc2 = pk2(P.scale, P.scale), nds2 = pk2(nds, nds);
+      const uint64_t a2 = pk2(a_mul, a_mul), sc2 = pk2(P.scale, P.scale);
+      uint32_t pp[16], dd[16];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {                   // this thread's two 32-key panels: the stores of the first run under
-        uint32_t pp[16], dd[16];                      //  the exponentials of the second
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          float x0, x1;
-          exp2_pair<MMN_MHA_POLY_BWD>(fma2(pk2u(vs[32 * c + 2 * e], vs[32 * c + 2 * e + 1]), a2, nl2), e, x0, x1);
-          pp[e] = pack_bf16x2(x0, x1);
-          dd[e] = pack_bf16x2(mul2(pk2(x0, x1), fma2(pk2u(vd[32 * c + 2 * e], vd[32 * c + 2 * e + 1]), sc2, nds2)));
+      for (int e = 0; e < 16; ++e) {
+        uint64_t nl2, nds2;
+        if (MODE == 0) {
+          const float4 rw = row[e];                   // the pair's queries (broadcast read)
+          nl2 = pk2(rw.x, rw.y); nds2 = pk2(rw.z, rw.w);
+        } else {
+          nl2 = pk2(nl_own, nl_own); nds2 = pk2(nds_own, nds_own);
         }
-        if (c == 0 && n > 0) mbar_wait(ps_free, (n - 1) & 1);   // the gradient MMAs of the previous block have read the P / dS tiles
-        uint8_t* prow = sdS + (hh * 2 + c) * 8192 + r * 64;
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          *reinterpret_cast<uint4*>(prow + ((q4 ^ rsw) << 4)) = make_uint4(dd[4 * q4], dd[4 * q4 + 1], dd[4 * q4 + 2], dd[4 * q4 + 3]);
-          if (MODE == 0)
-            *reinterpret_cast<uint4*>(prow + (sP - sdS) + ((q4 ^ rsw) << 4)) = make_uint4(pp[4 * q4], pp[4 * q4 + 1], pp[4 * q4 + 2], pp[4 * q4 + 3]);
-        }
+        float x0, x1;
+        exp2_pair<MMN_MHA_POLY_BWD>(fma2(pk2u(vs[2 * e], vs[2 * e + 1]), a2, nl2), e, x0, x1);
+        pp[e] = pack_bf16x2(x0, x1);
+        dd[e] = pack_bf16x2(mul2(pk2(x0, x1), fma2(pk2u(vd[2 * e], vd[2 * e + 1]), sc2, nds2)));
       }
-      fence_proxy_async_smem();
+      if (n > 0) {                                    // the gradient MMAs of the previous block have read P / dS
+        mbar_wait(ps_free, (n - 1) & 1);
+        tcgen05_fence_after();
+      }
+      tmem_st_32x32b_x16(tdS + lane_base + hh * 16, dd);
+      if (MODE == 0) tmem_st_32x32b_x16(tP + lane_base + hh * 16, pp);
+      tmem_st_wait();
+      tcgen05_fence_before();
       mbar_arrive_warp(ps_ready);
     }
-    // ---- epilogue: the accumulators -> bf16 rows (warpgroup 0: dV / dQ, warpgroup 1: dK)
-    const int row = o0 + r;
+    // ---- epilogue: the accumulators -> bf16 rows (panel 0's warps: dV / dQ, panel 1's: dK)
+    const int orow = o0 + r;
     const int limit = MODE == 0 ? P.S : P.T;
     if (n_tiles > 0) {
       mbar_wait(acc_done, 0);
@@ -627,8 +631,8 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) v[e] = 0u;
         }
-        if (row < limit) {
-          uint4* dst = reinterpret_cast<uint4*>(base + (long long)row * st + (long long)b * sb + h * D + c * 32);
+        if (orow < limit) {
+          uint4* dst = reinterpret_cast<uint4*>(base + (long long)orow * st + (long long)b * sb + h * D + c * 32);
 #pragma unroll
           for (int e = 0; e < 4; ++e)
             dst[e] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * e]), __uint_as_float(v[8 * e + 1])),
@@ -641,7 +645,7 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc<512>(tmem);
+  if (warp == kMComputeWarpsB + 1) tmem_dealloc<512>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -712,11 +716,11 @@ int mha_fwd(const mmn_mha_desc* d, const void* q, const void* k, const void* v, 
 
 template <int D, int MODE>
 static int mha_bwd_launch(const MhaParams& P, cudaStream_t st) {
-  constexpr size_t smem = 1024 + (size_t)(2 + 2 * kMStagesB) * D * 256 + (MODE == 0 ? 2 : 1) * 32768 + 16 * 8 + 16;
+  constexpr size_t smem = 1024 + (size_t)(2 + 2 * kMStagesB) * D * 256 + 128 * 16 + 16 * 8 + 16;
   static std::once_flag once;
   std::call_once(once, [] { cudaFuncSetAttribute(mha_bwd_tc_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
   dim3 grid(((MODE == 0 ? P.S : P.T) + 127) / 128, P.nH, P.B);
-  mha_bwd_tc_kernel<D, MODE><<<grid, kMThreads, smem, st>>>(P);
+  mha_bwd_tc_kernel<D, MODE><<<grid, kMThreadsB, smem, st>>>(P);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
