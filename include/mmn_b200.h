@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define MMN_ABI_VERSION 2
+#define MMN_ABI_VERSION 3
 /* scratch every window-attention launch needs: the tensor-core kernels keep the counters of their run-time work queue
  * there (zeroed by the library on the launch's stream; one buffer per launch, never shared between launches in flight) */
 #define MMN_WINATTN_WORK_BYTES 2048
@@ -128,7 +128,7 @@ int mmn_mha_fwd(const mmn_mha_desc* desc, const void* q, const void* k, const vo
 
 int mmn_mha_bwd(const mmn_mha_desc* desc, const void* q, const void* k, const void* v,
                 const float* mask, const void* out, const float* lse, const void* dout,
-                void* dq, void* dk, void* dv, float* workspace /* 2*batch*num_heads*T floats */,
+                void* dq, void* dk, void* dv, float* workspace /* 2*batch*num_heads*roundup(T,128) floats */,
                 int device, void* stream);
 
 /* avg (batch,T,S) fp32 = mean over heads of the (dropped-out) attention probabilities. */

@@ -44,7 +44,7 @@ struct MhaParams {
   const float* mask;                           // (T, S) additive, MMN_MASK_TENSOR
   __nv_bfloat16* out; long long o_st, o_sb;    // forward output rows (t, b): out + t * o_st + b * o_sb + h * D
   float* lse;                                  // (B * nH, T) natural-log log-sum-exp
-  const float* delta;                          // (B * nH, T) rowsum(dO o O)       (backward)
+  const float* rowdata; int Tpad;              // backward: (B * nH, Tpad / 2, 4) per query pair {-lse2, -lse2, -delta scale, -delta scale}
   __nv_bfloat16 *dq, *dk, *dv;                 // backward outputs
   long long dq_st, dq_sb, dk_st, dk_sb, dv_st, dv_sb;
 };
@@ -387,26 +387,47 @@ mha_fwd_tc_kernel(const __grid_constant__ MhaParams P) {
 // ------------------------------------------------------------------------------------------
 // Backward
 // ------------------------------------------------------------------------------------------
-// delta[(b, h), t] = sum_e dO[t, b, h D + e] * O[t, b, h D + e]
+// Pre-pass: per query row (b, h, t) the two numbers the backward kernels need, already in the form their inner loop uses
+// and interleaved per PAIR of queries -- rowdata[(b, h)][t / 2] = {-lse2(t), -lse2(t + 1), -delta(t) scale, -delta(t + 1) scale}
+// with lse2 = lse log2(e) and delta = sum_e dO[t, b, h D + e] * O[t, b, h D + e] -- so that the dK/dV kernel gets the 128
+// queries of a streamed tile as ONE 1 KB bulk copy that lands with the tile.  Rows are padded to Tpad = a multiple of 128 per
+// (b, h) with {-inf, 0} (P = 0, dS = 0); a fully masked row (lse = -inf) gets -inf as well.
+// D / 8 threads per row, 16 bytes each, channels fastest: a warp reads 512 contiguous bytes of a (t, b) row.
 template <int D>
-__global__ void mha_delta_kernel(const __nv_bfloat16* __restrict__ o, long long o_st, long long o_sb, const __nv_bfloat16* __restrict__ dout,
-                                 long long do_st, long long do_sb, int T, int B, int nH, float* __restrict__ delta) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // ((b, h), t)
-  if (idx >= (long long)B * nH * T) return;
-  const int t = (int)(idx % T);
-  const int bh = (int)(idx / T), b = bh / nH, h = bh - b * nH;
-  const uint4* po = reinterpret_cast<const uint4*>(o + (long long)t * o_st + (long long)b * o_sb + h * D);
-  const uint4* pd = reinterpret_cast<const uint4*>(dout + (long long)t * do_st + (long long)b * do_sb + h * D);
+__global__ void mha_rowdata_kernel(const __nv_bfloat16* __restrict__ o, long long o_st, long long o_sb, const __nv_bfloat16* __restrict__ dout,
+                                   long long do_st, long long do_sb, const float* __restrict__ lse, int T, int Tpad, int B, int nH,
+                                   float scale, float* __restrict__ rowdata) {
+  constexpr int G = D / 8;                              // threads per row
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // (((t, b), h), c)
+  const long long row = idx / G;
+  const int c = (int)(idx - row * G);
+  const bool live = row < (long long)Tpad * B * nH;
+  const int h = live ? (int)(row % nH) : 0;
+  const long long tb = live ? row / nH : 0;
+  const int b = (int)(tb % B), t = (int)(tb / B);
   float s = 0.f;
-#pragma unroll
-  for (int e = 0; e < D / 8; ++e) {
-    const uint4 a = __ldg(po + e), c = __ldg(pd + e);
-    const uint32_t ua[4] = {a.x, a.y, a.z, a.w}, uc[4] = {c.x, c.y, c.z, c.w};
+  if (live && t < T) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(o + (long long)t * o_st + (long long)b * o_sb + h * D) + c);
+    const uint4 g = __ldg(reinterpret_cast<const uint4*>(dout + (long long)t * do_st + (long long)b * do_sb + h * D) + c);
+    const uint32_t ua[4] = {a.x, a.y, a.z, a.w}, ug[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      s += __uint_as_float(ua[k] << 16) * __uint_as_float(uc[k] << 16) + __uint_as_float(ua[k] & 0xffff0000u) * __uint_as_float(uc[k] & 0xffff0000u);
+      s += __uint_as_float(ua[k] << 16) * __uint_as_float(ug[k] << 16) + __uint_as_float(ua[k] & 0xffff0000u) * __uint_as_float(ug[k] & 0xffff0000u);
   }
-  delta[idx] = s;
+#pragma unroll
+  for (int m = G / 2; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  if (live && c == 0) {
+    const long long bh = (long long)b * nH + h;
+    float nl = -INFINITY, nds = 0.f;
+    if (t < T) {
+      const float l = __ldg(lse + bh * T + t);
+      nl = l == -INFINITY ? -INFINITY : -l * kMLog2e;
+      nds = -s * scale;
+    }
+    float* dst = rowdata + (bh * (Tpad >> 1) + (t >> 1)) * 4 + (t & 1);
+    dst[0] = nl;
+    dst[2] = nds;
+  }
 }
 
 // MODE 0: dK, dV (CTA = key tile, query tiles stream).  MODE 1: dQ (CTA = query tile, key tiles stream).
@@ -419,11 +440,17 @@ __global__ void mha_delta_kernel(const __nv_bfloat16* __restrict__ o, long long 
 // gradient MMAs and go back into TENSOR MEMORY as bf16 pairs (tcgen05.st), never through shared memory.  (With P and dS as
 // shared-memory tiles the kernels were bound by shared-memory bandwidth: an M128 N64 K16 MMA with both operands in shared
 // memory reads 6 KB per 32 tensor cycles, 192 B/clk of the SM's 128, on top of 64 KB of P / dS stores per block.)
+//
 // Sixteen compute warps: warps w, w + 4, w + 8, w + 12 share the TMEM lane quadrant 32 (w % 4) and take one 32-column
 // panel of the block each.  A thread loads its 32 logits and 32 dP values into registers in one go and hands the S / dP
 // buffer back: the MMA warp issues S and dP of the next block at once (they run under this block's exponentials), then
 // this block's gradient MMAs when P / dS are in TMEM.  lse and delta belong to the query: the thread's own row in mode 1;
-// in mode 0 the streamed tile's 128 values, staged in shared memory (double-buffered, loaded one block ahead).
+// in mode 0 the streamed tile's 128 query pairs, which arrive in shared memory WITH the tile (one 1 KB bulk copy of the
+// pre-pass's row data on the tile's barrier: no staging through registers, no CTA-wide barrier per block).
+// (Tried and dropped: two independent groups of eight warps, each on its own 64 streamed rows of the block with M128 N64
+// MMAs, so that one group's exponentials overlap the other's TMEM traffic -- 7 % SLOWER: with both operands in shared memory
+// an N64 MMA reads 6 KB per 32 tensor cycles, 192 B/clk against the SM's 128 B/clk, and per block the operand reads of the
+// seven GEMMs plus the TMA writes already add up to ~1000 shared-memory cycles, as many as the tensor and MUFU pipes need.)
 // TMEM columns: S 0 | dP 128 | accumulators 256 (dV or dQ), 256 + D (dK) | P 384 | dS 448.   576 threads x 96 registers.
 template <int D, int MODE>
 __global__ void __launch_bounds__(kMThreadsB, 1)
@@ -435,8 +462,8 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
   uint8_t* sR1 = sR0 + kTileB;                          // resident: V (mode 0) / dO (mode 1)
   uint8_t* sS0 = sR1 + kTileB;                          // [kMStagesB] streamed: Q (mode 0) / K (mode 1)
   uint8_t* sS1 = sS0 + kMStagesB * kTileB;              // [kMStagesB] streamed: dO (mode 0) / V (mode 1)
-  float4* sRow = reinterpret_cast<float4*>(sS1 + kMStagesB * kTileB);   // mode 0: [2][64] {-lse2(q), -lse2(q + 1), -delta scale (q), (q + 1)}
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRow + 128);
+  float4* sRow = reinterpret_cast<float4*>(sS1 + kMStagesB * kTileB);   // mode 0: [kMStagesB][64] row data of the streamed queries
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRow + kMStagesB * 64);
   uint64_t* r_full = bars;
   uint64_t* full = bars + 1;                            // [kMStagesB]
   uint64_t* empty = full + kMStagesB;                   // [kMStagesB]
@@ -453,6 +480,8 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
   if (MODE == 0) { n_begin = first_query_tile(P, o0); n_end = (P.T + 127) >> 7; }
   else { n_begin = 0; n_end = visible_key_tiles(P, o0); }
   const int n_tiles = max(0, n_end - n_begin);
+  const long long item = (long long)b * P.nH + h;
+  const float4* rowdata = reinterpret_cast<const float4*>(P.rowdata) + item * (P.Tpad >> 1);
 
   if (tid == 0) {
     mbar_init(r_full, 1);
@@ -466,7 +495,7 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tdP = tmem + 128, tA0 = tmem + 256, tA1 = tmem + 256 + D, tP = tmem + 384, tdS = tmem + 448;
+  const uint32_t tA0 = tmem + 256, tA1 = tmem + 256 + D, tP = tmem + 384, tdS = tmem + 448;
 
   if (warp >= kMComputeWarpsB) {
     if (warp == kMComputeWarpsB) {
@@ -477,9 +506,10 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
         for (int n = 0; n < n_tiles; ++n) {
           const int s = n % kMStagesB, row0 = (n_begin + n) * 128;
           mbar_wait(&empty[s], ((n / kMStagesB) & 1) ^ 1);
-          mbar_arrive_expect_tx(&full[s], 2 * kTileB);
+          mbar_arrive_expect_tx(&full[s], 2 * kTileB + (MODE == 0 ? 1024 : 0));
           tma_load_4d(MODE == 0 ? &P.q : &P.k, &full[s], sS0 + s * kTileB, 0, row0, h * (D / 32), b);
           tma_load_4d(MODE == 0 ? &P.dout : &P.v, &full[s], sS1 + s * kTileB, 0, row0, h * (D / 32), b);
+          if (MODE == 0) bulk_load_1d(sRow + s * 64, rowdata + (row0 >> 1), 1024, &full[s]);
         }
       }
     } else {
@@ -488,6 +518,7 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
       const uint64_t dKm = umma_smem_desc(0, 0, 512, kSwz64);           // K-major
       const uint64_t dMn = umma_smem_desc(0, 8192, 512, kSwz64);        // MN-major, 32-wide panels 8 KB (128 rows) apart
       const uint32_t r0 = smem_u32(sR0) >> 4, r1 = smem_u32(sR1) >> 4, s0b = smem_u32(sS0) >> 4, s1b = smem_u32(sS1) >> 4;
+      const uint32_t tS = tmem, tdP = tmem + 128;
       auto issue_grad = [&](int n) {                                     // gradient MMAs of streamed tile n
         const int s = n % kMStagesB;
         mbar_wait(ps_ready, n & 1);
@@ -538,38 +569,25 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
     }
   } else {
     // ============================== P / dS: thread = (resident row, one 32-column panel of the block) ==============================
-    const int r = tid & 127, hh = warp >> 2;            // lane = resident row; streamed columns 32 hh .. 32 hh + 31
+    const int r = tid & 127, col0 = (warp >> 2) * 32;   // lane = resident row; streamed columns col0 .. col0 + 31
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem + lane_base + col0, tdP = tS + 128;
     const float sc = P.scale * kMLog2e;
-    const long long item = (long long)b * P.nH + h;
-    // per-query inputs, loaded one block ahead (threads 0..127 in mode 0: the streamed tile's rows; every thread in mode 1:
-    // its own row, once)
-    auto load_row = [&](int t, float& lse_out, float& dl_out) {
-      lse_out = INFINITY; dl_out = 0.f;
-      if (t < P.T) { lse_out = __ldg(P.lse + item * P.T + t); dl_out = __ldg(P.delta + item * P.T + t); }
-    };
-    float lse_nx = INFINITY, dl_nx = 0.f;
-    if (n_tiles > 0 && (MODE == 1 || tid < 128)) load_row(MODE == 0 ? n_begin * 128 + tid : o0 + r, lse_nx, dl_nx);
-    // a fully masked row (lse = -inf) has P = 0: exp2(s - inf)
-    const float nl_own = lse_nx == -INFINITY ? -INFINITY : -lse_nx * kMLog2e, nds_own = -dl_nx * P.scale;   // mode 1
+    float nl_own = -INFINITY, nds_own = 0.f;            // mode 1: the thread's own query
+    if (MODE == 1 && n_tiles > 0) {
+      const float* rd = reinterpret_cast<const float*>(rowdata + ((o0 + r) >> 1)) + (r & 1);
+      nl_own = __ldg(rd); nds_own = __ldg(rd + 2);
+    }
     for (int n = 0; n < n_tiles; ++n) {
       const int t0 = MODE == 0 ? (n_begin + n) * 128 : o0, s0 = MODE == 0 ? o0 : (n_begin + n) * 128;
-      const float4* row = sRow + (n & 1) * 64 + hh * 16;
-      if (MODE == 0) {
-        if (tid < 128) {
-          float* dst = reinterpret_cast<float*>(sRow + (n & 1) * 64 + (tid >> 1)) + (tid & 1);
-          dst[0] = lse_nx == -INFINITY ? -INFINITY : -lse_nx * kMLog2e;
-          dst[2] = -dl_nx * P.scale;
-          if (n + 1 < n_tiles) load_row(t0 + 128 + tid, lse_nx, dl_nx);
-        }
-        named_bar_sync(1, kMComputeWarpsB * 32);        // also: everybody has finished reading the buffer of block n - 1
-      }
+      const float4* row = sRow + (n % kMStagesB) * 64 + (col0 >> 1);
       const bool masked = tile_needs_mask(P, t0, s0);
+      if (MODE == 0) mbar_wait(&full[n % kMStagesB], (n / kMStagesB) & 1);   // the row data came with the tile (long complete: one test)
       mbar_wait(s_full, n & 1);
       tcgen05_fence_after();
       uint32_t vs[32], vd[32];
-      tmem_ld_32x32b_x32(tS + lane_base + hh * 32, vs);
-      tmem_ld_32x32b_x32(tdP + lane_base + hh * 32, vd);
+      tmem_ld_32x32b_x32(tS, vs);
+      tmem_ld_32x32b_x32(tdP, vd);
       tmem_ld_wait();
       tcgen05_fence_before();
       mbar_arrive_warp(sdp_free);
@@ -578,7 +596,7 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
       if (masked) {                                   // rare blocks: fold scale and mask into vs (kept out of the main loop:
 #pragma unroll                                        //  a branch per element defeated the instruction prefetch)
         for (int e = 0; e < 32; ++e) {
-          const int col = hh * 32 + e;
+          const int col = col0 + e;
           const float mt = MODE == 0 ? mask_term(P, t0 + col, s0 + r) : mask_term(P, t0 + r, s0 + col);
           vs[e] = __float_as_uint(fmaf(__uint_as_float(vs[e]), sc, mt));
         }
@@ -604,21 +622,21 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
         mbar_wait(ps_free, (n - 1) & 1);
         tcgen05_fence_after();
       }
-      tmem_st_32x32b_x16(tdS + lane_base + hh * 16, dd);
-      if (MODE == 0) tmem_st_32x32b_x16(tP + lane_base + hh * 16, pp);
+      tmem_st_32x32b_x16(tdS + lane_base + (col0 >> 1), dd);
+      if (MODE == 0) tmem_st_32x32b_x16(tP + lane_base + (col0 >> 1), pp);
       tmem_st_wait();
       tcgen05_fence_before();
       mbar_arrive_warp(ps_ready);
     }
-    // ---- epilogue: the accumulators -> bf16 rows (panel 0's warps: dV / dQ, panel 1's: dK)
+    // ---- epilogue: the accumulators -> bf16 rows (warps 0-3: dV / dQ, warps 4-7: dK)
     const int orow = o0 + r;
     const int limit = MODE == 0 ? P.S : P.T;
+    const int which = warp >> 2;
     if (n_tiles > 0) {
       mbar_wait(acc_done, 0);
       tcgen05_fence_after();
     }
-    if (hh < (MODE == 0 ? 2 : 1)) {
-      const int which = hh;
+    if (which < (MODE == 0 ? 2 : 1)) {
       __nv_bfloat16* base = MODE == 0 ? (which == 0 ? P.dv : P.dk) : P.dq;
       const long long st = MODE == 0 ? (which == 0 ? P.dv_st : P.dk_st) : P.dq_st, sb = MODE == 0 ? (which == 0 ? P.dv_sb : P.dk_sb) : P.dq_sb;
 #pragma unroll
@@ -716,7 +734,7 @@ int mha_fwd(const mmn_mha_desc* d, const void* q, const void* k, const void* v, 
 
 template <int D, int MODE>
 static int mha_bwd_launch(const MhaParams& P, cudaStream_t st) {
-  constexpr size_t smem = 1024 + (size_t)(2 + 2 * kMStagesB) * D * 256 + 128 * 16 + 16 * 8 + 16;
+  constexpr size_t smem = 1024 + (size_t)(2 + 2 * kMStagesB) * D * 256 + kMStagesB * 64 * 16 + (2 * kMStagesB + 6) * 8 + 16;
   static std::once_flag once;
   std::call_once(once, [] { cudaFuncSetAttribute(mha_bwd_tc_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
   dim3 grid(((MODE == 0 ? P.S : P.T) + 127) / 128, P.nH, P.B);
@@ -739,19 +757,22 @@ int mha_bwd(const mmn_mha_desc* d, const void* q, const void* k, const void* v, 
     return MMN_ERR_CUDA;
   }
   P.lse = const_cast<float*>(lse);
-  P.delta = workspace;
+  P.rowdata = workspace;
+  P.Tpad = (P.T + 127) / 128 * 128;
   P.dq = static_cast<__nv_bfloat16*>(dq); P.dk = static_cast<__nv_bfloat16*>(dk); P.dv = static_cast<__nv_bfloat16*>(dv);
   P.dq_st = d->dq_stride_t; P.dq_sb = d->dq_stride_b; P.dk_st = d->dk_stride_t; P.dk_sb = d->dk_stride_b;
   P.dv_st = d->dv_stride_t; P.dv_sb = d->dv_stride_b;
-  const long long n = (long long)P.B * P.nH * P.T;
+  const long long n = (long long)P.B * P.nH * P.Tpad * (D / 8);
   const unsigned blocks = (unsigned)((n + 255) / 256);
   if (D == 32)
-    mha_delta_kernel<32><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(out), d->o_stride_t, d->o_stride_b,
-                                                 static_cast<const __nv_bfloat16*>(dout), d->do_stride_t, d->do_stride_b, P.T, P.B, P.nH, workspace);
+    mha_rowdata_kernel<32><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(out), d->o_stride_t, d->o_stride_b,
+                                                   static_cast<const __nv_bfloat16*>(dout), d->do_stride_t, d->do_stride_b, lse, P.T, P.Tpad,
+                                                   P.B, P.nH, P.scale, workspace);
   else
-    mha_delta_kernel<64><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(out), d->o_stride_t, d->o_stride_b,
-                                                 static_cast<const __nv_bfloat16*>(dout), d->do_stride_t, d->do_stride_b, P.T, P.B, P.nH, workspace);
-  if (cudaGetLastError() != cudaSuccess) { snprintf(err, errlen, "mha_delta_kernel launch failed"); return MMN_ERR_CUDA; }
+    mha_rowdata_kernel<64><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(out), d->o_stride_t, d->o_stride_b,
+                                                   static_cast<const __nv_bfloat16*>(dout), d->do_stride_t, d->do_stride_b, lse, P.T, P.Tpad,
+                                                   P.B, P.nH, P.scale, workspace);
+  if (cudaGetLastError() != cudaSuccess) { snprintf(err, errlen, "mha_rowdata_kernel launch failed"); return MMN_ERR_CUDA; }
   ++*launches;
   int rc = D == 32 ? mha_bwd_launch<32, 0>(P, st) : mha_bwd_launch<64, 0>(P, st);
   if (!rc) { ++*launches; rc = D == 32 ? mha_bwd_launch<32, 1>(P, st) : mha_bwd_launch<64, 1>(P, st); }

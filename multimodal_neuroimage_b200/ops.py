@@ -294,7 +294,7 @@ def mha_bwd(dout: Tensor, q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor
     d.dq_stride_t, d.dq_stride_b = _tb_strides(dq)
     d.dk_stride_t, d.dk_stride_b = _tb_strides(dk)
     d.dv_stride_t, d.dv_stride_b = _tb_strides(dv)
-    ws = lse.new_empty(2 * lse.numel())
+    ws = lse.new_empty(2 * lse.shape[0] * ((lse.shape[1] + 127) // 128 * 128))      # row data per query, padded to whole tiles
     with _timed("mha_bwd", q):
         _lib.check(lib.mmn_mha_bwd(C.byref(d), _ptr(q), _ptr(k), _ptr(v), _ptr(mask), _ptr(out), _ptr(lse), _ptr(dout),
                                    _ptr(dq), _ptr(dk), _ptr(dv), _ptr(ws), q.device.index, _stream(q)), "mmn_mha_bwd")
