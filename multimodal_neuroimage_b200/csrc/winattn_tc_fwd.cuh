@@ -86,16 +86,16 @@ __device__ __forceinline__ void trace_stamp(const TraceCfg& t, int role, int ite
 __device__ __forceinline__ void trace_cta_time(const TraceCfg& t, int which) {
   if (t.buf && threadIdx.x == 0 && blockIdx.x < 1024) t.buf[kTraceCtaOfs + 2 * blockIdx.x + which] = global_ns();
 }
-// Backward kernel: compiled in only with -DMMN_TC_TRACING (MMN_BUILD_TRACE=1); it costs that kernel 20 %.
+// Both kernels: the stamps are compiled in only with -DMMN_TC_TRACING (tools/build_variant.sh trace winattn_tc -DMMN_TC_TRACING,
+// then MMN_LIB=<that build> tools/trace_{fwd,bwd}.py); they cost the backward 20 % and the forward 7 %.  (Round 1's forward
+// kept them in production because its never-taken branches happened to stop ptxas from interleaving the softmax phases;
+// with the current phase structure the build without them is the faster one: 0.182 -> 0.170 ms at BASELINE cfg2.)
 __device__ __forceinline__ void trace_ev(const TraceCfg& trace, int role, int item, int ev) {
 #ifdef MMN_TC_TRACING
   trace_stamp(trace, role, item, ev);
 #endif
 }
-// Forward kernel: always compiled in.  The (never taken, when not tracing) branches are phase boundaries that
-// keep ptxas from interleaving the softmax phases; measured on B200 at BASELINE cfg2, the forward runs
-// 0.30 ms with them and 0.37 ms without.
-__device__ __forceinline__ void trace_evf(const TraceCfg& trace, int role, int item, int ev) { trace_stamp(trace, role, item, ev); }
+__device__ __forceinline__ void trace_evf(const TraceCfg& trace, int role, int item, int ev) { trace_ev(trace, role, item, ev); }
 
 // sum of squares of one 64-byte bf16 row.  `row` = the row's index in its tile: chunk c is read at its
 // swizzled place, which also spreads the lanes of a warp over all banks (plain order is a 4-way conflict).
