@@ -27,6 +27,7 @@ train   BASELINE configs[2] ("cfg3") inside the same line: a full bf16 training 
 from __future__ import annotations
 
 import argparse
+import atexit
 import json
 import math
 import os
@@ -74,9 +75,14 @@ class ClockSampler:
                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
+            atexit.register(self._kill)         # never leave the sampler behind if the bench dies in between
         except Exception:
             self.proc = None
         return self
+
+    def _kill(self):
+        if self.proc is not None and self.proc.poll() is None:
+            self.proc.kill()
 
     def _read(self):
         for line in self.proc.stdout:
@@ -723,8 +729,10 @@ def main():
         except Exception as exc:                   # capture not possible in this environment: eager timing
             print(f"bench: CUDA graph capture failed ({type(exc).__name__}: {exc}); timing eager launches", file=sys.stderr)
             torch.cuda.synchronize()
-    with ClockSampler(local) as clk:
-        ms, _, _ = timed(step_fn, args.steps)
+    # clocks / throttle reasons are sampled from here to the end of the nested training step: every timed region of the line
+    clk = ClockSampler(local)
+    clk.__enter__()
+    ms, _, _ = timed(step_fn, args.steps)
     e2e_prepare()
     for _ in range(2):
         step_e2e()
@@ -779,6 +787,7 @@ def main():
         except Exception as exc:
             train = {"error": f"{type(exc).__name__}: {exc}"}
             print(f"bench: nested cfg3 training step failed: {train['error']}", file=sys.stderr)
+    clk.__exit__(None, None, None)
     eager = None
     if rank == 0 and not args.no_eager_baseline:
         try:

@@ -20,6 +20,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "dropout_rng.cuh"
+
 namespace mmn {
 
 constexpr int kGenericThreads = 128;
@@ -35,6 +37,7 @@ struct GenericProblem {
   int mask_kind, mask_diag, mask_windows;
   float scale, dropout_p;
   unsigned long long seed, offset;
+  DropoutCfg drop;                // the mask generator's constants (make_dropout(dropout_p, seed, offset))
   const float* bias;              // (nH, nq, nk) or null
   const float* head_scale;        // (nH) when cosine
   const float* mask;              // MMN_MASK_TENSOR
@@ -76,26 +79,11 @@ __device__ __forceinline__ long long row_offset(const GenericProblem& P, int ite
   return (long long)row * s0 + (long long)outer * s1 + (long long)h * P.d;
 }
 
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x, hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-    k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
-  }
-  return c;
-}
-
-// Dropout keep-scale for probability (item, i, j): 0 or 1/(1-p).  Counter-based, so the
-// forward and both backward kernels regenerate the same mask without storing it.
+// Dropout keep-scale for probability (item, i, j): 0 or 1/(1-p).  Counter-based (dropout_rng.cuh), so the
+// forward and both backward kernels -- and the tensor-core MHA kernels -- regenerate the same mask without storing it.
 __device__ __forceinline__ float keep_scale(const GenericProblem& P, int item, int i, int j) {
   if (P.dropout_p <= 0.f) return 1.f;
-  uint4 c = make_uint4((uint32_t)j, (uint32_t)i, (uint32_t)item, (uint32_t)P.offset);
-  uint2 k = make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32) ^ (uint32_t)(P.offset >> 32));
-  uint32_t r = philox4x32_10(c, k).x;
-  float u = (float)(r >> 8) * (1.0f / 16777216.0f);
-  return u >= P.dropout_p ? 1.f / (1.f - P.dropout_p) : 0.f;
+  return dropout_keep(P.drop, item, i, j) ? P.drop.inv_keep : 0.f;
 }
 
 // Logit for (i, j) from the raw dot product.

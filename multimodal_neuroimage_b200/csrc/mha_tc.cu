@@ -2,7 +2,8 @@
 // softmax, bmm) on the Blackwell tensor cores, flash style: nothing T x S ever reaches HBM.
 //
 // Tuned shapes: bf16, head_dim 32 or 64, any T / S / batch / heads, masks NONE / FUTURE (generated from indices,
-// crossmodal_transformer.py:179-186) / TENSOR ((T,S) additive fp32).  q, k, v, out are addressed in place in the reference's
+// crossmodal_transformer.py:179-186) / TENSOR ((T,S) additive fp32), attention dropout (multihead_attention.py:123; DROP
+// instantiations: the mask is regenerated from (seed, offset, item, t, s) by every kernel, dropout_rng.cuh).  q, k, v, out are addressed in place in the reference's
 // (len, batch, embed) layout (row strides from the descriptor: q/k/v may be column slices of one packed projection), through
 // 4-D tensor maps (element-in-panel, row, 32-channel panel, batch) whose boxes land as 64B-swizzled [panel][128 rows][64 B]
 // tiles -- the K-major operand of Q K^T and, read transposed (MN-major), the operand of P V, dS^T Q, P^T dO and dS K alike.
@@ -20,6 +21,7 @@
 #include <cstdio>
 #include <mutex>
 
+#include "dropout_rng.cuh"
 #include "tc_window.cuh"
 #include "winattn_tc.h"
 
@@ -44,6 +46,7 @@ struct MhaParams {
   const float* mask;                           // (T, S) additive, MMN_MASK_TENSOR
   __nv_bfloat16* out; long long o_st, o_sb;    // forward output rows (t, b): out + t * o_st + b * o_sb + h * D
   float* lse;                                  // (B * nH, T) natural-log log-sum-exp
+  DropoutCfg drop;                             // attention dropout (dropout_rng.cuh); thr == 0: none
   const float* rowdata; int Tpad;              // backward: (B * nH, Tpad / 2, 4) per query pair {-lse2, -lse2, -delta scale, -delta scale}
   __nv_bfloat16 *dq, *dk, *dv;                 // backward outputs
   long long dq_st, dq_sb, dk_st, dk_sb, dv_st, dv_sb;
@@ -132,7 +135,7 @@ __device__ __forceinline__ void exp2_pair(uint64_t x2, int e, float& e0, float& 
 // once -- Q K^T of the next key tile is issued while this one's exponentials are computed.  O accumulates in TMEM over all
 // key tiles (the MMA's accumulate flag); it is rescaled only when a row's maximum grows by more than 2^tau since the last
 // rescale (P then stays <= 2^tau, exact in fp32 / fine in bf16), which after the first key tiles practically never happens.
-template <int D>
+template <int D, bool DROP>
 __global__ void __launch_bounds__(kMThreads, 1)
 mha_fwd_tc_kernel(const __grid_constant__ MhaParams P) {
   constexpr int kTileB = D * 256;                       // 128 rows x D bf16
@@ -333,6 +336,11 @@ mha_fwd_tc_kernel(const __grid_constant__ MhaParams P) {
         float x0, x1;
         exp2_pair<MMN_MHA_POLY_FWD>(fma2(pk2u(v[2 * e], v[2 * e + 1]), a2, nm2), e, x0, x1);
         rs2[e & 1] = add2(rs2[e & 1], pk2(x0, x1));
+        if (DROP) {                                   // dropped probabilities leave the row sum untouched, not P V; 1 / (1 - p) is folded into 1 / l
+          const uint4 rr = dropout_block(P.drop, b * P.nH + h, t >> 1, (s0 >> 1) + e);
+          if (!dropout_keep_word((t & 1) ? rr.z : rr.x, P.drop.thr)) x0 = 0.f;
+          if (!dropout_keep_word((t & 1) ? rr.w : rr.y, P.drop.thr)) x1 = 0.f;
+        }
         pk[e] = pack_bf16x2(x0, x1);
       }
       if (j > 0 && !pv_waited) {                      // P V(j - 1) has read the P buffer
@@ -356,7 +364,7 @@ mha_fwd_tc_kernel(const __grid_constant__ MhaParams P) {
       mbar_wait(&pv_done[g], (n_tiles - 1) & 1);
       tcgen05_fence_after();
     }
-    const float inv = l > 0.f ? __frcp_rn(l) : 0.f;
+    const float inv = l > 0.f ? __frcp_rn(l) * (DROP ? P.drop.inv_keep : 1.f) : 0.f;
     uint4* dst = reinterpret_cast<uint4*>(P.out + (long long)t * P.o_st + (long long)b * P.o_sb + h * D);
 #pragma unroll
     for (int c = 0; c < D / 32; ++c) {
@@ -452,7 +460,7 @@ __global__ void mha_rowdata_kernel(const __nv_bfloat16* __restrict__ o, long lon
 // an N64 MMA reads 6 KB per 32 tensor cycles, 192 B/clk against the SM's 128 B/clk, and per block the operand reads of the
 // seven GEMMs plus the TMA writes already add up to ~1000 shared-memory cycles, as many as the tensor and MUFU pipes need.)
 // TMEM columns: S 0 | dP 128 | accumulators 256 (dV or dQ), 256 + D (dK) | P 384 | dS 448.   576 threads x 96 registers.
-template <int D, int MODE>
+template <int D, int MODE, bool DROP>
 __global__ void __launch_bounds__(kMThreadsB, 1)
 mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
   constexpr int kTileB = D * 256;
@@ -602,7 +610,8 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
         }
         a_mul = 1.f;
       }
-      const uint64_t a2 = pk2(a_mul, a_mul), sc2 = pk2(P.scale, P.scale);
+      const float scd = DROP ? P.scale * P.drop.inv_keep : P.scale;
+      const uint64_t a2 = pk2(a_mul, a_mul), sc2 = pk2(scd, scd);
       uint32_t pp[16], dd[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
@@ -615,7 +624,25 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
         }
         float x0, x1;
         exp2_pair<MMN_MHA_POLY_BWD>(fma2(pk2u(vs[2 * e], vs[2 * e + 1]), a2, nl2), e, x0, x1);
-        pp[e] = pack_bf16x2(x0, x1);
+        if (DROP) {
+          // the forward's mask: dP of a dropped probability is 0, of a kept one dP / (1 - p) (sc2 carries the factor); P^T dO
+          // uses the dropped P (its 1 / (1 - p) is applied to dV in the epilogue)
+          bool k0, k1;
+          if (MODE == 0) {                            // lane = key, the pair = two queries of one block row pair
+            const uint4 rr = dropout_block(P.drop, (int)item, ((t0 + col0) >> 1) + e, (s0 + r) >> 1);
+            const bool odd = (s0 + r) & 1;
+            k0 = dropout_keep_word(odd ? rr.y : rr.x, P.drop.thr); k1 = dropout_keep_word(odd ? rr.w : rr.z, P.drop.thr);
+          } else {                                    // lane = query, the pair = two keys
+            const uint4 rr = dropout_block(P.drop, (int)item, (t0 + r) >> 1, ((s0 + col0) >> 1) + e);
+            const bool odd = (t0 + r) & 1;
+            k0 = dropout_keep_word(odd ? rr.z : rr.x, P.drop.thr); k1 = dropout_keep_word(odd ? rr.w : rr.y, P.drop.thr);
+          }
+          if (!k0) vd[2 * e] = 0u;
+          if (!k1) vd[2 * e + 1] = 0u;
+          pp[e] = pack_bf16x2(k0 ? x0 : 0.f, k1 ? x1 : 0.f);
+        } else {
+          pp[e] = pack_bf16x2(x0, x1);
+        }
         dd[e] = pack_bf16x2(mul2(pk2(x0, x1), fma2(pk2u(vd[2 * e], vd[2 * e + 1]), sc2, nds2)));
       }
       if (n > 0) {                                    // the gradient MMAs of the previous block have read P / dS
@@ -648,6 +675,10 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
         } else {
 #pragma unroll
           for (int e = 0; e < 32; ++e) v[e] = 0u;
+        }
+        if (DROP && MODE == 0 && which == 0) {         // dV = (P_drop / (1 - p))^T dO
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * P.drop.inv_keep);
         }
         if (orow < limit) {
           uint4* dst = reinterpret_cast<uint4*>(base + (long long)orow * st + (long long)b * sb + h * D + c * 32);
@@ -687,7 +718,6 @@ static bool aligned(const void* p, long long st, long long sb) {
 const char* mha_why_not(const mmn_mha_desc* d, bool backward) {
   if (d->io_dtype != MMN_DT_BF16) return "io dtype is not bf16";
   if (d->head_dim != 32 && d->head_dim != 64) return "head_dim is not 32 or 64";
-  if (d->dropout_p > 0.f) return "attention dropout is only implemented in the generic path";
   if (d->q_stride_t % 8 || d->q_stride_b % 8 || d->k_stride_t % 8 || d->k_stride_b % 8 || d->v_stride_t % 8 || d->v_stride_b % 8 ||
       d->o_stride_t % 8 || d->o_stride_b % 8)
     return "row strides not 16-byte aligned";
@@ -702,15 +732,16 @@ const char* mha_why_not(const mmn_mha_desc* d, bool backward) {
 static void fill_common(MhaParams& P, const mmn_mha_desc* d, const float* mask) {
   P.T = d->tgt_len; P.S = d->src_len; P.B = d->batch; P.nH = d->num_heads;
   P.mask_kind = d->mask_kind; P.mask_diag = d->mask_diagonal; P.scale = d->scale; P.mask = mask;
+  P.drop = make_dropout(d->dropout_p, d->seed, d->offset);
 }
 
-template <int D>
+template <int D, bool DROP>
 static int mha_fwd_launch(const MhaParams& P, cudaStream_t st) {
   constexpr size_t smem = 1024 + (size_t)(2 + 2 * kMStagesF) * D * 256 + 24 * 8 + 16;
   static std::once_flag once;
-  std::call_once(once, [] { cudaFuncSetAttribute(mha_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+  std::call_once(once, [] { cudaFuncSetAttribute(mha_fwd_tc_kernel<D, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
   dim3 grid((P.T + 255) / 256, P.nH, P.B);
-  mha_fwd_tc_kernel<D><<<grid, kMThreads, smem, st>>>(P);
+  mha_fwd_tc_kernel<D, DROP><<<grid, kMThreads, smem, st>>>(P);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
@@ -726,19 +757,21 @@ int mha_fwd(const mmn_mha_desc* d, const void* q, const void* k, const void* v, 
     return MMN_ERR_CUDA;
   }
   P.out = static_cast<__nv_bfloat16*>(out); P.o_st = d->o_stride_t; P.o_sb = d->o_stride_b; P.lse = lse;
-  const int rc = D == 32 ? mha_fwd_launch<32>(P, st) : mha_fwd_launch<64>(P, st);
+  const bool drop = P.drop.thr != 0;
+  const int rc = D == 32 ? (drop ? mha_fwd_launch<32, true>(P, st) : mha_fwd_launch<32, false>(P, st))
+                         : (drop ? mha_fwd_launch<64, true>(P, st) : mha_fwd_launch<64, false>(P, st));
   if (rc) { snprintf(err, errlen, "mha_fwd_tc_kernel: %s", cudaGetErrorString(cudaGetLastError())); return MMN_ERR_CUDA; }
   ++*launches;
   return MMN_OK;
 }
 
-template <int D, int MODE>
+template <int D, int MODE, bool DROP>
 static int mha_bwd_launch(const MhaParams& P, cudaStream_t st) {
   constexpr size_t smem = 1024 + (size_t)(2 + 2 * kMStagesB) * D * 256 + kMStagesB * 64 * 16 + (2 * kMStagesB + 6) * 8 + 16;
   static std::once_flag once;
-  std::call_once(once, [] { cudaFuncSetAttribute(mha_bwd_tc_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+  std::call_once(once, [] { cudaFuncSetAttribute(mha_bwd_tc_kernel<D, MODE, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
   dim3 grid(((MODE == 0 ? P.S : P.T) + 127) / 128, P.nH, P.B);
-  mha_bwd_tc_kernel<D, MODE><<<grid, kMThreadsB, smem, st>>>(P);
+  mha_bwd_tc_kernel<D, MODE, DROP><<<grid, kMThreadsB, smem, st>>>(P);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
@@ -774,8 +807,14 @@ int mha_bwd(const mmn_mha_desc* d, const void* q, const void* k, const void* v, 
                                                    P.B, P.nH, P.scale, workspace);
   if (cudaGetLastError() != cudaSuccess) { snprintf(err, errlen, "mha_rowdata_kernel launch failed"); return MMN_ERR_CUDA; }
   ++*launches;
-  int rc = D == 32 ? mha_bwd_launch<32, 0>(P, st) : mha_bwd_launch<64, 0>(P, st);
-  if (!rc) { ++*launches; rc = D == 32 ? mha_bwd_launch<32, 1>(P, st) : mha_bwd_launch<64, 1>(P, st); }
+  const bool drop = P.drop.thr != 0;
+  int rc = D == 32 ? (drop ? mha_bwd_launch<32, 0, true>(P, st) : mha_bwd_launch<32, 0, false>(P, st))
+                   : (drop ? mha_bwd_launch<64, 0, true>(P, st) : mha_bwd_launch<64, 0, false>(P, st));
+  if (!rc) {
+    ++*launches;
+    rc = D == 32 ? (drop ? mha_bwd_launch<32, 1, true>(P, st) : mha_bwd_launch<32, 1, false>(P, st))
+                 : (drop ? mha_bwd_launch<64, 1, true>(P, st) : mha_bwd_launch<64, 1, false>(P, st));
+  }
   if (rc) { snprintf(err, errlen, "mha_bwd_tc_kernel: %s", cudaGetErrorString(cudaGetLastError())); return MMN_ERR_CUDA; }
   ++*launches;
   return MMN_OK;

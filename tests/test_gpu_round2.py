@@ -565,6 +565,46 @@ def test_mha_tensor_core_matches_generic_at_scale(mm):
         assert rel_err(res["tc"][i], res["gen"][i]) < BF16_TOL, n
 
 
+@pytest.mark.parametrize("d,nH,T,S,B,mask_kind", [(64, 3, 256, 256, 2, "none"), (64, 2, 300, 421, 1, "future"),
+                                                    (32, 4, 257, 130, 2, "tensor"), (32, 2, 128, 512, 3, "future")], ids=lambda v: str(v))
+def test_mha_tensor_core_dropout_matches_generic(mm, d, nH, T, S, B, mask_kind):
+    """Attention dropout on the tcgen05 path (multihead_attention.py:123; main.py's default attn_dropout is 0.1): the mask is a
+    pure function of (seed, offset, item, t, s) shared with the generic kernels (dropout_rng.cuh), so the tensor-core forward and
+    both backward kernels must reproduce the generic fp32-arithmetic kernels' outputs and gradients on the same bf16 inputs
+    -- element for element the same probabilities dropped -- and the keep rate must be 1 - p."""
+    E, p, seed, off = d * nH, 0.3, 1234, 77
+    g = torch.Generator(device="cuda").manual_seed(T + S)
+    q, k, v = (torch.randn(n, B, E, device="cuda", generator=g).bfloat16() for n in (T, S, S))
+    cot = torch.randn(T, B, E, device="cuda", generator=g).bfloat16()
+    kind = {"none": mm.lib.MASK_NONE, "future": mm.lib.MASK_FUTURE, "tensor": mm.lib.MASK_TENSOR}[mask_kind]
+    diag = 1 + abs(S - T) if mask_kind == "future" else 0
+    mk = None
+    if mask_kind == "tensor":
+        mk = torch.randn(T, S, device="cuda", generator=g) * 2
+        mk[torch.rand(T, S, device="cuda", generator=g) < 0.2] = float("-inf")
+        mk[:, 0] = 0.0
+    dsc = mm.lib.MhaDesc()
+    dsc.tgt_len, dsc.src_len, dsc.batch, dsc.num_heads, dsc.head_dim, dsc.io_dtype = T, S, B, nH, d, mm.lib.DT_BF16
+    dsc.dropout_p = p
+    dsc.q_stride_t, dsc.q_stride_b = q.stride(0), q.stride(1)
+    assert mm.lib.load().mmn_mha_path(dsc).decode() == "tcgen05"
+    res = {}
+    for name, dt in (("tc", torch.bfloat16), ("gen", torch.float32)):
+        ins = [t.to(dt).requires_grad_(True) for t in (q, k, v)]
+        out, lse = torch.ops.mmn_b200.mha_fwd(*ins, mk, nH, kind, diag, d ** -0.5, p, seed, off)
+        gs = torch.autograd.grad((out.float() * cot.float()).sum(), ins)
+        res[name] = [out.float(), lse] + [x.float() for x in gs]
+    for i, n in enumerate(("out", "lse", "dq", "dk", "dv")):
+        assert rel_err(res["tc"][i], res["gen"][i]) < BF16_TOL, n
+    # a different offset is a different mask; p = 0 differs from both
+    out2, _ = torch.ops.mmn_b200.mha_fwd(q, k, v, mk, nH, kind, diag, d ** -0.5, p, seed, off + 1)
+    out0, _ = torch.ops.mmn_b200.mha_fwd(q, k, v, mk, nH, kind, diag, d ** -0.5, 0.0, 0, 0)
+    assert rel_err(out2.float(), res["tc"][0]) > 0.05 and rel_err(out0.float(), res["tc"][0]) > 0.05
+    if mask_kind == "none":                                # keep rate through the head-averaged weights (generic kernel, same mask)
+        avg = torch.ops.mmn_b200.mha_avg_weights(q.float(), k.float(), None, res["gen"][1], nH, kind, diag, d ** -0.5, p, seed, off)
+        assert abs(avg.sum(-1).mean().item() - 1.0) < 0.02
+
+
 def test_parallel_branches_match_serial(mm):
     """fused.parallel: the two modalities' independent groups on two streams (eager and under CUDA-graph capture) give the
     serial result -- outputs and every gradient."""
