@@ -466,6 +466,7 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="cfg2 line without the nested cfg3 training step")
     ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--train-steps", type=int, default=10)
+    ap.add_argument("--sustain-s", type=float, default=2.0, help="also time the step back to back for this many seconds (0: skip)")
     ap.add_argument("--train-batch", type=int, default=0, help="per-GPU batch of the training-step workload (0: its default)")
     ap.add_argument("--ddp", default="flat", choices=["flat", "torch"],
                     help="gradient exchange of the training step: one all-reduce of the flat gradient buffer after a graph-replayed "
@@ -745,6 +746,14 @@ def main():
         raise RuntimeError(f"e2e pipeline output differs from the module call (rel err {chk:.2e})")
     ms_e2e, _, _ = timed(step_e2e, max(5, args.steps // 2))
 
+    # the K-step region is a burst of a few tens of milliseconds; the same step back to back for >= 2 s is the sustained
+    # number (clocks and power settle: VERDICT r1 weak #8).  Reported beside `value`, never instead of it.
+    sustained = None
+    if args.sustain_s > 0:
+        n_sus = max(args.steps, int(math.ceil(args.sustain_s * 1e3 / ms)))
+        ms_sus, _, _ = timed(step_fn, n_sus)
+        sustained = {"steps": n_sus, "seconds": n_sus * ms_sus * 1e-3, "ms_per_step": ms_sus}
+
     LAUNCH_MODE[0] = "cuda-graph replay of forward+backward" if graphed else "eager"
     windows = B * world * WINDOWS_PER_SAMPLE
     value = windows * FLOP_PER_WINDOW / (ms * 1e-3) / 1e12
@@ -805,6 +814,8 @@ def main():
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic", "config": workload_config(B, world),
                 "samples_per_s": B * world / (ms * 1e-3),
+                "sustained": None if sustained is None else dict(sustained, value=windows * FLOP_PER_WINDOW / (sustained["ms_per_step"] * 1e-3) / 1e12,
+                                                                 unit=UNIT, note="the same step back to back; value above is the K-step region"),
                 "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": 2 * B * L * C * elem,
                         "d2h_bytes_per_step": 2 * B * L * C * elem, "chunks": E2E_CHUNKS,
                         "note": "x, dy from pinned host memory; y, dx back to pinned host memory; 8 chunks through 3 streams and "

@@ -18,6 +18,7 @@
 //               mode dKdV: CTA = (128 keys, head, batch), query tiles stream;  dV += P^T dO,  dK += dS^T Q   (TMEM)
 //               mode dQ  : CTA = (128 queries, head, batch), key tiles stream; dQ += dS K                    (TMEM)
 //             delta = rowsum(dO o O) comes from a small pre-pass.  No atomics: deterministic.
+#include <algorithm>
 #include <cstdio>
 #include <mutex>
 
@@ -460,41 +461,58 @@ __global__ void mha_rowdata_kernel(const __nv_bfloat16* __restrict__ o, long lon
 // an N64 MMA reads 6 KB per 32 tensor cycles, 192 B/clk against the SM's 128 B/clk, and per block the operand reads of the
 // seven GEMMs plus the TMA writes already add up to ~1000 shared-memory cycles, as many as the tensor and MUFU pipes need.)
 // TMEM columns: S 0 | dP 128 | accumulators 256 (dV or dQ), 256 + D (dK) | P 384 | dS 448.   576 threads x 96 registers.
+// PERSISTENT: one CTA per SM walks the (resident tile, head, batch) items with stride gridDim.x.  All pipelines run on
+// across item boundaries -- the streamed-tile ring, the S / dP and P / dS hand-offs (running step counter g), the resident
+// tiles (double-buffered: the next item's K / V or Q / dO land while this item streams) -- so the only per-item cost left is
+// the accumulator read-out, and that overlaps the next item's first S / dP MMAs and loads (the gradient MMAs of the next
+// item wait for acc_free).  One CTA per item paid TMEM allocation, barrier setup, the resident loads' latency and the
+// drain of every item in the open: ~15 % at 16 streamed tiles per item.
+struct BwdItem { int o0, h, b, n_begin, n_tiles; };
+template <int MODE>
+__device__ __forceinline__ BwdItem bwd_item(const MhaParams& P, int w) {
+  const int n_ot = ((MODE == 0 ? P.S : P.T) + 127) >> 7;
+  BwdItem it;
+  const int ot = w % n_ot, hb = w / n_ot;
+  it.o0 = ot * 128; it.h = hb % P.nH; it.b = hb / P.nH;
+  int n_end;
+  if (MODE == 0) { it.n_begin = first_query_tile(P, it.o0); n_end = (P.T + 127) >> 7; }
+  else { it.n_begin = 0; n_end = visible_key_tiles(P, it.o0); }
+  it.n_tiles = max(0, n_end - it.n_begin);
+  return it;
+}
+
 template <int D, int MODE, bool DROP>
 __global__ void __launch_bounds__(kMThreadsB, 1)
 mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
   constexpr int kTileB = D * 256;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sR0 = smem;                                  // resident: K (mode 0) / Q (mode 1)
-  uint8_t* sR1 = sR0 + kTileB;                          // resident: V (mode 0) / dO (mode 1)
-  uint8_t* sS0 = sR1 + kTileB;                          // [kMStagesB] streamed: Q (mode 0) / K (mode 1)
+  uint8_t* sR = smem;                                   // [2][2] resident, double-buffered over items: K | V (mode 0) / Q | dO (mode 1)
+  uint8_t* sS0 = sR + 4 * kTileB;                       // [kMStagesB] streamed: Q (mode 0) / K (mode 1)
   uint8_t* sS1 = sS0 + kMStagesB * kTileB;              // [kMStagesB] streamed: dO (mode 0) / V (mode 1)
   float4* sRow = reinterpret_cast<float4*>(sS1 + kMStagesB * kTileB);   // mode 0: [kMStagesB][64] row data of the streamed queries
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRow + kMStagesB * 64);
-  uint64_t* r_full = bars;
-  uint64_t* full = bars + 1;                            // [kMStagesB]
+  uint64_t* r_full = bars;                              // [2]
+  uint64_t* r_empty = bars + 2;                         // [2] the item's S / dP MMAs have all read the resident tiles
+  uint64_t* full = bars + 4;                            // [kMStagesB]
   uint64_t* empty = full + kMStagesB;                   // [kMStagesB]
   uint64_t* s_full = empty + kMStagesB;                 // S and dP in TMEM
   uint64_t* sdp_free = s_full + 1;                      // ... and in the threads' registers (one arrival per compute warp)
   uint64_t* ps_ready = s_full + 2;                      // P / dS in TMEM (one arrival per compute warp)
   uint64_t* ps_free = s_full + 3;                       // the gradient MMAs have read them
-  uint64_t* acc_done = s_full + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 5);
+  uint64_t* acc_done = s_full + 4;                      // the item's last gradient MMAs have completed
+  uint64_t* acc_free = s_full + 5;                      // ... and the accumulators are in the epilogue warps' registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
+  constexpr int kEpiWarpsB = MODE == 0 ? 8 : 4;         // warps that read accumulators: dV, dK (mode 0) / dQ (mode 1)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int o0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;     // first key (mode 0) / query (mode 1) of this CTA
-  int n_begin, n_end;                                                   // streamed tiles
-  if (MODE == 0) { n_begin = first_query_tile(P, o0); n_end = (P.T + 127) >> 7; }
-  else { n_begin = 0; n_end = visible_key_tiles(P, o0); }
-  const int n_tiles = max(0, n_end - n_begin);
-  const long long item = (long long)b * P.nH + h;
-  const float4* rowdata = reinterpret_cast<const float4*>(P.rowdata) + item * (P.Tpad >> 1);
+  const int total = (((MODE == 0 ? P.S : P.T) + 127) >> 7) * P.nH * P.B;
 
   if (tid == 0) {
-    mbar_init(r_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&r_full[i], 1); mbar_init(&r_empty[i], 1); }
     for (int s = 0; s < kMStagesB; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(s_full, 1); mbar_init(sdp_free, kMComputeWarpsB); mbar_init(ps_ready, kMComputeWarpsB); mbar_init(ps_free, 1); mbar_init(acc_done, 1);
+    mbar_init(s_full, 1); mbar_init(sdp_free, kMComputeWarpsB); mbar_init(ps_ready, kMComputeWarpsB); mbar_init(ps_free, 1);
+    mbar_init(acc_done, 1); mbar_init(acc_free, kEpiWarpsB);
     fence_barrier_init();
   }
   if (warp == kMComputeWarpsB && lane == 0) { tma_prefetch_desc(&P.q); tma_prefetch_desc(&P.k); tma_prefetch_desc(&P.v); tma_prefetch_desc(&P.dout); }
@@ -507,32 +525,47 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
 
   if (warp >= kMComputeWarpsB) {
     if (warp == kMComputeWarpsB) {
-      if (elect_one() && n_tiles > 0) {
-        mbar_arrive_expect_tx(r_full, 2 * kTileB);
-        tma_load_4d(MODE == 0 ? &P.k : &P.q, r_full, sR0, 0, o0, h * (D / 32), b);
-        tma_load_4d(MODE == 0 ? &P.v : &P.dout, r_full, sR1, 0, o0, h * (D / 32), b);
-        for (int n = 0; n < n_tiles; ++n) {
-          const int s = n % kMStagesB, row0 = (n_begin + n) * 128;
-          mbar_wait(&empty[s], ((n / kMStagesB) & 1) ^ 1);
-          mbar_arrive_expect_tx(&full[s], 2 * kTileB + (MODE == 0 ? 1024 : 0));
-          tma_load_4d(MODE == 0 ? &P.q : &P.k, &full[s], sS0 + s * kTileB, 0, row0, h * (D / 32), b);
-          tma_load_4d(MODE == 0 ? &P.dout : &P.v, &full[s], sS1 + s * kTileB, 0, row0, h * (D / 32), b);
-          if (MODE == 0) bulk_load_1d(sRow + s * 64, rowdata + (row0 >> 1), 1024, &full[s]);
+      // ============================== TMA producer ==============================
+      if (elect_one()) {
+        int g = 0, ri = 0;                              // streamed tiles / items with work so far (this CTA)
+        for (int w = blockIdx.x; w < total; w += gridDim.x) {
+          const BwdItem it = bwd_item<MODE>(P, w);
+          if (it.n_tiles == 0) continue;
+          const int rb = ri & 1;
+          mbar_wait(&r_empty[rb], ((ri >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&r_full[rb], 2 * kTileB);
+          tma_load_4d(MODE == 0 ? &P.k : &P.q, &r_full[rb], sR + rb * 2 * kTileB, 0, it.o0, it.h * (D / 32), it.b);
+          tma_load_4d(MODE == 0 ? &P.v : &P.dout, &r_full[rb], sR + rb * 2 * kTileB + kTileB, 0, it.o0, it.h * (D / 32), it.b);
+          const float4* rowdata = reinterpret_cast<const float4*>(P.rowdata) + ((long long)it.b * P.nH + it.h) * (P.Tpad >> 1);
+          for (int n = 0; n < it.n_tiles; ++n, ++g) {
+            const int s = g % kMStagesB, row0 = (it.n_begin + n) * 128;
+            mbar_wait(&empty[s], ((g / kMStagesB) & 1) ^ 1);
+            mbar_arrive_expect_tx(&full[s], 2 * kTileB + (MODE == 0 ? 1024 : 0));
+            tma_load_4d(MODE == 0 ? &P.q : &P.k, &full[s], sS0 + s * kTileB, 0, row0, it.h * (D / 32), it.b);
+            tma_load_4d(MODE == 0 ? &P.dout : &P.v, &full[s], sS1 + s * kTileB, 0, row0, it.h * (D / 32), it.b);
+            if (MODE == 0) bulk_load_1d(sRow + s * 64, rowdata + (row0 >> 1), 1024, &full[s]);
+          }
+          ++ri;
         }
       }
     } else {
+      // ============================== MMA issuer ==============================
       constexpr uint32_t idescS = umma_idesc_bf16(128, 128, 0, 0);      // A = resident tile, B = streamed tile, both K-major
       constexpr uint32_t idescG = umma_idesc_bf16(128, D, 0, 1);        // A = P / dS (TMEM), B = streamed tile read MN-major
       const uint64_t dKm = umma_smem_desc(0, 0, 512, kSwz64);           // K-major
       const uint64_t dMn = umma_smem_desc(0, 8192, 512, kSwz64);        // MN-major, 32-wide panels 8 KB (128 rows) apart
-      const uint32_t r0 = smem_u32(sR0) >> 4, r1 = smem_u32(sR1) >> 4, s0b = smem_u32(sS0) >> 4, s1b = smem_u32(sS1) >> 4;
+      const uint32_t rbase = smem_u32(sR) >> 4, s0b = smem_u32(sS0) >> 4, s1b = smem_u32(sS1) >> 4;
       const uint32_t tS = tmem, tdP = tmem + 128;
-      auto issue_grad = [&](int n) {                                     // gradient MMAs of streamed tile n
-        const int s = n % kMStagesB;
-        mbar_wait(ps_ready, n & 1);
+      // gradient MMAs of step pg (deferred by one step so that the next S / dP run first); first / last: of their item
+      int pg = -1, p_ri = 0;
+      bool p_first = false, p_last = false;
+      auto issue_grad = [&]() {
+        const int s = pg % kMStagesB;
+        mbar_wait(ps_ready, pg & 1);
+        if (p_first && p_ri > 0) mbar_wait(acc_free, (p_ri - 1) & 1);   // the previous item's accumulators have been read out
         tcgen05_fence_after();
         if (elect_one()) {
-          const uint32_t acc = n > 0 ? 1u : 0u;
+          const uint32_t acc = p_first ? 0u : 1u;
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {                               // 16 streamed rows = 8 TMEM columns of P / dS per step
             if (MODE == 0) {
@@ -544,36 +577,44 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
           }
           umma_commit(ps_free);
           umma_commit(&empty[s]);
+          if (p_last) umma_commit(acc_done);
         }
         __syncwarp();
+        pg = -1;
       };
-      if (n_tiles > 0) mbar_wait(r_full, 0);
-      for (int n = 0; n < n_tiles; ++n) {
-        const int s = n % kMStagesB;
-        mbar_wait(&full[s], (n / kMStagesB) & 1);
-        if (n > 0) mbar_wait(sdp_free, (n - 1) & 1);                     // S(n - 1), dP(n - 1) are in registers
-        tcgen05_fence_after();
-        if (elect_one()) {
+      int g = 0, ri = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const BwdItem it = bwd_item<MODE>(P, w);
+        if (it.n_tiles == 0) continue;
+        const int rb = ri & 1;
+        const uint32_t r0 = rbase + rb * (2 * kTileB >> 4), r1 = r0 + (kTileB >> 4);
+        mbar_wait(&r_full[rb], (ri >> 1) & 1);
+        for (int n = 0; n < it.n_tiles; ++n, ++g) {
+          const int s = g % kMStagesB;
+          mbar_wait(&full[s], (g / kMStagesB) & 1);
+          if (g > 0) mbar_wait(sdp_free, (g - 1) & 1);                   // S, dP of the previous step are in registers
+          tcgen05_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < D / 16; ++ks) {
-            const uint32_t o = (ks >> 1) * (8192 >> 4) + (ks & 1) * 2;
-            umma_bf16_ss(tS, dKm + (r0 + o), dKm + (s0b + s * (kTileB >> 4) + o), idescS, ks > 0 ? 1u : 0u);      // S(^T) = R0 S0^T
-          }
+            for (int ks = 0; ks < D / 16; ++ks) {
+              const uint32_t o = (ks >> 1) * (8192 >> 4) + (ks & 1) * 2;
+              umma_bf16_ss(tS, dKm + (r0 + o), dKm + (s0b + s * (kTileB >> 4) + o), idescS, ks > 0 ? 1u : 0u);      // S(^T) = R0 S0^T
+            }
 #pragma unroll
-          for (int ks = 0; ks < D / 16; ++ks) {
-            const uint32_t o = (ks >> 1) * (8192 >> 4) + (ks & 1) * 2;
-            umma_bf16_ss(tdP, dKm + (r1 + o), dKm + (s1b + s * (kTileB >> 4) + o), idescS, ks > 0 ? 1u : 0u);     // dP(^T) = R1 S1^T
+            for (int ks = 0; ks < D / 16; ++ks) {
+              const uint32_t o = (ks >> 1) * (8192 >> 4) + (ks & 1) * 2;
+              umma_bf16_ss(tdP, dKm + (r1 + o), dKm + (s1b + s * (kTileB >> 4) + o), idescS, ks > 0 ? 1u : 0u);     // dP(^T) = R1 S1^T
+            }
+            umma_commit(s_full);
+            if (n == it.n_tiles - 1) umma_commit(&r_empty[rb]);          // the resident buffer can take the item after next
           }
-          umma_commit(s_full);
+          __syncwarp();
+          if (pg >= 0) issue_grad();
+          pg = g; p_ri = ri; p_first = n == 0; p_last = n == it.n_tiles - 1;
         }
-        __syncwarp();
-        if (n > 0) issue_grad(n - 1);
+        ++ri;
       }
-      if (n_tiles > 0) {
-        issue_grad(n_tiles - 1);
-        if (elect_one()) umma_commit(acc_done);
-        __syncwarp();
-      }
+      if (pg >= 0) issue_grad();
     }
   } else {
     // ============================== P / dS: thread = (resident row, one 32-column panel of the block) ==============================
@@ -581,115 +622,121 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t tS = tmem + lane_base + col0, tdP = tS + 128;
     const float sc = P.scale * kMLog2e;
-    float nl_own = -INFINITY, nds_own = 0.f;            // mode 1: the thread's own query
-    if (MODE == 1 && n_tiles > 0) {
-      const float* rd = reinterpret_cast<const float*>(rowdata + ((o0 + r) >> 1)) + (r & 1);
-      nl_own = __ldg(rd); nds_own = __ldg(rd + 2);
-    }
-    for (int n = 0; n < n_tiles; ++n) {
-      const int t0 = MODE == 0 ? (n_begin + n) * 128 : o0, s0 = MODE == 0 ? o0 : (n_begin + n) * 128;
-      const float4* row = sRow + (n % kMStagesB) * 64 + (col0 >> 1);
-      const bool masked = tile_needs_mask(P, t0, s0);
-      if (MODE == 0) mbar_wait(&full[n % kMStagesB], (n / kMStagesB) & 1);   // the row data came with the tile (long complete: one test)
-      mbar_wait(s_full, n & 1);
-      tcgen05_fence_after();
-      uint32_t vs[32], vd[32];
-      tmem_ld_32x32b_x32(tS, vs);
-      tmem_ld_32x32b_x32(tdP, vd);
-      tmem_ld_wait();
-      tcgen05_fence_before();
-      mbar_arrive_warp(sdp_free);
-      // P = exp2(s sc - lse), dS = P (dP - delta) scale  ->  bf16 pairs
-      float a_mul = sc;                               // logit (log2 domain) = vs * a_mul
-      if (masked) {                                   // rare blocks: fold scale and mask into vs (kept out of the main loop:
-#pragma unroll                                        //  a branch per element defeated the instruction prefetch)
-        for (int e = 0; e < 32; ++e) {
-          const int col = col0 + e;
-          const float mt = MODE == 0 ? mask_term(P, t0 + col, s0 + r) : mask_term(P, t0 + r, s0 + col);
-          vs[e] = __float_as_uint(fmaf(__uint_as_float(vs[e]), sc, mt));
-        }
-        a_mul = 1.f;
+    const int which = warp >> 2;                        // epilogue: warps 0-3 dV / dQ, warps 4-7 dK
+    int g = 0, ri = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const BwdItem itm = bwd_item<MODE>(P, w);
+      const int o0 = itm.o0, h = itm.h, b = itm.b, n_begin = itm.n_begin, n_tiles = itm.n_tiles;
+      const long long item = (long long)b * P.nH + h;
+      float nl_own = -INFINITY, nds_own = 0.f;          // mode 1: the thread's own query
+      if (MODE == 1 && n_tiles > 0) {
+        const float* rd = reinterpret_cast<const float*>(reinterpret_cast<const float4*>(P.rowdata) + item * (P.Tpad >> 1) + ((o0 + r) >> 1)) + (r & 1);
+        nl_own = __ldg(rd); nds_own = __ldg(rd + 2);
       }
-      const float scd = DROP ? P.scale * P.drop.inv_keep : P.scale;
-      const uint64_t a2 = pk2(a_mul, a_mul), sc2 = pk2(scd, scd);
-      uint32_t pp[16], dd[16];
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        uint64_t nl2, nds2;
-        if (MODE == 0) {
-          const float4 rw = row[e];                   // the pair's queries (broadcast read)
-          nl2 = pk2(rw.x, rw.y); nds2 = pk2(rw.z, rw.w);
-        } else {
-          nl2 = pk2(nl_own, nl_own); nds2 = pk2(nds_own, nds_own);
-        }
-        float x0, x1;
-        exp2_pair<MMN_MHA_POLY_BWD>(fma2(pk2u(vs[2 * e], vs[2 * e + 1]), a2, nl2), e, x0, x1);
-        if (DROP) {
-          // the forward's mask: dP of a dropped probability is 0, of a kept one dP / (1 - p) (sc2 carries the factor); P^T dO
-          // uses the dropped P (its 1 / (1 - p) is applied to dV in the epilogue)
-          bool k0, k1;
-          if (MODE == 0) {                            // lane = key, the pair = two queries of one block row pair
-            const uint4 rr = dropout_block(P.drop, (int)item, ((t0 + col0) >> 1) + e, (s0 + r) >> 1);
-            const bool odd = (s0 + r) & 1;
-            k0 = dropout_keep_word(odd ? rr.y : rr.x, P.drop.thr); k1 = dropout_keep_word(odd ? rr.w : rr.z, P.drop.thr);
-          } else {                                    // lane = query, the pair = two keys
-            const uint4 rr = dropout_block(P.drop, (int)item, (t0 + r) >> 1, ((s0 + col0) >> 1) + e);
-            const bool odd = (t0 + r) & 1;
-            k0 = dropout_keep_word(odd ? rr.z : rr.x, P.drop.thr); k1 = dropout_keep_word(odd ? rr.w : rr.y, P.drop.thr);
-          }
-          if (!k0) vd[2 * e] = 0u;
-          if (!k1) vd[2 * e + 1] = 0u;
-          pp[e] = pack_bf16x2(k0 ? x0 : 0.f, k1 ? x1 : 0.f);
-        } else {
-          pp[e] = pack_bf16x2(x0, x1);
-        }
-        dd[e] = pack_bf16x2(mul2(pk2(x0, x1), fma2(pk2u(vd[2 * e], vd[2 * e + 1]), sc2, nds2)));
-      }
-      if (n > 0) {                                    // the gradient MMAs of the previous block have read P / dS
-        mbar_wait(ps_free, (n - 1) & 1);
+      for (int n = 0; n < n_tiles; ++n, ++g) {
+        const int t0 = MODE == 0 ? (n_begin + n) * 128 : o0, s0 = MODE == 0 ? o0 : (n_begin + n) * 128;
+        const float4* row = sRow + (g % kMStagesB) * 64 + (col0 >> 1);
+        const bool masked = tile_needs_mask(P, t0, s0);
+        if (MODE == 0) mbar_wait(&full[g % kMStagesB], (g / kMStagesB) & 1);   // the row data came with the tile (long complete: one test)
+        mbar_wait(s_full, g & 1);
         tcgen05_fence_after();
-      }
-      tmem_st_32x32b_x16(tdS + lane_base + (col0 >> 1), dd);
-      if (MODE == 0) tmem_st_32x32b_x16(tP + lane_base + (col0 >> 1), pp);
-      tmem_st_wait();
-      tcgen05_fence_before();
-      mbar_arrive_warp(ps_ready);
-    }
-    // ---- epilogue: the accumulators -> bf16 rows (warps 0-3: dV / dQ, warps 4-7: dK)
-    const int orow = o0 + r;
-    const int limit = MODE == 0 ? P.S : P.T;
-    const int which = warp >> 2;
-    if (n_tiles > 0) {
-      mbar_wait(acc_done, 0);
-      tcgen05_fence_after();
-    }
-    if (which < (MODE == 0 ? 2 : 1)) {
-      __nv_bfloat16* base = MODE == 0 ? (which == 0 ? P.dv : P.dk) : P.dq;
-      const long long st = MODE == 0 ? (which == 0 ? P.dv_st : P.dk_st) : P.dq_st, sb = MODE == 0 ? (which == 0 ? P.dv_sb : P.dk_sb) : P.dq_sb;
+        uint32_t vs[32], vd[32];
+        tmem_ld_32x32b_x32(tS, vs);
+        tmem_ld_32x32b_x32(tdP, vd);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        mbar_arrive_warp(sdp_free);
+        // P = exp2(s sc - lse), dS = P (dP - delta) scale  ->  bf16 pairs
+        float a_mul = sc;                             // logit (log2 domain) = vs * a_mul
+        if (masked) {                                 // rare blocks: fold scale and mask into vs (kept out of the main loop:
+#pragma unroll                                        //  a branch per element defeated the instruction prefetch)
+          for (int e = 0; e < 32; ++e) {
+            const int col = col0 + e;
+            const float mt = MODE == 0 ? mask_term(P, t0 + col, s0 + r) : mask_term(P, t0 + r, s0 + col);
+            vs[e] = __float_as_uint(fmaf(__uint_as_float(vs[e]), sc, mt));
+          }
+          a_mul = 1.f;
+        }
+        const float scd = DROP ? P.scale * P.drop.inv_keep : P.scale;
+        const uint64_t a2 = pk2(a_mul, a_mul), sc2 = pk2(scd, scd);
+        uint32_t pp[16], dd[16];
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
-        uint32_t v[32];
+        for (int e = 0; e < 16; ++e) {
+          uint64_t nl2, nds2;
+          if (MODE == 0) {
+            const float4 rw = row[e];                 // the pair's queries (broadcast read)
+            nl2 = pk2(rw.x, rw.y); nds2 = pk2(rw.z, rw.w);
+          } else {
+            nl2 = pk2(nl_own, nl_own); nds2 = pk2(nds_own, nds_own);
+          }
+          float x0, x1;
+          exp2_pair<MMN_MHA_POLY_BWD>(fma2(pk2u(vs[2 * e], vs[2 * e + 1]), a2, nl2), e, x0, x1);
+          if (DROP) {
+            // the forward's mask: dP of a dropped probability is 0, of a kept one dP / (1 - p) (sc2 carries the factor); P^T dO
+            // uses the dropped P (its 1 / (1 - p) is applied to dV in the epilogue)
+            bool k0, k1;
+            if (MODE == 0) {                          // lane = key, the pair = two queries of one block row pair
+              const uint4 rr = dropout_block(P.drop, (int)item, ((t0 + col0) >> 1) + e, (s0 + r) >> 1);
+              const bool odd = (s0 + r) & 1;
+              k0 = dropout_keep_word(odd ? rr.y : rr.x, P.drop.thr); k1 = dropout_keep_word(odd ? rr.w : rr.z, P.drop.thr);
+            } else {                                  // lane = query, the pair = two keys
+              const uint4 rr = dropout_block(P.drop, (int)item, (t0 + r) >> 1, ((s0 + col0) >> 1) + e);
+              const bool odd = (t0 + r) & 1;
+              k0 = dropout_keep_word(odd ? rr.z : rr.x, P.drop.thr); k1 = dropout_keep_word(odd ? rr.w : rr.y, P.drop.thr);
+            }
+            if (!k0) vd[2 * e] = 0u;
+            if (!k1) vd[2 * e + 1] = 0u;
+            pp[e] = pack_bf16x2(k0 ? x0 : 0.f, k1 ? x1 : 0.f);
+          } else {
+            pp[e] = pack_bf16x2(x0, x1);
+          }
+          dd[e] = pack_bf16x2(mul2(pk2(x0, x1), fma2(pk2u(vd[2 * e], vd[2 * e + 1]), sc2, nds2)));
+        }
+        if (g > 0) {                                  // the gradient MMAs of the previous step have read P / dS
+          mbar_wait(ps_free, (g - 1) & 1);
+          tcgen05_fence_after();
+        }
+        tmem_st_32x32b_x16(tdS + lane_base + (col0 >> 1), dd);
+        if (MODE == 0) tmem_st_32x32b_x16(tP + lane_base + (col0 >> 1), pp);
+        tmem_st_wait();
+        tcgen05_fence_before();
+        mbar_arrive_warp(ps_ready);
+      }
+      // ---- epilogue of the item: the accumulators -> bf16 rows (warps 0-3: dV / dQ, warps 4-7: dK); the other warps go on
+      if (which < (MODE == 0 ? 2 : 1)) {
+        const int orow = o0 + r;
+        const int limit = MODE == 0 ? P.S : P.T;
+        __nv_bfloat16* base = MODE == 0 ? (which == 0 ? P.dv : P.dk) : P.dq;
+        const long long st = MODE == 0 ? (which == 0 ? P.dv_st : P.dk_st) : P.dq_st, sb = MODE == 0 ? (which == 0 ? P.dv_sb : P.dk_sb) : P.dq_sb;
+        uint32_t v[D];
         if (n_tiles > 0) {
-          tmem_ld_32x32b_x32((which == 0 ? tA0 : tA1) + lane_base + c * 32, v);
+          mbar_wait(acc_done, ri & 1);
+          tcgen05_fence_after();
+          uint32_t (*v32)[32] = reinterpret_cast<uint32_t (*)[32]>(v);
+#pragma unroll
+          for (int c = 0; c < D / 32; ++c) tmem_ld_32x32b_x32((which == 0 ? tA0 : tA1) + lane_base + c * 32, v32[c]);
           tmem_ld_wait();
+          tcgen05_fence_before();
+          mbar_arrive_warp(acc_free);                 // the next item's gradient MMAs may overwrite the accumulators
         } else {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = 0u;
+          for (int e = 0; e < D; ++e) v[e] = 0u;
         }
         if (DROP && MODE == 0 && which == 0) {         // dV = (P_drop / (1 - p))^T dO
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * P.drop.inv_keep);
+          for (int e = 0; e < D; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * P.drop.inv_keep);
         }
         if (orow < limit) {
-          uint4* dst = reinterpret_cast<uint4*>(base + (long long)orow * st + (long long)b * sb + h * D + c * 32);
+          uint4* dst = reinterpret_cast<uint4*>(base + (long long)orow * st + (long long)b * sb + h * D);
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
+          for (int e = 0; e < D / 8; ++e)
             dst[e] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * e]), __uint_as_float(v[8 * e + 1])),
                                 pack_bf16x2(__uint_as_float(v[8 * e + 2]), __uint_as_float(v[8 * e + 3])),
                                 pack_bf16x2(__uint_as_float(v[8 * e + 4]), __uint_as_float(v[8 * e + 5])),
                                 pack_bf16x2(__uint_as_float(v[8 * e + 6]), __uint_as_float(v[8 * e + 7])));
         }
       }
+      if (n_tiles > 0) ++ri;
     }
   }
   tcgen05_fence_before();
@@ -725,6 +772,7 @@ const char* mha_why_not(const mmn_mha_desc* d, bool backward) {
                    d->dk_stride_b % 8 || d->dv_stride_t % 8 || d->dv_stride_b % 8))
     return "gradient row strides not 16-byte aligned";
   if (d->batch > 65535 || d->num_heads > 65535) return "batch or head count beyond the grid limits";
+  if ((long long)((std::max(d->tgt_len, d->src_len) + 127) / 128) * d->num_heads * d->batch > 0x7fffffffLL) return "too many tiles";
   if (!encode_fn()) return "cuTensorMapEncodeTiled unavailable";
   return nullptr;
 }
@@ -767,10 +815,11 @@ int mha_fwd(const mmn_mha_desc* d, const void* q, const void* k, const void* v, 
 
 template <int D, int MODE, bool DROP>
 static int mha_bwd_launch(const MhaParams& P, cudaStream_t st) {
-  constexpr size_t smem = 1024 + (size_t)(2 + 2 * kMStagesB) * D * 256 + kMStagesB * 64 * 16 + (2 * kMStagesB + 6) * 8 + 16;
+  constexpr size_t smem = 1024 + (size_t)(4 + 2 * kMStagesB) * D * 256 + kMStagesB * 64 * 16 + (2 * kMStagesB + 10) * 8 + 16;
   static std::once_flag once;
   std::call_once(once, [] { cudaFuncSetAttribute(mha_bwd_tc_kernel<D, MODE, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
-  dim3 grid(((MODE == 0 ? P.S : P.T) + 127) / 128, P.nH, P.B);
+  const long long total = (long long)(((MODE == 0 ? P.S : P.T) + 127) / 128) * P.nH * P.B;
+  const int grid = (int)std::min<long long>(total, num_sms_cached());      // persistent: one CTA per SM
   mha_bwd_tc_kernel<D, MODE, DROP><<<grid, kMThreadsB, smem, st>>>(P);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
