@@ -472,7 +472,11 @@ template <int MODE>
 __device__ __forceinline__ BwdItem bwd_item(const MhaParams& P, int w) {
   const int n_ot = ((MODE == 0 ? P.S : P.T) + 127) >> 7;
   BwdItem it;
-  const int ot = w % n_ot, hb = w / n_ot;
+  const int hb = w / n_ot;
+  int ot = w % n_ot;
+  // With the future mask an item's work grows (mode 1) or shrinks (mode 0) with its tile index, and a CTA's stride over w
+  // visits only a few residues of it: every other (head, batch) runs its tiles in reverse, so heavy and light items mix.
+  if (hb & 1) ot = n_ot - 1 - ot;
   it.o0 = ot * 128; it.h = hb % P.nH; it.b = hb / P.nH;
   int n_end;
   if (MODE == 0) { it.n_begin = first_query_tile(P, it.o0); n_end = (P.T + 127) >> 7; }
