@@ -286,10 +286,19 @@ mha_fwd_tc_kernel(const __grid_constant__ MhaParams P) {
       tcgen05_fence_before();
       mbar_arrive_warp(&s_free[g]);
       float a_mul = sc;                               // logit (log2 domain) = v * a_mul
-      if (masked) {                                   // rare tiles: fold scale and mask into v
+      if (masked) {                                   // the diagonal / ragged tiles of a row block, outside the main path
+        if (P.mask_kind == MMN_MASK_TENSOR) {         // an additive mask tensor: fold scale and mask into v
 #pragma unroll
-        for (int e = 0; e < 128; ++e) v[e] = __float_as_uint(fmaf(__uint_as_float(v[e]), sc, mask_term(P, t, s0 + e)));
-        a_mul = 1.f;
+          for (int e = 0; e < 128; ++e) v[e] = __float_as_uint(fmaf(__uint_as_float(v[e]), sc, mask_term(P, t, s0 + e)));
+          a_mul = 1.f;
+        } else {
+          // future mask and / or the ragged last key tile: the row sees the keys e < e_lim of this tile.  One compare and
+          // one select per logit (the general form above is ~25 instructions per logit: a diagonal tile cost 3.5 tiles).
+          int e_lim = P.S - s0;
+          if (P.mask_kind == MMN_MASK_FUTURE) e_lim = min(e_lim, t + P.mask_diag - s0);
+#pragma unroll
+          for (int e = 0; e < 128; ++e) v[e] = e < e_lim ? v[e] : 0xff800000u;      // -inf survives the positive scale
+        }
       }
       // row maximum: a tree of three-input maxima (the scale is positive, so it commutes with the maximum)
       float mx;
@@ -652,14 +661,30 @@ mha_bwd_tc_kernel(const __grid_constant__ MhaParams P) {
         mbar_arrive_warp(sdp_free);
         // P = exp2(s sc - lse), dS = P (dP - delta) scale  ->  bf16 pairs
         float a_mul = sc;                             // logit (log2 domain) = vs * a_mul
-        if (masked) {                                 // rare blocks: fold scale and mask into vs (kept out of the main loop:
-#pragma unroll                                        //  a branch per element defeated the instruction prefetch)
-          for (int e = 0; e < 32; ++e) {
-            const int col = col0 + e;
-            const float mt = MODE == 0 ? mask_term(P, t0 + col, s0 + r) : mask_term(P, t0 + r, s0 + col);
-            vs[e] = __float_as_uint(fmaf(__uint_as_float(vs[e]), sc, mt));
+        if (masked) {                                 // diagonal / ragged blocks, kept out of the main path
+          if (P.mask_kind == MMN_MASK_TENSOR) {       // an additive mask tensor: fold scale and mask into vs
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int col = col0 + e;
+              const float mt = MODE == 0 ? mask_term(P, t0 + col, s0 + r) : mask_term(P, t0 + r, s0 + col);
+              vs[e] = __float_as_uint(fmaf(__uint_as_float(vs[e]), sc, mt));
+            }
+            a_mul = 1.f;
+          } else if (MODE == 0) {
+            // lane = key s, columns = queries: the key is seen by the queries t > s - diag, i.e. columns e >= e_min; a key
+            // beyond S by none (queries beyond T carry -inf in their row data)
+            const int sk = s0 + r;
+            int e_min = P.mask_kind == MMN_MASK_FUTURE ? sk - P.mask_diag + 1 - t0 - col0 : 0;
+            if (sk >= P.S) e_min = 32;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) vs[e] = e >= e_min ? vs[e] : 0xff800000u;
+          } else {
+            // lane = query t, columns = keys: the row sees the keys e < e_lim of this panel
+            int e_lim = P.S - s0 - col0;
+            if (P.mask_kind == MMN_MASK_FUTURE) e_lim = min(e_lim, t0 + r + P.mask_diag - s0 - col0);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) vs[e] = e < e_lim ? vs[e] : 0xff800000u;
           }
-          a_mul = 1.f;
         }
         const float scd = DROP ? P.scale * P.drop.inv_keep : P.scale;
         const uint64_t a2 = pk2(a_mul, a_mul), sc2 = pk2(scd, scd);
