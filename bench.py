@@ -376,6 +376,8 @@ def run_mha(args, dev, rank, emit):
     rows = []
     for name, E, nH, T, S, Bm, dt in (("cfg1 cross (E=84, 12 heads, d=7)", 84, 12, 368, 368, 2, torch.float32),
                                       ("cfg1 self (E=168, 12 heads, d=14)", 168, 12, 368, 368, 2, torch.float32),
+                                      ("cfg1 cross, bf16 autocast (d=7 zero-padded to 32 by the projections)", 84, 12, 368, 368, 2, torch.bfloat16),
+                                      ("cfg1 self, bf16 autocast (d=14 zero-padded to 32 by the projections)", 168, 12, 368, 368, 2, torch.bfloat16),
                                       ("scaled (E=768, 12 heads, d=64)", 768, 12, 2048, 2048, 32, torch.bfloat16)):
         m = mh.MultiheadAttention(E, nH).to(dev)
         m.need_weights = False
@@ -384,7 +386,9 @@ def run_mha(args, dev, rank, emit):
         dy = torch.randn(T, Bm, E, device=dev)
         mask = None
         d = _lib.MhaDesc()
-        d.tgt_len, d.src_len, d.batch, d.num_heads, d.head_dim = T, S, Bm, nH, E // nH
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dt == torch.bfloat16):
+            hd = m._padded_head_dim(q) or E // nH             # the head dim the core kernels see
+        d.tgt_len, d.src_len, d.batch, d.num_heads, d.head_dim = T, S, Bm, nH, hd
         d.io_dtype = _lib.DT_BF16 if dt == torch.bfloat16 else _lib.DT_F32
         path = _lib.load().mmn_mha_path(d).decode()
         from multimodal_neuroimage_b200 import ops

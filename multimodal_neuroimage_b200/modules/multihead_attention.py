@@ -84,20 +84,27 @@ class MultiheadAttention(nn.Module):
         assert key.size() == value.size()
         # Projection branches as in the reference (multihead_attention.py:59-84): identical
         # tensors share one GEMM; the results are the same slices of in_proj_weight.
+        # Head dims the tensor-core kernels do not take (the reference's own 7 and 14: embed 84 / 168, 12 heads) run on them
+        # all the same when the projections compute in 16 bits anyway (autocast): each head is padded to 32 (or 64) channels
+        # by zero ROWS in the in-projection weights -- q, k, v come out of the GEMM already padded, 64-byte aligned per head --
+        # and zero COLUMNS in the out-projection weight.  Zero channels change neither q.k nor the output; the gradient
+        # reaches the true weights through the pad.  (fp32 calls keep the exact generic kernels.)
+        pad = self._padded_head_dim(query)
+        E = self.embed_dim
         if query is key and key is value or (query.data_ptr() == key.data_ptr() == value.data_ptr()):
-            q, k, v = self._in_proj(query).chunk(3, dim=-1)
+            q, k, v = self._in_proj(query, pad=pad).chunk(3, dim=-1)
         elif key is value or key.data_ptr() == value.data_ptr():
-            q = self._in_proj(query, end=self.embed_dim)
-            k, v = self._in_proj(key, start=self.embed_dim).chunk(2, dim=-1)
+            q = self._in_proj(query, end=E, pad=pad)
+            k, v = self._in_proj(key, start=E, pad=pad).chunk(2, dim=-1)
         else:
-            q = self._in_proj(query, end=self.embed_dim)
-            k = self._in_proj(key, start=self.embed_dim, end=2 * self.embed_dim)
-            v = self._in_proj(value, start=2 * self.embed_dim)
+            q = self._in_proj(query, end=E, pad=pad)
+            k = self._in_proj(key, start=E, end=2 * E, pad=pad)
+            v = self._in_proj(value, start=2 * E, pad=pad)
 
         diagonal = future_mask_diagonal_of(attn_mask)
         if self.bias_k is not None:
-            k = torch.cat([k, self.bias_k.repeat(1, bsz, 1)])
-            v = torch.cat([v, self.bias_v.repeat(1, bsz, 1)])
+            k = torch.cat([k, self._pad_heads(self.bias_k, pad).to(k.dtype).repeat(1, bsz, 1)])
+            v = torch.cat([v, self._pad_heads(self.bias_v, pad).to(v.dtype).repeat(1, bsz, 1)])
             if attn_mask is not None:
                 attn_mask = torch.cat([attn_mask, attn_mask.new_zeros(attn_mask.size(0), 1)], dim=1)
                 diagonal = None
@@ -121,7 +128,11 @@ class MultiheadAttention(nn.Module):
         q, k, v = ops.kernel_io(q), ops.kernel_io(k), ops.kernel_io(v)
         attn, lse = torch.ops.mmn_b200.mha_fwd(q, k, v, mask, self.num_heads_mult, kind, diag, float(self.scaling),
                                                p, seed, off)
-        attn = self.out_proj(attn.to(io))
+        if pad:
+            w_out = F.pad(self.out_proj.weight.view(E, self.num_heads_mult, self.head_dim), (0, pad - self.head_dim))
+            attn = F.linear(attn.to(io), w_out.reshape(E, self.num_heads_mult * pad), self.out_proj.bias)
+        else:
+            attn = self.out_proj(attn.to(io))
         need = self.need_weights if need_weights is None else need_weights
         weights = None
         if need:
@@ -145,10 +156,34 @@ class MultiheadAttention(nn.Module):
     def in_proj_v(self, value):
         return self._in_proj(value, start=2 * self.embed_dim)
 
-    def _in_proj(self, input, start=0, end=None, **kwargs):
+    def _padded_head_dim(self, query):
+        """0, or the head dim (32 / 64) the tensor-core kernels run this module at: CUDA, 16-bit projections, head_dim that
+        is not 32 / 64 itself and fits."""
+        d = self.head_dim
+        if not query.is_cuda or d in (32, 64) or d > 64:
+            return 0
+        dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else query.dtype
+        if dt not in (torch.bfloat16, torch.float16):
+            return 0
+        return 32 if d < 32 else 64
+
+    def _pad_heads(self, t, pad):
+        """(..., heads * head_dim) -> (..., heads * pad) with zero channels at the end of every head."""
+        if not pad:
+            return t
+        lead = t.shape[:-1]
+        return F.pad(t.reshape(*lead, self.num_heads_mult, self.head_dim), (0, pad - self.head_dim)).reshape(*lead, self.num_heads_mult * pad)
+
+    def _in_proj(self, input, start=0, end=None, pad=0, **kwargs):
         weight = kwargs.get('weight', self.in_proj_weight)
         bias = kwargs.get('bias', self.in_proj_bias)
         weight = weight[start:end, :]
         if bias is not None:
             bias = bias[start:end]
+        if pad:                                       # zero rows after every head's head_dim rows: the output is head-padded
+            nb = weight.shape[0] // self.embed_dim
+            weight = F.pad(weight.view(nb * self.num_heads_mult, self.head_dim, -1), (0, 0, 0, pad - self.head_dim))
+            weight = weight.reshape(nb * self.num_heads_mult * pad, -1)
+            if bias is not None:
+                bias = self._pad_heads(bias.view(nb, -1), pad).reshape(-1)
         return F.linear(input, weight, bias)

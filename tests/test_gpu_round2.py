@@ -143,8 +143,20 @@ def test_mha_cfg1_size_fp32(mm, E, cross):
 @pytest.mark.parametrize("E,nH,T,S,cross,causal", [(84, 12, 368, 368, True, True), (168, 12, 368, 368, False, True),
                                                   (256, 4, 200, 333, True, False), (64, 2, 96, 96, False, True)],
                          ids=["cfg1_cross_d7", "cfg1_self_d14", "d64_TneS", "d32_causal"])
-def test_mha_bf16(mm, E, nH, T, S, cross, causal):
+def test_mha_bf16(mm, E, nH, T, S, cross, causal, monkeypatch):
+    # every bf16 case must reach the tensor-core kernels: d = 32 / 64 directly, the reference's own d = 7 / 14 through the
+    # zero-padded projections (multihead_attention.py: _padded_head_dim)
+    import ctypes
+    lib, seen = mm.lib.load(), []
+    real = lib.mmn_mha_fwd
+
+    def spy(dref, *a):
+        d = ctypes.cast(dref, ctypes.POINTER(mm.lib.MhaDesc)).contents
+        seen.append((d.head_dim, lib.mmn_mha_path(dref).decode()))
+        return real(dref, *a)
+    monkeypatch.setattr(lib, "mmn_mha_fwd", spy)
     _mha_case(mm, E, nH, T, S, 2, cross, causal, torch.bfloat16, BF16_TOL)
+    assert seen and all(p == "tcgen05" and hd in (32, 64) for hd, p in seen), seen
 
 
 # ------------------------------------------------------------------------------------------

@@ -197,3 +197,29 @@ def test_shard_range():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_mha_head_padding_is_exact():
+    """The zero-padded projections MultiheadAttention uses to put head dims 7 / 14 on the tensor-core kernels (16-bit
+    autocast on CUDA): padded q.k logits and the padded out-projection equal the unpadded ones, bit for bit in fp32."""
+    import torch
+    import torch.nn.functional as F
+    from multimodal_neuroimage_b200.modules.multihead_attention import MultiheadAttention
+    torch.manual_seed(3)
+    for E, nH in ((84, 12), (168, 12)):
+        m = MultiheadAttention(E, nH, add_bias_kv=True)
+        d, pad = E // nH, 32
+        x = torch.randn(5, 2, E)
+        assert m._padded_head_dim(x) == 0                       # CPU / fp32 tensors never take the padded route
+        for kw in ({}, {"end": E}, {"start": E}, {"start": E, "end": 2 * E}, {"start": 2 * E}):
+            plain, padded = m._in_proj(x, **kw), m._in_proj(x, pad=pad, **kw)
+            assert padded.shape[-1] == plain.shape[-1] // d * pad
+            back = padded.view(5, 2, -1, pad)
+            assert torch.equal(back[..., :d].reshape(plain.shape), plain) and not back[..., d:].any()
+        assert torch.equal(m._pad_heads(m.bias_k, pad).view(1, 1, nH, pad)[..., :d].reshape(1, 1, E), m.bias_k)
+        a = torch.randn(5, 2, nH, pad)
+        a[..., d:] = 7.0                                          # whatever sits in the pad channels must not reach the output
+        w_out = F.pad(m.out_proj.weight.view(E, nH, d), (0, pad - d)).reshape(E, nH * pad)
+        got = F.linear(a.reshape(5, 2, nH * pad), w_out, m.out_proj.bias)
+        want = m.out_proj(a[..., :d].reshape(5, 2, E))
+        assert torch.allclose(got, want, atol=1e-5)

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Kernel-time breakdown of one training step of a workload (cfg3 / cfg5) with torch.profiler (CUPTI): which kernels the
+"""Kernel-time breakdown of one training step of a workload (cfg3 / cfg4 / cfg5) with torch.profiler (CUPTI): which kernels the
 step spends its GPU time in, own kernels vs PyTorch's.  Eager launches (a CUDA graph hides the kernels from the profiler's
 per-op view); times are GPU durations, so host launch gaps do not count.
 
@@ -19,15 +19,20 @@ from multimodal_neuroimage_b200 import workloads as W  # noqa: E402
 
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
-    batch = int(sys.argv[2]) if len(sys.argv) > 2 else (8 if name == "cfg3" else 1)
+    batch = int(sys.argv[2]) if len(sys.argv) > 2 else (1 if name == "cfg5" else 8)
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
-    model = (W.SwinFusion3D() if name == "cfg3" else W.SwinV2CrossModal3D())
+    model = (W.SwinFusion3D() if name == "cfg3" else W.FuncStructCross3D() if name == "cfg4" else W.SwinV2CrossModal3D())
     W.randomise_norms(model)
     model = model.to(dev)
-    img = 96 if name == "cfg3" else 128
-    A, B, y = W.synthetic_batch(batch, img, dev, pinned=True)
-    ts = TS.TrainStep(model, torch.nn.functional.binary_cross_entropy_with_logits, (A, B), y, use_graph=False)
+    img = 128 if name == "cfg5" else 96
+    if name == "cfg4":
+        *ins, y = W.synthetic_batch_cfg4(batch, img, dev, pinned=True)
+        ins = tuple(ins)
+    else:
+        A, B, y = W.synthetic_batch(batch, img, dev, pinned=True)
+        ins = (A, B)
+    ts = TS.TrainStep(model, torch.nn.functional.binary_cross_entropy_with_logits, ins, y, use_graph=False)
     for _ in range(2):
         ts()
     torch.cuda.synchronize()
