@@ -4,6 +4,7 @@ fp16 autocast + GradScaler as the reference trainer runs it (trainer.py:84,378-4
 the eval-time CPB cache, and the residual groups (BasicLayer / RSTB / CRSTB) of SURVEY.md 8a row a11.
 """
 import math
+import os
 
 import pytest
 import torch
@@ -403,22 +404,41 @@ def test_linear_bwd_tensor_core(mm, rows, n_in, n_out):
     assert only_dw[0].numel() == 0 and rel_err(only_dw[1], dyd.t() @ xd) < 2e-3
 
 
+@pytest.mark.parametrize("rep", range(int(os.environ.get("MMN_REPEAT", "1"))))     # MMN_REPEAT=n: n draws of the weights
 @pytest.mark.parametrize("C,act", [(96, "gelu"), (192, "gelu"), (768, "relu")])
-def test_fused_mlp_matches_pytorch(mm, C, act):
-    """fused.mlp (two GEMMs + epilogues, three-pass backward) against the same Mlp evaluated by PyTorch in fp64."""
+def test_fused_mlp_matches_pytorch(mm, C, act, rep):
+    """fused.mlp (two GEMMs + epilogues, three-pass backward) against the same Mlp evaluated by PyTorch in fp64.
+
+    relu'(pre) is discontinuous at 0: of the 6.4 M pre-activations of the C = 768 case a handful lie within fp32 round-off
+    of 0, and there the kernel's sign may legitimately differ from the fp64 one.  One such flip moves one row of dW1 by a
+    single token's contribution, 2-4 % of max |dW1| -- a sporadic failure of the max-norm check (seen in about one run in
+    five) that is no kernel error.  So the reference takes the kernel's own act'(pre) wherever the two disagree, and the
+    test asserts that they disagree only within round-off of 0."""
     from multimodal_neuroimage_b200 import fused
+    F = torch.nn.functional
     g = torch.Generator().manual_seed(C)
     fc1, fc2 = torch.nn.Linear(C, 4 * C), torch.nn.Linear(4 * C, C)
     x = torch.randn(3, 700, C, generator=g).bfloat16().float()
     cot = torch.randn(3, 700, C, generator=g)
-    f = torch.nn.functional.gelu if act == "gelu" else torch.relu
     ps = [p.detach().bfloat16().double().requires_grad_(True) if p.dim() == 2 else p.detach().double().requires_grad_(True)
           for p in (fc1.weight, fc1.bias, fc2.weight, fc2.bias)]
     xo = x.double().requires_grad_(True)
-    want = torch.nn.functional.linear(f(torch.nn.functional.linear(xo, ps[0], ps[1])), ps[2], ps[3])
-    gw = torch.autograd.grad((want * cot.double()).sum(), [xo] + ps)
     fc1, fc2 = fc1.cuda(), fc2.cuda()
     xc = x.cuda().requires_grad_(True)
+    pre = F.linear(xo, ps[0], ps[1])
+    if act == "gelu":
+        hid = F.gelu(pre)
+    else:
+        with torch.no_grad():
+            _, dact = torch.ops.mmn_b200.linear_fwd(xc.detach().bfloat16().reshape(-1, C), fc1.weight.detach().bfloat16(),
+                                                    fc1.bias.detach().float(), mm.lib.ACT_RELU, True)
+        on = dact.double().cpu().view_as(pre)
+        assert ((on == 0) | (on == 1)).all()
+        flipped = on != (pre.detach() > 0)
+        assert flipped.sum() <= 16 and (pre.detach().abs()[flipped] < 1e-5).all(), "relu'(pre) differs away from pre = 0"
+        hid = pre * on
+    want = F.linear(hid, ps[2], ps[3])
+    gw = torch.autograd.grad((want * cot.double()).sum(), [xo] + ps)
     with torch.autocast("cuda", dtype=torch.bfloat16):
         got = fused.mlp(xc, fc1, fc2, act)
     assert got.dtype == torch.bfloat16
