@@ -578,8 +578,14 @@ def main():
     # transfers of one chunk overlap the kernels of another -- within a step and across consecutive steps.  The
     # forward+backward of a chunk is one CUDA-graph replay per slot (captured with the gradient buffers in place, so
     # weight gradients accumulate over the chunks exactly as over one batch).
-    E2E_CHUNKS = 8 if B % 8 == 0 else (4 if B % 4 == 0 else 1)
-    NSLOT = 3
+    # 16 chunks through 4 slots: 8.65 ms per step against 9.27 ms for 8 chunks / 3 slots on the same box (r2x sweep; the
+    # fourth slot lets a chunk's H2D copy start while three earlier chunks are still computing / draining)
+    E2E_CHUNKS = 16 if B % 16 == 0 else (8 if B % 8 == 0 else (4 if B % 4 == 0 else 1))
+    NSLOT = 4
+    if os.environ.get("MMN_E2E_CHUNKS"):             # tuning aid: chunk count / device slots of the pipeline
+        E2E_CHUNKS = int(os.environ["MMN_E2E_CHUNKS"])
+        assert B % E2E_CHUNKS == 0
+    NSLOT = int(os.environ.get("MMN_E2E_SLOTS", NSLOT))
     cb = B // E2E_CHUNKS
     s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     x_slot = [torch.zeros(cb, L, C, device=dev, dtype=torch.bfloat16).requires_grad_(True) for _ in range(NSLOT)]
@@ -822,9 +828,10 @@ def main():
                                                                  unit=UNIT, note="the same step back to back; value above is the K-step region"),
                 "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": 2 * B * L * C * elem,
                         "d2h_bytes_per_step": 2 * B * L * C * elem, "chunks": E2E_CHUNKS,
-                        "note": "x, dy from pinned host memory; y, dx back to pinned host memory; 8 chunks through 3 streams and "
-                                "3 device slots, one CUDA-graph replay per chunk: PCIe-bound (measured duplex floor of this box: "
-                                "8.7 ms for these bytes, tools/pcie_probe.py)"},
+                        "slots": NSLOT,
+                        "note": f"x, dy from pinned host memory; y, dx back to pinned host memory; {E2E_CHUNKS} chunks through 3 streams and "
+                                f"{NSLOT} device slots, one CUDA-graph replay per chunk: PCIe-bound (measured duplex floor of these bytes on "
+                                "the pool's boxes: 8.0-8.7 ms, tools/pcie_probe.py)"},
                 "gpu_launches": launches, "launch": LAUNCH_MODE[0], "roofline": roofline, "cpu_baseline": cpu,
                 "gpu_eager_baseline": eager, "train": train, "clocks": clk.summary(),
                 "paths": {"fwd": ops.winattn_path_name(torch.empty(1, *GRID, 3 * C, device=dev, dtype=torch.bfloat16), None, GRID,

@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""LayerNorm + residual kernels (csrc/layernorm.cu) at a workload's shape: time per launch and fraction of the HBM floor.
+    python tools/bench_ln.py [rows] [cols]        (default: cfg3's 8 x 24^3 rows x 96 channels, fp32 stream, bf16 activations)"""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from multimodal_neuroimage_b200 import _lib, ops  # noqa: E402,F401
+
+rows = int(sys.argv[1]) if len(sys.argv) > 1 else 8 * 24 ** 3
+cols = int(sys.argv[2]) if len(sys.argv) > 2 else 96
+dev = "cuda"
+try:
+    peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+    peak = float(peak.get("hbm_gbps", peak.get("hbm_GBps", 6548.2)))
+except Exception:
+    peak = 6548.2
+torch.manual_seed(0)
+resid = torch.randn(rows, cols, device=dev)
+delta = torch.randn(rows, cols, device=dev).bfloat16()
+gamma, beta = torch.rand(cols, device=dev) + 0.5, torch.randn(cols, device=dev)
+g_sum = torch.randn(rows, cols, device=dev)
+g_norm = torch.randn(rows, cols, device=dev).bfloat16()
+# enough distinct buffers that no launch finds its inputs in the 126 MB L2
+NB = 6
+resids = [resid.clone() for _ in range(NB)]
+gsums = [g_sum.clone() for _ in range(NB)]
+
+
+def timeit(fn, n=60):
+    for i in range(6):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+
+
+for mode, name in ((_lib.LN_PRE, "pre-norm"), (_lib.LN_POST, "post-norm")):
+    outs = torch.ops.mmn_b200.layernorm_fwd(resid, delta, gamma, beta, 1e-5, mode, True, 1)
+    s, n, mean, rstd = outs
+    x_saved = s if mode == _lib.LN_PRE else delta
+    us_f = timeit(lambda i: torch.ops.mmn_b200.layernorm_fwd(resids[i % NB], delta, gamma, beta, 1e-5, mode, True, 1))
+    # backward: grad of the sum (fp32) + grad of the normalised copy (bf16) in, d_resid fp32 + d_delta bf16 out
+    us_b = timeit(lambda i: torch.ops.mmn_b200.layernorm_bwd(gsums[i % NB], g_norm if mode == _lib.LN_PRE else None, x_saved, gamma, mean, rstd,
+                                                              mode, 0, 1, True))
+    el = rows * cols
+    bytes_f = el * (4 + 2 + 4 + 2)
+    bytes_b = el * ((4 + 2 + 4 + 4 + 2) if mode == _lib.LN_PRE else (4 + 2 + 4 + 2))
+    print(f"{name}: rows {rows} cols {cols}  fwd {us_f:6.1f} us ({bytes_f / us_f / 1e3 / peak:.2f} of HBM peak)   "
+          f"bwd {us_b:6.1f} us ({bytes_b / us_b / 1e3 / peak:.2f})   [MMN_LN_BPS={os.environ.get('MMN_LN_BPS', 'default')}]")
