@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define MMN_ABI_VERSION 3
+#define MMN_ABI_VERSION 4
 /* scratch every window-attention launch needs: the tensor-core kernels keep the counters of their run-time work queue
  * there (zeroed by the library on the launch's stream; one buffer per launch, never shared between launches in flight) */
 #define MMN_WINATTN_WORK_BYTES 2048
@@ -152,6 +152,16 @@ int mmn_cpb_bias_fwd(const float* coords, const float* w1, const float* b1, cons
 int mmn_cpb_bias_bwd(const float* coords, const float* w1, const float* b1, const float* w2, const int64_t* index,
                      const float* tab16, const float* dbias, int32_t T, int32_t n_in, int32_t J, int32_t num_heads, int32_t NN,
                      float* scratch, float* dw1, float* db1, float* dw2, int device, void* stream);
+
+/* Learned relative-position bias table of the fusion blocks (swinfusion_module.py:58-60,127-130,228-231), fp32:
+ *   fwd: bias[h][e] = table[index[e]][h]            table (T, nH), index (NN) int64 in [0, T), bias (nH, NN)
+ *   bwd: dtable[t][h] = sum over e with index[e] == t of dbias[h][e]     (dtable OVERWRITTEN; float atomics)
+ * i.e. `table[index].view(N, N, nH).permute(2, 0, 1).contiguous()` and its backward in one launch each (PyTorch: index_select +
+ * permute copy forward, zeros + index_add backward). */
+int mmn_table_bias_fwd(const float* table, const int64_t* index, int32_t T, int32_t num_heads, int32_t NN, float* bias,
+                       int device, void* stream);
+int mmn_table_bias_bwd(const float* dbias, const int64_t* index, int32_t T, int32_t num_heads, int32_t NN, float* dtable,
+                       int device, void* stream);
 
 /* Projections on the tensor cores (csrc/gemm_tc.cu, csrc/linbwd_tc.cu).  They replace the F.linear calls of the path and
  * their autograd backward: swin_v2_module.py:148,176 (qkv, proj) and :27-31 (Mlp: fc1 -> GELU -> fc2),

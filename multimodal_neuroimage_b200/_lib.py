@@ -41,13 +41,13 @@ MASK_NONE, MASK_SHIFT, MASK_TENSOR, MASK_FUTURE = 0, 1, 2, 3
 PATH_AUTO, PATH_GENERIC, PATH_TCGEN05 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 LN_PRE, LN_POST = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 WINATTN_WORK_BYTES = 2048
 
 EXPORTS = ["mmn_abi_version", "mmn_last_error", "mmn_winattn_path", "mmn_mha_path", "mmn_launch_count",
            "mmn_winattn_fwd", "mmn_winattn_bwd", "mmn_mha_fwd", "mmn_mha_bwd", "mmn_mha_avg_weights", "mmn_colsum",
            "mmn_linear_supported", "mmn_linear_fwd", "mmn_linear_bwd", "mmn_linear_bwd_supported", "mmn_linear_bwd_workspace_bytes",
-           "mmn_cpb_bias_fwd", "mmn_cpb_bias_bwd", "mmn_layernorm_supported", "mmn_layernorm_fwd", "mmn_layernorm_bwd"]
+           "mmn_cpb_bias_fwd", "mmn_cpb_bias_bwd", "mmn_table_bias_fwd", "mmn_table_bias_bwd", "mmn_layernorm_supported", "mmn_layernorm_fwd", "mmn_layernorm_bwd"]
 
 
 class WinAttnDesc(C.Structure):
@@ -149,6 +149,10 @@ def load() -> C.CDLL:
         lib.mmn_colsum.argtypes = [vp, C.c_int, C.c_int64, C.c_int32, C.c_int64, fp, C.c_int, vp]
         lib.mmn_cpb_bias_fwd.restype = C.c_int
         lib.mmn_cpb_bias_fwd.argtypes = [fp, fp, fp, fp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, fp, fp, C.c_int, vp]
+        lib.mmn_table_bias_fwd.restype = C.c_int
+        lib.mmn_table_bias_fwd.argtypes = [fp, vp, C.c_int32, C.c_int32, C.c_int32, fp, C.c_int, vp]
+        lib.mmn_table_bias_bwd.restype = C.c_int
+        lib.mmn_table_bias_bwd.argtypes = [fp, vp, C.c_int32, C.c_int32, C.c_int32, fp, C.c_int, vp]
         lib.mmn_cpb_bias_bwd.restype = C.c_int
         lib.mmn_cpb_bias_bwd.argtypes = [fp, fp, fp, fp, vp, fp, fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                          fp, fp, fp, fp, C.c_int, vp]

@@ -166,6 +166,23 @@ size_t cpb_bwd_smem_bytes(int T) {
   return ((size_t)((T * kCpbMaxIn + 3) & ~3) + (size_t)T * 8 + (size_t)kCpbBwdSlices * 8 * kCpbBwdUnits) * sizeof(float);
 }
 
+// Learned relative-position bias table (swinfusion_module.py:127-130): the same gather / scatter without the MLP.
+cudaError_t table_bias_fwd(const float* table, const long long* index, int nH, int NN, float* bias, cudaStream_t st, int* launches) {
+  cpb_gather_kernel<<<(NN + 255) / 256, 256, 0, st>>>(table, index, NN, nH, bias);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) *launches += 1;
+  return e;
+}
+
+cudaError_t table_bias_bwd(const float* dbias, const long long* index, int T, int nH, int NN, float* dtable, cudaStream_t st, int* launches) {
+  cudaError_t e = cudaMemsetAsync(dtable, 0, (size_t)T * nH * sizeof(float), st);
+  if (e != cudaSuccess) return e;
+  cpb_scatter_kernel<<<(NN + 255) / 256, 256, 0, st>>>(dbias, index, NN, nH, dtable);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) *launches += 1;
+  return e;
+}
+
 cudaError_t cpb_bias_fwd(const float* coords, const float* w1, const float* b1, const float* w2, const long long* index, int T,
                          int n_in, int J, int nH, int NN, float* tab16, float* bias, cudaStream_t st, int* launches) {
   cpb_table_kernel<<<T, 128, 0, st>>>(coords, w1, b1, w2, n_in, J, nH, tab16);

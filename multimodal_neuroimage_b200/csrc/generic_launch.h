@@ -17,6 +17,8 @@ cudaError_t colsum(int io_dtype, const void* x, long long rows, int cols, long l
                    int* launches);
 // continuous relative-position bias (cpb_bias.cu)
 size_t cpb_bwd_smem_bytes(int T);
+cudaError_t table_bias_fwd(const float* table, const long long* index, int nH, int NN, float* bias, cudaStream_t st, int* launches);
+cudaError_t table_bias_bwd(const float* dbias, const long long* index, int T, int nH, int NN, float* dtable, cudaStream_t st, int* launches);
 cudaError_t cpb_bias_fwd(const float* coords, const float* w1, const float* b1, const float* w2, const long long* index, int T,
                          int n_in, int J, int nH, int NN, float* tab16, float* bias, cudaStream_t st, int* launches);
 cudaError_t cpb_bias_bwd(const float* coords, const float* w1, const float* b1, const float* w2, const long long* index,

@@ -272,6 +272,28 @@ static int cpb_check(int T, int n_in, int J, int nH, int NN) {
   return MMN_OK;
 }
 
+int mmn_table_bias_fwd(const float* table, const int64_t* index, int32_t T, int32_t nH, int32_t NN, float* bias, int device, void* stream) {
+  if (!table || !index || !bias) return fail(MMN_ERR_INVALID, "null tensor pointer");
+  if (T < 1 || nH < 1 || NN < 1) return fail(MMN_ERR_INVALID, "bad bias table dimensions");
+  if (!have_device()) return fail(MMN_ERR_CUDA, "no CUDA device: libmmn_b200 has no CPU path");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(MMN_ERR_CUDA, "cannot select device %d", device);
+  int n = 0;
+  cudaError_t e = mmn::table_bias_fwd(table, (const long long*)index, nH, NN, bias, (cudaStream_t)stream, &n);
+  return finish(e, n, "table_bias_fwd");
+}
+
+int mmn_table_bias_bwd(const float* dbias, const int64_t* index, int32_t T, int32_t nH, int32_t NN, float* dtable, int device, void* stream) {
+  if (!dbias || !index || !dtable) return fail(MMN_ERR_INVALID, "null tensor pointer");
+  if (T < 1 || nH < 1 || NN < 1) return fail(MMN_ERR_INVALID, "bad bias table dimensions");
+  if (!have_device()) return fail(MMN_ERR_CUDA, "no CUDA device: libmmn_b200 has no CPU path");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(MMN_ERR_CUDA, "cannot select device %d", device);
+  int n = 0;
+  cudaError_t e = mmn::table_bias_bwd(dbias, (const long long*)index, T, nH, NN, dtable, (cudaStream_t)stream, &n);
+  return finish(e, n, "table_bias_bwd");
+}
+
 int mmn_cpb_bias_fwd(const float* coords, const float* w1, const float* b1, const float* w2, const int64_t* index, int32_t T,
                      int32_t n_in, int32_t J, int32_t nH, int32_t NN, float* tab16, float* bias, int device, void* stream) {
   if (!coords || !w1 || !b1 || !w2 || !index || !tab16 || !bias) return fail(MMN_ERR_INVALID, "null tensor pointer");

@@ -51,7 +51,8 @@ class WindowAttentionModuleFn(torch.autograd.Function):
         with torch.autocast("cuda", enabled=False):
             cast = lambda t: None if t is None else t.to(cdt)
             xc, yc = cast(x).reshape(B * L, C), (cast(y).reshape(B * L, C) if y is not None else None)
-            wa, wb, wp = cast(w_a), cast(w_b), cast(w_proj)          # biases stay in their own dtype: added in fp32
+            castw = (lambda t: None if t is None else ops.weight_bf16(t)) if cdt == torch.bfloat16 else cast
+            wa, wb, wp = castw(w_a), castw(w_b), castw(w_proj)       # biases stay in their own dtype: added in fp32
             a = _project(xc, wa, b_a).view(B, *grid, -1)
             b = _project(yc, wb, b_b).view(B, *grid, -1) if y is not None else None
             p, seed, off = dropout
@@ -131,7 +132,7 @@ class MlpFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, act):
         x2 = x.reshape(-1, x.shape[-1])
-        w1c, w2c = w1.to(torch.bfloat16), w2.to(torch.bfloat16)
+        w1c, w2c = ops.weight_bf16(w1), ops.weight_bf16(w2)
         h, dact = torch.ops.mmn_b200.linear_fwd(x2, w1c, None if b1 is None else b1.float(), act, True)   # act(pre), act'(pre)
         y, _ = torch.ops.mmn_b200.linear_fwd(h, w2c, None if b2 is None else b2.float(), _lib.ACT_NONE, False)
         ctx.save_for_backward(x2, dact, h, w1c, w2c)

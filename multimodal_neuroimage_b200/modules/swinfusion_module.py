@@ -62,7 +62,11 @@ class _TableBiasAttention(nn.Module):
     def position_bias(self) -> torch.Tensor:
         """(nH, N, N) fp32 = table[index] (swinfusion_module.py:127-130)."""
         N = math.prod(self.window_size)
-        b = _GatherRows.apply(self.relative_position_bias_table.float(), self.relative_position_index.view(-1))
+        table, index = self.relative_position_bias_table, self.relative_position_index.view(-1)
+        if table.is_cuda and table.dtype == torch.float32 and table.is_contiguous() and index.is_contiguous():
+            # libmmn_b200 cpb_bias.cu: gather + head-major layout in one launch, scatter-add backward in one
+            return torch.ops.mmn_b200.table_bias_fwd(table, index).view(-1, N, N)
+        b = _GatherRows.apply(table.float(), index)
         return b.view(N, N, -1).permute(2, 0, 1).contiguous()
 
     def _core(self, a, b, grid, window, shift, mask_kind, mask):

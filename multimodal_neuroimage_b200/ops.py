@@ -35,6 +35,56 @@ def kernel_io(t: Optional[Tensor]) -> Optional[Tensor]:
     return t.to(torch.bfloat16) if t is not None and t.dtype == torch.float16 else t
 
 
+# ------------------------------------------------------------------------------------------
+# bf16 copies of the master weights
+# ------------------------------------------------------------------------------------------
+# Every projection casts its fp32 master weight to bf16 on the way in: one tiny kernel per weight and step (276 of them in
+# the cfg3 step, ~2.5 us each even inside a CUDA graph).  A training loop that owns the optimizer step can keep the copies
+# alive instead and refresh them all with one multi-tensor copy after the step (train_step.TrainStep does).  A copy is
+# used only while the weight's version counter is the one seen at the last refresh: load_state_dict, .to(), or any other
+# in-place update from outside invalidates it by construction and the cast happens as before.
+_BF16_SHADOWS = {}
+
+
+def weight_bf16(w: Tensor) -> Tensor:
+    """w as bfloat16: w itself, its registered up-to-date copy, or a fresh cast."""
+    if w.dtype == torch.bfloat16:
+        return w
+    hit = _BF16_SHADOWS.get(id(w))
+    if hit is not None and hit[0]() is w and hit[2] == w._version:
+        return hit[1]
+    return w.to(torch.bfloat16)
+
+
+class Bf16Shadows:
+    """bf16 copies of the (>= 2-D, fp32) parameters in `params`, served by `weight_bf16`.  Call refresh() after every
+    update of the parameters (inside a CUDA-graph capture of the optimizer step it is captured with it)."""
+
+    def __init__(self, params):
+        import weakref
+        self._ref = weakref.ref
+        self.src = [p for p in params if p.dtype == torch.float32 and p.dim() >= 2]
+        self.dst = [torch.empty_like(p, dtype=torch.bfloat16) for p in self.src]
+        self.refresh()
+
+    def refresh(self):
+        if not self.src:
+            return
+        with torch.no_grad():
+            torch._foreach_copy_(self.dst, self.src)
+        for p, d in zip(self.src, self.dst):
+            key = id(p)
+            # the entry (and the copy it holds) goes when the weight does
+            _BF16_SHADOWS[key] = (self._ref(p, lambda _r, key=key: _BF16_SHADOWS.pop(key, None)), d, p._version)
+
+    def close(self):
+        for p in self.src:
+            hit = _BF16_SHADOWS.get(id(p))
+            if hit is not None and hit[0]() is p:
+                del _BF16_SHADOWS[id(p)]
+        self.src, self.dst = [], []
+
+
 def _require_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -360,6 +410,55 @@ def _(x):
     return x.new_empty(x.shape[1], dtype=torch.float32)
 
 
+@torch.library.custom_op("mmn_b200::table_bias_fwd", mutates_args=())
+def table_bias_fwd(table: Tensor, index: Tensor) -> Tensor:
+    """(T, nH) fp32 table, (NN,) int64 index -> (nH, NN) bias = table[index].T in one launch (swinfusion_module.py:127-130)."""
+    _require_cuda(table, index)
+    if table.dim() != 2 or table.dtype != torch.float32 or not table.is_contiguous() or index.dtype != torch.int64 or \
+            not index.is_contiguous():
+        raise RuntimeError("table_bias_fwd expects a contiguous fp32 (T, heads) table and a contiguous int64 index")
+    T, nH, NN = table.shape[0], table.shape[1], index.numel()
+    bias = torch.empty(nH, NN, dtype=torch.float32, device=table.device)
+    _lib.check(_lib.load().mmn_table_bias_fwd(_ptr(table), _ptr(index), T, nH, NN, _ptr(bias), table.device.index, _stream(table)),
+               "mmn_table_bias_fwd")
+    return bias
+
+
+@table_bias_fwd.register_fake
+def _(table, index):
+    return table.new_empty(table.shape[1], index.numel())
+
+
+@torch.library.custom_op("mmn_b200::table_bias_bwd", mutates_args=())
+def table_bias_bwd(dbias: Tensor, index: Tensor, table_rows: int) -> Tensor:
+    _require_cuda(dbias, index)
+    dbias = dbias.contiguous()
+    nH, NN = dbias.shape[0], index.numel()
+    dtable = torch.empty(table_rows, nH, dtype=torch.float32, device=dbias.device)
+    _lib.check(_lib.load().mmn_table_bias_bwd(_ptr(dbias), _ptr(index), table_rows, nH, NN, _ptr(dtable), dbias.device.index,
+                                             _stream(dbias)), "mmn_table_bias_bwd")
+    return dtable
+
+
+@table_bias_bwd.register_fake
+def _(dbias, index, table_rows):
+    return dbias.new_empty(table_rows, dbias.shape[0])
+
+
+def _table_bias_setup(ctx, inputs, output):
+    table, index = inputs
+    ctx.save_for_backward(index)
+    ctx.rows = table.shape[0]
+
+
+def _table_bias_backward(ctx, dbias):
+    index, = ctx.saved_tensors
+    return torch.ops.mmn_b200.table_bias_bwd(dbias.float().reshape(dbias.shape[0], -1), index, ctx.rows), None
+
+
+torch.library.register_autograd("mmn_b200::table_bias_fwd", _table_bias_backward, setup_context=_table_bias_setup)
+
+
 def cpb_bias_supported(coords: Tensor, w1: Tensor, w2: Tensor) -> bool:
     """True when the fused continuous-position-bias kernels take these operands (fp32 CUDA, <= 3 coordinates,
     <= 64 heads, table x heads <= 12288)."""
@@ -506,7 +605,7 @@ class LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, act):
         x2 = x.reshape(-1, x.shape[-1])
-        wc = w.to(torch.bfloat16)
+        wc = weight_bf16(w)
         y, pre = torch.ops.mmn_b200.linear_fwd(x2, wc, None if b is None else b.float(), act, act != _lib.ACT_NONE)
         ctx.save_for_backward(x2, wc, pre)
         ctx.meta = (x.shape, w.dtype, None if b is None else b.dtype, act, x.requires_grad)

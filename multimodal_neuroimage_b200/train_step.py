@@ -45,6 +45,10 @@ class TrainStep:
             off += p.numel()
         self.opt = torch.optim.AdamW(self.params, lr=lr, weight_decay=weight_decay, fused=True, capturable=self.use_graph)
         self.loss = torch.zeros((), device=dev)
+        # bf16 copies of the weights, refreshed by one multi-tensor copy after every optimizer step instead of one cast
+        # kernel per weight inside the forward (ops.weight_bf16)
+        from . import ops
+        self.shadows = ops.Bf16Shadows(self.params) if autocast_dtype == torch.bfloat16 else None
         self.g_fb = self.g_opt = None
         self._load(example_inputs, example_target)
         if world > 1 and self.fwd_model is model:
@@ -57,7 +61,7 @@ class TrainStep:
                 for _ in range(warmup):                      # allocator / autotune / lazy-init warm-up off the capture
                     self._fwd_bwd()
                     self._exchange()
-                    self.opt.step()
+                    self._opt_step()
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
             torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
@@ -66,7 +70,7 @@ class TrainStep:
                 self._fwd_bwd()
             self.g_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.g_opt, pool=self.g_fb.pool()):
-                self.opt.step()
+                self._opt_step()
 
     # -- pieces -------------------------------------------------------------------------------------------------------
     def _load(self, inputs, target):
@@ -91,6 +95,11 @@ class TrainStep:
             for p, v in zip(self.params, self.views):
                 p.grad = v
 
+    def _opt_step(self):
+        self.opt.step()
+        if self.shadows is not None:
+            self.shadows.refresh()
+
     def _exchange(self):
         """The path's one collective: average the weight gradients over the ranks."""
         if self.world > 1 and self.fwd_model is self.model:
@@ -109,7 +118,7 @@ class TrainStep:
         else:
             self._fwd_bwd()
             self._exchange()
-            self.opt.step()
+            self._opt_step()
         return self.loss
 
     def grad_bytes(self) -> int:

@@ -701,6 +701,64 @@ def test_cfg4_workload_steps(mm):
     assert torch.isfinite(ts.flat).all() and (ts.flat != 0).float().mean() > 0.5      # every parameter's gradient arrived in the flat buffer
 
 
+@pytest.mark.parametrize("window,nH", [((4, 4, 4), 3), ((8, 8), 6), ((7, 7), 4), ((4, 4, 2), 48)], ids=["3d_w4", "2d_w8", "2d_w7", "3d_442_48h"])
+def test_table_bias_gather_scatter(mm, window, nH):
+    """The learned relative-position bias of the fusion blocks (swinfusion_module.py:127-130) through the one-launch
+    gather / scatter: forward bit-exact against table[index] (pure data movement), backward against index_add in fp64."""
+    from multimodal_neuroimage_b200 import geometry
+    N = math.prod(window)
+    index = geometry.relative_position_index(window).view(-1).cuda()
+    T = math.prod(2 * w - 1 for w in window)
+    assert int(index.max()) == T - 1
+    g = torch.Generator().manual_seed(N + nH)
+    table = torch.randn(T, nH, generator=g).cuda().requires_grad_(True)
+    cot = torch.randn(nH, N, N, generator=g).cuda()
+    got = torch.ops.mmn_b200.table_bias_fwd(table, index).view(nH, N, N)
+    want = table.detach()[index].view(N, N, nH).permute(2, 0, 1)
+    assert torch.equal(got, want)
+    dgot, = torch.autograd.grad((got * cot).sum(), table)
+    dwant = torch.zeros(T, nH, dtype=torch.float64).index_add_(0, index.cpu(), cot.double().cpu().permute(1, 2, 0).reshape(N * N, nH))
+    check(dgot, dwant, FP32_TOL, "table bias backward")
+    # and through the module: the attention class hands the kernel the same tensor the PyTorch expression gives
+    attn = mm.fu.WindowAttention_fusion(32 * nH, window, nH).cuda()
+    with torch.no_grad():
+        attn.relative_position_bias_table.normal_(0, 0.5)
+    b = attn.position_bias()
+    assert torch.equal(b, attn.relative_position_bias_table.detach()[attn.relative_position_index.view(-1)].view(N, N, nH).permute(2, 0, 1))
+
+
+def test_train_step_bf16_weight_copies_change_nothing(mm):
+    """TrainStep keeps bf16 copies of the weights and refreshes them after the optimizer step (ops.Bf16Shadows) instead of
+    casting every weight inside the forward: the loss trajectory must be the one of the casting step, bit for bit in the
+    forward (the copies hold exactly what the casts produce), graph-replayed and eager."""
+    from multimodal_neuroimage_b200 import train_step as TS
+    from multimodal_neuroimage_b200 import workloads as W
+
+    def run(shadows, use_graph):
+        torch.manual_seed(0)
+        model = W.SwinFusion3D(img_size=32, Ex_depths=(2,), Fusion_depths=(2,), Re_depths=(2,))
+        W.randomise_norms(model)
+        model = model.cuda()
+        A, B, y = W.synthetic_batch(2, 32, "cuda")
+        ts = TS.TrainStep(model, torch.nn.functional.binary_cross_entropy_with_logits, (A, B), y, lr=1e-3, warmup=2, use_graph=use_graph)
+        if not shadows:
+            ts.shadows.close()
+            ts.shadows = None
+            assert all(mm.ops.weight_bf16(p) is not mm.ops.weight_bf16(p) for p in ts.params if p.dim() >= 2)    # fresh casts
+        else:
+            assert len(ts.shadows.src) > 20 and all(mm.ops.weight_bf16(p) is d for p, d in zip(ts.shadows.src, ts.shadows.dst))
+        out = [float(ts().item()) for _ in range(4)]
+        if ts.shadows is not None:
+            ts.shadows.close()
+        return out
+
+    eager_cast, eager_copy = run(False, False), run(True, False)
+    assert eager_cast[-1] < eager_cast[0]
+    assert all(abs(a - b) <= 2e-3 * abs(a) for a, b in zip(eager_cast, eager_copy)), (eager_cast, eager_copy)
+    graph_copy = run(True, True)
+    assert all(abs(a - b) <= 2e-3 * abs(a) for a, b in zip(eager_cast, graph_copy)), (eager_cast, graph_copy)
+
+
 def test_patch_embed_3d_projection_matches_conv(mm):
     """PatchEmbed3D as gather + tensor-core projection against the Conv3d it replaces (outputs and parameter gradients)."""
     pe = mm.v2.PatchEmbed3D(32, 4, 1, 96, torch.nn.LayerNorm).cuda()

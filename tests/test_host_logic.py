@@ -223,3 +223,28 @@ def test_mha_head_padding_is_exact():
         got = F.linear(a.reshape(5, 2, nH * pad), w_out, m.out_proj.bias)
         want = m.out_proj(a[..., :d].reshape(5, 2, E))
         assert torch.allclose(got, want, atol=1e-5)
+
+
+def test_bf16_weight_shadows_follow_the_version_counter():
+    """ops.weight_bf16 serves a registered bf16 copy only while the weight is the one last refreshed: any in-place update
+    from outside (optimizer step without refresh, load_state_dict) falls back to a fresh cast."""
+    import torch
+    from multimodal_neuroimage_b200 import ops
+    lin = torch.nn.Linear(8, 4)
+    assert ops.weight_bf16(lin.weight).data_ptr() != ops.weight_bf16(lin.weight).data_ptr()      # no copy registered: casts
+    sh = ops.Bf16Shadows(lin.parameters())
+    assert len(sh.src) == 1                                          # the bias (1-D) keeps its own dtype
+    a = ops.weight_bf16(lin.weight)
+    assert a is sh.dst[0] and torch.equal(a, lin.weight.detach().bfloat16())
+    with torch.no_grad():
+        lin.weight.mul_(2.0)                                         # update without refresh: the copy is stale and not served
+    b = ops.weight_bf16(lin.weight)
+    assert b is not sh.dst[0] and torch.equal(b, lin.weight.detach().bfloat16())
+    sh.refresh()
+    assert ops.weight_bf16(lin.weight) is sh.dst[0] and torch.equal(sh.dst[0], lin.weight.detach().bfloat16())
+    lin.load_state_dict({"weight": torch.ones(4, 8), "bias": torch.zeros(4)})
+    assert torch.equal(ops.weight_bf16(lin.weight), torch.ones(4, 8, dtype=torch.bfloat16))
+    sh.close()
+    assert ops.weight_bf16(lin.weight) is not ops.weight_bf16(lin.weight)
+    w16 = torch.zeros(2, 2, dtype=torch.bfloat16)
+    assert ops.weight_bf16(w16) is w16
