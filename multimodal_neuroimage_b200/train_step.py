@@ -21,7 +21,7 @@ import torch.nn as nn
 class TrainStep:
     def __init__(self, model: nn.Module, loss_fn: Callable, example_inputs: Sequence[torch.Tensor], example_target: torch.Tensor,
                  lr: float = 1e-4, weight_decay: float = 0.05, autocast_dtype=torch.bfloat16, world: int = 1,
-                 use_graph: bool = True, ddp: str = "flat", warmup: int = 3):
+                 use_graph: bool = True, ddp: str = "flat", warmup: int = 3, bf16_weight_copies: bool = True):
         self.model, self.loss_fn, self.world, self.dtype = model, loss_fn, world, autocast_dtype
         self.params = [p for p in model.parameters() if p.requires_grad]
         dev = self.params[0].device
@@ -48,7 +48,7 @@ class TrainStep:
         # bf16 copies of the weights, refreshed by one multi-tensor copy after every optimizer step instead of one cast
         # kernel per weight inside the forward (ops.weight_bf16)
         from . import ops
-        self.shadows = ops.Bf16Shadows(self.params) if autocast_dtype == torch.bfloat16 else None
+        self.shadows = ops.Bf16Shadows(self.params) if autocast_dtype == torch.bfloat16 and bf16_weight_copies else None
         self.g_fb = self.g_opt = None
         self._load(example_inputs, example_target)
         if world > 1 and self.fwd_model is model:

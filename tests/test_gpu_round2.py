@@ -740,23 +740,23 @@ def test_train_step_bf16_weight_copies_change_nothing(mm):
         W.randomise_norms(model)
         model = model.cuda()
         A, B, y = W.synthetic_batch(2, 32, "cuda")
-        ts = TS.TrainStep(model, torch.nn.functional.binary_cross_entropy_with_logits, (A, B), y, lr=1e-3, warmup=2, use_graph=use_graph)
-        if not shadows:
-            ts.shadows.close()
-            ts.shadows = None
-            assert all(mm.ops.weight_bf16(p) is not mm.ops.weight_bf16(p) for p in ts.params if p.dim() >= 2)    # fresh casts
-        else:
+        ts = TS.TrainStep(model, torch.nn.functional.binary_cross_entropy_with_logits, (A, B), y, lr=1e-3, warmup=2, use_graph=use_graph,
+                          bf16_weight_copies=shadows)
+        big = [p for p in ts.params if p.dim() >= 2]
+        if shadows:
             assert len(ts.shadows.src) > 20 and all(mm.ops.weight_bf16(p) is d for p, d in zip(ts.shadows.src, ts.shadows.dst))
+        else:
+            assert ts.shadows is None and all(mm.ops.weight_bf16(p) is not mm.ops.weight_bf16(p) for p in big)    # fresh casts
         out = [float(ts().item()) for _ in range(4)]
-        if ts.shadows is not None:
+        if shadows:                       # still the current weights after four optimizer steps
+            assert all(mm.ops.weight_bf16(p) is d and torch.equal(d, p.detach().bfloat16()) for p, d in zip(ts.shadows.src, ts.shadows.dst))
             ts.shadows.close()
         return out
 
-    eager_cast, eager_copy = run(False, False), run(True, False)
-    assert eager_cast[-1] < eager_cast[0]
-    assert all(abs(a - b) <= 2e-3 * abs(a) for a, b in zip(eager_cast, eager_copy)), (eager_cast, eager_copy)
-    graph_copy = run(True, True)
-    assert all(abs(a - b) <= 2e-3 * abs(a) for a, b in zip(eager_cast, graph_copy)), (eager_cast, graph_copy)
+    for use_graph in (False, True):      # (a graphed TrainStep takes its warm-up steps before the capture: compare like with like)
+        cast, copy = run(False, use_graph), run(True, use_graph)
+        assert cast[-1] < cast[0]
+        assert all(abs(a - b) <= 2e-3 * abs(a) for a, b in zip(cast, copy)), (use_graph, cast, copy)
 
 
 def test_patch_embed_3d_projection_matches_conv(mm):
