@@ -43,6 +43,8 @@ def kernel_io(t: Optional[Tensor]) -> Optional[Tensor]:
 # alive instead and refresh them all with one multi-tensor copy after the step (train_step.TrainStep does).  A copy is
 # used only while the weight's version counter is the one seen at the last refresh: load_state_dict, .to(), or any other
 # in-place update from outside invalidates it by construction and the cast happens as before.
+# (Writes through `w.data` have their own version counter and are NOT seen: refresh() after them, as TrainStep does after
+# broadcasting the initial weights.)
 _BF16_SHADOWS = {}
 
 

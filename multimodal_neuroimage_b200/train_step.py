@@ -54,6 +54,8 @@ class TrainStep:
         if world > 1 and self.fwd_model is model:
             for p in model.parameters():
                 dist.broadcast(p.data, 0)
+            if self.shadows is not None:          # `.data` updates do not move the version counter the copies are guarded by
+                self.shadows.refresh()
         if self.use_graph:
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
