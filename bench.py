@@ -369,16 +369,21 @@ def run_cfg5_sweep(args, dev, rank, emit):
 # ------------------------------------------------------------------------------------------
 # Cross-modal multi-head attention (modules/multihead_attention.py:85-127): cfg1 sizes and a scaled shape
 # ------------------------------------------------------------------------------------------
-def run_mha(args, dev, rank, emit):
+MHA_SHAPES = (("cfg1 cross (E=84, 12 heads, d=7)", 84, 12, 368, 368, 2, torch.float32),
+              ("cfg1 self (E=168, 12 heads, d=14)", 168, 12, 368, 368, 2, torch.float32),
+              ("cfg1 cross, bf16 autocast (d=7 zero-padded to 32 by the projections)", 84, 12, 368, 368, 2, torch.bfloat16),
+              ("cfg1 self, bf16 autocast (d=14 zero-padded to 32 by the projections)", 168, 12, 368, 368, 2, torch.bfloat16),
+              ("scaled (E=768, 12 heads, d=64)", 768, 12, 2048, 2048, 32, torch.bfloat16))
+
+
+def measure_mha(steps, warmup, dev, shapes=MHA_SHAPES):
+    """Rows of the cross-modal MHA measurement: module fwd+bwd time and the attention-core kernels' own times (CUDA events
+    around mmn_mha_fwd / mmn_mha_bwd), per shape."""
     from multimodal_neuroimage_b200 import _lib
     from multimodal_neuroimage_b200.modules import multihead_attention as mh
     pk = peaks()
     rows = []
-    for name, E, nH, T, S, Bm, dt in (("cfg1 cross (E=84, 12 heads, d=7)", 84, 12, 368, 368, 2, torch.float32),
-                                      ("cfg1 self (E=168, 12 heads, d=14)", 168, 12, 368, 368, 2, torch.float32),
-                                      ("cfg1 cross, bf16 autocast (d=7 zero-padded to 32 by the projections)", 84, 12, 368, 368, 2, torch.bfloat16),
-                                      ("cfg1 self, bf16 autocast (d=14 zero-padded to 32 by the projections)", 168, 12, 368, 368, 2, torch.bfloat16),
-                                      ("scaled (E=768, 12 heads, d=64)", 768, 12, 2048, 2048, 32, torch.bfloat16)):
+    for name, E, nH, T, S, Bm, dt in shapes:
         m = mh.MultiheadAttention(E, nH).to(dev)
         m.need_weights = False
         q = torch.randn(T, Bm, E, device=dev, requires_grad=True)
@@ -395,9 +400,9 @@ def run_mha(args, dev, rank, emit):
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dt == torch.bfloat16):
             fn = lambda t: m(t, k, k, attn_mask=mask)[0]
             dyc = dy.to(dt) if dt == torch.bfloat16 else dy
-            ms = _time_fwd_bwd(fn, q, dyc, args.steps, args.warmup)
+            ms = _time_fwd_bwd(fn, q, dyc, steps, warmup)
             ops.KERNEL_EVENTS = {}                            # one more pass with CUDA events around the attention-core C calls
-            _time_fwd_bwd(fn, q, dyc, args.steps, 0)
+            _time_fwd_bwd(fn, q, dyc, steps, 0)
             kern = {n: sum(a.elapsed_time(b) for a, b in ev) / len(ev) for n, ev in ops.KERNEL_EVENTS.items()}
             ops.KERNEL_EVENTS = None
         flops = 3 * 4 * T * S * E * Bm
@@ -413,6 +418,12 @@ def run_mha(args, dev, rank, emit):
                      "module_tflops": flops / ms / 1e9, "path": path})
         del m, q, k, dy
         torch.cuda.empty_cache()
+    return rows
+
+
+def run_mha(args, dev, rank, emit):
+    pk = peaks()
+    rows = measure_mha(args.steps, args.warmup, dev)
     if rank == 0:
         last = rows[-1]
         emit({"metric": "crossmodal_mha_fwd_bwd", "value": last["core_tflops"], "unit": UNIT, "n_gpus": 1, "steps": args.steps,
@@ -469,6 +480,7 @@ def main():
                          "a training-step workload, the cfg5 per-stage roofline sweep, or cross-modal multi-head attention")
     ap.add_argument("--no-train", action="store_true", help="cfg2 line without the nested cfg3 training step")
     ap.add_argument("--no-eager-baseline", action="store_true")
+    ap.add_argument("--no-mha", action="store_true", help="cfg2 line without the nested cross-modal MHA measurement")
     ap.add_argument("--train-steps", type=int, default=10)
     ap.add_argument("--sustain-s", type=float, default=2.0, help="also time the step back to back for this many seconds (0: skip)")
     ap.add_argument("--train-batch", type=int, default=0, help="per-GPU batch of the training-step workload (0: its default)")
@@ -806,6 +818,21 @@ def main():
         except Exception as exc:
             train = {"error": f"{type(exc).__name__}: {exc}"}
             print(f"bench: nested cfg3 training step failed: {train['error']}", file=sys.stderr)
+    # the cross-modal MHA hot op (north_star's second path) at its scaled shape, nested like `train`: rank 0 only, no collective
+    mha = None
+    if rank == 0 and not args.no_mha:
+        try:
+            torch.cuda.empty_cache()
+            r = measure_mha(5, 3, dev, MHA_SHAPES[-1:])[0]
+            mha = {"workload": "cross-modal MultiheadAttention (multihead_attention.py:85-127) fwd+bwd, " + r["shape"] +
+                               ", T=S=2048, batch 32, bf16, no mask; TFLOP/s = attention-core algorithmic flops 12 T S E per sample "
+                               "over the core kernels' time", "path": r["path"], "core_fwd_ms": r["core_fwd_ms"],
+                   "core_bwd_ms": r["core_bwd_ms"], "core_tflops": r["core_tflops"], "frac_of_bf16_peak": r["core_frac_bf16_peak"],
+                   "module_fwd_bwd_ms": r["ms_fwd_bwd_module"], "module_tflops": r["module_tflops"],
+                   "more": "python bench.py --workload mha (cfg1 shapes, fp32 and bf16)"}
+        except Exception as exc:
+            mha = {"error": f"{type(exc).__name__}: {exc}"}
+            print(f"bench: nested MHA measurement failed: {mha['error']}", file=sys.stderr)
     clk.__exit__(None, None, None)
     eager = None
     if rank == 0 and not args.no_eager_baseline:
@@ -833,7 +860,7 @@ def main():
                                 f"{NSLOT} device slots, one CUDA-graph replay per chunk: PCIe-bound (measured duplex floor of these bytes on "
                                 "the pool's boxes: 8.0-8.7 ms, tools/pcie_probe.py)"},
                 "gpu_launches": launches, "launch": LAUNCH_MODE[0], "roofline": roofline, "cpu_baseline": cpu,
-                "gpu_eager_baseline": eager, "train": train, "clocks": clk.summary(),
+                "gpu_eager_baseline": eager, "train": train, "mha": mha, "clocks": clk.summary(),
                 "paths": {"fwd": ops.winattn_path_name(torch.empty(1, *GRID, 3 * C, device=dev, dtype=torch.bfloat16), None, GRID,
                                                        (WINDOW,) * 3, (SHIFT,) * 3, HEADS, _lib.SCORE_COSINE, _lib.MASK_SHIFT)}}
         emit(line)

@@ -15,6 +15,8 @@
 //
 // One warp per row; lane l owns the column pairs 2 (l + 32 k): 4-byte (bf16x2) or 8-byte (float2) accesses, fully
 // coalesced, values stay in registers between the statistics pass and the normalisation pass.  fp32 arithmetic.
+#include <unordered_map>
+#include <mutex>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -433,6 +435,26 @@ V4Cfg v4_cfg(int cols) {
 }
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// Blocks of `kern` that fit on one SM at kLnWarps * 32 threads (registers decide: 64 -> 4, 80 -> 3).  The grid-stride kernels
+// are launched as whole resident waves: 8 blocks per SM for a kernel of which 3 fit ran 2.67 waves -- the last one a third
+// empty -- and cost the LayerNorm backward 9-12 % at cfg3's 110 592 rows (tools/bench_ln.py: 46.6 -> 42.5 us pre-norm,
+// 44.3 -> 39.3 us post-norm; two waves are no better than one at any width); its per-block column-sum flush (192 atomics)
+// also runs 2.7x less often.
+int resident_blocks(const void* kern) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, int> cache;
+  std::lock_guard<std::mutex> g(mu);
+  auto it = cache.find(kern);
+  if (it != cache.end()) return it->second;
+  int b = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kLnWarps * 32, 0) != cudaSuccess || b < 1) {
+    cudaGetLastError();
+    b = 2;
+  }
+  cache[kern] = b;
+  return b;
+}
+
 // up to blocks_per_sm x 148 blocks (grid-stride loops inside)
 int ln_grid_v4(long long rows, int lpr, int unroll, int blocks_per_sm) {
   const long long per_block = (long long)kLnWarps * (32 / lpr) * unroll;
@@ -481,9 +503,11 @@ cudaError_t layernorm_fwd(const void* resid, int resid_dt, const void* delta, in
   const V4Cfg vc = v4_cfg(cols);
   if (vc.lpr && aligned16(resid) && aligned16(delta) && aligned16(out_sum) && aligned16(out_norm) && aligned16(gamma) && aligned16(beta)) {
 #define MMN_LN_V4(L_, V_) if (vc.lpr == L_ && vc.v == V_) {                                                                       \
-      constexpr int U0 = 1, U1 = 1, BPS = 8;                                                         \
-      if (mode == 0) ln_fwd_v4_kernel<L_, V_, 0, U0><<<ln_grid_v4(rows, L_, U0, BPS), kLnWarps * 32, 0, st>>>(r, d, gamma, beta, eps, os, on, mean, rstd, rows, cols); \
-      else ln_fwd_v4_kernel<L_, V_, 1, U1><<<ln_grid_v4(rows, L_, U1, BPS), kLnWarps * 32, 0, st>>>(r, d, gamma, beta, eps, os, on, mean, rstd, rows, cols);           \
+      constexpr int U0 = 1, U1 = 1;                                                                  \
+      auto k0 = ln_fwd_v4_kernel<L_, V_, 0, U0>;                                                     \
+      auto k1 = ln_fwd_v4_kernel<L_, V_, 1, U1>;                                                     \
+      if (mode == 0) k0<<<ln_grid_v4(rows, L_, U0, resident_blocks((const void*)k0)), kLnWarps * 32, 0, st>>>(r, d, gamma, beta, eps, os, on, mean, rstd, rows, cols); \
+      else k1<<<ln_grid_v4(rows, L_, U1, resident_blocks((const void*)k1)), kLnWarps * 32, 0, st>>>(r, d, gamma, beta, eps, os, on, mean, rstd, rows, cols);           \
     }
     MMN_LN_V4(8, 1) MMN_LN_V4(8, 2) MMN_LN_V4(8, 3) MMN_LN_V4(16, 2) MMN_LN_V4(16, 3) MMN_LN_V4(32, 2) MMN_LN_V4(32, 3) MMN_LN_V4(32, 4) MMN_LN_V4(32, 6)
 #undef MMN_LN_V4
@@ -506,9 +530,11 @@ cudaError_t layernorm_bwd(const void* g_sum, int gs_dt, const void* g_norm, int 
   const V4Cfg vc = v4_cfg(cols);
   if (vc.lpr && aligned16(g_sum) && aligned16(g_norm) && aligned16(x) && aligned16(d_resid) && aligned16(d_delta) && aligned16(gamma)) {
 #define MMN_LN_V4(L_, V_) if (vc.lpr == L_ && vc.v == V_) {                                                                       \
-      constexpr int U = 1, BPS = 8;                                                                  \
-      if (mode == 0) ln_bwd_v4_kernel<L_, V_, 0, U><<<ln_grid_v4(rows, L_, U, BPS), kLnWarps * 32, 0, st>>>(gs, gn, xx, gamma, mean, rstd, dr, dd, dgamma, dbeta, rows, cols); \
-      else ln_bwd_v4_kernel<L_, V_, 1, U><<<ln_grid_v4(rows, L_, U, BPS), kLnWarps * 32, 0, st>>>(gs, gn, xx, gamma, mean, rstd, dr, dd, dgamma, dbeta, rows, cols);           \
+      constexpr int U = 1;                                                                           \
+      auto k0 = ln_bwd_v4_kernel<L_, V_, 0, U>;                                                      \
+      auto k1 = ln_bwd_v4_kernel<L_, V_, 1, U>;                                                      \
+      if (mode == 0) k0<<<ln_grid_v4(rows, L_, U, resident_blocks((const void*)k0)), kLnWarps * 32, 0, st>>>(gs, gn, xx, gamma, mean, rstd, dr, dd, dgamma, dbeta, rows, cols); \
+      else k1<<<ln_grid_v4(rows, L_, U, resident_blocks((const void*)k1)), kLnWarps * 32, 0, st>>>(gs, gn, xx, gamma, mean, rstd, dr, dd, dgamma, dbeta, rows, cols);           \
     }
     MMN_LN_V4(8, 1) MMN_LN_V4(8, 2) MMN_LN_V4(8, 3) MMN_LN_V4(16, 2) MMN_LN_V4(16, 3) MMN_LN_V4(32, 2) MMN_LN_V4(32, 3) MMN_LN_V4(32, 4) MMN_LN_V4(32, 6)
 #undef MMN_LN_V4
