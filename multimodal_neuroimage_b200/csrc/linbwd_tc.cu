@@ -210,26 +210,36 @@ linbwd_tc_kernel(const __grid_constant__ LinBwdParams P) {
 }
 
 // out[e] = sum over CTAs of ws[cta][e]; element e = (row i in 0..96, out-channel o): rows 0..95 -> dW[o][i], row 96 -> db[o].
-// Block = 128 elements (one float4 of four out-channels per lane) x 8 slices of the CTA range.
-__global__ void __launch_bounds__(256)
+// Block = 128 elements (one float4 of four out-channels per lane) x 32 slices of the CTA range: with 148 partials a thread
+// issues at most five independent loads (the kernel is pure latency: 8 slices = 19 loads per thread took 6.2 us per launch,
+// 192 launches in a cfg3 step).  Summation order is fixed: deterministic.
+constexpr int kRedSlices = 32;
+__global__ void __launch_bounds__(kRedSlices * 32)
 linbwd_reduce_kernel(const float* __restrict__ ws, int n_cta, int ncol, float* __restrict__ dw, float* __restrict__ db) {
-  __shared__ float4 part[8][32];
+  __shared__ float4 part[kRedSlices][32];
   const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int e = (blockIdx.x * 32 + lane) * 4;
   const int n = 97 * ncol;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (e < n) {
-#pragma unroll 4
-    for (int c = sl; c < n_cta; c += 8) {
+#pragma unroll 5
+    for (int c = sl; c < n_cta; c += kRedSlices) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(ws + (size_t)c * n + e));
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
   }
   part[sl][lane] = s;
   __syncthreads();
+  if (sl < 4) {                                                // slices 8 sl .. 8 sl + 7
+    s = part[8 * sl][lane];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { const float4 v = part[8 * sl + k][lane]; s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+    part[8 * sl][lane] = s;
+  }
+  __syncthreads();
   if (sl == 0 && e < n) {
 #pragma unroll
-    for (int k = 1; k < 8; ++k) { const float4 v = part[k][lane]; s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+    for (int k = 1; k < 4; ++k) { const float4 v = part[8 * k][lane]; s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
     const int i = e / ncol, o = e - i * ncol;                // ncol % 4 == 0: the four elements share the row
     if (i < 96) { dw[o * 96 + i] = s.x; dw[(o + 1) * 96 + i] = s.y; dw[(o + 2) * 96 + i] = s.z; dw[(o + 3) * 96 + i] = s.w; }
     else if (db) *reinterpret_cast<float4*>(db + o) = s;
@@ -284,7 +294,7 @@ int linbwd(const void* dy, const void* x, const void* w, void* dx, float* dw, fl
   if (e != cudaSuccess) { snprintf(err, errlen, "linbwd_tc_kernel: %s", cudaGetErrorString(e)); return MMN_ERR_CUDA; }
   ++*launches;
   const int n = out_features * 97;
-  linbwd_reduce_kernel<<<(n / 4 + 31) / 32, 256, 0, st>>>(workspace, grid, out_features, dw, db);   // ncol = out_features
+  linbwd_reduce_kernel<<<(n / 4 + 31) / 32, kRedSlices * 32, 0, st>>>(workspace, grid, out_features, dw, db);   // ncol = out_features
   e = cudaGetLastError();
   if (e != cudaSuccess) { snprintf(err, errlen, "linbwd_reduce_kernel: %s", cudaGetErrorString(e)); return MMN_ERR_CUDA; }
   ++*launches;
