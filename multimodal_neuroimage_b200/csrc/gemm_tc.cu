@@ -267,25 +267,34 @@ gemm_tc_kernel(const __grid_constant__ GemmParams P) {
   if (warp == kGMmaWarp) tmem_dealloc<kGTmemCols>(tmem);
 }
 
-// out[e] = sum over splits of part[s][e].  Block = 128 elements (one float4 per lane) x 8 slices of the split range.
-__global__ void __launch_bounds__(256)
+// out[e] = sum over splits of part[s][e].  Block = 128 elements (one float4 per lane) x 32 slices of the split range (pure
+// latency: a thread issues at most ceil(splits / 32) independent loads); fixed summation order.
+constexpr int kGRedSlices = 32;
+__global__ void __launch_bounds__(kGRedSlices * 32)
 gemm_reduce_kernel(const float* __restrict__ part, int splits, long long n, float* __restrict__ out) {
-  __shared__ float4 red[8][32];
+  __shared__ float4 red[kGRedSlices][32];
   const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const long long e = ((long long)blockIdx.x * 32 + lane) * 4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (e < n) {
 #pragma unroll 4
-    for (int s = sl; s < splits; s += 8) {
+    for (int s = sl; s < splits; s += kGRedSlices) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(part + (size_t)s * n + e));
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
   }
   red[sl][lane] = acc;
   __syncthreads();
+  if (sl < 4) {                                                // slices 8 sl .. 8 sl + 7
+    acc = red[8 * sl][lane];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { const float4 v = red[8 * sl + k][lane]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+    red[8 * sl][lane] = acc;
+  }
+  __syncthreads();
   if (sl == 0 && e < n) {
 #pragma unroll
-    for (int k = 1; k < 8; ++k) { const float4 v = red[k][lane]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+    for (int k = 1; k < 4; ++k) { const float4 v = red[8 * k][lane]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
     *reinterpret_cast<float4*>(out + e) = acc;
   }
 }
@@ -427,7 +436,7 @@ int linear_bwd_general(const void* dy, const void* x, const void* w, void* dx, f
     ++*launches;
     if (P.splits > 1) {
       const long long n = (long long)out_features * in_features;
-      gemm_reduce_kernel<<<(unsigned)((n / 4 + 31) / 32), 256, 0, st>>>(workspace, P.splits, n, dw);
+      gemm_reduce_kernel<<<(unsigned)((n / 4 + 31) / 32), kGRedSlices * 32, 0, st>>>(workspace, P.splits, n, dw);
       if (cudaGetLastError() != cudaSuccess) { snprintf(err, errlen, "gemm_reduce_kernel launch failed"); return MMN_ERR_CUDA; }
       ++*launches;
     }
