@@ -235,10 +235,10 @@ __device__ __forceinline__ float row_sum(float v) {          // sum over the LPR
 __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
 // MODE (pre- / post-norm) is a template parameter: the pre-norm forward keeps no residual copy and fits 64 registers (four
-// blocks per SM).  U row groups per iteration with all their loads issued up front (U = 2 at two blocks per SM measured
+// blocks per SM); the post-norm one took 80-85 (three blocks) until it was asked for four as well: 32.3 -> 30.7 us at 110 592 x 96.  U row groups per iteration with all their loads issued up front (U = 2 at two blocks per SM measured
 // no better than U = 1 at three or four: tools/bench_blocks.py, r2o vs r2k), so the launches use U = 1.
 template <int LPR, int V, int MODE, int U>
-__global__ void __launch_bounds__(kLnWarps * 32)
+__global__ void __launch_bounds__(kLnWarps * 32, V <= 3 ? 4 : 0)      // 0 = no occupancy request (as before) for the wide rows
 ln_fwd_v4_kernel(LnTensor resid, LnTensor delta, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                  LnOut out_sum, LnOut out_norm, float* __restrict__ mean, float* __restrict__ rstd, long long rows, int cols) {
   constexpr int R = 32 / LPR;
