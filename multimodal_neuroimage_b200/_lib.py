@@ -17,14 +17,15 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 # MMN_LIB=<path>: load another build of the library (A/B timing of kernel variants on one GPU box)
 LIB_PATH = os.environ.get("MMN_LIB") or os.path.join(PKG_DIR, "libmmn_b200.so")
 # translation unit -> headers it depends on (besides include/mmn_b200.h)
-SOURCES = {"mmn_abi.cu": ["generic_launch.h", "attn_generic.cuh", "winattn_tc.h", "dropout_rng.cuh"],
-           "generic_launch.cu": ["generic_launch.h", "attn_generic.cuh", "dropout_rng.cuh"],
-           "winattn_tc.cu": ["winattn_tc.h", "winattn_tc_fwd.cuh", "winattn_tc_bwd.cuh", "tc_window.cuh", "tc_sched.cuh", "tc_common.cuh"],
+SOURCES = {"mmn_abi.cu": ["generic_launch.h", "attn_generic.cuh", "winattn_tc.h", "dropout_rng.cuh", "zero_fill.h"],
+           "generic_launch.cu": ["generic_launch.h", "attn_generic.cuh", "dropout_rng.cuh", "zero_fill.h"],
+           "winattn_tc.cu": ["winattn_tc.h", "winattn_tc_fwd.cuh", "winattn_tc_bwd.cuh", "tc_window.cuh", "tc_sched.cuh", "tc_common.cuh",
+                             "zero_fill.h"],
            "linbwd_tc.cu": ["winattn_tc.h", "tc_window.cuh", "tc_common.cuh"],
            "gemm_tc.cu": ["winattn_tc.h", "tc_window.cuh", "tc_common.cuh"],
            "mha_tc.cu": ["winattn_tc.h", "tc_window.cuh", "tc_common.cuh", "dropout_rng.cuh"],
            "layernorm.cu": ["generic_launch.h", "attn_generic.cuh", "dropout_rng.cuh"],
-           "cpb_bias.cu": ["generic_launch.h", "attn_generic.cuh", "dropout_rng.cuh"]}
+           "cpb_bias.cu": ["generic_launch.h", "attn_generic.cuh", "dropout_rng.cuh", "zero_fill.h"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 # MMN_BUILD_TRACE=1 compiles the per-phase clock tracing into the tensor-core kernels (tools/trace_*.py);

@@ -12,6 +12,7 @@
 #include <mutex>
 
 #include "generic_launch.h"
+#include "zero_fill.h"
 
 namespace mmn {
 
@@ -175,7 +176,7 @@ cudaError_t table_bias_fwd(const float* table, const long long* index, int nH, i
 }
 
 cudaError_t table_bias_bwd(const float* dbias, const long long* index, int T, int nH, int NN, float* dtable, cudaStream_t st, int* launches) {
-  cudaError_t e = cudaMemsetAsync(dtable, 0, (size_t)T * nH * sizeof(float), st);
+  cudaError_t e = zero_words_async(dtable, (size_t)T * nH, st);
   if (e != cudaSuccess) return e;
   cpb_scatter_kernel<<<(NN + 255) / 256, 256, 0, st>>>(dbias, index, NN, nH, dtable);
   e = cudaGetLastError();
@@ -195,7 +196,7 @@ cudaError_t cpb_bias_fwd(const float* coords, const float* w1, const float* b1, 
 cudaError_t cpb_bias_bwd(const float* coords, const float* w1, const float* b1, const float* w2, const long long* index,
                          const float* tab16, const float* dbias, int T, int n_in, int J, int nH, int NN, float* dtab16, float* dw1,
                          float* db1, float* dw2, cudaStream_t st, int* launches) {
-  cudaError_t e = cudaMemsetAsync(dtab16, 0, (size_t)T * nH * sizeof(float), st);
+  cudaError_t e = zero_words_async(dtab16, (size_t)T * nH, st);
   if (e != cudaSuccess) return e;
   cpb_scatter_kernel<<<(NN + 255) / 256, 256, 0, st>>>(dbias, index, NN, nH, dtab16);
   const size_t smem = cpb_bwd_smem_bytes(T);

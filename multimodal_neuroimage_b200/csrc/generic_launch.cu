@@ -1,5 +1,6 @@
 // generic_launch.cu -- instantiates and launches the shape-generic kernels.
 #include "generic_launch.h"
+#include "zero_fill.h"
 
 #include "../../include/mmn_b200.h"
 
@@ -113,6 +114,17 @@ cudaError_t colsum(int dt, const void* x, long long rows, int cols, long long ro
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) ++*launches;
   return e;
+}
+
+__global__ void zero_words_kernel(uint32_t* __restrict__ p, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0u;
+}
+
+cudaError_t zero_words_async(void* p, size_t words, cudaStream_t st) {
+  if (words == 0) return cudaSuccess;
+  const size_t want = (words + 255) / 256;
+  zero_words_kernel<<<(unsigned)(want < 592 ? want : 592), 256, 0, st>>>(static_cast<uint32_t*>(p), words);
+  return cudaGetLastError();
 }
 
 }  // namespace mmn

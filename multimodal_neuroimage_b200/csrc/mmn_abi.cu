@@ -9,6 +9,7 @@
 
 #include "../../include/mmn_b200.h"
 #include "generic_launch.h"
+#include "zero_fill.h"
 #include "winattn_tc.h"
 
 namespace {
@@ -385,7 +386,7 @@ int mmn_linear_bwd(const void* dy, const void* x, const void* w, void* dx, float
                                      ld_x, ld_dx, st, g_err, sizeof(g_err), &n);
     if (rc == MMN_OK && db) {
       // bias gradient: column sums of dy, 2048 columns per launch (colsum_kernel's block covers 256 x 8)
-      cudaError_t e = cudaMemsetAsync(db, 0, (size_t)out_features * sizeof(float), st);
+      cudaError_t e = mmn::zero_words_async(db, (size_t)out_features, st);
       for (int c0 = 0; e == cudaSuccess && c0 < out_features; c0 += 2048)
         e = mmn::colsum(MMN_DT_BF16, static_cast<const uint16_t*>(dy) + c0, rows, out_features - c0 < 2048 ? out_features - c0 : 2048, ld_dy,
                         db + c0, st, &n);

@@ -33,6 +33,7 @@
 #include <mutex>
 
 #include "tc_sched.cuh"
+#include "zero_fill.h"
 
 namespace mmn { namespace tc {
 
@@ -588,13 +589,13 @@ inline TraceCfg trace_setup(const char* path, cudaStream_t st) {
 }
 
 // Work counters of the dynamic schedule (tc_sched.cuh: ClassQueue): kWorkSlotInts ints that belong to ONE launch -- the
-// caller's `workspace` -- zeroed on the launch's stream right before the kernel (a memset node when captured).  Nothing
+// caller's `workspace` -- zeroed on the launch's stream right before the kernel (by a one-block kernel: zero_fill.h).  Nothing
 // is shared between launches, so launches on different streams, captured graphs replayed side by side and any number
 // of launches in flight are independent by construction.
 inline int* arm_work_counters(void* workspace, cudaStream_t st, char* err, size_t errlen) {
   if (!workspace || reinterpret_cast<uintptr_t>(workspace) % 4) { snprintf(err, errlen, "workspace missing or misaligned"); return nullptr; }
-  if (cudaMemsetAsync(workspace, 0, kWorkSlotInts * sizeof(int), st) != cudaSuccess) {
-    snprintf(err, errlen, "cudaMemsetAsync(work counters): %s", cudaGetErrorString(cudaGetLastError()));
+  if (mmn::zero_words_async(workspace, kWorkSlotInts, st) != cudaSuccess) {       // a kernel, not a memset node: zero_fill.h
+    snprintf(err, errlen, "zeroing the work counters: %s", cudaGetErrorString(cudaGetLastError()));
     return nullptr;
   }
   return static_cast<int*>(workspace);
