@@ -43,6 +43,27 @@ def future_mask_diagonal_of(mask):
     return geometry.future_mask_diagonal(mask.shape[0], mask.shape[1]) if _future_masks.get(key) is mask else None
 
 
+class _SplitRows(torch.autograd.Function):
+    """t -> row blocks t[0:s0], t[s0:s0+s1], ... (views), with the gradient assembled by ONE torch.cat.  Autograd's own
+    slicing gives every block a SliceBackward -- a zero fill of the full tensor, a device-to-device memcpy into the slice and
+    an add of the partial gradients -- and inside a CUDA graph each of those memcpy nodes costs ~8 us of dependency latency
+    between kernel nodes (tools/find_memcpy.py: 48 of them per cfg4 training step, all from the in-projection slices)."""
+
+    @staticmethod
+    def forward(ctx, t, *sizes):
+        ctx.sizes = sizes
+        ctx.set_materialize_grads(False)
+        ctx.like = (t.shape[1:], t.dtype, t.device)
+        return tuple(t.split(list(sizes), dim=0))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        shape, dtype, device = ctx.like
+        parts = [g if g is not None else torch.zeros((n,) + tuple(shape), dtype=dtype, device=device)
+                 for g, n in zip(grads, ctx.sizes)]
+        return (torch.cat(parts, dim=0),) + (None,) * len(ctx.sizes)
+
+
 class MultiheadAttention(nn.Module):
     def __init__(self, embed_dim, num_heads_mult, attn_dropout=0., bias=True, add_bias_kv=False, add_zero_attn=False):
         super().__init__()
@@ -92,14 +113,16 @@ class MultiheadAttention(nn.Module):
         pad = self._padded_head_dim(query)
         E = self.embed_dim
         if query is key and key is value or (query.data_ptr() == key.data_ptr() == value.data_ptr()):
-            q, k, v = self._in_proj(query, pad=pad).chunk(3, dim=-1)
+            q, k, v = self._project(query, self.in_proj_weight, self.in_proj_bias, pad).chunk(3, dim=-1)
         elif key is value or key.data_ptr() == value.data_ptr():
-            q = self._in_proj(query, end=E, pad=pad)
-            k, v = self._in_proj(key, start=E, pad=pad).chunk(2, dim=-1)
+            (wq, wkv), (bq, bkv) = self._split_in_proj(E, 2 * E)
+            q = self._project(query, wq, bq, pad)
+            k, v = self._project(key, wkv, bkv, pad).chunk(2, dim=-1)
         else:
-            q = self._in_proj(query, end=E, pad=pad)
-            k = self._in_proj(key, start=E, end=2 * E, pad=pad)
-            v = self._in_proj(value, start=2 * E, pad=pad)
+            (wq, wk, wv), (bq, bk, bv) = self._split_in_proj(E, E, E)
+            q = self._project(query, wq, bq, pad)
+            k = self._project(key, wk, bk, pad)
+            v = self._project(value, wv, bv, pad)
 
         diagonal = future_mask_diagonal_of(attn_mask)
         if self.bias_k is not None:
@@ -174,12 +197,22 @@ class MultiheadAttention(nn.Module):
         lead = t.shape[:-1]
         return F.pad(t.reshape(*lead, self.num_heads_mult, self.head_dim), (0, pad - self.head_dim)).reshape(*lead, self.num_heads_mult * pad)
 
+    def _split_in_proj(self, *sizes):
+        """Row blocks of in_proj_weight / in_proj_bias whose gradients come back through one torch.cat (_SplitRows)."""
+        w = _SplitRows.apply(self.in_proj_weight, *sizes)
+        b = _SplitRows.apply(self.in_proj_bias, *sizes) if self.in_proj_bias is not None else (None,) * len(sizes)
+        return w, b
+
     def _in_proj(self, input, start=0, end=None, pad=0, **kwargs):
         weight = kwargs.get('weight', self.in_proj_weight)
         bias = kwargs.get('bias', self.in_proj_bias)
         weight = weight[start:end, :]
         if bias is not None:
             bias = bias[start:end]
+        return self._project(input, weight, bias, pad)
+
+    def _project(self, input, weight, bias, pad=0):
+        """F.linear with the rows of `weight` / `bias` (whole heads) zero-padded per head to `pad` channels (0: as they are)."""
         if pad:                                       # zero rows after every head's head_dim rows: the output is head-padded
             nb = weight.shape[0] // self.embed_dim
             weight = F.pad(weight.view(nb * self.num_heads_mult, self.head_dim, -1), (0, 0, 0, pad - self.head_dim))

@@ -248,3 +248,51 @@ def test_bf16_weight_shadows_follow_the_version_counter():
     assert ops.weight_bf16(lin.weight) is not ops.weight_bf16(lin.weight)
     w16 = torch.zeros(2, 2, dtype=torch.bfloat16)
     assert ops.weight_bf16(w16) is w16
+
+
+def test_in_proj_row_split_gradients_match_slicing():
+    """MultiheadAttention hands the q / kv (or q / k / v) row blocks of in_proj_weight and in_proj_bias to the projections
+    through _SplitRows, whose backward is one torch.cat instead of autograd's zero-fill + memcpy + add per slice: values are
+    the slices themselves and the parameter gradients equal those of plain slicing, including an unused block."""
+    import torch
+    from multimodal_neuroimage_b200.modules.multihead_attention import MultiheadAttention
+    torch.manual_seed(5)
+    E = 24
+    m = MultiheadAttention(E, 4)
+    with torch.no_grad():
+        m.in_proj_bias.normal_()
+    x, y, z = torch.randn(5, 2, E), torch.randn(7, 2, E), torch.randn(7, 2, E)
+
+    def grads(fn):
+        m.zero_grad()
+        fn().backward()
+        return m.in_proj_weight.grad.clone(), m.in_proj_bias.grad.clone()
+
+    def split2():
+        (wq, wkv), (bq, bkv) = m._split_in_proj(E, 2 * E)
+        assert torch.equal(wq, m.in_proj_weight[:E]) and torch.equal(wkv, m.in_proj_weight[E:]) and torch.equal(bkv, m.in_proj_bias[E:])
+        return m._project(x, wq, bq).sin().sum() + m._project(y, wkv, bkv).pow(2).sum()
+
+    def slice2():
+        return m._in_proj(x, end=E).sin().sum() + m._in_proj(y, start=E).pow(2).sum()
+
+    def split3():
+        (wq, wk, wv), (bq, bk, bv) = m._split_in_proj(E, E, E)
+        return m._project(x, wq, bq).sin().sum() + m._project(y, wk, bk).pow(2).sum() + m._project(z, wv, bv).cos().sum()
+
+    def slice3():
+        return m._in_proj(x, end=E).sin().sum() + m._in_proj(y, start=E, end=2 * E).pow(2).sum() + m._in_proj(z, start=2 * E).cos().sum()
+
+    def split_unused():
+        (wq, _), (bq, _) = m._split_in_proj(E, 2 * E)
+        return m._project(x, wq, bq).sin().sum()
+
+    def slice_unused():
+        return m._in_proj(x, end=E).sin().sum()
+
+    for a, b in ((split2, slice2), (split3, slice3), (split_unused, slice_unused)):
+        (gw, gb), (hw, hb) = grads(a), grads(b)
+        assert torch.allclose(gw, hw, atol=1e-6) and torch.allclose(gb, hb, atol=1e-6)
+    m2 = MultiheadAttention(E, 4, bias=False)
+    (wq, wkv), (bq, bkv) = m2._split_in_proj(E, 2 * E)
+    assert bq is None and bkv is None and wkv.shape == (2 * E, E)
